@@ -1,0 +1,229 @@
+/*
+ * b200yolo.h -- C ABI of libb200yolo.so (sm_100a kernels for the Darknet YOLOv3/v4 hot path).
+ *
+ * The reference (SpursLipu/YOLOv3v4-ModelCompression-MultidatasetTraining-Multibackbone) is pure
+ * Python on top of torch ATen; it has no FFI of its own.  The drop-in boundary is therefore the
+ * Python module API (models.Darknet, utils.utils.compute_loss, utils/quantized/...), and this
+ * header is the native boundary *underneath* it: every entry point replaces
+ * the ATen/cuDNN call(s) issued at the cited reference file:line.
+ *
+ * Conventions
+ *   - plain C, device pointers + explicit shapes, no allocation inside, no exceptions;
+ *   - every function returns 0 on success, <0 on error (b2y_strerror);
+ *   - `stream` is a cudaStream_t passed as void*; kernels are enqueued, never synchronised;
+ *   - activations are NHWC ("pixel-major"): element (n,y,x,c) at ((n*H+y)*W+x)*pitch + c, where
+ *     `pitch` >= C lets a tensor live as a channel slice of a wider (route/concat) buffer;
+ *   - fp16 activations/weights for the dense path, fp32 for the YOLO head, loss and statistics.
+ */
+#ifndef B200YOLO_H_
+#define B200YOLO_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2Y_ABI_VERSION 1
+
+/* status codes */
+#define B2Y_OK 0
+#define B2Y_ERR_INVALID (-1)
+#define B2Y_ERR_CUDA (-2)
+#define B2Y_ERR_UNSUPPORTED (-3)
+#define B2Y_ERR_DRIVER (-4)
+
+/* activation ids -- models.py:102-113 (leaky/relu6/h_swish/relu/mish), utils/layers.py:141-173 */
+#define B2Y_ACT_LINEAR 0
+#define B2Y_ACT_LEAKY 1
+#define B2Y_ACT_MISH 2
+#define B2Y_ACT_RELU 3
+#define B2Y_ACT_RELU6 4
+#define B2Y_ACT_HSWISH 5
+#define B2Y_ACT_SWISH 6
+
+/* output dtypes of the conv epilogue */
+#define B2Y_OUT_F16 0
+#define B2Y_OUT_F32 1
+#define B2Y_OUT_I8 2
+
+int b2y_abi_version(void);
+const char* b2y_strerror(int status);
+int b2y_last_cuda_error(void);   /* raw cudaError_t of the last B2Y_ERR_CUDA on this thread */
+int b2y_device_sm_count(void);   /* -1 without a CUDA device */
+
+/* ------------------------------------------------------------------------------------------------
+ * Dense convolution block: Conv2d (+ folded BatchNorm) + activation (+ residual add)
+ * replaces nn.Conv2d / nn.BatchNorm2d(eval) / activation / Shortcut  (models.py:92-113,
+ * utils/layers.py:43-72, utils/torch_utils.py:65-89).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct b2y_conv_desc {
+    int batch, in_h, in_w, in_c; /* logical NHWC input */
+    long long in_pitch;          /* elements between consecutive input pixels (>= in_c, multiple of 8) */
+    int out_c, ksize, stride, pad;
+    int out_h, out_w;
+    long long out_pitch; /* elements between consecutive output pixels */
+    int act;             /* B2Y_ACT_* */
+    float slope;         /* leaky slope (0.1; 0.25 with maxabsscaler, models.py:103) */
+    int out_dtype;       /* B2Y_OUT_F16 or B2Y_OUT_F32 */
+    long long res_pitch; /* pitch of the residual tensor (ignored when residual == NULL) */
+} b2y_conv_desc;
+
+/* y = act(conv(x, w) + bias) [+ residual]
+ *   x        fp16 NHWC
+ *   w_packed fp16 [out_c][k][k][in_c]  (see b2y_pack_conv_weights)
+ *   bias     fp32 [out_c] or NULL
+ *   residual fp16 NHWC [.., out_c] or NULL (added after the activation = the following Shortcut layer)
+ *   y        fp16 / fp32 NHWC
+ * in_c must be a multiple of 16 (the Cin=3 stem uses b2y_stem_conv_fwd). */
+int b2y_conv2d_fwd(const b2y_conv_desc* d, const void* x, const void* w_packed, const float* bias,
+                   const void* residual, void* y, void* stream);
+
+/* Same GEMM, but also accumulates per-channel sum / sum-of-squares of the *raw* conv output into
+ * stat_sum / stat_sqsum (fp32 [out_c], caller zeroes them): the batch statistics of training-mode
+ * BatchNorm2d (models.py:100) come out of the conv epilogue instead of two extra passes. */
+int b2y_conv2d_fwd_stats(const b2y_conv_desc* d, const void* x, const void* w_packed, const float* bias,
+                         void* y, float* stat_sum, float* stat_sqsum, void* stream);
+
+/* First layer (in_c = 1..4, NCHW fp32 image straight from the data loader, models.py:20,92):
+ * direct convolution on CUDA cores, fused folded-BN bias + activation, writes NHWC fp16.
+ *   x      fp32 NCHW [batch][in_c][in_h][in_w]
+ *   w      fp32 [out_c][in_c][k][k]  (BN already folded), bias fp32 [out_c] */
+int b2y_stem_conv_fwd(const b2y_conv_desc* d, const float* x_nchw, const float* w, const float* bias, void* y,
+                      void* stream);
+
+/* Fold BatchNorm (running stats) into conv weights and repack OIHW fp32 -> [O][kh][kw][I] fp16.
+ *   w_f = w * gamma/sqrt(var+eps);  b_f = beta - gamma*mean/sqrt(var+eps) (+ conv_bias*scale)
+ * (utils/torch_utils.py:65-89, utils/quantized/quantized_ptq_cos.py:193-206).
+ * gamma==NULL: no BN, bias_out = conv_bias (or 0).  w_fp32_out (optional, OIHW) receives the folded
+ * fp32 weights (used by the stem). */
+int b2y_pack_conv_weights(const float* w_oihw, const float* conv_bias, const float* gamma, const float* beta,
+                          const float* mean, const float* var, float eps, int out_c, int in_c, int ksize,
+                          void* w_packed_f16, float* bias_out, float* w_fp32_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Pointwise / data-movement layers (NHWC fp16)
+ * ------------------------------------------------------------------------------------------------ */
+/* nn.Upsample(scale_factor=s) nearest, models.py:224-225 */
+int b2y_upsample_nearest(const void* x, long long x_pitch, void* y, long long y_pitch, int batch, int in_h, int in_w,
+                         int c, int scale, void* stream);
+/* nn.MaxPool2d(k, stride, (k-1)//2) and the yolov3-tiny ZeroPad2d((0,1,0,1))+MaxPool2d(2,1), models.py:207-215.
+ * pad_mode 0: symmetric (k-1)//2 with -inf padding; pad_mode 1: pad right/bottom by one with zeros. */
+int b2y_maxpool(const void* x, long long x_pitch, void* y, long long y_pitch, int batch, int in_h, int in_w, int c,
+                int ksize, int stride, int pad_mode, void* stream);
+/* channel-slice copy (FeatureConcat fallback when a producer cannot write in place), utils/layers.py:26-40 */
+int b2y_copy_channels(const void* x, long long x_pitch, void* y, long long y_pitch, long long pixels, int c,
+                      void* stream);
+/* y = a + b (Shortcut fallback when the add is not fused in the conv epilogue), utils/layers.py:43-72 */
+int b2y_add(const void* a, long long a_pitch, const void* b, long long b_pitch, void* y, long long y_pitch,
+            long long pixels, int c, void* stream);
+/* standalone activation fwd/bwd on fp32 (Mish: utils/layers.py:117-128,146-148) */
+int b2y_act_fwd_f32(const float* x, float* y, long long n, int act, float slope, void* stream);
+int b2y_act_bwd_f32(const float* x, const float* dy, float* dx, long long n, int act, float slope, void* stream);
+/* layout converters */
+int b2y_nchw_f32_to_nhwc_f16(const float* x, void* y, long long y_pitch, int batch, int c, int h, int w,
+                             void* stream);
+int b2y_nhwc_f16_to_nchw_f32(const void* x, long long x_pitch, float* y, int batch, int c, int h, int w,
+                             void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * YOLO head: models.py:350-437 (YOLOLayer.forward)
+ *   raw : fp32 [batch][ny][nx][raw_pitch] head-conv output, channel = a*no + o
+ *   p   : fp32 [batch][na][ny][nx][no]  (the "training output", models.py:406)      (may be NULL)
+ *   io  : fp32 rows of a [batch][total_rows][no] tensor; this layer fills rows
+ *         [row_offset, row_offset + na*ny*nx) with row = a*ny*nx + y*nx + x             (may be NULL)
+ *         xy=(sigmoid+grid)*stride, wh=exp*anchor_px, obj/cls=sigmoid  (models.py:415-418)
+ * ------------------------------------------------------------------------------------------------ */
+int b2y_yolo_decode(const float* raw, long long raw_pitch, float* p, float* io, long long total_rows,
+                    long long row_offset, int batch, int na, int no, int ny, int nx, const float* anchors_px,
+                    float stride, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * YOLO loss: utils/utils.py:368-432 (compute_loss), 725-779 (build_targets), 254-297 (bbox_iou)
+ * Single yolo layer; the host sums the three layers and applies the hyp gains.
+ *   p        fp32 [batch][na][ny][nx][no]
+ *   targets  fp32 [nt][6] (image, class, x, y, w, h) normalised
+ *   anchors  fp32 [na][2] = anchors_px / stride  (YOLOLayer.anchor_vec)
+ *   out[0]=sum(1-giou) out[1]=matches out[2]=sum BCE(cls) out[3]=sum BCE(obj) (fp32[4], overwritten)
+ *   dp       fp32 same shape as p: d(lbox*w_box + lobj*w_obj + lcls*w_cls)/dp with the reference's
+ *            'mean' reductions (NULL = forward only)
+ *   workspace: b2y_yolo_loss_workspace_bytes(...) bytes
+ * ------------------------------------------------------------------------------------------------ */
+size_t b2y_yolo_loss_workspace_bytes(int batch, int na, int ny, int nx, int nt);
+int b2y_yolo_loss(const float* p, const float* targets, int nt, const float* anchors, int batch, int na, int no,
+                  int ny, int nx, float iou_t, float gr, float cls_pw, float obj_pw, float w_box, float w_obj,
+                  float w_cls, float* out4, float* dp, void* workspace, void* stream);
+/* build_targets only: writes up to na*nt matches in reference order (anchor-major, target-minor);
+ *   idx int64 [4][na*nt] rows (b, a, gj, gi), tbox fp32 [na*nt][4], tcls int64 [na*nt], count int32[1] */
+int b2y_build_targets(const float* targets, int nt, const float* anchors, int na, int ny, int nx, float iou_t,
+                      long long* idx, float* tbox, long long* tcls, int* count, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Quantisation (power-of-two scale fake-quant, BN fold, INT8 conv):
+ * utils/quantized/quantized_ptq_cos.py:14-113,131-738; utils/quantized/quantized_google.py:81-219
+ * ------------------------------------------------------------------------------------------------ */
+/* y = clamp(round_half_away(x/scale), lo, hi) * scale   (ptq_cos.py:89-92) */
+int b2y_fakequant_f32(const float* x, float* y, long long n, float scale, float lo, float hi, void* stream);
+/* q = int8(clamp(round_half_away(x/scale), lo, hi)) from fp16 NHWC -> int8 NHWC */
+int b2y_quantize_f16_to_i8(const void* x, long long x_pitch, void* q, long long q_pitch, long long pixels, int c,
+                           float scale, float lo, float hi, void* stream);
+/* COSPTQ scale search (ptq_cos.py:71-87): for each candidate step i-5, i in [0,n_cand): cosine similarity
+ * between x and fakequant(x; 2^step/2^(bits-1)); out_cos fp32 [n_cand]. One pass over x. */
+int b2y_cos_scale_search(const float* x, long long n, int bits, int n_cand, float* out_cos, void* workspace,
+                         size_t workspace_bytes, void* stream);
+/* per-tensor or per-channel min/max (google.py:16-77); x fp32 [rows][cols], per_row!=0 -> out [rows][2] */
+int b2y_minmax_f32(const float* x, long long rows, long long cols, int per_row, float* out_minmax, void* stream);
+
+typedef struct b2y_qconv_desc {
+    b2y_conv_desc conv;   /* shapes as for the dense conv; x/w are int8, in_c multiple of 32 */
+    float acc_scale;      /* s_act * s_weight (both powers of two) */
+    float out_scale;      /* activation quantiser scale of this layer's output */
+    float q_lo, q_hi;     /* clamp range, -2^(b-1) .. 2^(b-1)-1 */
+    int out_kind;         /* B2Y_OUT_I8: requantised int8; B2Y_OUT_F32/F16: fake-quant value (heads: linear) */
+    int requant;          /* 0: write act(acc*acc_scale+bias) without requantisation (linear head, ptq_cos.py:718) */
+} b2y_qconv_desc;
+/* INT8 conv on tcgen05 kind::i8 with int32 accumulation (exact whenever the fp32 reference is). */
+int b2y_qconv2d_fwd(const b2y_qconv_desc* d, const void* x_i8, const void* w_i8, const float* bias, void* y,
+                    void* stream);
+/* BN-fold + weight quantisation + pack: OIHW fp32 -> int8 [O][kh][kw][I] with scale w_scale (ptq_cos.py:193-212) */
+int b2y_pack_qconv_weights(const float* w_oihw_folded, int out_c, int in_c, int ksize, float w_scale, float lo,
+                           float hi, void* w_i8, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Training: BatchNorm (batch statistics), backward convolutions, optimiser
+ * models.py:92-113 under autograd; train.py:135-151,437-459
+ * ------------------------------------------------------------------------------------------------ */
+/* finalize: mean/var from sums, update running stats (momentum, unbiased var), emit scale/shift:
+ *   scale = gamma*rsqrt(var_b+eps), shift = beta - mean*scale                         (models.py:100) */
+int b2y_bn_finalize(const float* stat_sum, const float* stat_sqsum, long long count, const float* gamma,
+                    const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                    float* save_mean, float* save_invstd, float* scale, float* shift, int c, void* stream);
+/* y = act(x*scale[c] + shift[c]) [+ residual]   fp16 NHWC in/out */
+int b2y_bn_act_fwd(const void* x, long long x_pitch, const float* scale, const float* shift, const void* residual,
+                   long long res_pitch, void* y, long long y_pitch, long long pixels, int c, int act, float slope,
+                   void* stream);
+/* backward of the above + BN:  given dy (grad wrt y), raw conv output x, recompute z = x*scale+shift,
+ * dz = dy*act'(z); reduce dgamma = sum(dz*xhat), dbeta = sum(dz)  (pass 1), then
+ * dx = (gamma*invstd) * (dz - dbeta/N - xhat*dgamma/N)                            (pass 2). */
+int b2y_bn_act_bwd_reduce(const void* x, long long x_pitch, const void* dy, long long dy_pitch, const float* scale,
+                          const float* shift, const float* save_mean, const float* save_invstd, float* dgamma,
+                          float* dbeta, long long pixels, int c, int act, float slope, void* stream);
+int b2y_bn_act_bwd_apply(const void* x, long long x_pitch, const void* dy, long long dy_pitch, const float* scale,
+                         const float* shift, const float* gamma, const float* save_mean, const float* save_invstd,
+                         const float* dgamma, const float* dbeta, void* dx, long long dx_pitch, long long pixels,
+                         int c, int act, float slope, void* stream);
+/* dX = conv_transpose(dY, W)   (data gradient; implicit GEMM on tcgen05) */
+int b2y_conv2d_bwd_data(const b2y_conv_desc* d, const void* dy, const void* w_packed_t, void* dx, int accumulate,
+                        void* stream);
+/* dW[o][kh][kw][i] = sum_pixels dY[p][o] * X[p+(kh,kw)][i]  (weight gradient; fp32 [O][kh][kw][I]) */
+int b2y_conv2d_bwd_weight(const b2y_conv_desc* d, const void* x, const void* dy, float* dw, void* stream);
+/* SGD + Nesterov momentum + weight decay over a flat fp32 buffer (train.py:135-144), grads pre-scaled by
+ * grad_scale (1/world_size after the NCCL sum) */
+int b2y_sgd_nesterov(float* param, const float* grad, float* momentum_buf, long long n, float lr, float momentum,
+                     float weight_decay, float grad_scale, int first_step, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200YOLO_H_ */

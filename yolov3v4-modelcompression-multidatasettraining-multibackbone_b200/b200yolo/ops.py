@@ -1,0 +1,202 @@
+"""Tensor-level wrappers over the C ABI: torch tensors in, torch tensors out, all math in libb200yolo.so.
+
+Activations are NHWC fp16 tensors of shape [B, H, W, C]; a tensor may be a channel-slice *view* of a wider
+buffer (stride(2) = pitch >= C), which is how route/concat layers are made zero-copy.
+"""
+import ctypes as C
+
+import torch
+
+from . import lib
+from .lib import ACT, ConvDesc, QConvDesc, OUT_F16, OUT_F32, OUT_I8, call, ptr, stream_ptr
+
+
+def _pitch(t):
+    """Pixel pitch (elements) of an NHWC view; checks that only the channel dim is sliced."""
+    assert t.dim() == 4 and (t.shape[3] == 1 or t.stride(3) == 1), "expected NHWC with unit channel stride"
+    B, H, W, _ = t.shape
+    p = t.stride(2) if W > 1 else (t.stride(1) if H > 1 else (t.stride(0) if B > 1 else t.shape[3]))
+    if W == 1 and H > 1:
+        p = t.stride(1)
+    assert W == 1 or H == 1 or t.stride(1) == W * p, "not a pixel-contiguous NHWC view"
+    assert B == 1 or t.stride(0) == H * W * p, "not a pixel-contiguous NHWC view"
+    return p
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise lib.B2YError("b200yolo ops need CUDA tensors; there is no CPU fallback")
+
+
+def conv_out_hw(h, w, k, stride, pad):
+    return (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+
+
+def make_conv_desc(x_shape, in_pitch, out_c, k, stride, pad, out_pitch, act="linear", slope=0.1,
+                   out_dtype=OUT_F16, res_pitch=0):
+    B, H, W, Cin = x_shape
+    Ho, Wo = conv_out_hw(H, W, k, stride, pad)
+    return ConvDesc(B, H, W, Cin, in_pitch, out_c, k, stride, pad, Ho, Wo, out_pitch, ACT[act] if isinstance(act, str)
+                    else int(act), float(slope), out_dtype, res_pitch)
+
+
+def pack_conv_weights(w, conv_bias=None, bn=None, eps=1e-5, want_fp32=False):
+    """OIHW fp32 (+BN running stats) -> ([O][kh][kw][I] fp16, bias fp32[O], optional folded OIHW fp32)."""
+    _require_cuda(w)
+    O, I, k, _ = w.shape
+    w = w.contiguous().float()
+    wp = torch.empty((O, k, k, I), dtype=torch.float16, device=w.device)
+    bias = torch.empty((O,), dtype=torch.float32, device=w.device)
+    w32 = torch.empty_like(w) if want_fp32 else None
+    g = b = m = v = None
+    if bn is not None:
+        g, b, m, v = [t.contiguous().float() for t in bn]
+    cb = conv_bias.contiguous().float() if conv_bias is not None else None
+    call("b2y_pack_conv_weights", ptr(w), ptr(cb), ptr(g), ptr(b), ptr(m), ptr(v), float(eps), O, I, k, ptr(wp),
+         ptr(bias), ptr(w32), stream_ptr())
+    return wp, bias, w32
+
+
+def conv2d(x, w_packed, bias, k, stride, pad, act="linear", slope=0.1, residual=None, out=None,
+           out_dtype=torch.float16, stats=None):
+    """y = act(conv(x, w) + bias) [+ residual]; x NHWC fp16 view, w_packed [O][k][k][I] fp16."""
+    _require_cuda(x, w_packed)
+    B, H, W, Cin = x.shape
+    O = w_packed.shape[0]
+    Ho, Wo = conv_out_hw(H, W, k, stride, pad)
+    if out is None:
+        out = torch.empty((B, Ho, Wo, O), dtype=out_dtype, device=x.device)
+    assert out.shape == (B, Ho, Wo, O)
+    od = OUT_F32 if out.dtype == torch.float32 else OUT_F16
+    d = make_conv_desc(x.shape, _pitch(x), O, k, stride, pad, _pitch(out), act, slope, od,
+                       _pitch(residual) if residual is not None else 0)
+    if stats is not None:
+        assert residual is None
+        call("b2y_conv2d_fwd_stats", C.byref(d), ptr(x), ptr(w_packed), ptr(bias), ptr(out), ptr(stats[0]),
+             ptr(stats[1]), stream_ptr())
+    else:
+        call("b2y_conv2d_fwd", C.byref(d), ptr(x), ptr(w_packed), ptr(bias), ptr(residual), ptr(out), stream_ptr())
+    return out
+
+
+def stem_conv(x_nchw, w_oihw, bias, k, stride, pad, act="linear", slope=0.1, out=None):
+    _require_cuda(x_nchw, w_oihw)
+    B, Cin, H, W = x_nchw.shape
+    O = w_oihw.shape[0]
+    Ho, Wo = conv_out_hw(H, W, k, stride, pad)
+    if out is None:
+        out = torch.empty((B, Ho, Wo, O), dtype=torch.float16, device=x_nchw.device)
+    d = make_conv_desc((B, H, W, Cin), Cin, O, k, stride, pad, _pitch(out), act, slope, OUT_F16)
+    call("b2y_stem_conv_fwd", C.byref(d), ptr(x_nchw.contiguous()), ptr(w_oihw.contiguous()), ptr(bias), ptr(out),
+         stream_ptr())
+    return out
+
+
+def upsample(x, scale, out=None):
+    B, H, W, Cc = x.shape
+    if out is None:
+        out = torch.empty((B, H * scale, W * scale, Cc), dtype=x.dtype, device=x.device)
+    call("b2y_upsample_nearest", ptr(x), _pitch(x), ptr(out), _pitch(out), B, H, W, Cc, int(scale), stream_ptr())
+    return out
+
+
+def maxpool(x, k, stride, tiny_pad=False, out=None):
+    B, H, W, Cc = x.shape
+    if tiny_pad:
+        Ho, Wo = (H + 1 - k) // stride + 1, (W + 1 - k) // stride + 1
+    else:
+        p = (k - 1) // 2
+        Ho, Wo = (H + 2 * p - k) // stride + 1, (W + 2 * p - k) // stride + 1
+    if out is None:
+        out = torch.empty((B, Ho, Wo, Cc), dtype=x.dtype, device=x.device)
+    call("b2y_maxpool", ptr(x), _pitch(x), ptr(out), _pitch(out), B, H, W, Cc, int(k), int(stride),
+         1 if tiny_pad else 0, stream_ptr())
+    return out
+
+
+def copy_channels(x, out):
+    B, H, W, Cc = x.shape
+    call("b2y_copy_channels", ptr(x), _pitch(x), ptr(out), _pitch(out), B * H * W, Cc, stream_ptr())
+    return out
+
+
+def add(a, b, out=None):
+    B, H, W, Cc = a.shape
+    if out is None:
+        out = torch.empty((B, H, W, Cc), dtype=a.dtype, device=a.device)
+    call("b2y_add", ptr(a), _pitch(a), ptr(b), _pitch(b), ptr(out), _pitch(out), B * H * W, Cc, stream_ptr())
+    return out
+
+
+def act_fwd(x, act, slope=0.1):
+    x = x.contiguous().float()
+    y = torch.empty_like(x)
+    call("b2y_act_fwd_f32", ptr(x), ptr(y), x.numel(), ACT[act], float(slope), stream_ptr())
+    return y
+
+
+def act_bwd(x, dy, act, slope=0.1):
+    x = x.contiguous().float()
+    dy = dy.contiguous().float()
+    dx = torch.empty_like(x)
+    call("b2y_act_bwd_f32", ptr(x), ptr(dy), ptr(dx), x.numel(), ACT[act], float(slope), stream_ptr())
+    return dx
+
+
+def nchw_to_nhwc(x, out=None):
+    B, Cc, H, W = x.shape
+    x = x.contiguous().float()
+    if out is None:
+        out = torch.empty((B, H, W, Cc), dtype=torch.float16, device=x.device)
+    call("b2y_nchw_f32_to_nhwc_f16", ptr(x), ptr(out), _pitch(out), B, Cc, H, W, stream_ptr())
+    return out
+
+
+def nhwc_to_nchw(x):
+    B, H, W, Cc = x.shape
+    out = torch.empty((B, Cc, H, W), dtype=torch.float32, device=x.device)
+    call("b2y_nhwc_f16_to_nchw_f32", ptr(x), _pitch(x), ptr(out), B, Cc, H, W, stream_ptr())
+    return out
+
+
+def yolo_decode(raw, na, no, anchors_px, stride, io=None, row_offset=0, want_p=True):
+    """raw: fp32 [B, ny, nx, pitch>=na*no] head output. Returns (io_rows_view_or_None, p)."""
+    B, ny, nx, _ = raw.shape
+    p = torch.empty((B, na, ny, nx, no), dtype=torch.float32, device=raw.device) if want_p else None
+    total_rows = io.shape[1] if io is not None else 0
+    call("b2y_yolo_decode", ptr(raw), raw.stride(2), ptr(p), ptr(io), total_rows, row_offset, B, na, no, ny, nx,
+         ptr(anchors_px), float(stride), stream_ptr())
+    return io, p
+
+
+def yolo_loss_layer(p, targets, anchor_vec, iou_t, gr, cls_pw, obj_pw, w_box, w_obj, w_cls, want_grad=True):
+    """One yolo layer of compute_loss. Returns (out4 fp32[4] = [sum(1-giou), nb, sum bce cls, sum bce obj], dp)."""
+    B, na, ny, nx, no = p.shape
+    p = p.contiguous()
+    nt = int(targets.shape[0])
+    out4 = torch.empty(4, dtype=torch.float32, device=p.device)
+    dp = torch.empty_like(p) if want_grad else None
+    ws_bytes = lib.raw().b2y_yolo_loss_workspace_bytes(B, na, ny, nx, nt)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=p.device)
+    t = targets.contiguous().float() if nt else None
+    call("b2y_yolo_loss", ptr(p), ptr(t), nt, ptr(anchor_vec), B, na, no, ny, nx, float(iou_t), float(gr),
+         float(cls_pw), float(obj_pw), float(w_box), float(w_obj), float(w_cls), ptr(out4), ptr(dp), ptr(ws),
+         stream_ptr())
+    return out4, dp
+
+
+def build_targets_layer(targets, anchor_vec, ny, nx, iou_t):
+    nt = int(targets.shape[0])
+    na = int(anchor_vec.shape[0])
+    cap = max(1, na * nt)
+    dev = anchor_vec.device
+    idx = torch.zeros((4, cap), dtype=torch.int64, device=dev)
+    tbox = torch.zeros((cap, 4), dtype=torch.float32, device=dev)
+    tcls = torch.zeros((cap,), dtype=torch.int64, device=dev)
+    count = torch.zeros((1,), dtype=torch.int32, device=dev)
+    t = targets.contiguous().float() if nt else None
+    call("b2y_build_targets", ptr(t), nt, ptr(anchor_vec), na, ny, nx, float(iou_t), ptr(idx), ptr(tbox), ptr(tcls),
+         ptr(count), stream_ptr())
+    n = int(count.item())
+    return idx[:, :n], tbox[:n], tcls[:n]

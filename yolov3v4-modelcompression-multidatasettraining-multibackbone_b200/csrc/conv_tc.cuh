@@ -1,0 +1,371 @@
+// tcgen05 implicit-GEMM convolution, sm_100a.
+//
+//   D[M = B*Ho*Wo pixels][N = Cout] = sum_{tap (r,s)} sum_{c} A_tap[M][c] * W[N][(r,s,c)]
+//
+// * A (activations, NHWC) is never im2col'ed in memory: the TMA unit gathers each
+//   (tap, 64-channel) slab straight from the NHWC tensor in im2col mode (zero fill for the
+//   padding halo, traversal stride = conv stride) into a 128B-swizzled K-major smem tile.
+// * B (weights, [Cout][R][S][Cin]) comes in through a tiled 2-D TMA map.
+// * One elected thread issues tcgen05.mma (M=128, N=BLOCK_N, K=32 bytes) with the fp32/int32
+//   accumulator in TMEM, double-buffered so the epilogue of tile i overlaps the MMAs of tile i+1.
+// * Persistent grid (<= #SMs CTAs), warp-specialised: warp0 = TMA producer, warp1 = MMA issuer,
+//   warp2 = TMEM allocator, warps 4-7 = epilogue (TMEM -> regs -> bias/act/residual -> global).
+#pragma once
+#include "common.cuh"
+
+namespace b2y {
+
+enum { CONV_KIND_F16 = 0, CONV_KIND_I8 = 1 };
+enum { A_MODE_IM2COL = 0, A_MODE_TILED2D = 1 };
+enum { OUT_F16 = 0, OUT_F32 = 1, OUT_I8 = 2 };
+
+struct ConvTcParams {
+    int M_total;      // B*Ho*Wo
+    int Cout;         // valid output channels
+    int num_m_tiles;  // ceil(M_total/128)
+    int num_n_tiles;  // ceil(Cout/BLOCK_N)
+    int k_chunks;     // Cin*esize / KBYTES
+    int Cin;          // elements
+    int R, S;
+    int Ho, Wo;
+    int stride, pad;
+    int a_mode;
+    // epilogue
+    const float* bias;  // [Cout] or null
+    int act;
+    float slope;
+    float acc_scale;        // multiplies the accumulator (1 for fp16; s_a*s_w for int8)
+    const __half* res;      // optional residual (fp16, NHWC) added after the activation
+    long long res_pitch;    // elements per pixel row
+    void* out;
+    long long out_pitch;    // elements per pixel row
+    int out_dtype;          // OUT_*
+    float out_inv_scale;    // int8 output: q = clamp(round_half_away(v * out_inv_scale))
+    float out_scale;        //              (and v_dequant = q * out_scale when out is fp16/fp32 fake-quant)
+    int out_fakequant;      // 1: write the dequantised value q*out_scale in out_dtype (fp16/fp32)
+    float q_lo, q_hi;       // clamp range, e.g. -128, 127
+    // training extras: per-channel sum / sum of squares of the raw (pre-bias) output, fp32 atomics
+    float* stat_sum;
+    float* stat_sqsum;
+};
+
+template <int BLOCK_N, int KBYTES>
+struct ConvTcCfg {
+    static constexpr int BLOCK_M = 128;
+    static constexpr int A_BYTES = BLOCK_M * KBYTES;
+    static constexpr int B_BYTES = BLOCK_N * KBYTES;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;  // always a multiple of 1024
+    static constexpr int MAX_STAGE_SMEM = 196 * 1024;
+    static constexpr int NUM_STAGES_RAW = MAX_STAGE_SMEM / STAGE_BYTES;
+    static constexpr int NUM_STAGES = NUM_STAGES_RAW > 8 ? 8 : NUM_STAGES_RAW;
+    static constexpr int TMEM_COLS = (2 * BLOCK_N) < 32 ? 32 : (2 * BLOCK_N);
+    static constexpr int AUX_BYTES = 1024;  // barriers + tmem ptr + bias staging
+    static constexpr int BIAS_BYTES = BLOCK_N * 4;
+    static constexpr int SMEM_BYTES = 1024 /*align slack*/ + NUM_STAGES * STAGE_BYTES + AUX_BYTES + BIAS_BYTES;
+};
+
+__device__ __forceinline__ float round_half_away(float x) {
+    // reference utils/quantized/quantized_ptq_cos.py:14-20  sign(x)*floor(|x|+0.5)
+    return copysignf(floorf(fabsf(x) + 0.5f), x);
+}
+
+template <int BLOCK_N, int KBYTES, int KIND>
+__global__ void __launch_bounds__(256, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const ConvTcParams p) {
+    using Cfg = ConvTcCfg<BLOCK_N, KBYTES>;
+    constexpr int NS = Cfg::NUM_STAGES;
+    constexpr int ESIZE = (KIND == CONV_KIND_F16) ? 2 : 1;
+    constexpr int BLOCK_K = KBYTES / ESIZE;  // elements per k-chunk
+    constexpr uint32_t LAYOUT = swizzle_layout_type(KBYTES);
+    constexpr uint32_t IDESC = (KIND == CONV_KIND_F16)
+                                   ? make_idesc(/*c=F32*/ 1, /*a=F16*/ 0, /*b=F16*/ 0, 0, 0, 128, BLOCK_N)
+                                   : make_idesc(/*c=S32*/ 2, /*a=S8*/ 1, /*b=S8*/ 1, 0, 0, 128, BLOCK_N);
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* aux = smem + NS * Cfg::STAGE_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);           // [NS]
+    uint64_t* empty_bar = full_bar + NS;                             // [NS]
+    uint64_t* tmem_full_bar = empty_bar + NS;                        // [2]
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;                    // [2]
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+    float* sbias = reinterpret_cast<float*>(aux + Cfg::AUX_BYTES);   // [BLOCK_N]
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA);
+        prefetch_tmap(&tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < NS; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full_bar[i], 1);
+            mbar_init(&tmem_empty_bar[i], 4);  // one arrive per epilogue warp
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+    const int taps = p.R * p.S;
+    const int k_steps = taps * p.k_chunks;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const int HoWo = p.Ho * p.Wo;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m_tile = tile / p.num_n_tiles;
+                const int n_tile = tile - m_tile * p.num_n_tiles;
+                const int m0 = m_tile * 128;
+                const int img = m0 / HoWo;
+                const int rem = m0 - img * HoWo;
+                const int po = rem / p.Wo;
+                const int qo = rem - po * p.Wo;
+                const int base_w = qo * p.stride - p.pad;
+                const int base_h = po * p.stride - p.pad;
+                for (int tap = 0; tap < taps; ++tap) {
+                    const int r = tap / p.S;
+                    const int s = tap - r * p.S;
+                    for (int kc = 0; kc < p.k_chunks; ++kc) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        uint8_t* a_dst = smem + stage * Cfg::STAGE_BYTES;
+                        uint8_t* b_dst = a_dst + Cfg::A_BYTES;
+                        mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                        if (p.a_mode == A_MODE_IM2COL) {
+                            tma_load_im2col_4d(a_dst, &tmA, &full_bar[stage], kc * BLOCK_K, base_w, base_h, img,
+                                               (uint16_t)s, (uint16_t)r);
+                        } else {
+                            tma_load_2d(a_dst, &tmA, &full_bar[stage], kc * BLOCK_K, m0);
+                        }
+                        tma_load_2d(b_dst, &tmB, &full_bar[stage], tap * p.Cin + kc * BLOCK_K, n_tile * BLOCK_N);
+                        if (++stage == NS) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            const uint64_t desc_base = smem_desc_base(16, 8 * KBYTES, LAYOUT);
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+                for (int ks = 0; ks < k_steps; ++ks) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                    const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+                    const uint64_t adesc = smem_desc_at(desc_base, a_addr);
+                    const uint64_t bdesc = smem_desc_at(desc_base, b_addr);
+#pragma unroll
+                    for (int k = 0; k < KBYTES / 32; ++k) {
+                        const uint32_t accum = (ks > 0 || k > 0) ? 1u : 0u;
+                        if (KIND == CONV_KIND_F16)
+                            mma_f16_ss(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC, accum);
+                        else
+                            mma_i8_ss(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC, accum);
+                    }
+                    tc_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+                    if (++stage == NS) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                tc_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_phase ^= 1;
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int ew = warp - 4;            // TMEM lanes [32*ew, 32*ew+32)
+        const int et = threadIdx.x - 128;   // 0..127
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m_tile = tile / p.num_n_tiles;
+            const int n_tile = tile - m_tile * p.num_n_tiles;
+            const int n0 = n_tile * BLOCK_N;
+            const long long row = (long long)m_tile * 128 + ew * 32 + lane;
+            const bool row_ok = row < p.M_total;
+
+            // stage the bias slice for this tile
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            for (int i = et; i < BLOCK_N; i += 128) {
+                const int n = n0 + i;
+                sbias[i] = (p.bias != nullptr && n < p.Cout) ? __ldg(p.bias + n) : 0.f;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+
+            mbar_wait(&tmem_full_bar[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+
+#pragma unroll 1
+            for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+                uint32_t raw[32];
+                tmem_ld_32x32(taddr_row + (uint32_t)c0, raw);
+                tc_wait_ld();
+                if (n0 + c0 >= p.Cout) continue;  // warp-uniform
+
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float a = (KIND == CONV_KIND_F16) ? __uint_as_float(raw[j]) : (float)(int)raw[j];
+                    v[j] = a * p.acc_scale;
+                }
+
+                if (p.stat_sum != nullptr) {
+                    // per-channel batch statistics of the raw conv output (training BN):
+                    // butterfly-reduce each column over the 32 rows of this warp.
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float s1 = row_ok ? v[j] : 0.f;
+                        float s2 = s1 * s1;
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+                        }
+                        if (lane == j && n0 + c0 + j < p.Cout) {
+                            atomicAdd(p.stat_sum + n0 + c0 + j, s1);
+                            atomicAdd(p.stat_sqsum + n0 + c0 + j, s2);
+                        }
+                    }
+                }
+
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j] + sbias[c0 + j], p.act, p.slope);
+
+                const int nvalid = min(32, p.Cout - (n0 + c0));
+                if (row_ok) {
+                    if (p.res != nullptr) {
+                        const __half* rp = p.res + row * p.res_pitch + n0 + c0;
+                        if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                uint4 u = __ldg(reinterpret_cast<const uint4*>(rp) + q);
+                                const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+                                for (int t = 0; t < 4; ++t) {
+                                    float2 f = __half22float2(h2[t]);
+                                    v[q * 8 + t * 2] += f.x;
+                                    v[q * 8 + t * 2 + 1] += f.y;
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (j < nvalid) v[j] += __half2float(rp[j]);
+                        }
+                    }
+
+                    if (p.out_fakequant || p.out_dtype == OUT_I8) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            float q = round_half_away(v[j] * p.out_inv_scale);
+                            q = fminf(fmaxf(q, p.q_lo), p.q_hi);
+                            v[j] = (p.out_dtype == OUT_I8) ? q : q * p.out_scale;
+                        }
+                    }
+
+                    if (p.out_dtype == OUT_F16) {
+                        __half* op = reinterpret_cast<__half*>(p.out) + row * p.out_pitch + n0 + c0;
+                        if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                uint4 u;
+                                __half2* h2 = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+                                for (int t = 0; t < 4; ++t)
+                                    h2[t] = __floats2half2_rn(v[q * 8 + t * 2], v[q * 8 + t * 2 + 1]);
+                                reinterpret_cast<uint4*>(op)[q] = u;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (j < nvalid) op[j] = __float2half_rn(v[j]);
+                        }
+                    } else if (p.out_dtype == OUT_F32) {
+                        float* op = reinterpret_cast<float*>(p.out) + row * p.out_pitch + n0 + c0;
+                        if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q)
+                                reinterpret_cast<float4*>(op)[q] =
+                                    make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (j < nvalid) op[j] = v[j];
+                        }
+                    } else {  // OUT_I8
+                        int8_t* op = reinterpret_cast<int8_t*>(p.out) + row * p.out_pitch + n0 + c0;
+                        if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+#pragma unroll
+                            for (int q = 0; q < 2; ++q) {
+                                uint32_t w[4];
+#pragma unroll
+                                for (int t = 0; t < 4; ++t) {
+                                    const int b = q * 16 + t * 4;
+                                    w[t] = ((uint32_t)(uint8_t)(int8_t)(int)v[b]) |
+                                           ((uint32_t)(uint8_t)(int8_t)(int)v[b + 1] << 8) |
+                                           ((uint32_t)(uint8_t)(int8_t)(int)v[b + 2] << 16) |
+                                           ((uint32_t)(uint8_t)(int8_t)(int)v[b + 3] << 24);
+                                }
+                                reinterpret_cast<uint4*>(op)[q] = make_uint4(w[0], w[1], w[2], w[3]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (j < nvalid) op[j] = (int8_t)(int)v[j];
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            // release this accumulator stage back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+            if (++acc == 2) {
+                acc = 0;
+                acc_phase ^= 1;
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+}  // namespace b2y
