@@ -171,7 +171,7 @@ def test_pointwise_layers():
     for k in (5, 9, 13):
         mp = ops.maxpool(xn, k, 1)
         assert torch.equal(mp.permute(0, 3, 1, 2).cpu(), F.max_pool2d(x.float(), k, 1, (k - 1) // 2).half())
-    mp = ops.maxpool(xn[:, :12, :12], 2, 2)
+    mp = ops.maxpool(xn[:, :12, :12].contiguous(), 2, 2)
     assert torch.equal(mp.permute(0, 3, 1, 2).cpu(), F.max_pool2d(x[:, :, :12, :12].float(), 2, 2).half())
     # yolov3-tiny ZeroPad2d((0,1,0,1)) + MaxPool2d(2,1)
     mp = ops.maxpool(xn, 2, 1, tiny_pad=True)

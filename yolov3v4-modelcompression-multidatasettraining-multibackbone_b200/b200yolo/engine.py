@@ -1,0 +1,359 @@
+"""Graph executor for Darknet models on sm_100a.
+
+Replaces the reference's per-module Python loop (models.py:508-561, ~250-520 ATen/cuDNN launches per forward)
+by a static plan over NHWC fp16 buffers:
+
+  * conv + folded BN + activation (+ the following Shortcut) = one tcgen05 implicit-GEMM launch,
+  * route/concat is zero-copy: producers write straight into their channel slot of the concat buffer,
+  * the stem reads the NCHW fp32 image directly, the head convs emit fp32 for the decode kernel,
+  * the launch sequence is captured once into a CUDA graph per input shape and replayed.
+
+Parameters stay in the nn.Module tree (fp32, NCHW) and are folded/packed on the device whenever they change.
+"""
+import torch
+import torch.nn as nn
+
+from . import ops
+
+_ACT_OF_CLASS = {'LeakyReLU': 'leaky', 'Mish': 'mish', 'ReLU6': 'relu6', 'HardSwish': 'h_swish', 'ReLU': 'relu',
+                 'Swish': 'swish'}
+
+
+class LazyFeatures(list):
+    """feature_out of the reference API (models.py:542-543): one entry per conv block that does not feed a YOLO layer.
+    Entries are materialised (NHWC fp16 -> NCHW fp32) on access; they alias engine buffers and are only valid
+    until the next forward."""
+
+    def __init__(self, views):
+        super().__init__([None] * len(views))
+        self._views = views
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(len(self)))]
+        v = self._views[i]
+        if v is None:
+            raise RuntimeError("feature_out[%d] was not kept: set model.keep_features = True before the forward" % i)
+        return ops.nhwc_to_nchw(v)
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+
+class _Tensor:
+    """Logical activation tensor: NHWC view = buffer[..., c0:c0+C]."""
+    __slots__ = ('C', 'H', 'W', 'buf', 'c0', 'dtype')
+
+    def __init__(self, C, H, W, dtype=torch.float16):
+        self.C, self.H, self.W, self.dtype = C, H, W, dtype
+        self.buf, self.c0 = None, 0
+
+    def view(self):
+        return self.buf[..., self.c0:self.c0 + self.C]
+
+
+def _block_parts(block):
+    """nn.Sequential conv block -> (conv, bn or None, activation name, slope)."""
+    conv, bn, act, slope = None, None, 'linear', 0.1
+    for m in block:
+        name = m.__class__.__name__
+        if isinstance(m, nn.Conv2d):
+            conv = m
+        elif isinstance(m, nn.BatchNorm2d):
+            bn = m
+        elif name in _ACT_OF_CLASS:
+            act = _ACT_OF_CLASS[name]
+            if name == 'LeakyReLU':
+                slope = m.negative_slope
+    return conv, bn, act, slope
+
+
+class Plan:
+    def __init__(self, model, x_shape, device, training, keep_features=False):
+        if training:
+            raise NotImplementedError("training plan is built by b200yolo.train_engine")
+        self.model = model
+        self.keep_features = bool(keep_features)
+        self.device = device
+        self.B, self.Cin, self.H, self.W = x_shape
+        self.steps = []
+        self.weights = {}       # layer index -> packed weights
+        self.param_version = None
+        self.graph = None
+        self.runs = 0
+        self.static_x = None
+        self._build()
+
+    # ---------------------------------------------------------------------------------------------------------
+    def _build(self):
+        model, B = self.model, self.B
+        defs, mods, routs = model.module_defs, model.module_list, model.routs
+        n = len(defs)
+        dev = self.device
+
+        # 1) shapes
+        shapes = []  # (C,H,W) of every layer output
+        prev = (self.Cin, self.H, self.W)
+        for i, (d, m) in enumerate(zip(defs, mods)):
+            t = d['type']
+            C, H, W = prev
+            if t == 'convolutional':
+                conv = _block_parts(m)[0]
+                k, s, p = conv.kernel_size[0], conv.stride[0], conv.padding[0]
+                H, W = ops.conv_out_hw(H, W, k, s, p)
+                C = conv.out_channels
+            elif t == 'maxpool':
+                k, s = d['size'], d['stride']
+                if k == 2 and s == 1:
+                    H, W = (H + 1 - k) // s + 1, (W + 1 - k) // s + 1
+                else:
+                    p = (k - 1) // 2
+                    H, W = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+            elif t == 'upsample':
+                H, W = H * d['stride'], W * d['stride']
+            elif t == 'route':
+                srcs = [i + l if l < 0 else l for l in d['layers']]
+                C = sum(shapes[s][0] for s in srcs)
+                if 'groups' in d:
+                    C //= 2
+                H, W = shapes[srcs[0]][1], shapes[srcs[0]][2]
+            elif t in ('shortcut', 'yolo'):
+                pass
+            else:
+                raise NotImplementedError("layer type '%s' is not supported by the sm_100a engine yet" % t)
+            prev = (C, H, W)
+            shapes.append(prev)
+
+        # 2) fusion decisions
+        is_head = [False] * n       # conv directly followed by a yolo layer -> fp32 output
+        fused_into = [None] * n     # shortcut i fused into conv i-1
+        for i, d in enumerate(defs):
+            if d['type'] == 'yolo' and i > 0 and defs[i - 1]['type'] == 'convolutional':
+                is_head[i - 1] = True
+            if d['type'] == 'shortcut' and i > 0:
+                frm = [i + l if l < 0 else l for l in d['from']]
+                if (not self.keep_features  # feature_out must expose the conv output *before* the add
+                        and len(frm) == 1 and defs[i - 1]['type'] == 'convolutional' and not routs[i - 1]
+                        and not getattr(mods[i], 'weight', False) and shapes[frm[0]] == shapes[i - 1]
+                        and shapes[i - 1][0] % 8 == 0 and i - 1 > 0):
+                    fused_into[i] = i - 1
+
+        # 3) logical tensors; aliases for single-source routes
+        tens = [None] * n
+        for i, d in enumerate(defs):
+            t = d['type']
+            if t == 'yolo':
+                continue
+            if t == 'route' and len(d['layers']) == 1 and 'groups' not in d:
+                continue  # alias, resolved below
+            C, H, W = shapes[i]
+            tens[i] = _Tensor(C, H, W, torch.float32 if is_head[i] else torch.float16)
+        for i, d in enumerate(defs):
+            if fused_into[i] is not None:
+                tens[fused_into[i]] = tens[i]  # the conv writes the shortcut's output tensor
+        alias = {}
+        for i, d in enumerate(defs):
+            if d['type'] == 'route' and len(d['layers']) == 1 and 'groups' not in d:
+                l = d['layers'][0]
+                src = i + l if l < 0 else l
+                while src in alias:
+                    src = alias[src]
+                alias[i] = src
+                tens[i] = tens[src]
+
+        # 4) concat placement: multi-source routes become pre-allocated buffers their producers write into
+        placed = set()
+        copies = {}  # route index -> list of (src tensor, channel offset) that must be copied
+        for i, d in enumerate(defs):
+            if d['type'] != 'route' or len(d['layers']) == 1:
+                continue
+            srcs = [i + l if l < 0 else l for l in d['layers']]
+            dst = tens[i]
+            dst.buf = torch.empty((B, dst.H, dst.W, dst.C), dtype=torch.float16, device=dev)
+            off = 0
+            for s in srcs:
+                st = tens[s]
+                if (id(st) not in placed and st.buf is None and off % 8 == 0 and st.dtype == torch.float16
+                        and st is not dst):
+                    st.buf, st.c0 = dst.buf, off
+                    placed.add(id(st))
+                else:
+                    copies.setdefault(i, []).append((st, off))
+                off += st.C
+        for i, d in enumerate(defs):  # grouped routes: upper half of the channels of the previous layer
+            if d['type'] == 'route' and 'groups' in d:
+                pass  # resolved at allocation time below (needs the source buffer)
+
+        # 5) allocate what is left and emit the launch list
+        def alloc(t):
+            if t.buf is None:
+                pitch = t.C if t.dtype == torch.float16 else ((t.C + 3) // 4) * 4
+                t.buf = torch.empty((B, t.H, t.W, pitch), dtype=t.dtype, device=dev)
+                t.c0 = 0
+            return t
+
+        self.yolo = []
+        self.feature_views = []
+        row_off = 0
+        for i, (d, m) in enumerate(zip(defs, mods)):
+            t = d['type']
+            if t == 'convolutional':
+                conv, bn, act, slope = _block_parts(m)
+                if conv.groups != 1:
+                    raise NotImplementedError("grouped convolution is not supported by the sm_100a engine yet")
+                out = alloc(tens[i])
+                res = None
+                if i + 1 < n and fused_into[i + 1] == i:
+                    l = defs[i + 1]['from'][0]
+                    res = tens[i + 1 + l if l < 0 else l]
+                src = None if i == 0 else tens[i - 1]
+                self.steps.append(('conv', i, src, out, res, conv, bn, act, slope))
+            elif t == 'shortcut':
+                if fused_into[i] is not None:
+                    continue
+                frm = [i + l if l < 0 else l for l in d['from']]
+                if getattr(m, 'weight', False):
+                    raise NotImplementedError("weighted shortcut is not supported by the sm_100a engine yet")
+                out = alloc(tens[i])
+                cur = tens[i - 1]
+                for s in frm:
+                    if tens[s].C != cur.C:
+                        raise NotImplementedError("channel-sliced shortcut is not supported by the sm_100a engine yet")
+                    self.steps.append(('add', cur, tens[s], out))
+                    cur = out
+            elif t == 'route':
+                if len(d['layers']) == 1:
+                    if 'groups' in d:
+                        src = tens[i - 1]
+                        g = tens[i]
+                        g.buf, g.c0 = src.buf, src.c0 + src.C // 2
+                    continue
+                for st, off in copies.get(i, []):
+                    self.steps.append(('copy', st, tens[i], off))
+            elif t == 'upsample':
+                self.steps.append(('upsample', tens[i - 1], alloc(tens[i]), d['stride']))
+            elif t == 'maxpool':
+                k, s = d['size'], d['stride']
+                self.steps.append(('maxpool', tens[i - 1], alloc(tens[i]), k, s, k == 2 and s == 1))
+            elif t == 'yolo':
+                raw = tens[i - 1]
+                rows = m.na * raw.H * raw.W
+                self.yolo.append((m, raw, row_off, rows))
+                row_off += rows
+        self.total_rows = row_off
+        # feature_out (models.py:542-543): every nn.Sequential block whose successor is not a YOLO layer
+        for i, m in enumerate(mods):
+            if m.__class__.__name__ == 'Sequential' and i + 1 < n and defs[i + 1]['type'] != 'yolo':
+                self.feature_views.append(tens[i] if (self.keep_features and tens[i] is not None) else None)
+        self.anchors_px = [m.anchors.to(dev).float().contiguous() for (m, _, _, _) in self.yolo]
+
+    # ---------------------------------------------------------------------------------------------------------
+    def _params_version(self):
+        return sum(p._version for p in self.model.parameters()) + sum(b._version for b in self.model.buffers())
+
+    def _pack_weights(self):
+        for st in self.steps:
+            if st[0] != 'conv':
+                continue
+            _, i, src, out, res, conv, bn, act, slope = st
+            bnp = None
+            eps = 1e-5
+            if bn is not None:
+                bnp = (bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var)
+                eps = bn.eps
+            stem = conv.in_channels <= 4
+            wp, bias, w32 = ops.pack_conv_weights(conv.weight.detach(), conv.bias.detach() if conv.bias is not None
+                                                  else None, bnp, eps, want_fp32=stem)
+            self.weights[i] = (wp, bias, w32)
+
+    def _launch_all(self, x):
+        for st in self.steps:
+            kind = st[0]
+            if kind == 'conv':
+                _, i, src, out, res, conv, bn, act, slope = st
+                wp, bias, w32 = self.weights[i]
+                k, s, p = conv.kernel_size[0], conv.stride[0], conv.padding[0]
+                if src is None:
+                    if conv.in_channels > 4:
+                        raise NotImplementedError("first layer with more than 4 input channels")
+                    ops.stem_conv(x, w32, bias, k, s, p, act=act, slope=slope, out=out.view())
+                else:
+                    ops.conv2d(src.view(), wp, bias, k, s, p, act=act, slope=slope,
+                               residual=res.view() if res is not None else None, out=out.view())
+            elif kind == 'add':
+                ops.add(st[1].view(), st[2].view(), out=st[3].view())
+            elif kind == 'copy':
+                _, srct, dst, off = st
+                ops.copy_channels(srct.view(), dst.buf[..., off:off + srct.C])
+            elif kind == 'upsample':
+                ops.upsample(st[1].view(), st[3], out=st[2].view())
+            elif kind == 'maxpool':
+                ops.maxpool(st[1].view(), st[3], st[4], tiny_pad=st[5], out=st[2].view())
+        for (m, raw, row_off, rows), anc in zip(self.yolo, self.anchors_px):
+            ops_io = self.io
+            _, p = ops.yolo_decode(raw.buf, m.na, m.no, anc, m.stride, io=ops_io, row_offset=row_off)
+            self.p_out.append(p)
+
+    def forward(self, x):
+        model = self.model
+        ver = self._params_version()
+        if ver != self.param_version:
+            self._pack_weights()
+            self.param_version = ver
+            self.graph = None
+        x = x.contiguous().float()
+        no = self.yolo[0][0].no
+        use_graph = getattr(model, 'use_cuda_graph', True)
+        if not use_graph or self.runs < 1:
+            self.io = torch.empty((self.B, self.total_rows, no), dtype=torch.float32, device=self.device)
+            self.p_out = []
+            self._launch_all(x)
+            self.runs += 1
+            io, p = self.io, tuple(self.p_out)
+        else:
+            if self.graph is None:
+                self.static_x = torch.empty_like(x)
+                self.static_x.copy_(x)
+                self.io = torch.empty((self.B, self.total_rows, no), dtype=torch.float32, device=self.device)
+                g = torch.cuda.CUDAGraph()
+                torch.cuda.synchronize()
+                with torch.cuda.graph(g):
+                    self.p_out = []
+                    self._launch_all(self.static_x)
+                self.graph = g
+                self.static_p = tuple(self.p_out)
+            self.static_x.copy_(x)
+            self.graph.replay()
+            if getattr(model, 'static_outputs', False):
+                io, p = self.io, self.static_p
+            else:
+                io, p = self.io.clone(), tuple(t.clone() for t in self.static_p)
+        for (m, raw, _, _) in self.yolo:
+            m.nx, m.ny = raw.W, raw.H
+        feats = LazyFeatures([None if t is None else t.view() for t in self.feature_views])
+        return io, p, feats
+
+
+class Engine:
+    def __init__(self, model):
+        self.model = model
+        self.plans = {}
+
+    def invalidate(self):
+        self.plans.clear()
+
+    def forward(self, x):
+        model = self.model
+        if model.quantized != -1:
+            raise NotImplementedError("quantized execution goes through b200yolo.qengine")
+        keep = bool(model.keep_features) if model.keep_features is not None else bool(model.training)
+        key = (tuple(x.shape), bool(model.training), x.device.index, keep)
+        plan = self.plans.get(key)
+        if plan is None:
+            if model.training:
+                from .train_engine import TrainPlan
+                plan = TrainPlan(model, tuple(x.shape), x.device)
+            else:
+                plan = Plan(model, tuple(x.shape), x.device, False, keep)
+            self.plans[key] = plan
+        return plan.forward(x)
