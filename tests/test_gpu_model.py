@@ -1,0 +1,132 @@
+"""GPU: whole-model parity of the B200 engine (through models.Darknet / utils.utils.compute_loss, i.e. the
+reference-facing API on top of the C ABI) against the oracle and the committed reference fixtures."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import anchor_vecs, attach_hyp, build_model, golden, module_defs, orc
+
+pytestmark = pytest.mark.gpu
+
+# fp16 activation policy of config C1: documented tolerances vs the fp32 reference
+BOX_REL_TOL_FP32REF = 3e-2      # xywh, relative to max(|ref|, 1 px)
+PROB_ABS_TOL_FP32REF = 1.5e-2   # obj / cls probabilities
+# against the oracle that follows the same precision policy (fp16 weights/activations, fp32 accumulate)
+BOX_REL_TOL_EMU = 1e-2
+PROB_ABS_TOL_EMU = 5e-3
+
+
+def _errs(got, ref):
+    box_rel = ((got[..., :4] - ref[..., :4]).abs() / ref[..., :4].abs().clamp(min=1.0)).max().item()
+    prob = (got[..., 4:] - ref[..., 4:]).abs().max().item()
+    return box_rel, prob
+
+
+@pytest.mark.parametrize("name,B,S,seed", [("yolov3-tiny", 2, 96, 3), ("yolov3", 2, 64, 0), ("yolov4", 2, 64, 0),
+                                           ("yolov3-tiny", 1, 416, 0)])
+def test_eval_forward_parity(name, B, S, seed):
+    g = golden("%s_%d_eval" % (name, S))
+    model = build_model(name, device="cuda").eval()
+    x = orc.synth_images(B, S, S, seed=seed)
+    with torch.no_grad():
+        io, p, feats = model(x.cuda())
+        io2, p2, _ = model(x.cuda())          # second call replays the captured CUDA graph
+    torch.cuda.synchronize()
+    assert io.shape == g["io"].shape and len(p) == len([k for k in g.files if k.startswith("p")])
+    assert torch.equal(io, io2), "CUDA-graph replay differs from the eager launch sequence"
+    io = io.cpu()
+    # (1) decode is exact given our own raw head outputs: grid/anchor indexing + fp32 math
+    ys = [d for d in module_defs(name) if d['type'] == 'yolo']
+    strides = orc.yolo_strides(name, len(ys))
+    rows = 0
+    for d, s, pi in zip(ys, strides, p):
+        pi = pi.cpu()
+        Bq, na, ny, nx, no = pi.shape
+        raw = pi.permute(0, 1, 4, 2, 3).reshape(Bq, na * no, ny, nx)
+        io_ref, _ = orc.yolo_layer(raw, np.asarray(d['anchors'])[d['mask']], s, int(d['classes']), False)
+        mine = io[:, rows:rows + na * ny * nx]
+        rows += na * ny * nx
+        torch.testing.assert_close(mine, io_ref, rtol=1e-5, atol=1e-5)
+        cell = torch.round(mine.view(Bq, na, ny, nx, no)[..., :2] / s - torch.sigmoid(pi[..., :2]))
+        gx = torch.arange(nx).view(1, 1, 1, nx).expand(Bq, na, ny, nx).float()
+        gy = torch.arange(ny).view(1, 1, ny, 1).expand(Bq, na, ny, nx).float()
+        assert torch.equal(cell[..., 0], gx) and torch.equal(cell[..., 1], gy), "grid indices must be bit exact"
+    # (2) vs the oracle under the same precision policy
+    import models
+    from helpers import cfg_path
+    sd = orc.synth_state_dict(models.Darknet(cfg_path(name)).state_dict(), 0)
+    with torch.no_grad():
+        io_emu, _ = orc.darknet_forward(module_defs(name), sd, x, name, emulate_fp16=True)
+    be, pe = _errs(io, io_emu)
+    # (3) vs the reference's own fp32 output
+    bf, pf = _errs(io, torch.from_numpy(g["io"]))
+    print("\n[%s %dx%d] vs fp16-policy oracle: box_rel=%.3g prob_abs=%.3g | vs fp32 reference: box_rel=%.3g prob_abs=%.3g"
+          % (name, S, S, be, pe, bf, pf))
+    assert be <= BOX_REL_TOL_EMU and pe <= PROB_ABS_TOL_EMU
+    assert bf <= BOX_REL_TOL_FP32REF and pf <= PROB_ABS_TOL_FP32REF
+
+
+def test_feature_out_lazy_and_graph_toggle():
+    model = build_model("yolov3-tiny", device="cuda").eval()
+    x = orc.synth_images(2, 96, 96, seed=3).cuda()
+    model.keep_features = True
+    with torch.no_grad():
+        io, p, feats = model(x)
+        f0 = feats[0]
+    assert len(feats) == 12 and f0.shape == (2, 16, 96, 96) and f0.dtype == torch.float32
+    model.keep_features = None
+    model.use_cuda_graph = False
+    with torch.no_grad():
+        io_b, _, feats_b = model(x)
+    torch.testing.assert_close(io, io_b, rtol=2e-3, atol=2e-3)   # shortcut fusion on/off: <= fp16 rounding
+    with pytest.raises(RuntimeError):
+        feats_b[0]
+
+
+def test_cpu_input_fails_loudly():
+    model = build_model("yolov3-tiny").eval()
+    with pytest.raises(RuntimeError):
+        model(orc.synth_images(1, 64, 64))
+
+
+def test_loss_parity_fp32():
+    """compute_loss / build_targets through utils.utils on the golden random predictions: fp32, rel 1e-4."""
+    from utils import utils as my_utils
+    g = golden("loss_case")
+    model = attach_hyp(build_model("yolov3", device="cuda"))
+    p = [torch.from_numpy(g["p%d" % i]).cuda().requires_grad_(True) for i in range(3)]
+    t = torch.from_numpy(g["targets"]).cuda()
+    loss, items = my_utils.compute_loss(p, t, model)
+    loss.backward()
+    np.testing.assert_allclose(items.cpu().numpy(), g["items"], rtol=1e-4)
+    for i in range(3):
+        np.testing.assert_allclose(p[i].grad.cpu().numpy(), g["dp%d" % i], rtol=1e-4, atol=1e-6)
+    tcls, tbox, idx, av = my_utils.build_targets([x.detach() for x in p], t, model)
+    for i in range(3):
+        assert np.array_equal(torch.stack(idx[i]).cpu().numpy(), g["idx%d" % i]), "indices must be bit exact"
+        assert np.array_equal(tcls[i].cpu().numpy(), g["tcls%d" % i])
+        np.testing.assert_allclose(tbox[i].cpu().numpy(), g["tbox%d" % i], rtol=1e-6, atol=1e-6)
+        np.testing.assert_allclose(av[i].cpu().numpy(), g["av%d" % i], rtol=1e-6)
+
+
+def test_loss_edge_cases():
+    from utils import utils as my_utils
+    model = attach_hyp(build_model("yolov3-tiny", device="cuda"))
+    g = torch.Generator().manual_seed(9)
+    p = [torch.randn(2, 3, s, s, 85, generator=g).cuda().requires_grad_(True) for s in (2, 4)]
+    av = anchor_vecs("yolov3-tiny")
+    # no targets at all
+    loss, items = my_utils.compute_loss(p, torch.zeros(0, 6).cuda(), model)
+    ref, ritems = orc.compute_loss([x.detach().cpu() for x in p], torch.zeros(0, 6), av, model.hyp, 80, 1.0)
+    np.testing.assert_allclose(items.cpu().numpy(), ritems.numpy(), rtol=1e-4)
+    # duplicates: many targets in the same cell -> last match (anchor-major, target-minor) owns tobj
+    t = torch.tensor([[0, 3, 0.26, 0.26, 0.3, 0.4], [0, 5, 0.27, 0.27, 0.3, 0.4], [0, 7, 0.27, 0.26, 0.31, 0.41],
+                      [1, 1, 0.8, 0.8, 0.2, 0.1]], dtype=torch.float32)
+    pr = [x.detach().cpu().requires_grad_(True) for x in p]
+    ref, ritems = orc.compute_loss(pr, t, av, model.hyp, 80, 1.0)
+    ref.backward()
+    loss, items = my_utils.compute_loss(p, t.cuda(), model)
+    loss.backward()
+    np.testing.assert_allclose(items.cpu().numpy(), ritems.numpy(), rtol=1e-4)
+    for a, b in zip(p, pr):
+        np.testing.assert_allclose(a.grad.cpu().numpy(), b.grad.numpy(), rtol=1e-4, atol=1e-6)

@@ -1,0 +1,102 @@
+"""CPU: pin the oracle (oracle/darknet_oracle.py) against fixtures produced by running the reference itself
+(oracle/gen_golden.py).  Tolerances are fp32 re-association only."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import anchor_vecs, golden, module_defs, orc
+
+
+def _state(name, requires_grad=False):
+    import models
+    from helpers import cfg_path
+    m = models.Darknet(cfg_path(name))
+    sd = orc.synth_state_dict(m.state_dict(), 0)
+    if requires_grad:
+        for k, v in sd.items():
+            if v.dtype.is_floating_point and not k.endswith(('running_mean', 'running_var')):
+                v.requires_grad_(True)
+    return sd
+
+
+@pytest.mark.parametrize("name,B,S,seed", [("yolov3-tiny", 2, 96, 3), ("yolov3", 2, 64, 0), ("yolov4", 2, 64, 0),
+                                           ("yolov3-tiny", 1, 416, 0)])
+def test_eval_forward_matches_reference(name, B, S, seed):
+    g = golden("%s_%d_eval" % (name, S))
+    x = orc.synth_images(B, S, S, seed=seed)
+    with torch.no_grad():
+        io, p = orc.darknet_forward(module_defs(name), _state(name), x, name)
+    assert io.shape == g["io"].shape
+    np.testing.assert_allclose(io.numpy(), g["io"], rtol=2e-4, atol=2e-4)
+    for i, pi in enumerate(p):
+        np.testing.assert_allclose(pi.numpy(), g["p%d" % i], rtol=2e-4, atol=2e-4)
+
+
+@pytest.mark.parametrize("name", ["yolov3-tiny", "yolov3", "yolov4"])
+def test_train_forward_loss_backward_matches_reference(name):
+    g = golden("%s_64_train" % name)
+    sd = _state(name, requires_grad=True)
+    x = orc.synth_images(2, 64, 64, seed=0)
+    t = orc.synth_targets(2, 6, 80, seed=1)
+    p, stats = orc.darknet_forward(module_defs(name), sd, x, name, training=True)
+    for i, pi in enumerate(p):
+        np.testing.assert_allclose(pi.detach().numpy(), g["p%d" % i], rtol=1e-3, atol=1e-3)
+    hyp = dict(orc.DEFAULT_HYP)
+    loss, items = orc.compute_loss(p, t, anchor_vecs(name), hyp, 80, 1.0)
+    np.testing.assert_allclose(items.numpy(), g["items"], rtol=1e-4)
+    loss.backward()
+    names = [str(n) for n in g["grad_names"]]
+    norms = dict(zip(names, g["grad_norms"]))
+    for k in names:
+        if ("grad::" + k) in g.files:
+            np.testing.assert_allclose(sd[k].grad.numpy(), g["grad::" + k], rtol=2e-3, atol=2e-4 * (1 + norms[k]))
+    worst = max(abs(float(sd[k].grad.norm()) - norms[k]) / (norms[k] + 1e-6) for k in names if norms[k] > 0)
+    assert worst < 5e-3, worst
+    for k in g.files:
+        if k.startswith("stat::"):
+            np.testing.assert_allclose(stats[k[6:]].numpy(), g[k], rtol=1e-4, atol=1e-5)
+
+
+def test_loss_and_build_targets_match_reference():
+    g = golden("loss_case")
+    p = [torch.from_numpy(g["p%d" % i]).requires_grad_(True) for i in range(3)]
+    av = [torch.from_numpy(g["anchor_vec%d" % i]) for i in range(3)]
+    t = torch.from_numpy(g["targets"])
+    loss, items = orc.compute_loss(p, t, av, dict(orc.DEFAULT_HYP), 80, 1.0)
+    np.testing.assert_allclose(items.numpy(), g["items"], rtol=1e-5)
+    loss.backward()
+    for i in range(3):
+        np.testing.assert_allclose(p[i].grad.numpy(), g["dp%d" % i], rtol=1e-4, atol=1e-6)
+    tcls, tbox, idx, avs = orc.build_targets([x.detach() for x in p], t, av, 0.20)
+    for i in range(3):
+        assert np.array_equal(torch.stack(idx[i]).numpy(), g["idx%d" % i])       # int64, bit exact
+        assert np.array_equal(tcls[i].numpy(), g["tcls%d" % i])
+        np.testing.assert_array_equal(tbox[i].numpy(), g["tbox%d" % i])
+        np.testing.assert_array_equal(avs[i].numpy(), g["av%d" % i])
+
+
+def test_quantizer_matches_reference():
+    g = golden("quant_case")
+    x = torch.from_numpy(g["x"])
+    best_i, _ = orc.cos_scale_search(x, 8)
+    assert best_i == int(np.argmax(g["scale_list"]))
+    scale = orc.pow2_scale(best_i - 5, 8)
+    assert scale == float(g["scale"])
+    np.testing.assert_array_equal(orc.fake_quant(x, scale, 8).numpy(), g["y_train"])
+    np.testing.assert_array_equal(orc.fake_quant(x * 1.7, scale, 8).numpy(), g["y_eval"])
+    np.testing.assert_array_equal(orc.round_half_away(torch.from_numpy(g["round_in"]).float()).numpy(), g["round_out"])
+
+
+def test_bn_fold_and_mish_backward_match_reference():
+    g = golden("misc_case")
+    sd = _state("yolov3-tiny")
+    pre = "module_list.2."
+    wf, bf = orc.fold_bn(sd[pre + "Conv2d.weight"], None, sd[pre + "BatchNorm2d.weight"], sd[pre + "BatchNorm2d.bias"],
+                         sd[pre + "BatchNorm2d.running_mean"], sd[pre + "BatchNorm2d.running_var"], 1e-5)
+    np.testing.assert_allclose(wf.numpy(), g["fused_w"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(bf.numpy(), g["fused_b"], rtol=1e-5, atol=1e-6)
+    x = torch.from_numpy(g["mish_x"])
+    np.testing.assert_allclose(orc.activation(x, 'mish').numpy(), g["mish_y"], rtol=1e-6, atol=1e-7)
+    dx = orc.mish_backward(x, torch.from_numpy(g["mish_g"]))
+    np.testing.assert_allclose(dx.numpy(), g["mish_dx_formula"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(dx.numpy(), g["mish_dx_autograd"], rtol=1e-4, atol=1e-5)

@@ -294,6 +294,92 @@ class Plan:
             _, p = ops.yolo_decode(raw.buf, m.na, m.no, anc, m.stride, io=ops_io, row_offset=row_off)
             self.p_out.append(p)
 
+    # ---- measurement helpers (bench.py) -----------------------------------------------------------------------
+    def _launch_step(self, st, x):
+        saved = self.steps
+        self.steps = [st]
+        yolo = self.yolo
+        self.yolo = []
+        try:
+            self._launch_all(x)
+        finally:
+            self.steps, self.yolo = saved, yolo
+
+    def launches_per_forward(self):
+        return len(self.steps) + len(self.yolo)
+
+    def step_info(self, st):
+        """(label, algorithmic FLOPs, algorithmic HBM bytes) of one launch."""
+        kind = st[0]
+        B = self.B
+        if kind == 'conv':
+            _, i, src, out, res, conv, bn, act, slope = st
+            k = conv.kernel_size[0]
+            M = B * out.H * out.W
+            flops = 2.0 * M * conv.out_channels * conv.in_channels * k * k
+            in_hw = (self.H * self.W) if src is None else (src.H * src.W)
+            in_bytes = B * in_hw * conv.in_channels * (4 if src is None else 2)
+            out_bytes = M * conv.out_channels * (4 if out.dtype == torch.float32 else 2)
+            w_bytes = conv.out_channels * conv.in_channels * k * k * 2
+            res_bytes = M * conv.out_channels * 2 if res is not None else 0
+            label = "L%03d conv %dx%d s%d %d->%d @%dx%d %s%s" % (i, k, k, conv.stride[0], conv.in_channels,
+                                                                 conv.out_channels, out.H, out.W, act,
+                                                                 "+res" if res is not None else "")
+            return label, flops, in_bytes + out_bytes + w_bytes + res_bytes, src is None
+        t_in, t_out = st[1], (st[3] if kind == 'add' else st[2])
+        if kind == 'copy':
+            n = B * st[1].H * st[1].W * st[1].C * 2
+            return "copy C=%d @%dx%d" % (st[1].C, st[1].H, st[1].W), 0.0, 2 * n, False
+        n_in = B * t_in.H * t_in.W * t_in.C * 2
+        n_out = B * t_out.H * t_out.W * t_out.C * 2
+        if kind == 'add':
+            n_in *= 2
+        return "%s C=%d @%dx%d" % (kind, t_out.C, t_out.H, t_out.W), 0.0, n_in + n_out, False
+
+    def profile_layers(self, x, reps=5):
+        """Per-launch CUDA-event timing (eager launches on the current stream). Returns a list of dicts."""
+        x = x.contiguous().float()
+        if self.param_version is None:
+            self.forward(x)
+        rows = []
+        self.io = torch.empty((self.B, self.total_rows, self.yolo[0][0].no), dtype=torch.float32, device=self.device)
+        for st in self.steps:
+            label, flops, nbytes, is_stem = self.step_info(st)
+            self._launch_step(st, x)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                self._launch_step(st, x)
+            e1.record()
+            e1.synchronize()
+            ms = e0.elapsed_time(e1) / reps
+            rows.append({"label": label, "ms": ms, "tflops": flops / ms / 1e9 if ms > 0 else 0.0,
+                         "gbs": nbytes / ms / 1e6 if ms > 0 else 0.0, "flops": flops, "bytes": nbytes,
+                         "kind": "stem" if is_stem else st[0]})
+        return rows
+
+    def time_tc_convs(self, x, iters=5):
+        """Time only the tcgen05 conv launches of one forward, back to back on the current stream.
+        Returns (ms per forward-worth of conv launches, algorithmic FLOPs of those launches, n launches)."""
+        x = x.contiguous().float()
+        if self.param_version is None:
+            self.forward(x)
+        convs = [st for st in self.steps if st[0] == 'conv' and st[2] is not None]
+        flops = sum(self.step_info(st)[1] for st in convs)
+        saved, yolo = self.steps, self.yolo
+        self.steps, self.yolo = convs, []
+        try:
+            self._launch_all(x)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                self._launch_all(x)
+            e1.record()
+            e1.synchronize()
+        finally:
+            self.steps, self.yolo = saved, yolo
+        return e0.elapsed_time(e1) / iters, flops, len(convs)
+
     def forward(self, x):
         model = self.model
         ver = self._params_version()
@@ -322,7 +408,8 @@ class Plan:
                     self._launch_all(self.static_x)
                 self.graph = g
                 self.static_p = tuple(self.p_out)
-            self.static_x.copy_(x)
+            if x.data_ptr() != self.static_x.data_ptr():
+                self.static_x.copy_(x)
             self.graph.replay()
             if getattr(model, 'static_outputs', False):
                 io, p = self.io, self.static_p
@@ -341,6 +428,12 @@ class Engine:
 
     def invalidate(self):
         self.plans.clear()
+
+    def plan_for(self, x):
+        self.forward(x)
+        model = self.model
+        keep = bool(model.keep_features) if model.keep_features is not None else bool(model.training)
+        return self.plans[(tuple(x.shape), bool(model.training), x.device.index, keep)]
 
     def forward(self, x):
         model = self.model
