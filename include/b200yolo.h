@@ -216,8 +216,18 @@ int b2y_bn_act_bwd_apply(const void* x, long long x_pitch, const void* dy, long 
 /* dX = conv_transpose(dY, W)   (data gradient; implicit GEMM on tcgen05) */
 int b2y_conv2d_bwd_data(const b2y_conv_desc* d, const void* dy, const void* w_packed_t, void* dx, int accumulate,
                         void* stream);
-/* dW[o][kh][kw][i] = sum_pixels dY[p][o] * X[p+(kh,kw)][i]  (weight gradient; fp32 [O][kh][kw][I]) */
-int b2y_conv2d_bwd_weight(const b2y_conv_desc* d, const void* x, const void* dy, float* dw, void* stream);
+/* weights for b2y_conv2d_bwd_data: OIHW fp32 -> per output-phase slabs [phase][in_c][tap][out_c] fp16
+ * (stride-s data gradients are decomposed into s*s stride-1 implicit GEMMs over dY; out_c*ksize^2*in_c elements) */
+int b2y_pack_dgrad_weights(const b2y_conv_desc* d, const float* w_oihw, void* w_packed_t, void* stream);
+/* dW[o][kh][kw][i] += scale * sum_pixels dY[p][o] * X[p@(kh,kw)][i]  (weight gradient, tcgen05 GEMM over the pixel
+ * dimension with MN-major operands; dw fp32 [O][kh][kw][I], caller zeroes it; split-K reduced with red.global.add) */
+int b2y_conv2d_bwd_weight(const b2y_conv_desc* d, const void* x, const void* dy, float* dw, float scale,
+                          void* stream);
+/* [O][kh][kw][I] fp32 -> OIHW fp32 parameter-gradient layout: dst = alpha*src (+ dst if accumulate) */
+int b2y_unpack_wgrad(const float* dw_packed, float* dw_oihw, int out_c, int in_c, int ksize, float alpha,
+                     int accumulate, void* stream);
+/* dst = alpha*src + beta*dst (fp32) */
+int b2y_axpby_f32(const float* src, float* dst, long long n, float alpha, float beta, void* stream);
 /* SGD + Nesterov momentum + weight decay over a flat fp32 buffer (train.py:135-144), grads pre-scaled by
  * grad_scale (1/world_size after the NCCL sum) */
 int b2y_sgd_nesterov(float* param, const float* grad, float* momentum_buf, long long n, float lr, float momentum,

@@ -1,0 +1,176 @@
+"""GPU parity of the training kernels (dgrad / wgrad tcgen05 GEMMs, BN+activation fwd/bwd, SGD) and the
+quantisation kernels against torch autograd / the oracle on identical fp16-rounded operands."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import golden, orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from b200yolo import ops
+    return ops
+
+
+def _nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous().half().cuda()
+
+
+def _nchw(t):
+    return t.float().permute(0, 3, 1, 2).cpu()
+
+
+def conv_grads_case(B, H, W, Cin, Cout, k, stride, seed=0, accumulate=False):
+    ops = _ops()
+    g = torch.Generator().manual_seed(seed)
+    pad = (k - 1) // 2
+    x = torch.randn(B, Cin, H, W, generator=g).half().double().requires_grad_(True)
+    w = (torch.randn(Cout, Cin, k, k, generator=g) / math.sqrt(Cin * k * k)).half().double().requires_grad_(True)
+    y = F.conv2d(x, w, None, stride=stride, padding=pad)
+    dy = torch.randn(y.shape, generator=g).half().double()
+    y.backward(dy)
+    dxr, dwr = x.grad.float(), w.grad.float()
+    wt = ops.pack_dgrad_weights(w.detach().float().cuda(), stride, pad, (H, W))
+    dyn = _nhwc(dy.float())
+    if accumulate:
+        base = torch.randn(B, Cin, H, W, generator=g).half()
+        out = _nhwc(base.float())
+        dx = ops.conv2d_bwd_data(dyn, wt, (B, H, W, Cin), k, stride, pad, out=out, accumulate=True)
+        dxr = dxr + base.float()
+    else:
+        dx = ops.conv2d_bwd_data(dyn, wt, (B, H, W, Cin), k, stride, pad)
+    dw = ops.conv2d_bwd_weight(_nhwc(x.detach().float()), dyn, k, stride, pad)
+    torch.cuda.synchronize()
+    e_dx = (_nchw(dx) - dxr).abs().max().item() / max(dxr.pow(2).mean().sqrt().item(), 1e-6)
+    dwg = dw.permute(0, 3, 1, 2).cpu()
+    e_dw = (dwg - dwr).abs().max().item() / max(dwr.pow(2).mean().sqrt().item(), 1e-6)
+    return e_dx, e_dw
+
+
+GRAD_CASES = [
+    (2, 16, 16, 64, 128, 1, 1),
+    (2, 16, 16, 64, 128, 3, 1),
+    (2, 20, 20, 128, 256, 3, 1),
+    (2, 16, 16, 64, 128, 3, 2),     # stride-2 data gradient = 4 phase GEMMs
+    (1, 26, 38, 64, 64, 3, 2),      # non-square, even
+    (1, 13, 13, 64, 64, 3, 2),      # odd input size: ragged phases
+    (2, 16, 16, 32, 64, 3, 1),      # Cin=32 (64B swizzle atoms)
+    (2, 16, 16, 16, 32, 3, 1),      # Cin=16
+    (2, 10, 10, 512, 256, 1, 1),    # yolo head sized (Cout padded to 256 by the caller)
+    (2, 12, 12, 256, 512, 3, 1),    # 4 co tiles, N=256
+    (4, 40, 40, 128, 128, 3, 1),    # many k-steps -> split-K > 1
+]
+
+
+@pytest.mark.parametrize("case", GRAD_CASES, ids=[str(c) for c in GRAD_CASES])
+def test_conv_bwd_data_and_weight(case):
+    e_dx, e_dw = conv_grads_case(*case)
+    print("\n%s dx err/rms=%.3g dw err/rms=%.3g" % (case, e_dx, e_dw))
+    assert e_dx < 6e-3      # fp16 store of dx
+    assert e_dw < 2e-4      # fp32 accumulate + fp32 atomics
+
+
+def test_conv_bwd_data_accumulate():
+    e_dx, _ = conv_grads_case(2, 16, 16, 64, 128, 3, 2, accumulate=True)
+    assert e_dx < 8e-3
+
+
+@pytest.mark.parametrize("act", ["leaky", "mish", "linear"])
+def test_bn_act_fwd_bwd(act):
+    ops = _ops()
+    g = torch.Generator().manual_seed(3)
+    B, C, H, W = 4, 64, 12, 10
+    z = (torch.randn(B, C, H, W, generator=g) * 2 + 0.3).half().float()
+    gamma = torch.rand(C, generator=g) + 0.5
+    beta = torch.randn(C, generator=g) * 0.2
+    res = torch.randn(B, C, H, W, generator=g).half().float()
+    dy = torch.randn(B, C, H, W, generator=g).half().float()
+    rm, rv = torch.zeros(C), torch.ones(C)
+    # reference: torch BN (training) + activation + residual, autograd
+    zr = z.clone().double().requires_grad_(True)
+    gr, br = gamma.clone().double().requires_grad_(True), beta.clone().double().requires_grad_(True)
+    rm_r, rv_r = rm.clone().double(), rv.clone().double()
+    u = F.batch_norm(zr, rm_r, rv_r, gr, br, True, 0.1, 1e-5)
+    y = orc.activation(u, act) + res.double()
+    y.backward(dy.double())
+    # ours: statistics as the conv epilogue would deliver them
+    zn = _nhwc(z)
+    s1 = z.sum(dim=(0, 2, 3)).cuda()
+    s2 = (z * z).sum(dim=(0, 2, 3)).cuda()
+    rmc, rvc = rm.cuda(), rv.cuda()
+    mean, invstd, scale, shift = ops.bn_finalize(s1, s2, B * H * W, gamma.cuda(), beta.cuda(), 1e-5, 0.1, rmc, rvc)
+    out = ops.bn_act_fwd(zn, scale, shift, act, residual=_nhwc(res))
+    dz, dgamma, dbeta = ops.bn_act_bwd(zn, _nhwc(dy), scale, shift, gamma.cuda(), mean, invstd, act)
+    torch.cuda.synchronize()
+    assert (_nchw(out) - y.detach().float()).abs().max() < 6e-3
+    np.testing.assert_allclose(rmc.cpu().numpy(), rm_r.float().numpy(), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(rvc.cpu().numpy(), rv_r.float().numpy(), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(dgamma.cpu().numpy(), gr.grad.float().numpy(), rtol=2e-3, atol=2e-3)
+    np.testing.assert_allclose(dbeta.cpu().numpy(), br.grad.float().numpy(), rtol=2e-3, atol=2e-3)
+    ref_dz = zr.grad.float()
+    assert (_nchw(dz) - ref_dz).abs().max() < 4e-3 * max(1.0, ref_dz.abs().max().item())
+
+
+def test_sgd_nesterov_matches_torch():
+    ops = _ops()
+    g = torch.Generator().manual_seed(4)
+    p0 = torch.randn(10007, generator=g)
+    pt = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.SGD([pt], lr=0.01, momentum=0.937, nesterov=True, weight_decay=5e-4)
+    pc, buf = p0.clone().cuda(), torch.zeros(10007, device="cuda")
+    for step in range(3):
+        gr = torch.randn(10007, generator=g)
+        pt.grad = gr.clone()
+        opt.step()
+        ops.sgd_nesterov(pc, (gr * 4).cuda(), buf, 0.01, 0.937, 5e-4, grad_scale=0.25, first_step=(step == 0))
+    np.testing.assert_allclose(pc.cpu().numpy(), pt.detach().numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_fakequant_and_cos_search_match_reference():
+    ops = _ops()
+    gq = golden("quant_case")
+    x = torch.from_numpy(gq["x"])
+    cos = ops.cos_scale_search(x.cuda(), 8).cpu()
+    _, sims = orc.cos_scale_search(x, 8)
+    np.testing.assert_allclose(cos.numpy(), np.array(sims, dtype=np.float32), rtol=2e-6, atol=2e-6)
+    assert int(torch.argmax(cos)) == int(np.argmax(gq["scale_list"]))
+    scale = float(gq["scale"])
+    y = ops.fakequant(x.cuda(), scale, 8).cpu()
+    assert np.array_equal(y.numpy(), gq["y_train"]), "fake-quant must be bit exact"
+    y2 = ops.fakequant((x * 1.7).cuda(), scale, 8).cpu()
+    assert np.array_equal(y2.numpy(), gq["y_eval"])
+    mm = ops.minmax(x.view(4, -1).cuda(), per_row=True).cpu()
+    assert torch.equal(mm[:, 0], x.view(4, -1).min(1).values) and torch.equal(mm[:, 1], x.view(4, -1).max(1).values)
+    mm = ops.minmax(x.view(4, -1).cuda(), per_row=False).cpu()
+    assert float(mm[0, 0]) == float(x.min()) and float(mm[0, 1]) == float(x.max())
+
+
+@pytest.mark.parametrize("case", [(2, 20, 20, 64, 128, 3, 1), (2, 20, 20, 128, 256, 1, 1), (1, 40, 40, 32, 64, 3, 2),
+                                  (2, 13, 13, 512, 1024, 3, 1)])
+def test_int8_conv_bit_exact(case):
+    """INT8 tcgen05 conv (int32 accumulate) vs the reference's fp32 fake-quant arithmetic: requantised outputs equal."""
+    ops = _ops()
+    B, H, W, Cin, Cout, k, stride = case
+    pad = (k - 1) // 2
+    g = torch.Generator().manual_seed(5)
+    bits = 8
+    sa, sw, so = orc.pow2_scale(2, bits), orc.pow2_scale(-1, bits), orc.pow2_scale(3, bits)
+    xq = torch.randint(-128, 128, (B, Cin, H, W), generator=g).float()
+    wq = torch.clamp(orc.round_half_away(torch.randn(Cout, Cin, k, k, generator=g) * 40), -128, 127)
+    bias = orc.fake_quant(torch.randn(Cout, generator=g), orc.pow2_scale(1, bits), bits)
+    # reference arithmetic: F.conv2d on dequantised fp32 values (ptq_cos.py:288-296) -> leaky -> fake-quant (717)
+    ref = F.conv2d(xq * sa, wq * sw, bias, stride=stride, padding=pad)
+    ref = F.leaky_relu(ref, 0.1)
+    ref_q = torch.clamp(orc.round_half_away(ref / so), -128, 127)
+    x8 = xq.permute(0, 2, 3, 1).contiguous().to(torch.int8).cuda()
+    w8 = wq.permute(0, 2, 3, 1).contiguous().to(torch.int8).cuda()
+    out = ops.qconv2d(x8, w8, bias.cuda(), k, stride, pad, sa * sw, so, act="leaky")
+    torch.cuda.synchronize()
+    got = out.permute(0, 3, 1, 2).cpu().float()
+    mism = (got != ref_q).float().mean().item()
+    assert mism == 0.0, "int8 conv differs from fake-quant fp32 reference on %.4g of outputs" % mism

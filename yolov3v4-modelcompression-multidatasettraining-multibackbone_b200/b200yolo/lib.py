@@ -81,7 +81,10 @@ _PROTOS = {
     "b2y_bn_act_bwd_reduce": (i32, [vp, ll, vp, ll, vp, vp, vp, vp, vp, vp, ll, i32, i32, f32, vp]),
     "b2y_bn_act_bwd_apply": (i32, [vp, ll, vp, ll, vp, vp, vp, vp, vp, vp, vp, vp, ll, ll, i32, i32, f32, vp]),
     "b2y_conv2d_bwd_data": (i32, [C.POINTER(ConvDesc), vp, vp, vp, i32, vp]),
-    "b2y_conv2d_bwd_weight": (i32, [C.POINTER(ConvDesc), vp, vp, vp, vp]),
+    "b2y_pack_dgrad_weights": (i32, [C.POINTER(ConvDesc), vp, vp, vp]),
+    "b2y_conv2d_bwd_weight": (i32, [C.POINTER(ConvDesc), vp, vp, vp, f32, vp]),
+    "b2y_unpack_wgrad": (i32, [vp, vp, i32, i32, i32, f32, i32, vp]),
+    "b2y_axpby_f32": (i32, [vp, vp, ll, f32, f32, vp]),
     "b2y_sgd_nesterov": (i32, [vp, vp, vp, ll, f32, f32, f32, f32, i32, vp]),
 }
 

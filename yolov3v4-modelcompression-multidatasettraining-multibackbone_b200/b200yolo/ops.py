@@ -200,3 +200,171 @@ def build_targets_layer(targets, anchor_vec, ny, nx, iou_t):
          ptr(count), stream_ptr())
     n = int(count.item())
     return idx[:, :n], tbox[:n], tcls[:n]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# training kernels
+# ---------------------------------------------------------------------------------------------------------------
+def dgrad_weight_numel(out_c, in_c, k):
+    return out_c * in_c * k * k
+
+
+def pack_dgrad_weights(w_oihw, stride, pad, in_hw):
+    """OIHW fp32 -> phase-decomposed dgrad weights (fp16) for b2y_conv2d_bwd_data."""
+    O, I, k, _ = w_oihw.shape
+    H, W = in_hw
+    Ho, Wo = conv_out_hw(H, W, k, stride, pad)
+    out = torch.empty(O * I * k * k, dtype=torch.float16, device=w_oihw.device)
+    d = ConvDesc(1, H, W, I, I, O, k, stride, pad, Ho, Wo, O, 0, 0.0, OUT_F16, 0)
+    call("b2y_pack_dgrad_weights", C.byref(d), ptr(w_oihw.contiguous().float()), ptr(out), stream_ptr())
+    return out
+
+
+def conv2d_bwd_data(dy, w_packed_t, in_shape, k, stride, pad, out=None, accumulate=False):
+    """dx = conv^T(dy, W): dy NHWC fp16 [B,Ho,Wo,O] -> dx NHWC fp16 [B,H,W,I]."""
+    B, H, W, I = in_shape
+    _, Ho, Wo, O = dy.shape
+    if out is None:
+        out = torch.empty((B, H, W, I), dtype=torch.float16, device=dy.device)
+        assert not accumulate
+    d = ConvDesc(B, H, W, I, _pitch(out), O, k, stride, pad, Ho, Wo, _pitch(dy), 0, 0.0, OUT_F16, 0)
+    call("b2y_conv2d_bwd_data", C.byref(d), ptr(dy), ptr(w_packed_t), ptr(out), 1 if accumulate else 0, stream_ptr())
+    return out
+
+
+def conv2d_bwd_weight(x, dy, k, stride, pad, scale=1.0, dw=None):
+    """dW [O][k][k][I] fp32 (+)= scale * sum_pixels dy (x) x."""
+    B, H, W, I = x.shape
+    _, Ho, Wo, O = dy.shape
+    if dw is None:
+        dw = torch.zeros((O, k, k, I), dtype=torch.float32, device=x.device)
+    d = ConvDesc(B, H, W, I, _pitch(x), O, k, stride, pad, Ho, Wo, _pitch(dy), 0, 0.0, OUT_F16, 0)
+    call("b2y_conv2d_bwd_weight", C.byref(d), ptr(x), ptr(dy), ptr(dw), float(scale), stream_ptr())
+    return dw
+
+
+def unpack_wgrad(dw_packed, out_oihw, alpha=1.0, accumulate=False):
+    O, k, _, I = dw_packed.shape
+    call("b2y_unpack_wgrad", ptr(dw_packed), ptr(out_oihw), O, I, k, float(alpha), 1 if accumulate else 0,
+         stream_ptr())
+    return out_oihw
+
+
+def axpby(src, dst, alpha=1.0, beta=0.0):
+    call("b2y_axpby_f32", ptr(src), ptr(dst), src.numel(), float(alpha), float(beta), stream_ptr())
+    return dst
+
+
+def bn_finalize(s1, s2, count, gamma, beta, eps, momentum, running_mean, running_var):
+    Cn = s1.numel()
+    dev = s1.device
+    mean, invstd, scale, shift = [torch.empty(Cn, dtype=torch.float32, device=dev) for _ in range(4)]
+    call("b2y_bn_finalize", ptr(s1), ptr(s2), int(count), ptr(gamma), ptr(beta), float(eps), float(momentum),
+         ptr(running_mean), ptr(running_var), ptr(mean), ptr(invstd), ptr(scale), ptr(shift), Cn, stream_ptr())
+    return mean, invstd, scale, shift
+
+
+def bn_act_fwd(x, scale, shift, act, slope=0.1, residual=None, out=None):
+    B, H, W, Cc = x.shape
+    if out is None:
+        out = torch.empty((B, H, W, Cc), dtype=torch.float16, device=x.device)
+    call("b2y_bn_act_fwd", ptr(x), _pitch(x), ptr(scale), ptr(shift), ptr(residual),
+         _pitch(residual) if residual is not None else 0, ptr(out), _pitch(out), B * H * W, Cc,
+         ACT[act] if isinstance(act, str) else int(act), float(slope), stream_ptr())
+    return out
+
+
+def bn_act_bwd(x, dy, scale, shift, gamma, mean, invstd, act, slope=0.1, dx=None, dgamma=None, dbeta=None):
+    """Returns (dx fp16, dgamma fp32, dbeta fp32) for y = act(x*scale+shift) with batch statistics."""
+    B, H, W, Cc = x.shape
+    dev = x.device
+    if dgamma is None:
+        dgamma = torch.zeros(Cc, dtype=torch.float32, device=dev)
+        dbeta = torch.zeros(Cc, dtype=torch.float32, device=dev)
+    a = ACT[act] if isinstance(act, str) else int(act)
+    call("b2y_bn_act_bwd_reduce", ptr(x), _pitch(x), ptr(dy), _pitch(dy), ptr(scale), ptr(shift), ptr(mean),
+         ptr(invstd), ptr(dgamma), ptr(dbeta), B * H * W, Cc, a, float(slope), stream_ptr())
+    if dx is None:
+        dx = torch.empty((B, H, W, Cc), dtype=torch.float16, device=dev)
+    call("b2y_bn_act_bwd_apply", ptr(x), _pitch(x), ptr(dy), _pitch(dy), ptr(scale), ptr(shift), ptr(gamma), ptr(mean),
+         ptr(invstd), ptr(dgamma), ptr(dbeta), ptr(dx), _pitch(dx), B * H * W, Cc, a, float(slope), stream_ptr())
+    return dx, dgamma, dbeta
+
+
+def bias_act_bwd_reduce(x, dy, scale, shift, act, slope=0.1, dbeta=None):
+    """dbias = sum dy*act'(x*scale+shift) for a conv without BN (dgamma not needed)."""
+    B, H, W, Cc = x.shape
+    if dbeta is None:
+        dbeta = torch.zeros(Cc, dtype=torch.float32, device=x.device)
+    call("b2y_bn_act_bwd_reduce", ptr(x), _pitch(x), ptr(dy), _pitch(dy), ptr(scale), ptr(shift), None, None, None,
+         ptr(dbeta), B * H * W, Cc, ACT[act] if isinstance(act, str) else int(act), float(slope), stream_ptr())
+    return dbeta
+
+
+def sgd_nesterov(param, grad, buf, lr, momentum, weight_decay, grad_scale=1.0, first_step=False):
+    call("b2y_sgd_nesterov", ptr(param), ptr(grad), ptr(buf), param.numel(), float(lr), float(momentum),
+         float(weight_decay), float(grad_scale), 1 if first_step else 0, stream_ptr())
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# quantisation kernels
+# ---------------------------------------------------------------------------------------------------------------
+def fakequant(x, scale, bits=8):
+    x = x.contiguous().float()
+    y = torch.empty_like(x)
+    lo, hi = -(1 << (bits - 1)), (1 << (bits - 1)) - 1
+    call("b2y_fakequant_f32", ptr(x), ptr(y), x.numel(), float(scale), float(lo), float(hi), stream_ptr())
+    return y
+
+
+def quantize_to_i8(x, scale, bits=8, out=None):
+    B, H, W, Cc = x.shape
+    if out is None:
+        out = torch.empty((B, H, W, Cc), dtype=torch.int8, device=x.device)
+    lo, hi = -(1 << (bits - 1)), (1 << (bits - 1)) - 1
+    call("b2y_quantize_f16_to_i8", ptr(x), _pitch(x), ptr(out), _pitch(out), B * H * W, Cc, float(scale), float(lo),
+         float(hi), stream_ptr())
+    return out
+
+
+def cos_scale_search(x, bits=8):
+    """Cosine similarities of x vs fakequant(x; 2^(i-5)/2^(bits-1)), i in range(bits+7) -> fp32 [bits+7] (device)."""
+    x = x.contiguous().float()
+    n_cand = bits + 7
+    out = torch.empty(n_cand, dtype=torch.float32, device=x.device)
+    ws = torch.empty(8 * (1 + 2 * n_cand), dtype=torch.uint8, device=x.device)
+    call("b2y_cos_scale_search", ptr(x), x.numel(), bits, n_cand, ptr(out), ptr(ws), ws.numel(), stream_ptr())
+    return out
+
+
+def minmax(x2d, per_row=False):
+    x2d = x2d.contiguous().float()
+    rows, cols = x2d.shape
+    out = torch.empty((rows if per_row else 1, 2), dtype=torch.float32, device=x2d.device)
+    call("b2y_minmax_f32", ptr(x2d), rows, cols, 1 if per_row else 0, ptr(out), stream_ptr())
+    return out
+
+
+def pack_qconv_weights(w_folded_oihw, w_scale, bits=8):
+    O, I, k, _ = w_folded_oihw.shape
+    out = torch.empty((O, k, k, I), dtype=torch.int8, device=w_folded_oihw.device)
+    lo, hi = -(1 << (bits - 1)), (1 << (bits - 1)) - 1
+    call("b2y_pack_qconv_weights", ptr(w_folded_oihw.contiguous().float()), O, I, k, float(w_scale), float(lo),
+         float(hi), ptr(out), stream_ptr())
+    return out
+
+
+def qconv2d(x_i8, w_i8, bias, k, stride, pad, acc_scale, out_scale, act="linear", slope=0.1, bits=8, out=None,
+            out_kind=OUT_I8, requant=True):
+    """INT8 conv: y = requant(act(acc*acc_scale + bias)); x int8 NHWC, w int8 [O][k][k][I]."""
+    B, H, W, Cin = x_i8.shape
+    O = w_i8.shape[0]
+    Ho, Wo = conv_out_hw(H, W, k, stride, pad)
+    if out is None:
+        dt = {OUT_I8: torch.int8, OUT_F16: torch.float16, OUT_F32: torch.float32}[out_kind]
+        out = torch.empty((B, Ho, Wo, O), dtype=dt, device=x_i8.device)
+    lo, hi = -(1 << (bits - 1)), (1 << (bits - 1)) - 1
+    cd = make_conv_desc(x_i8.shape, _pitch(x_i8), O, k, stride, pad, _pitch(out), act, slope, out_kind)
+    qd = QConvDesc(cd, float(acc_scale), float(out_scale), float(lo), float(hi), out_kind, 1 if requant else 0)
+    call("b2y_qconv2d_fwd", C.byref(qd), ptr(x_i8), ptr(w_i8), ptr(bias), ptr(out), stream_ptr())
+    return out

@@ -60,18 +60,19 @@ static int make_map_2d(CUtensorMap* m, const void* base, int esize, long long ro
 
 // im2col map over an NHWC activation tensor (dims C,W,H,N) for an RxS / stride / pad convolution.
 static int make_map_im2col(CUtensorMap* m, const void* base, int esize, int N, int H, int W, int C,
-                           long long pitch_elems, int R, int S, int stride, int pad, int block_k, int kbytes) {
+                           long long pitch_elems, int lower_w, int lower_h, int upper_w, int upper_h, int stride,
+                           int block_k, int kbytes, int pixels_per_column = 128) {
     if (!g_encodeIm2col) return B2Y_ERR_DRIVER;
     cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     cuuint64_t gstride[3] = {(cuuint64_t)(pitch_elems * esize), (cuuint64_t)(pitch_elems * esize * W),
                              (cuuint64_t)(pitch_elems * esize * W * (long long)H)};
-    // bounding box of the *base pixel* (top-left tap): lower = -pad, upper = pad - (filter-1)
-    int lower[2] = {-pad, -pad};
-    int upper[2] = {pad - (S - 1), pad - (R - 1)};
+    // bounding box of the *base pixel* (the tap with offset 0): for fprop lower = -pad, upper = pad - (filter-1)
+    int lower[2] = {lower_w, lower_h};
+    int upper[2] = {upper_w, upper_h};
     cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
     CUresult r = g_encodeIm2col(m, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 4,
                                 const_cast<void*>(base), gdim, gstride, lower, upper, (cuuint32_t)block_k,
-                                /*pixelsPerColumn*/ 128, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_enum(kbytes),
+                                (cuuint32_t)pixels_per_column, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_enum(kbytes),
                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return B2Y_ERR_DRIVER;
     // Drivers <= 13.1 mis-encode im2col maps of tensors smaller than 128 KiB (same workaround as CUTLASS).
@@ -128,40 +129,62 @@ struct EpilogueArgs {
     float* stat_sqsum = nullptr;
 };
 
-// Shared launcher: x NHWC (esize 2 = fp16, 1 = int8), w [Cout][R][S][Cin].
-int conv_tc_launch(int kind, const b2y_conv_desc* d, const void* x, const void* w, const EpilogueArgs& e,
-                   cudaStream_t st) {
-    std::call_once(g_once, resolve_driver);
-    const int esize = kind == CONV_KIND_F16 ? 2 : 1;
-    if (!d || !x || !w || !e.out) return B2Y_ERR_INVALID;
-    if (d->batch <= 0 || d->in_c <= 0 || d->out_c <= 0 || d->ksize <= 0 || d->stride <= 0) return B2Y_ERR_INVALID;
-    const long long kb_total = (long long)d->in_c * esize;
-    if (kb_total % 32 != 0) return B2Y_ERR_UNSUPPORTED;
-    int kbytes = kb_total % 128 == 0 ? 128 : (kb_total % 64 == 0 ? 64 : 32);
-    if ((d->in_pitch * esize) % 16 != 0) return B2Y_ERR_INVALID;
-    if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(w) & 15)) return B2Y_ERR_INVALID;
-    const int Ho = (d->in_h + 2 * d->pad - d->ksize) / d->stride + 1;
-    const int Wo = (d->in_w + 2 * d->pad - d->ksize) / d->stride + 1;
-    if (Ho != d->out_h || Wo != d->out_w) return B2Y_ERR_INVALID;
-    const long long M = (long long)d->batch * Ho * Wo;
-    if (M > 0x7fffff00LL) return B2Y_ERR_UNSUPPORTED;
+// Generic implicit-GEMM launch description: A = NHWC activation-like tensor gathered tap by tap, B = [Nout][ntaps*C].
+struct GemmConvSpec {
+    int kind = CONV_KIND_F16;
+    const void* a = nullptr;
+    int N = 0, H = 0, W = 0, C = 0;
+    long long a_pitch = 0;
+    int MH = 0, MW = 0;          // base-pixel grid per image (GEMM rows = N*MH*MW)
+    int stride = 1;              // TMA traversal stride
+    int lower_w = 0, lower_h = 0, upper_w = 0, upper_h = 0;
+    int ntaps = 1;
+    unsigned char tap_ow[16] = {0}, tap_oh[16] = {0};
+    bool pointwise = false;      // plain GEMM over [N*H*W][C] (2-D tiled TMA)
+    const void* w = nullptr;
+    int Nout = 0;
+    int out_identity = 1, out_OH = 0, out_OW = 0, out_ys = 1, out_xs = 1, out_y0 = 0, out_x0 = 0;
+};
 
-    int block_n = d->out_c <= 32 ? 32 : (d->out_c <= 64 ? 64 : (d->out_c <= 128 ? 128 : 256));
+int gemm_conv_launch(const GemmConvSpec& g, const EpilogueArgs& e, cudaStream_t st) {
+    std::call_once(g_once, resolve_driver);
+    const int esize = g.kind == CONV_KIND_F16 ? 2 : 1;
+    if (!g.a || !g.w || !e.out) return B2Y_ERR_INVALID;
+    if (g.N <= 0 || g.C <= 0 || g.Nout <= 0 || g.ntaps < 1 || g.ntaps > 16) return B2Y_ERR_INVALID;
+    const long long kb_total = (long long)g.C * esize;
+    if (kb_total % 32 != 0) return B2Y_ERR_UNSUPPORTED;
+    const int kbytes = kb_total % 128 == 0 ? 128 : (kb_total % 64 == 0 ? 64 : 32);
+    if ((g.a_pitch * esize) % 16 != 0) return B2Y_ERR_INVALID;
+    if ((reinterpret_cast<uintptr_t>(g.a) & 15) || (reinterpret_cast<uintptr_t>(g.w) & 15)) return B2Y_ERR_INVALID;
+    const long long M = (long long)g.N * g.MH * g.MW;
+    if (M <= 0 || M > 0x7fffff00LL) return B2Y_ERR_UNSUPPORTED;
+    const int block_n = g.Nout <= 32 ? 32 : (g.Nout <= 64 ? 64 : (g.Nout <= 128 ? 128 : 256));
     const int block_k = kbytes / esize;
 
     ConvTcParams p{};
     p.M_total = (int)M;
-    p.Cout = d->out_c;
+    p.Cout = g.Nout;
     p.num_m_tiles = (int)((M + 127) / 128);
-    p.num_n_tiles = (d->out_c + block_n - 1) / block_n;
+    p.num_n_tiles = (g.Nout + block_n - 1) / block_n;
     p.k_chunks = (int)(kb_total / kbytes);
-    p.Cin = d->in_c;
-    p.R = d->ksize;
-    p.S = d->ksize;
-    p.Ho = Ho;
-    p.Wo = Wo;
-    p.stride = d->stride;
-    p.pad = d->pad;
+    p.Cin = g.C;
+    p.ntaps = g.ntaps;
+    p.MH = g.MH;
+    p.MW = g.MW;
+    p.stride = g.stride;
+    p.lower_w = g.lower_w;
+    p.lower_h = g.lower_h;
+    for (int t = 0; t < 16; ++t) {
+        p.tap_ow[t] = g.tap_ow[t];
+        p.tap_oh[t] = g.tap_oh[t];
+    }
+    p.out_identity = g.out_identity;
+    p.out_OH = g.out_OH;
+    p.out_OW = g.out_OW;
+    p.out_ys = g.out_ys;
+    p.out_xs = g.out_xs;
+    p.out_y0 = g.out_y0;
+    p.out_x0 = g.out_x0;
     p.bias = e.bias;
     p.act = e.act;
     p.slope = e.slope;
@@ -181,27 +204,209 @@ int conv_tc_launch(int kind, const b2y_conv_desc* d, const void* x, const void* 
 
     CUtensorMap tmA, tmB;
     int rc;
-    const bool pointwise = (d->ksize == 1 && d->stride == 1 && d->pad == 0);
-    if (pointwise) {
+    if (g.pointwise) {
         p.a_mode = A_MODE_TILED2D;
-        rc = make_map_2d(&tmA, x, esize, M, d->in_c, d->in_pitch, block_k, 128, kbytes);
+        rc = make_map_2d(&tmA, g.a, esize, M, g.C, g.a_pitch, block_k, 128, kbytes);
     } else {
         p.a_mode = A_MODE_IM2COL;
-        rc = make_map_im2col(&tmA, x, esize, d->batch, d->in_h, d->in_w, d->in_c, d->in_pitch, d->ksize, d->ksize,
-                             d->stride, d->pad, block_k, kbytes);
+        rc = make_map_im2col(&tmA, g.a, esize, g.N, g.H, g.W, g.C, g.a_pitch, g.lower_w, g.lower_h, g.upper_w,
+                             g.upper_h, g.stride, block_k, kbytes);
     }
     if (rc != B2Y_OK) return rc;
-    const long long Ktot = (long long)d->ksize * d->ksize * d->in_c;
-    rc = make_map_2d(&tmB, w, esize, d->out_c, Ktot, Ktot, block_k, block_n, kbytes);
+    const long long Ktot = (long long)g.ntaps * g.C;
+    rc = make_map_2d(&tmB, g.w, esize, g.Nout, Ktot, Ktot, block_k, block_n, kbytes);
     if (rc != B2Y_OK) return rc;
 
-    if (kind == CONV_KIND_F16) return dispatch<CONV_KIND_F16>(block_n, kbytes, tmA, tmB, p, st);
+    if (g.kind == CONV_KIND_F16) return dispatch<CONV_KIND_F16>(block_n, kbytes, tmA, tmB, p, st);
     return dispatch<CONV_KIND_I8>(block_n, kbytes, tmA, tmB, p, st);
+}
+
+// Forward convolution: x NHWC (fp16 or int8), w [Cout][R][S][Cin].
+int conv_tc_launch(int kind, const b2y_conv_desc* d, const void* x, const void* w, const EpilogueArgs& e,
+                   cudaStream_t st) {
+    if (!d) return B2Y_ERR_INVALID;
+    if (d->batch <= 0 || d->in_c <= 0 || d->out_c <= 0 || d->ksize <= 0 || d->stride <= 0) return B2Y_ERR_INVALID;
+    if (d->ksize * d->ksize > 16) return B2Y_ERR_UNSUPPORTED;
+    const int Ho = (d->in_h + 2 * d->pad - d->ksize) / d->stride + 1;
+    const int Wo = (d->in_w + 2 * d->pad - d->ksize) / d->stride + 1;
+    if (Ho != d->out_h || Wo != d->out_w) return B2Y_ERR_INVALID;
+    GemmConvSpec g;
+    g.kind = kind;
+    g.a = x;
+    g.N = d->batch;
+    g.H = d->in_h;
+    g.W = d->in_w;
+    g.C = d->in_c;
+    g.a_pitch = d->in_pitch;
+    g.MH = Ho;
+    g.MW = Wo;
+    g.stride = d->stride;
+    g.lower_w = g.lower_h = -d->pad;
+    g.upper_w = g.upper_h = d->pad - (d->ksize - 1);
+    g.ntaps = d->ksize * d->ksize;
+    for (int r = 0; r < d->ksize; ++r)
+        for (int s = 0; s < d->ksize; ++s) {
+            g.tap_oh[r * d->ksize + s] = (unsigned char)r;
+            g.tap_ow[r * d->ksize + s] = (unsigned char)s;
+        }
+    g.pointwise = (d->ksize == 1 && d->stride == 1 && d->pad == 0);
+    g.w = w;
+    g.Nout = d->out_c;
+    return gemm_conv_launch(g, e, st);
+}
+
+// ---- data gradient -------------------------------------------------------------------------------------------
+// dx[n, yi, xi, ci] = sum_{r,s} dy[n, (yi+pad-r)/stride, (xi+pad-s)/stride, co] * W[co][ci][r][s]
+// decomposed by output phase (yi mod stride, xi mod stride): each phase is a stride-1 implicit GEMM over dy with
+// the subset of taps whose parity matches, written to the strided dx positions of that phase.
+struct DgradPhase {
+    int py, px, nh, nw;       // taps per dimension
+    int r[4], dr[4], s[4], ds[4];
+    int min_dr, min_ds;
+    int MH, MW;
+    long long w_offset;       // element offset of this phase's [Cin][ntaps][Cout] slab in the packed buffer
+};
+
+static int enumerate_dgrad_phases(const b2y_conv_desc* d, DgradPhase* ph) {
+    int n = 0;
+    long long off = 0;
+    const int k = d->ksize, s = d->stride, pad = d->pad;
+    if (k > 4) return -1;
+    for (int py = 0; py < s; ++py)
+        for (int px = 0; px < s; ++px) {
+            DgradPhase& P = ph[n];
+            P.py = py;
+            P.px = px;
+            P.nh = P.nw = 0;
+            P.min_dr = P.min_ds = 1 << 20;
+            for (int r = 0; r < k; ++r) {
+                const int t = py + pad - r;
+                if (t % s == 0) {
+                    P.r[P.nh] = r;
+                    P.dr[P.nh] = t / s;
+                    if (t / s < P.min_dr) P.min_dr = t / s;
+                    P.nh++;
+                }
+            }
+            for (int c = 0; c < k; ++c) {
+                const int t = px + pad - c;
+                if (t % s == 0) {
+                    P.s[P.nw] = c;
+                    P.ds[P.nw] = t / s;
+                    if (t / s < P.min_ds) P.min_ds = t / s;
+                    P.nw++;
+                }
+            }
+            P.MH = (d->in_h - py + s - 1) / s;
+            P.MW = (d->in_w - px + s - 1) / s;
+            P.w_offset = off;
+            off += (long long)d->in_c * P.nh * P.nw * d->out_c;
+            n++;
+        }
+    return n;
 }
 
 }  // namespace b2y
 
 using namespace b2y;
+
+// pack W (OIHW fp32) into the per-phase dgrad layout [phase][Cin][tap][Cout] fp16
+__global__ void pack_dgrad_kernel(const float* __restrict__ w, __half* __restrict__ out, int O, int I, int k, int nh,
+                                  int nw, int r0, int r1, int r2, int r3, int s0, int s1, int s2, int s3) {
+    const int rr[4] = {r0, r1, r2, r3}, ss[4] = {s0, s1, s2, s3};
+    const int ntaps = nh * nw;
+    const long long total = (long long)I * ntaps * O;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int co = (int)(idx % O);
+        long long t = idx / O;
+        const int tap = (int)(t % ntaps);
+        const int ci = (int)(t / ntaps);
+        const int r = rr[tap / nw], s = ss[tap % nw];
+        out[idx] = __float2half_rn(w[(((long long)co * I + ci) * k + r) * k + s]);
+    }
+}
+
+extern "C" int b2y_pack_dgrad_weights(const b2y_conv_desc* d, const float* w_oihw, void* w_packed_t, void* stream) {
+    if (!d || !w_oihw || !w_packed_t) return B2Y_ERR_INVALID;
+    DgradPhase ph[16];
+    if (d->stride > 4) return B2Y_ERR_UNSUPPORTED;
+    const int n = enumerate_dgrad_phases(d, ph);
+    if (n < 0) return B2Y_ERR_UNSUPPORTED;
+    for (int i = 0; i < n; ++i) {
+        const DgradPhase& P = ph[i];
+        if (P.nh * P.nw == 0) continue;
+        const long long total = (long long)d->in_c * P.nh * P.nw * d->out_c;
+        int grid = (int)((total + 255) / 256);
+        if (grid > 148 * 16) grid = 148 * 16;
+        pack_dgrad_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+            w_oihw, reinterpret_cast<__half*>(w_packed_t) + P.w_offset, d->out_c, d->in_c, d->ksize, P.nh, P.nw,
+            P.r[0], P.r[1], P.r[2], P.r[3], P.s[0], P.s[1], P.s[2], P.s[3]);
+    }
+    B2Y_CUDA_CHECK(cudaGetLastError());
+    return B2Y_OK;
+}
+
+extern "C" int b2y_conv2d_bwd_data(const b2y_conv_desc* d, const void* dy, const void* w_packed_t, void* dx,
+                                   int accumulate, void* stream) {
+    if (!d || !dy || !w_packed_t || !dx) return B2Y_ERR_INVALID;
+    if (d->stride > 4) return B2Y_ERR_UNSUPPORTED;
+    DgradPhase ph[16];
+    const int n = enumerate_dgrad_phases(d, ph);
+    if (n < 0) return B2Y_ERR_UNSUPPORTED;
+    for (int i = 0; i < n; ++i) {
+        const DgradPhase& P = ph[i];
+        if (P.MH <= 0 || P.MW <= 0) continue;
+        if (P.nh * P.nw == 0) {
+            if (accumulate) continue;
+            return B2Y_ERR_UNSUPPORTED;  // (kernel smaller than the stride: untouched phase would need a zero fill)
+        }
+        GemmConvSpec g;
+        g.kind = CONV_KIND_F16;
+        g.a = dy;
+        g.N = d->batch;
+        g.H = d->out_h;
+        g.W = d->out_w;
+        g.C = d->out_c;
+        g.a_pitch = d->out_pitch;
+        g.MH = P.MH;
+        g.MW = P.MW;
+        g.stride = 1;
+        g.lower_w = P.min_ds;
+        g.lower_h = P.min_dr;
+        g.upper_w = P.min_ds + P.MW - d->out_w;
+        g.upper_h = P.min_dr + P.MH - d->out_h;
+        g.ntaps = P.nh * P.nw;
+        for (int a = 0; a < P.nh; ++a)
+            for (int b = 0; b < P.nw; ++b) {
+                g.tap_oh[a * P.nw + b] = (unsigned char)(P.dr[a] - P.min_dr);
+                g.tap_ow[a * P.nw + b] = (unsigned char)(P.ds[b] - P.min_ds);
+            }
+        g.pointwise = (d->ksize == 1 && d->stride == 1 && d->pad == 0);
+        g.w = reinterpret_cast<const __half*>(w_packed_t) + P.w_offset;
+        g.Nout = d->in_c;
+        g.out_identity = (d->stride == 1) ? 1 : 0;
+        g.out_OH = d->in_h;
+        g.out_OW = d->in_w;
+        g.out_ys = g.out_xs = d->stride;
+        g.out_y0 = P.py;
+        g.out_x0 = P.px;
+        EpilogueArgs e;
+        e.out = dx;
+        e.out_pitch = d->in_pitch;
+        e.out_dtype = OUT_F16;
+        if (accumulate) {
+            e.res = dx;
+            e.res_pitch = d->in_pitch;
+        }
+        int rc = gemm_conv_launch(g, e, static_cast<cudaStream_t>(stream));
+        if (rc != B2Y_OK) return rc;
+    }
+    return B2Y_OK;
+}
+
+
+
 
 extern "C" int b2y_conv2d_fwd(const b2y_conv_desc* d, const void* x, const void* w_packed, const float* bias,
                               const void* residual, void* y, void* stream) {

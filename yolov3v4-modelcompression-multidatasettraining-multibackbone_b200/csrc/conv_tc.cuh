@@ -25,11 +25,17 @@ struct ConvTcParams {
     int num_m_tiles;  // ceil(M_total/128)
     int num_n_tiles;  // ceil(Cout/BLOCK_N)
     int k_chunks;     // Cin*esize / KBYTES
-    int Cin;          // elements
-    int R, S;
-    int Ho, Wo;
-    int stride, pad;
+    int Cin;          // elements per tap (GEMM K per tap)
+    int ntaps;        // filter taps visited (9 for 3x3; a subset for the stride-2 data-gradient phases)
+    int MH, MW;       // GEMM row space = batch x MH x MW "base pixels"
+    int stride;       // TMA traversal stride (conv stride for fprop, 1 for dgrad)
+    int lower_w, lower_h;     // coordinate of base pixel (0,0): base = q*stride + lower
+    unsigned char tap_ow[16]; // per-tap im2col offsets (>= 0)
+    unsigned char tap_oh[16];
     int a_mode;
+    // row -> output pixel mapping: pixel(n,p,q) = ((n*out_OH + p*out_ys + out_y0)*out_OW + q*out_xs + out_x0)
+    int out_identity;         // 1: output pixel index == GEMM row index
+    int out_OH, out_OW, out_ys, out_xs, out_y0, out_x0;
     // epilogue
     const float* bias;  // [Cout] or null
     int act;
@@ -63,6 +69,9 @@ struct ConvTcCfg {
     static constexpr int BIAS_BYTES = BLOCK_N * 4;
     static constexpr int SMEM_BYTES = 1024 /*align slack*/ + NUM_STAGES * STAGE_BYTES + AUX_BYTES + BIAS_BYTES;
 };
+
+__device__ __noinline__ float mish_noinline(float x) { return mish_f(x); }
+__device__ __noinline__ float swish_noinline(float x) { return x * sigmoid_f(x); }
 
 __device__ __forceinline__ float round_half_away(float x) {
     // reference utils/quantized/quantized_ptq_cos.py:14-20  sign(x)*floor(|x|+0.5)
@@ -120,7 +129,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t tmem_base = *tmem_ptr_smem;
 
     const int num_tiles = p.num_m_tiles * p.num_n_tiles;
-    const int taps = p.R * p.S;
+    const int taps = p.ntaps;
     const int k_steps = taps * p.k_chunks;
 
     if (warp == 0) {
@@ -128,20 +137,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            const int HoWo = p.Ho * p.Wo;
+            const int HoWo = p.MH * p.MW;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int m_tile = tile / p.num_n_tiles;
                 const int n_tile = tile - m_tile * p.num_n_tiles;
                 const int m0 = m_tile * 128;
                 const int img = m0 / HoWo;
                 const int rem = m0 - img * HoWo;
-                const int po = rem / p.Wo;
-                const int qo = rem - po * p.Wo;
-                const int base_w = qo * p.stride - p.pad;
-                const int base_h = po * p.stride - p.pad;
+                const int po = rem / p.MW;
+                const int qo = rem - po * p.MW;
+                const int base_w = qo * p.stride + p.lower_w;
+                const int base_h = po * p.stride + p.lower_h;
                 for (int tap = 0; tap < taps; ++tap) {
-                    const int r = tap / p.S;
-                    const int s = tap - r * p.S;
+                    const int r = p.tap_oh[tap];
+                    const int s = p.tap_ow[tap];
                     for (int kc = 0; kc < p.k_chunks; ++kc) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         uint8_t* a_dst = smem + stage * Cfg::STAGE_BYTES;
@@ -212,8 +221,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int m_tile = tile / p.num_n_tiles;
             const int n_tile = tile - m_tile * p.num_n_tiles;
             const int n0 = n_tile * BLOCK_N;
-            const long long row = (long long)m_tile * 128 + ew * 32 + lane;
-            const bool row_ok = row < p.M_total;
+            const long long grow = (long long)m_tile * 128 + ew * 32 + lane;   // GEMM row
+            const bool row_ok = grow < p.M_total;
+            long long row = grow;                                              // output pixel index
+            if (!p.out_identity && row_ok) {
+                const int hw = p.MH * p.MW;
+                const int n_ = (int)(grow / hw);
+                const int r_ = (int)(grow - (long long)n_ * hw);
+                const int p_ = r_ / p.MW, q_ = r_ - p_ * p.MW;
+                row = ((long long)n_ * p.out_OH + (long long)p_ * p.out_ys + p.out_y0) * p.out_OW +
+                      (long long)q_ * p.out_xs + p.out_x0;
+            }
 
             // stage the bias slice for this tile
             asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -260,8 +278,38 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                 }
 
+                // bias + activation: the switch is hoisted out of the element loop so that the executed path is one
+                // short straight-line block (a per-element switch made the unrolled body ~64 KB and I-cache bound)
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j] + sbias[c0 + j], p.act, p.slope);
+                for (int j = 0; j < 32; ++j) v[j] += sbias[c0 + j];
+                switch (p.act) {
+                    case B2Y_ACT_LEAKY:
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * p.slope;
+                        break;
+                    case B2Y_ACT_MISH:
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = mish_noinline(v[j]);
+                        break;
+                    case B2Y_ACT_RELU:
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                        break;
+                    case B2Y_ACT_RELU6:
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = fminf(fmaxf(v[j], 0.f), 6.f);
+                        break;
+                    case B2Y_ACT_HSWISH:
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = v[j] * (fminf(fmaxf(v[j] + 3.f, 0.f), 6.f) / 6.f);
+                        break;
+                    case B2Y_ACT_SWISH:
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = swish_noinline(v[j]);
+                        break;
+                    default:
+                        break;
+                }
 
                 const int nvalid = min(32, p.Cout - (n0 + c0));
                 if (row_ok) {

@@ -1,0 +1,240 @@
+// Power-of-two fake quantisation, calibration reductions and int8 weight packing
+// (reference utils/quantized/quantized_ptq_cos.py:14-113, utils/quantized/quantized_google.py:16-219).
+// All HBM-bound: one pass over the data, 16-byte vector accesses, warp-shuffle + one atomic per CTA for reductions.
+#include "b200yolo.h"
+#include "common.cuh"
+
+using namespace b2y;
+
+static inline int grid_for(long long n, int block) {
+    long long g = (n + block - 1) / block;
+    if (g < 1) g = 1;
+    if (g > 148LL * 16) g = 148LL * 16;
+    return (int)g;
+}
+
+__device__ __forceinline__ float rha(float x) { return copysignf(floorf(fabsf(x) + 0.5f), x); }  // ptq_cos.py:14-20
+
+// y = clamp(round(x / s), lo, hi) * s      (ptq_cos.py:44-62, 89-92; the division is a true division, not
+// a multiply by 1/s, although for power-of-two s both are exact)
+__global__ void fakequant_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, float scale,
+                                 float lo, float hi) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        float q = rha(x[i] / scale);
+        y[i] = fminf(fmaxf(q, lo), hi) * scale;
+    }
+}
+
+extern "C" int b2y_fakequant_f32(const float* x, float* y, long long n, float scale, float lo, float hi,
+                                 void* stream) {
+    if (!x || !y || n < 0 || !(scale > 0.f)) return B2Y_ERR_INVALID;
+    fakequant_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, n, scale, lo, hi);
+    B2Y_CUDA_CHECK(cudaGetLastError());
+    return B2Y_OK;
+}
+
+// fp16 NHWC -> int8 NHWC integer codes
+__global__ void quantize_f16_i8_kernel(const __half* __restrict__ x, long long xp, int8_t* __restrict__ q,
+                                       long long qp, long long pixels, int C, float scale, float lo, float hi) {
+    const int CV = C / 8;
+    const long long total = pixels * CV;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int cv = (int)(idx % CV);
+        const long long pix = idx / CV;
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + pix * xp) + cv);
+        const __half* h = reinterpret_cast<const __half*>(&v);
+        uint2 o;
+        int8_t* ob = reinterpret_cast<int8_t*>(&o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float r = rha(__half2float(h[j]) / scale);
+            ob[j] = (int8_t)(int)fminf(fmaxf(r, lo), hi);
+        }
+        *reinterpret_cast<uint2*>(q + pix * qp + cv * 8) = o;
+    }
+}
+
+extern "C" int b2y_quantize_f16_to_i8(const void* x, long long x_pitch, void* q, long long q_pitch, long long pixels,
+                                      int c, float scale, float lo, float hi, void* stream) {
+    if (!x || !q || c % 8 != 0 || x_pitch % 8 != 0 || q_pitch % 8 != 0 || !(scale > 0.f)) return B2Y_ERR_INVALID;
+    quantize_f16_i8_kernel<<<grid_for(pixels * (c / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const __half*>(x), x_pitch, reinterpret_cast<int8_t*>(q), q_pitch, pixels, c, scale, lo, hi);
+    B2Y_CUDA_CHECK(cudaGetLastError());
+    return B2Y_OK;
+}
+
+// COSPTQ calibration (ptq_cos.py:71-87): all candidate power-of-two scales in ONE pass over x.
+// Per candidate k: dot_k = sum x*q_k, qq_k = sum q_k^2 ; xx = sum x^2.  cos_k = dot_k / sqrt(xx*qq_k).
+// Accumulated in double so that the argmax matches torch.cosine_similarity on the ties the reference resolves
+// with a strict '>'.
+#define B2Y_MAX_CAND 24
+__global__ void cos_search_kernel(const float* __restrict__ x, long long n, int bits, int n_cand,
+                                  double* __restrict__ acc /* [1 + 2*n_cand] */) {
+    __shared__ double sh[(1 + 2 * B2Y_MAX_CAND)];
+    for (int i = threadIdx.x; i < 1 + 2 * n_cand; i += blockDim.x) sh[i] = 0.0;
+    __syncthreads();
+    const float lo = -(float)(1 << (bits - 1)), hi = (float)((1 << (bits - 1)) - 1);
+    float xx = 0.f;
+    float dot[B2Y_MAX_CAND], qq[B2Y_MAX_CAND];
+#pragma unroll
+    for (int k = 0; k < B2Y_MAX_CAND; ++k) dot[k] = qq[k] = 0.f;
+    int cnt = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const float v = x[i];
+        xx += v * v;
+#pragma unroll
+        for (int k = 0; k < B2Y_MAX_CAND; ++k) {
+            if (k < n_cand) {
+                const float scale = exp2f((float)(k - 5)) / (float)(1 << (bits - 1));
+                const float q = fminf(fmaxf(rha(v / scale), lo), hi) * scale;
+                dot[k] += v * q;
+                qq[k] += q * q;
+            }
+        }
+        // flush fp32 partials into double every 64 elements to bound the rounding error
+        if (++cnt == 64) {
+            cnt = 0;
+            atomicAdd(&sh[0], (double)xx);
+            xx = 0.f;
+#pragma unroll
+            for (int k = 0; k < B2Y_MAX_CAND; ++k)
+                if (k < n_cand) {
+                    atomicAdd(&sh[1 + k], (double)dot[k]);
+                    atomicAdd(&sh[1 + n_cand + k], (double)qq[k]);
+                    dot[k] = qq[k] = 0.f;
+                }
+        }
+    }
+    atomicAdd(&sh[0], (double)xx);
+#pragma unroll
+    for (int k = 0; k < B2Y_MAX_CAND; ++k)
+        if (k < n_cand) {
+            atomicAdd(&sh[1 + k], (double)dot[k]);
+            atomicAdd(&sh[1 + n_cand + k], (double)qq[k]);
+        }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 1 + 2 * n_cand; i += blockDim.x) atomicAdd(acc + i, sh[i]);
+}
+
+__global__ void cos_finalize_kernel(const double* __restrict__ acc, int n_cand, float* __restrict__ out) {
+    const int k = threadIdx.x;
+    if (k < n_cand) {
+        const double xx = acc[0], dot = acc[1 + k], qq = acc[1 + n_cand + k];
+        // torch.cosine_similarity: dot / max(||x||*||q||, eps), eps = 1e-8
+        const double den = fmax(sqrt(xx) * sqrt(qq), 1e-8);
+        out[k] = (float)(dot / den);
+    }
+}
+
+extern "C" int b2y_cos_scale_search(const float* x, long long n, int bits, int n_cand, float* out_cos,
+                                    void* workspace, size_t workspace_bytes, void* stream) {
+    if (!x || !out_cos || !workspace || n_cand < 1 || n_cand > B2Y_MAX_CAND || bits < 2 || bits > 16)
+        return B2Y_ERR_INVALID;
+    if (workspace_bytes < sizeof(double) * (1 + 2 * (size_t)n_cand)) return B2Y_ERR_INVALID;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    double* acc = reinterpret_cast<double*>(workspace);
+    B2Y_CUDA_CHECK(cudaMemsetAsync(acc, 0, sizeof(double) * (1 + 2 * n_cand), st));
+    int grid = grid_for(n, 256);
+    if (grid > 148 * 4) grid = 148 * 4;
+    cos_search_kernel<<<grid, 256, 0, st>>>(x, n, bits, n_cand, acc);
+    cos_finalize_kernel<<<1, 32, 0, st>>>(acc, n_cand, out_cos);
+    B2Y_CUDA_CHECK(cudaGetLastError());
+    return B2Y_OK;
+}
+
+// min / max trackers (google.py:16-77): per tensor ('L') or per output channel ('C' = per row of [rows][cols])
+__device__ __forceinline__ void atomic_min_f(float* a, float v) {
+    int* ai = reinterpret_cast<int*>(a);
+    int old = *ai;
+    while (v < __int_as_float(old)) {
+        int assumed = old;
+        old = atomicCAS(ai, assumed, __float_as_int(v));
+        if (old == assumed) break;
+    }
+}
+__device__ __forceinline__ void atomic_max_f(float* a, float v) {
+    int* ai = reinterpret_cast<int*>(a);
+    int old = *ai;
+    while (v > __int_as_float(old)) {
+        int assumed = old;
+        old = atomicCAS(ai, assumed, __float_as_int(v));
+        if (old == assumed) break;
+    }
+}
+__global__ void minmax_init_kernel(float* out, long long n_pairs) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_pairs;
+         i += (long long)gridDim.x * blockDim.x) {
+        out[2 * i] = __int_as_float(0x7f800000);      // +inf
+        out[2 * i + 1] = __int_as_float(0xff800000);  // -inf
+    }
+}
+__global__ void minmax_kernel(const float* __restrict__ x, long long rows, long long cols, int per_row,
+                              float* __restrict__ out) {
+    // grid.y strides over rows (per_row) ; the tensor-level mode uses a single "row" of rows*cols elements
+    const long long nrow = per_row ? rows : 1;
+    const long long ncol = per_row ? cols : rows * cols;
+    for (long long r = blockIdx.y; r < nrow; r += gridDim.y) {
+        float mn = __int_as_float(0x7f800000), mx = __int_as_float(0xff800000);
+        const float* xr = x + r * ncol;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < ncol;
+             i += (long long)gridDim.x * blockDim.x) {
+            const float v = xr[i];
+            mn = fminf(mn, v);
+            mx = fmaxf(mx, v);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomic_min_f(out + 2 * r, mn);
+            atomic_max_f(out + 2 * r + 1, mx);
+        }
+    }
+}
+
+extern "C" int b2y_minmax_f32(const float* x, long long rows, long long cols, int per_row, float* out_minmax,
+                              void* stream) {
+    if (!x || !out_minmax || rows <= 0 || cols <= 0) return B2Y_ERR_INVALID;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long nrow = per_row ? rows : 1;
+    const long long ncol = per_row ? cols : rows * cols;
+    minmax_init_kernel<<<grid_for(nrow, 256), 256, 0, st>>>(out_minmax, nrow);
+    dim3 grid((unsigned)((ncol + 256 * 8 - 1) / (256 * 8) > 0 ? (ncol + 256 * 8 - 1) / (256 * 8) : 1),
+              (unsigned)(nrow > 65535 ? 65535 : nrow));
+    if (grid.x > 592) grid.x = 592;
+    minmax_kernel<<<grid, 256, 0, st>>>(x, rows, cols, per_row, out_minmax);
+    B2Y_CUDA_CHECK(cudaGetLastError());
+    return B2Y_OK;
+}
+
+// OIHW fp32 (already BN-folded) -> int8 [O][kh][kw][I] codes at scale w_scale
+__global__ void pack_qweights_kernel(const float* __restrict__ w, int O, int I, int k, float scale, float lo, float hi,
+                                     int8_t* __restrict__ out) {
+    const long long total = (long long)O * I * k * k;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(idx % I);
+        long long t = idx / I;
+        const int kw = (int)(t % k);
+        t /= k;
+        const int kh = (int)(t % k);
+        const int o = (int)(t / k);
+        const float v = w[(((long long)o * I + i) * k + kh) * k + kw];
+        out[idx] = (int8_t)(int)fminf(fmaxf(rha(v / scale), lo), hi);
+    }
+}
+
+extern "C" int b2y_pack_qconv_weights(const float* w_oihw_folded, int out_c, int in_c, int ksize, float w_scale,
+                                      float lo, float hi, void* w_i8, void* stream) {
+    if (!w_oihw_folded || !w_i8 || out_c <= 0 || in_c <= 0 || ksize <= 0 || !(w_scale > 0.f)) return B2Y_ERR_INVALID;
+    const long long total = (long long)out_c * in_c * ksize * ksize;
+    pack_qweights_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        w_oihw_folded, out_c, in_c, ksize, w_scale, lo, hi, reinterpret_cast<int8_t*>(w_i8));
+    B2Y_CUDA_CHECK(cudaGetLastError());
+    return B2Y_OK;
+}

@@ -1,0 +1,276 @@
+// Training-mode BatchNorm + activation (forward apply, backward reduce / apply) on NHWC fp16 tensors with fp32
+// statistics, and the fused SGD-Nesterov step over a flat fp32 parameter buffer.
+// Reference semantics: nn.BatchNorm2d(momentum=0.1, eps=1e-5) + activation under autograd (models.py:100-113),
+// optimizer train.py:135-144.  The batch sums themselves come out of the conv epilogue (conv_tc.cuh).
+#include "b200yolo.h"
+#include "common.cuh"
+
+using namespace b2y;
+
+static inline int grid_for(long long n, int block, int cap = 148 * 16) {
+    long long g = (n + block - 1) / block;
+    if (g < 1) g = 1;
+    if (g > cap) g = cap;
+    return (int)g;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void bn_finalize_kernel(const float* __restrict__ s1, const float* __restrict__ s2, float count,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                   float momentum, float* __restrict__ rmean, float* __restrict__ rvar,
+                                   float* __restrict__ save_mean, float* __restrict__ save_invstd,
+                                   float* __restrict__ scale, float* __restrict__ shift, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float mean = s1[c] / count;
+    float var = s2[c] / count - mean * mean;  // biased variance used for normalisation
+    var = fmaxf(var, 0.f);
+    const float invstd = 1.f / sqrtf(var + eps);
+    if (rmean != nullptr) {
+        const float unbiased = count > 1.f ? var * (count / (count - 1.f)) : var;
+        rmean[c] = (1.f - momentum) * rmean[c] + momentum * mean;
+        rvar[c] = (1.f - momentum) * rvar[c] + momentum * unbiased;
+    }
+    save_mean[c] = mean;
+    save_invstd[c] = invstd;
+    const float g = gamma != nullptr ? gamma[c] : 1.f;
+    const float sc = g * invstd;
+    scale[c] = sc;
+    shift[c] = (beta != nullptr ? beta[c] : 0.f) - mean * sc;
+}
+
+extern "C" int b2y_bn_finalize(const float* stat_sum, const float* stat_sqsum, long long count, const float* gamma,
+                               const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                               float* save_mean, float* save_invstd, float* scale, float* shift, int c,
+                               void* stream) {
+    if (!stat_sum || !stat_sqsum || !save_mean || !save_invstd || !scale || !shift || c <= 0 || count <= 0)
+        return B2Y_ERR_INVALID;
+    bn_finalize_kernel<<<(c + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        stat_sum, stat_sqsum, (float)count, gamma, beta, eps, momentum, running_mean, running_var, save_mean,
+        save_invstd, scale, shift, c);
+    B2Y_CUDA_CHECK(cudaGetLastError());
+    return B2Y_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void bn_act_fwd_kernel(const __half* __restrict__ x, long long xp, const float* __restrict__ scale,
+                                  const float* __restrict__ shift, const __half* __restrict__ res, long long rp,
+                                  __half* __restrict__ y, long long yp, long long pixels, int C, int act,
+                                  float slope) {
+    const int CV = C / 8;
+    const long long total = pixels * CV;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int cv = (int)(idx % CV);
+        const long long pix = idx / CV;
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + pix * xp) + cv);
+        const __half* h = reinterpret_cast<const __half*>(&v);
+        const float4 sa = __ldg(reinterpret_cast<const float4*>(scale) + cv * 2);
+        const float4 sb = __ldg(reinterpret_cast<const float4*>(scale) + cv * 2 + 1);
+        const float4 ta = __ldg(reinterpret_cast<const float4*>(shift) + cv * 2);
+        const float4 tb = __ldg(reinterpret_cast<const float4*>(shift) + cv * 2 + 1);
+        const float sc[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+        const float sh[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
+        float r[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = apply_act(fmaf(__half2float(h[j]), sc[j], sh[j]), act, slope);
+        if (res != nullptr) {
+            const uint4 rv = __ldg(reinterpret_cast<const uint4*>(res + pix * rp) + cv);
+            const __half* rh = reinterpret_cast<const __half*>(&rv);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] += __half2float(rh[j]);
+        }
+        uint4 o;
+        __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) oh[j] = __floats2half2_rn(r[2 * j], r[2 * j + 1]);
+        reinterpret_cast<uint4*>(y + pix * yp)[cv] = o;
+    }
+}
+
+extern "C" int b2y_bn_act_fwd(const void* x, long long x_pitch, const float* scale, const float* shift,
+                              const void* residual, long long res_pitch, void* y, long long y_pitch,
+                              long long pixels, int c, int act, float slope, void* stream) {
+    if (!x || !y || !scale || !shift || c % 8 != 0 || x_pitch % 8 != 0 || y_pitch % 8 != 0) return B2Y_ERR_INVALID;
+    if (residual != nullptr && res_pitch % 8 != 0) return B2Y_ERR_INVALID;
+    bn_act_fwd_kernel<<<grid_for(pixels * (c / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const __half*>(x), x_pitch, scale, shift, reinterpret_cast<const __half*>(residual), res_pitch,
+        reinterpret_cast<__half*>(y), y_pitch, pixels, c, act, slope);
+    B2Y_CUDA_CHECK(cudaGetLastError());
+    return B2Y_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward pass 1: dbeta[c] = sum du, dgamma[c] = sum du * xhat   with  u = x*scale+shift, du = dy*act'(u)
+// grid.y tiles the channels in slabs of 256 (32 lanes x 8 channels); each warp walks a strip of pixels.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+bn_act_bwd_reduce_kernel(const __half* __restrict__ x, long long xp, const __half* __restrict__ dy, long long dp,
+                         const float* __restrict__ scale, const float* __restrict__ shift,
+                         const float* __restrict__ mean, const float* __restrict__ invstd,
+                         float* __restrict__ dgamma, float* __restrict__ dbeta, long long pixels, int C, int act,
+                         float slope) {
+    __shared__ float red[8][32][17];
+    const int CV = C / 8;
+    const int cv0 = blockIdx.y * 32;
+    const int cvn = min(32, CV - cv0);                 // channel vectors in this slab
+    // lanes -> (pixel sub-index, channel vector); pack several pixels per warp when the slab is narrow
+    int lanes_c = 1;
+    while (lanes_c < cvn) lanes_c <<= 1;               // next pow2 >= cvn (<= 32)
+    const int ppw = 32 / lanes_c;                      // pixels per warp iteration
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lc = lane % lanes_c, lp = lane / lanes_c;
+    const bool active = lc < cvn;
+    const int cv = cv0 + lc;
+    float sc[8], sh[8], mu[8], is[8], gb[8], gg[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        gb[j] = gg[j] = 0.f;
+        const int c = cv * 8 + j;
+        sc[j] = active ? scale[c] : 0.f;
+        sh[j] = active ? shift[c] : 0.f;
+        mu[j] = (active && mean) ? mean[c] : 0.f;
+        is[j] = (active && invstd) ? invstd[c] : 1.f;
+    }
+    const long long warps_total = (long long)gridDim.x * 8;
+    const long long wid = (long long)blockIdx.x * 8 + warp;
+    for (long long p0 = wid * ppw; p0 < pixels; p0 += warps_total * ppw) {
+        const long long pix = p0 + lp;
+        if (active && pix < pixels) {
+            const uint4 xv = __ldg(reinterpret_cast<const uint4*>(x + pix * xp) + cv);
+            const uint4 gv = __ldg(reinterpret_cast<const uint4*>(dy + pix * dp) + cv);
+            const __half* xh = reinterpret_cast<const __half*>(&xv);
+            const __half* gh = reinterpret_cast<const __half*>(&gv);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float xf = __half2float(xh[j]);
+                const float u = fmaf(xf, sc[j], sh[j]);
+                const float du = __half2float(gh[j]) * act_grad(u, act, slope);
+                gb[j] += du;
+                gg[j] += du * ((xf - mu[j]) * is[j]);
+            }
+        }
+    }
+    // combine the pixel sub-lanes of a warp, then the 8 warps of the CTA, then one atomic per channel
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        for (int o = lanes_c; o < 32; o <<= 1) {
+            gb[j] += __shfl_xor_sync(0xffffffffu, gb[j], o);
+            gg[j] += __shfl_xor_sync(0xffffffffu, gg[j], o);
+        }
+    }
+    if (lp == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            red[warp][lc][j] = gb[j];
+            red[warp][lc][8 + j] = gg[j];
+        }
+    }
+    __syncthreads();
+    if (warp == 0 && lp == 0 && active) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float b = 0.f, g = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) {
+                b += red[w][lc][j];
+                g += red[w][lc][8 + j];
+            }
+            atomicAdd(dbeta + cv * 8 + j, b);
+            if (dgamma != nullptr) atomicAdd(dgamma + cv * 8 + j, g);
+        }
+    }
+}
+
+extern "C" int b2y_bn_act_bwd_reduce(const void* x, long long x_pitch, const void* dy, long long dy_pitch,
+                                     const float* scale, const float* shift, const float* save_mean,
+                                     const float* save_invstd, float* dgamma, float* dbeta, long long pixels, int c,
+                                     int act, float slope, void* stream) {
+    if (!x || !dy || !scale || !shift || !dbeta || c % 8 != 0 || x_pitch % 8 != 0 || dy_pitch % 8 != 0)
+        return B2Y_ERR_INVALID;
+    const int CV = c / 8;
+    dim3 grid(1, (CV + 31) / 32);
+    long long want = (pixels + 63) / 64;
+    grid.x = (unsigned)(want < 1 ? 1 : (want > 148 * 4 ? 148 * 4 : want));
+    bn_act_bwd_reduce_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const __half*>(x), x_pitch, reinterpret_cast<const __half*>(dy), dy_pitch, scale, shift,
+        save_mean, save_invstd, dgamma, dbeta, pixels, c, act, slope);
+    B2Y_CUDA_CHECK(cudaGetLastError());
+    return B2Y_OK;
+}
+
+// backward pass 2: dx = gamma*invstd * (du - dbeta/N - xhat*dgamma/N)
+__global__ void bn_act_bwd_apply_kernel(const __half* __restrict__ x, long long xp, const __half* __restrict__ dy,
+                                        long long dp, const float* __restrict__ scale, const float* __restrict__ shift,
+                                        const float* __restrict__ gamma, const float* __restrict__ mean,
+                                        const float* __restrict__ invstd, const float* __restrict__ dgamma,
+                                        const float* __restrict__ dbeta, __half* __restrict__ dx, long long dxp,
+                                        long long pixels, int C, int act, float slope) {
+    const int CV = C / 8;
+    const long long total = pixels * CV;
+    const float inv_n = 1.f / (float)pixels;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int cv = (int)(idx % CV);
+        const long long pix = idx / CV;
+        const uint4 xv = __ldg(reinterpret_cast<const uint4*>(x + pix * xp) + cv);
+        const uint4 gv = __ldg(reinterpret_cast<const uint4*>(dy + pix * dp) + cv);
+        const __half* xh = reinterpret_cast<const __half*>(&xv);
+        const __half* gh = reinterpret_cast<const __half*>(&gv);
+        float r[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = cv * 8 + j;
+            const float xf = __half2float(xh[j]);
+            const float u = fmaf(xf, scale[c], shift[c]);
+            const float du = __half2float(gh[j]) * act_grad(u, act, slope);
+            const float xhat = (xf - mean[c]) * invstd[c];
+            const float g = gamma != nullptr ? gamma[c] : 1.f;
+            r[j] = g * invstd[c] * (du - dbeta[c] * inv_n - xhat * dgamma[c] * inv_n);
+        }
+        uint4 o;
+        __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) oh[j] = __floats2half2_rn(r[2 * j], r[2 * j + 1]);
+        reinterpret_cast<uint4*>(dx + pix * dxp)[cv] = o;
+    }
+}
+
+extern "C" int b2y_bn_act_bwd_apply(const void* x, long long x_pitch, const void* dy, long long dy_pitch,
+                                    const float* scale, const float* shift, const float* gamma,
+                                    const float* save_mean, const float* save_invstd, const float* dgamma,
+                                    const float* dbeta, void* dx, long long dx_pitch, long long pixels, int c, int act,
+                                    float slope, void* stream) {
+    if (!x || !dy || !scale || !shift || !save_mean || !save_invstd || !dgamma || !dbeta || !dx || c % 8 != 0)
+        return B2Y_ERR_INVALID;
+    bn_act_bwd_apply_kernel<<<grid_for(pixels * (c / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const __half*>(x), x_pitch, reinterpret_cast<const __half*>(dy), dy_pitch, scale, shift, gamma,
+        save_mean, save_invstd, dgamma, dbeta, reinterpret_cast<__half*>(dx), dx_pitch, pixels, c, act, slope);
+    B2Y_CUDA_CHECK(cudaGetLastError());
+    return B2Y_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// SGD with Nesterov momentum (torch.optim.SGD semantics, train.py:135-144):
+//   g = grad*grad_scale + wd*p ; buf = first ? g : mu*buf + g ; p -= lr * (g + mu*buf)
+// ------------------------------------------------------------------------------------------------
+__global__ void sgd_nesterov_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf,
+                                    long long n, float lr, float mu, float wd, float gs, int first) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const float w = p[i];
+        const float grad = fmaf(wd, w, g[i] * gs);
+        const float b = first ? grad : fmaf(mu, buf[i], grad);
+        buf[i] = b;
+        p[i] = w - lr * fmaf(mu, b, grad);
+    }
+}
+
+extern "C" int b2y_sgd_nesterov(float* param, const float* grad, float* momentum_buf, long long n, float lr,
+                                float momentum, float weight_decay, float grad_scale, int first_step, void* stream) {
+    if (!param || !grad || !momentum_buf || n < 0) return B2Y_ERR_INVALID;
+    sgd_nesterov_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        param, grad, momentum_buf, n, lr, momentum, weight_decay, grad_scale, first_step);
+    B2Y_CUDA_CHECK(cudaGetLastError());
+    return B2Y_OK;
+}

@@ -1,0 +1,419 @@
+// Weight gradient of a dense convolution as a tcgen05 GEMM with the *pixel* dimension as K:
+//
+//   dW[co][tap][ci] = sum_{pixel m} dY[m][co] * X[m @ tap][ci]
+//
+// Both operands are pixel-major in HBM (NHWC), i.e. "MN-major" for the tensor core: the TMA boxes
+// [64 pixels][64 channels] land in smem exactly as a 128B-swizzled MN-major UMMA operand, so neither
+// tensor is ever transposed or im2col'ed in memory.  dY comes through a tiled 2-D map, X through the im2col
+// map (tap offset + zero fill for the halo).  Work = (Cout/128) x (Cin/BLOCK_N) x taps x split-K slices;
+// the fp32 accumulator tile is reduced into dW with vector red.global.add.
+#include "common.cuh"
+
+#include <mutex>
+
+namespace b2y {
+
+struct WgradParams {
+    int Cout, Cin;
+    int ntaps, ksize;
+    int K_total;              // B*Ho*Wo output pixels
+    int MH, MW;               // Ho, Wo
+    int stride, pad;
+    int m_tiles, n_tiles, ksplits;
+    int ksteps_total;         // ceil(K_total / BK)
+    int ksteps_per_split;
+    float scale;              // multiplies the accumulator (1 / loss-scale)
+    float* dw;                // fp32 [Cout][k][k][Cin], accumulated with atomics
+};
+
+template <int BLOCK_N, int NB_ROW_BYTES>
+struct WgradCfg {
+    static constexpr int BK = 64;                                   // pixels per pipeline stage
+    static constexpr int A_ATOMS = 2;                               // 2 x 64 output channels = M 128
+    static constexpr int A_ATOM_BYTES = BK * 128;
+    static constexpr int B_ATOM_CH = NB_ROW_BYTES / 2;              // channels per B atom
+    static constexpr int B_ATOMS = BLOCK_N / B_ATOM_CH;
+    static constexpr int B_ATOM_BYTES = BK * NB_ROW_BYTES;
+    static constexpr int A_BYTES = A_ATOMS * A_ATOM_BYTES;          // 16 KB
+    static constexpr int B_BYTES = B_ATOMS * B_ATOM_BYTES;
+    static constexpr int STAGE_BYTES = A_BYTES + ((B_BYTES + 1023) / 1024) * 1024;
+    static constexpr int NUM_STAGES_RAW = (192 * 1024) / STAGE_BYTES;
+    static constexpr int NUM_STAGES = NUM_STAGES_RAW > 6 ? 6 : NUM_STAGES_RAW;
+    static constexpr int TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+    static constexpr int SMEM_BYTES = 1024 + NUM_STAGES * STAGE_BYTES + 1024;
+};
+
+template <int BLOCK_N, int NB_ROW_BYTES>
+__global__ void __launch_bounds__(256, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUtensorMap tmX,
+                const WgradParams p) {
+    using Cfg = WgradCfg<BLOCK_N, NB_ROW_BYTES>;
+    constexpr int NS = Cfg::NUM_STAGES;
+    constexpr int BK = Cfg::BK;
+    constexpr uint32_t IDESC = make_idesc(/*c=F32*/ 1, /*a=F16*/ 0, /*b=F16*/ 0, /*a MN-major*/ 1, /*b MN-major*/ 1,
+                                          128, BLOCK_N);
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* aux = smem + NS * Cfg::STAGE_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);
+    uint64_t* empty_bar = full_bar + NS;
+    uint64_t* tmem_full_bar = empty_bar + NS;
+    uint64_t* tmem_empty_bar = tmem_full_bar + 1;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmDy);
+        prefetch_tmap(&tmX);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < NS; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        mbar_init(tmem_full_bar, 1);
+        mbar_init(tmem_empty_bar, 4);
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    const int num_tiles = p.m_tiles * p.n_tiles * p.ntaps * p.ksplits;
+
+    // tile -> (m_tile, n_tile, tap, split); split fastest so CTAs working on the same dW tile run concurrently
+    auto decode = [&](int tile, int& m_tile, int& n_tile, int& tap, int& split) {
+        split = tile % p.ksplits;
+        int t = tile / p.ksplits;
+        tap = t % p.ntaps;
+        t /= p.ntaps;
+        n_tile = t % p.n_tiles;
+        m_tile = t / p.n_tiles;
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const int HoWo = p.MH * p.MW;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                int m_tile, n_tile, tap, split;
+                decode(tile, m_tile, n_tile, tap, split);
+                const int r = tap / p.ksize, s = tap - r * p.ksize;
+                const int ks0 = split * p.ksteps_per_split;
+                const int ks1 = min(ks0 + p.ksteps_per_split, p.ksteps_total);
+                for (int ks = ks0; ks < ks1; ++ks) {
+                    const int k0 = ks * BK;
+                    const int img = k0 / HoWo;
+                    const int rem = k0 - img * HoWo;
+                    const int po = rem / p.MW, qo = rem - po * p.MW;
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* a_dst = smem + stage * Cfg::STAGE_BYTES;
+                    uint8_t* b_dst = a_dst + Cfg::A_BYTES;
+                    mbar_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::B_BYTES);
+#pragma unroll
+                    for (int at = 0; at < Cfg::A_ATOMS; ++at)
+                        tma_load_2d(a_dst + at * Cfg::A_ATOM_BYTES, &tmDy, &full_bar[stage], m_tile * 128 + at * 64,
+                                    k0);
+#pragma unroll
+                    for (int at = 0; at < Cfg::B_ATOMS; ++at)
+                        tma_load_im2col_4d(b_dst + at * Cfg::B_ATOM_BYTES, &tmX, &full_bar[stage],
+                                           n_tile * BLOCK_N + at * Cfg::B_ATOM_CH, qo * p.stride - p.pad,
+                                           po * p.stride - p.pad, img, (uint16_t)s, (uint16_t)r);
+                    if (++stage == NS) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            uint32_t acc_phase = 0;
+            // MN-major canonical layouts: LBO = distance between 64-channel atoms, SBO = 8 K-rows
+            const uint64_t adesc_base = smem_desc_base(Cfg::A_ATOM_BYTES, 8 * 128, swizzle_layout_type(128));
+            const uint64_t bdesc_base =
+                smem_desc_base(Cfg::B_ATOM_BYTES, 8 * NB_ROW_BYTES, swizzle_layout_type(NB_ROW_BYTES));
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                int m_tile, n_tile, tap, split;
+                decode(tile, m_tile, n_tile, tap, split);
+                const int ks0 = split * p.ksteps_per_split;
+                const int ks1 = min(ks0 + p.ksteps_per_split, p.ksteps_total);
+                mbar_wait(tmem_empty_bar, acc_phase ^ 1);
+                tc_fence_after();
+                for (int ks = ks0; ks < ks1; ++ks) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                    const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        const uint64_t adesc = smem_desc_at(adesc_base, a_addr + k * 16 * 128);
+                        const uint64_t bdesc = smem_desc_at(bdesc_base, b_addr + k * 16 * NB_ROW_BYTES);
+                        mma_f16_ss(tmem_base, adesc, bdesc, IDESC, (ks > ks0 || k > 0) ? 1u : 0u);
+                    }
+                    tc_commit(&empty_bar[stage]);
+                    if (++stage == NS) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                tc_commit(tmem_full_bar);
+                acc_phase ^= 1;
+            }
+        }
+    } else if (warp >= 4) {
+        const int ew = warp - 4;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            int m_tile, n_tile, tap, split;
+            decode(tile, m_tile, n_tile, tap, split);
+            const int ks0 = split * p.ksteps_per_split;
+            const bool has_work = ks0 < p.ksteps_total;
+            mbar_wait(tmem_full_bar, acc_phase);
+            tc_fence_after();
+            const int co = m_tile * 128 + ew * 32 + lane;
+            const uint32_t taddr_row = tmem_base + ((uint32_t)(ew * 32) << 16);
+#pragma unroll 1
+            for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+                uint32_t raw[32];
+                if (BLOCK_N >= 32) {
+                    tmem_ld_32x32(taddr_row + (uint32_t)c0, raw);
+                } else {
+                    // BLOCK_N == 16: the allocation is 32 columns wide, upper half is unused
+                    tmem_ld_32x32(taddr_row, raw);
+                }
+                tc_wait_ld();
+                const int ci0 = n_tile * BLOCK_N + c0;
+                if (has_work && co < p.Cout && ci0 < p.Cin) {
+                    float* dst = p.dw + ((long long)co * p.ntaps + tap) * p.Cin + ci0;
+                    const int nvalid = min(min(32, BLOCK_N), p.Cin - ci0);
+                    if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            float4 v = make_float4(__uint_as_float(raw[q * 4]) * p.scale,
+                                                   __uint_as_float(raw[q * 4 + 1]) * p.scale,
+                                                   __uint_as_float(raw[q * 4 + 2]) * p.scale,
+                                                   __uint_as_float(raw[q * 4 + 3]) * p.scale);
+                            atomicAdd(reinterpret_cast<float4*>(dst) + q, v);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < nvalid) atomicAdd(dst + j, __uint_as_float(raw[j]) * p.scale);
+                    }
+                }
+                __syncwarp();
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty_bar);
+            acc_phase ^= 1;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+// ---- host ------------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*PFN_encodeIm2col)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                     const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t,
+                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled w_encodeTiled = nullptr;
+static PFN_encodeIm2col w_encodeIm2col = nullptr;
+static int w_driver_version = 0;
+static int w_num_sms = 148;
+static std::once_flag w_once;
+
+static void w_resolve() {
+    cudaDriverEntryPointQueryResult q;
+    void* fn = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+        w_encodeTiled = reinterpret_cast<PFN_encodeTiled>(fn);
+    fn = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+        w_encodeIm2col = reinterpret_cast<PFN_encodeIm2col>(fn);
+    cudaDriverGetVersion(&w_driver_version);
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) ==
+                                                  cudaSuccess && n > 0)
+        w_num_sms = n;
+}
+
+template <int BLOCK_N, int NB_ROW_BYTES>
+static int wgrad_launch_cfg(const CUtensorMap& a, const CUtensorMap& b, const WgradParams& p, cudaStream_t st) {
+    using Cfg = WgradCfg<BLOCK_N, NB_ROW_BYTES>;
+    auto kern = wgrad_tc_kernel<BLOCK_N, NB_ROW_BYTES>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        B2Y_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    const int tiles = p.m_tiles * p.n_tiles * p.ntaps * p.ksplits;
+    const int grid = tiles < w_num_sms ? tiles : w_num_sms;
+    kern<<<grid, 256, Cfg::SMEM_BYTES, st>>>(a, b, p);
+    B2Y_CUDA_CHECK(cudaGetLastError());
+    return B2Y_OK;
+}
+
+}  // namespace b2y
+
+using namespace b2y;
+
+extern "C" int b2y_conv2d_bwd_weight(const b2y_conv_desc* d, const void* x, const void* dy, float* dw, float scale,
+                                     void* stream) {
+    std::call_once(w_once, w_resolve);
+    if (!d || !x || !dy || !dw) return B2Y_ERR_INVALID;
+    if (!w_encodeTiled || !w_encodeIm2col) return B2Y_ERR_DRIVER;
+    if (d->ksize * d->ksize > 16 || d->in_c % 16 != 0) return B2Y_ERR_UNSUPPORTED;
+    if ((d->in_pitch * 2) % 16 != 0 || (d->out_pitch * 2) % 16 != 0) return B2Y_ERR_INVALID;
+    const int Ho = (d->in_h + 2 * d->pad - d->ksize) / d->stride + 1;
+    const int Wo = (d->in_w + 2 * d->pad - d->ksize) / d->stride + 1;
+    if (Ho != d->out_h || Wo != d->out_w) return B2Y_ERR_INVALID;
+    const long long K = (long long)d->batch * Ho * Wo;
+    if (K > 0x7fffff00LL) return B2Y_ERR_UNSUPPORTED;
+
+    int block_n, row_bytes;
+    if (d->in_c % 64 == 0) {
+        row_bytes = 128;
+        block_n = d->in_c >= 256 ? 256 : (d->in_c >= 128 ? 128 : 64);
+        if (d->in_c % block_n != 0 && d->in_c > block_n) block_n = 64;  // e.g. Cin = 192/320/384: 64-wide tiles
+    } else if (d->in_c % 32 == 0) {
+        row_bytes = 64;
+        block_n = 32;
+    } else {
+        row_bytes = 32;
+        block_n = 16;
+    }
+
+    WgradParams p{};
+    p.Cout = d->out_c;
+    p.Cin = d->in_c;
+    p.ksize = d->ksize;
+    p.ntaps = d->ksize * d->ksize;
+    p.K_total = (int)K;
+    p.MH = Ho;
+    p.MW = Wo;
+    p.stride = d->stride;
+    p.pad = d->pad;
+    p.m_tiles = (d->out_c + 127) / 128;
+    p.n_tiles = (d->in_c + block_n - 1) / block_n;
+    p.ksteps_total = (int)((K + 63) / 64);
+    const int base_tiles = p.m_tiles * p.n_tiles * p.ntaps;
+    int splits = (2 * w_num_sms + base_tiles - 1) / base_tiles;     // aim for ~2 waves of CTAs
+    int max_splits = p.ksteps_total / 8;                             // keep >= 8 k-steps per slice
+    if (max_splits < 1) max_splits = 1;
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    p.ksteps_per_split = (p.ksteps_total + splits - 1) / splits;
+    p.ksplits = (p.ksteps_total + p.ksteps_per_split - 1) / p.ksteps_per_split;
+    p.scale = scale;
+    p.dw = dw;
+
+    CUtensorMap tmDy, tmX;
+    {
+        cuuint64_t gdim[2] = {(cuuint64_t)d->out_c, (cuuint64_t)K};
+        cuuint64_t gstride[1] = {(cuuint64_t)(d->out_pitch * 2)};
+        cuuint32_t box[2] = {64, 64};
+        cuuint32_t estr[2] = {1, 1};
+        if (w_encodeTiled(&tmDy, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(dy), gdim, gstride, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return B2Y_ERR_DRIVER;
+    }
+    {
+        cuuint64_t gdim[4] = {(cuuint64_t)d->in_c, (cuuint64_t)d->in_w, (cuuint64_t)d->in_h, (cuuint64_t)d->batch};
+        cuuint64_t gstride[3] = {(cuuint64_t)(d->in_pitch * 2), (cuuint64_t)(d->in_pitch * 2 * d->in_w),
+                                 (cuuint64_t)(d->in_pitch * 2 * d->in_w * (long long)d->in_h)};
+        int lower[2] = {-d->pad, -d->pad};
+        int upper[2] = {d->pad - (d->ksize - 1), d->pad - (d->ksize - 1)};
+        cuuint32_t estr[4] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1};
+        CUtensorMapSwizzle sw = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                                 : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                                    : CU_TENSOR_MAP_SWIZZLE_32B);
+        if (w_encodeIm2col(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(x), gdim, gstride, lower, upper,
+                           (cuuint32_t)(row_bytes / 2), 64, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return B2Y_ERR_DRIVER;
+        if (w_driver_version <= 13010) {
+            long long bytes = (long long)d->batch * d->in_h * d->in_w * d->in_pitch * 2;
+            if (bytes < 131072) reinterpret_cast<uint64_t*>(&tmX)[1] &= ~(1ull << 21);
+        }
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (row_bytes == 128) {
+        if (block_n == 256) return wgrad_launch_cfg<256, 128>(tmDy, tmX, p, st);
+        if (block_n == 128) return wgrad_launch_cfg<128, 128>(tmDy, tmX, p, st);
+        return wgrad_launch_cfg<64, 128>(tmDy, tmX, p, st);
+    }
+    if (row_bytes == 64) return wgrad_launch_cfg<32, 64>(tmDy, tmX, p, st);
+    return wgrad_launch_cfg<16, 32>(tmDy, tmX, p, st);
+}
+
+// [O][kh][kw][I] fp32 -> OIHW fp32: dst = alpha*src (+ dst when accumulate)
+__global__ void unpack_wgrad_kernel(const float* __restrict__ src, float* __restrict__ dst, int O, int I, int k,
+                                    float alpha, int accumulate) {
+    const long long total = (long long)O * I * k * k;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        // idx enumerates the OIHW destination
+        const int kw = (int)(idx % k);
+        long long t = idx / k;
+        const int kh = (int)(t % k);
+        t /= k;
+        const int i = (int)(t % I);
+        const int o = (int)(t / I);
+        const float v = alpha * src[(((long long)o * k + kh) * k + kw) * I + i];
+        dst[idx] = accumulate ? dst[idx] + v : v;
+    }
+}
+
+extern "C" int b2y_unpack_wgrad(const float* dw_packed, float* dw_oihw, int out_c, int in_c, int ksize, float alpha,
+                                int accumulate, void* stream) {
+    if (!dw_packed || !dw_oihw || out_c <= 0 || in_c <= 0 || ksize <= 0) return B2Y_ERR_INVALID;
+    const long long total = (long long)out_c * in_c * ksize * ksize;
+    int grid = (int)((total + 255) / 256);
+    if (grid > 148 * 16) grid = 148 * 16;
+    unpack_wgrad_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(dw_packed, dw_oihw, out_c, in_c, ksize,
+                                                                               alpha, accumulate);
+    B2Y_CUDA_CHECK(cudaGetLastError());
+    return B2Y_OK;
+}
+
+// dst = alpha*src + beta*dst (fp32), used to move scaled BN/bias gradients into parameter .grad buffers
+__global__ void axpby_kernel(const float* __restrict__ src, float* __restrict__ dst, long long n, float alpha,
+                             float beta) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x)
+        dst[i] = alpha * src[i] + (beta != 0.f ? beta * dst[i] : 0.f);
+}
+extern "C" int b2y_axpby_f32(const float* src, float* dst, long long n, float alpha, float beta, void* stream) {
+    if (!src || !dst || n < 0) return B2Y_ERR_INVALID;
+    int grid = (int)((n + 255) / 256);
+    if (grid < 1) grid = 1;
+    if (grid > 148 * 16) grid = 148 * 16;
+    axpby_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, dst, n, alpha, beta);
+    B2Y_CUDA_CHECK(cudaGetLastError());
+    return B2Y_OK;
+}
