@@ -93,6 +93,15 @@ int b2y_conv2d_fwd_stats(const b2y_conv_desc* d, const void* x, const void* w_pa
 int b2y_stem_conv_fwd(const b2y_conv_desc* d, const float* x_nchw, const float* w, const float* bias, void* y,
                       void* stream);
 
+/* Tensor-core stem (in_c*ksize <= 16): the image is re-laid as NHWC fp16 with the kw taps unrolled into 16 channels
+ * (workspace, b2y_stem_workspace_bytes), then the conv runs as a k x 1 implicit GEMM on the tcgen05 kernel.
+ *   w_stem fp16 [out_c][k][16] from b2y_pack_stem_weights (w already BN-folded, OIHW fp32)
+ *   stat_sum/stat_sqsum optional (training BN statistics, see b2y_conv2d_fwd_stats) */
+size_t b2y_stem_workspace_bytes(const b2y_conv_desc* d);
+int b2y_pack_stem_weights(const float* w_oihw_folded, int out_c, int in_c, int ksize, void* w_stem, void* stream);
+int b2y_stem_conv_fwd_tc(const b2y_conv_desc* d, const float* x_nchw, const void* w_stem, const float* bias,
+                         void* workspace, void* y, float* stat_sum, float* stat_sqsum, void* stream);
+
 /* Fold BatchNorm (running stats) into conv weights and repack OIHW fp32 -> [O][kh][kw][I] fp16.
  *   w_f = w * gamma/sqrt(var+eps);  b_f = beta - gamma*mean/sqrt(var+eps) (+ conv_bias*scale)
  * (utils/torch_utils.py:65-89, utils/quantized/quantized_ptq_cos.py:193-206).
@@ -228,6 +237,19 @@ int b2y_unpack_wgrad(const float* dw_packed, float* dw_oihw, int out_c, int in_c
                      int accumulate, void* stream);
 /* dst = alpha*src + beta*dst (fp32) */
 int b2y_axpby_f32(const float* src, float* dst, long long n, float alpha, float beta, void* stream);
+/* backward of the YOLO permute: dp fp32 [B][na][ny][nx][no] -> d(raw) fp16 [B][ny][nx][raw_pitch] * scale (models.py:406) */
+int b2y_yolo_grad_to_raw(const float* dp, void* draw, long long raw_pitch, int batch, int na, int no, int ny, int nx,
+                         float scale, void* stream);
+/* backward of nn.Upsample (nearest): dx += window sums of dy (in place accumulate) */
+int b2y_upsample_nearest_bwd(const void* dy, long long dy_pitch, void* dx, long long dx_pitch, int batch, int in_h,
+                             int in_w, int c, int scale, void* stream);
+/* backward of nn.MaxPool2d: dx[argmax] += dy (arg-max recomputed from x; first maximum wins like torch) */
+int b2y_maxpool_bwd(const void* x, long long x_pitch, const void* dy, long long dy_pitch, void* dx,
+                    long long dx_pitch, int batch, int in_h, int in_w, int c, int ksize, int stride, int pad_mode,
+                    void* stream);
+/* weight gradient of the stem (in_c <= 4): x fp32 NCHW, dz fp16 NHWC -> dw OIHW fp32 (+= scale * ...) */
+int b2y_stem_conv_bwd_weight(const b2y_conv_desc* d, const float* x_nchw, const void* dz, float* dw_oihw,
+                             float scale, void* stream);
 /* SGD + Nesterov momentum + weight decay over a flat fp32 buffer (train.py:135-144), grads pre-scaled by
  * grad_scale (1/world_size after the NCCL sum) */
 int b2y_sgd_nesterov(float* param, const float* grad, float* momentum_buf, long long n, float lr, float momentum,

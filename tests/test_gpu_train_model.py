@@ -1,0 +1,77 @@
+"""GPU: training step parity (forward with batch-stat BN, YOLO loss, full backward) of the B200 engine against the
+fixtures produced by the reference itself on CPU fp32 (tests/golden/*_64_train.npz)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import attach_hyp, build_model, golden, orc
+
+pytestmark = pytest.mark.gpu
+
+# fp16 activations / gradients (loss-scaled) vs the fp32 reference
+P_ABS_TOL = 5e-2
+LOSS_REL_TOL = 2e-2
+GRAD_NORM_REL_TOL = 6e-2
+GRAD_ELEM_TOL = 8e-2    # max |d| relative to the tensor's max |grad|
+
+
+@pytest.mark.parametrize("name", ["yolov3-tiny", "yolov3", "yolov4"])
+def test_train_step_parity(name):
+    from utils import utils as my_utils
+    g = golden("%s_64_train" % name)
+    model = attach_hyp(build_model(name, device="cuda")).train()
+    x = orc.synth_images(2, 64, 64, seed=0).cuda()
+    t = orc.synth_targets(2, 6, 80, seed=1).cuda()
+    pred, feats = model(x)
+    loss, items = my_utils.compute_loss(pred, t, model)
+    loss.backward()
+    torch.cuda.synchronize()
+    worst_p = max((pi.detach().cpu() - torch.from_numpy(g["p%d" % i])).abs().max().item() for i, pi in enumerate(pred))
+    items_c = items.cpu().numpy()
+    rel_items = np.abs(items_c - g["items"]) / np.abs(g["items"])
+    names = [str(n) for n in g["grad_names"]]
+    norms = dict(zip(names, g["grad_norms"]))
+    params = dict(model.named_parameters())
+    rel = {}
+    for k in names:
+        assert params[k].grad is not None, "no gradient for %s" % k
+        rel[k] = abs(float(params[k].grad.norm()) - norms[k]) / (norms[k] + 1e-8)
+    worst_k = max(rel, key=rel.get)
+    elem = {}
+    for k in names:
+        if ("grad::" + k) in g.files:
+            ref = torch.from_numpy(g["grad::" + k])
+            elem[k] = ((params[k].grad.cpu() - ref).abs().max() / ref.abs().max().clamp(min=1e-12)).item()
+    stat_err = 0.0
+    sd = model.state_dict()
+    for k in g.files:
+        if k.startswith("stat::"):
+            stat_err = max(stat_err, float((sd[k[6:]].cpu() - torch.from_numpy(g[k])).abs().max()))
+    print("\n[%s train] max|dp|=%.3g items_rel=%s worst grad-norm rel=%.3g (%s) median=%.3g elem=%s stat=%.3g"
+          % (name, worst_p, np.round(rel_items, 5), rel[worst_k], worst_k, float(np.median(list(rel.values()))),
+             {k.split('.')[1] + k[-12:]: round(v, 4) for k, v in elem.items()}, stat_err))
+    assert worst_p < P_ABS_TOL
+    assert rel_items.max() < LOSS_REL_TOL
+    assert float(np.median(list(rel.values()))) < GRAD_NORM_REL_TOL / 3
+    assert rel[worst_k] < GRAD_NORM_REL_TOL * 3
+    assert max(elem.values()) < GRAD_ELEM_TOL
+    assert stat_err < 2e-3
+    assert len(feats) > 0
+
+
+def test_train_step_then_optimizer_changes_output():
+    """weights change -> the plan re-packs them; two steps with torch SGD decrease the loss on a fixed batch."""
+    from utils import utils as my_utils
+    model = attach_hyp(build_model("yolov3-tiny", device="cuda")).train()
+    opt = torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.9, nesterov=True)
+    x = orc.synth_images(2, 64, 64, seed=0).cuda()
+    t = orc.synth_targets(2, 6, 80, seed=1).cuda()
+    losses = []
+    for _ in range(4):
+        opt.zero_grad()
+        pred, _ = model(x)
+        loss, _ = my_utils.compute_loss(pred, t, model)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses

@@ -264,19 +264,29 @@ class Plan:
             stem = conv.in_channels <= 4
             wp, bias, w32 = ops.pack_conv_weights(conv.weight.detach(), conv.bias.detach() if conv.bias is not None
                                                   else None, bnp, eps, want_fp32=stem)
-            self.weights[i] = (wp, bias, w32)
+            wstem = None
+            if stem and conv.in_channels * conv.kernel_size[0] <= 16:
+                wstem = ops.pack_stem_weights(w32)
+            self.weights[i] = (wp, bias, w32, wstem)
 
     def _launch_all(self, x):
         for st in self.steps:
             kind = st[0]
             if kind == 'conv':
                 _, i, src, out, res, conv, bn, act, slope = st
-                wp, bias, w32 = self.weights[i]
+                wp, bias, w32, wstem = self.weights[i]
                 k, s, p = conv.kernel_size[0], conv.stride[0], conv.padding[0]
                 if src is None:
                     if conv.in_channels > 4:
                         raise NotImplementedError("first layer with more than 4 input channels")
-                    ops.stem_conv(x, w32, bias, k, s, p, act=act, slope=slope, out=out.view())
+                    if wstem is not None:
+                        if getattr(self, 'stem_ws', None) is None:
+                            self.stem_ws = torch.empty((self.B, self.H, self.W, 16), dtype=torch.float16,
+                                                       device=self.device)
+                        ops.stem_conv_tc(x, wstem, bias, conv.in_channels, k, s, p, act=act, slope=slope,
+                                         out=out.view(), workspace=self.stem_ws)
+                    else:
+                        ops.stem_conv(x, w32, bias, k, s, p, act=act, slope=slope, out=out.view())
                 else:
                     ops.conv2d(src.view(), wp, bias, k, s, p, act=act, slope=slope,
                                residual=res.view() if res is not None else None, out=out.view())
@@ -306,7 +316,7 @@ class Plan:
             self.steps, self.yolo = saved, yolo
 
     def launches_per_forward(self):
-        return len(self.steps) + len(self.yolo)
+        return len(self.steps) + len(self.yolo) + (1 if getattr(self, 'stem_ws', None) is not None else 0)
 
     def step_info(self, st):
         """(label, algorithmic FLOPs, algorithmic HBM bytes) of one launch."""
@@ -432,21 +442,23 @@ class Engine:
     def plan_for(self, x):
         self.forward(x)
         model = self.model
-        keep = bool(model.keep_features) if model.keep_features is not None else bool(model.training)
+        keep = bool(model.keep_features)
         return self.plans[(tuple(x.shape), bool(model.training), x.device.index, keep)]
 
     def forward(self, x):
         model = self.model
         if model.quantized != -1:
             raise NotImplementedError("quantized execution goes through b200yolo.qengine")
-        keep = bool(model.keep_features) if model.keep_features is not None else bool(model.training)
+        keep = bool(model.keep_features)
         key = (tuple(x.shape), bool(model.training), x.device.index, keep)
         plan = self.plans.get(key)
         if plan is None:
             if model.training:
                 from .train_engine import TrainPlan
-                plan = TrainPlan(model, tuple(x.shape), x.device)
+                plan = TrainPlan(model, tuple(x.shape), x.device, keep)
             else:
                 plan = Plan(model, tuple(x.shape), x.device, False, keep)
             self.plans[key] = plan
+        if model.training:
+            return plan.run(x)
         return plan.forward(x)

@@ -56,6 +56,9 @@ _PROTOS = {
     "b2y_conv2d_fwd": (i32, [C.POINTER(ConvDesc), vp, vp, vp, vp, vp, vp]),
     "b2y_conv2d_fwd_stats": (i32, [C.POINTER(ConvDesc), vp, vp, vp, vp, vp, vp, vp]),
     "b2y_stem_conv_fwd": (i32, [C.POINTER(ConvDesc), vp, vp, vp, vp, vp]),
+    "b2y_stem_workspace_bytes": (sz, [C.POINTER(ConvDesc)]),
+    "b2y_pack_stem_weights": (i32, [vp, i32, i32, i32, vp, vp]),
+    "b2y_stem_conv_fwd_tc": (i32, [C.POINTER(ConvDesc), vp, vp, vp, vp, vp, vp, vp, vp]),
     "b2y_pack_conv_weights": (i32, [vp, vp, vp, vp, vp, vp, f32, i32, i32, i32, vp, vp, vp, vp]),
     "b2y_upsample_nearest": (i32, [vp, ll, vp, ll, i32, i32, i32, i32, i32, vp]),
     "b2y_maxpool": (i32, [vp, ll, vp, ll, i32, i32, i32, i32, i32, i32, i32, vp]),
@@ -85,6 +88,10 @@ _PROTOS = {
     "b2y_conv2d_bwd_weight": (i32, [C.POINTER(ConvDesc), vp, vp, vp, f32, vp]),
     "b2y_unpack_wgrad": (i32, [vp, vp, i32, i32, i32, f32, i32, vp]),
     "b2y_axpby_f32": (i32, [vp, vp, ll, f32, f32, vp]),
+    "b2y_yolo_grad_to_raw": (i32, [vp, vp, ll, i32, i32, i32, i32, i32, f32, vp]),
+    "b2y_upsample_nearest_bwd": (i32, [vp, ll, vp, ll, i32, i32, i32, i32, i32, vp]),
+    "b2y_maxpool_bwd": (i32, [vp, ll, vp, ll, vp, ll, i32, i32, i32, i32, i32, i32, i32, vp]),
+    "b2y_stem_conv_bwd_weight": (i32, [C.POINTER(ConvDesc), vp, vp, vp, f32, vp]),
     "b2y_sgd_nesterov": (i32, [vp, vp, vp, ll, f32, f32, f32, f32, i32, vp]),
 }
 

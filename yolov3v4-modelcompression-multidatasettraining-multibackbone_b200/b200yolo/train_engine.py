@@ -1,0 +1,441 @@
+"""Training-mode executor: forward with batch-statistics BatchNorm and the full backward pass on sm_100a.
+
+Replaces autograd over ~500 ATen/cuDNN calls (reference train.py:380-441 -> models.py:508-551) by a static plan:
+
+  forward   conv (tcgen05, per-channel sum / sum^2 from the epilogue) -> bn_finalize -> bn+act(+shortcut) apply
+  backward  yolo permute^T -> [bn+act backward reduce / apply -> wgrad (tcgen05, pixel-K GEMM) -> dgrad (tcgen05)]
+
+Activations z (raw conv output) and y (post activation) are kept in NHWC fp16; gradients flow in fp16 multiplied by
+a static loss scale (model.grad_scale, default 1024) and are un-scaled when written to the fp32 parameter gradients.
+The plan plugs into autograd as ONE torch.autograd.Function whose inputs are the model parameters, so
+loss.backward(), DistributedDataParallel hooks and torch optimisers work unchanged.
+"""
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .engine import LazyFeatures, _Tensor, _block_parts
+from .lib import ConvDesc, OUT_F16, call, ptr, stream_ptr
+
+HEAD_PAD = 256  # head convs (255 filters) are run with 256 output channels (zero row) so that K % 16 == 0 in dgrad
+
+
+def _round_up(v, m):
+    return (v + m - 1) // m * m
+
+
+class _ConvRec:
+    __slots__ = ('i', 'conv', 'bn', 'act', 'slope', 'src', 'z', 'y', 'res', 'head', 'stem', 'k', 's', 'p', 'Cout',
+                 'Cpad', 'w16', 'wT', 'stats', 'mean', 'invstd', 'scale', 'shift', 'ones', 'zeros', 'w32')
+
+    def __init__(self):
+        for k in self.__slots__:
+            setattr(self, k, None)
+
+
+class TrainPlan:
+    def __init__(self, model, x_shape, device, keep_features=False):
+        self.model = model
+        self.device = device
+        self.keep_features = bool(keep_features)
+        self.B, self.Cin, self.H, self.W = x_shape
+        self.convs = []
+        self.order = []        # forward step list
+        self.param_version = None
+        self._build()
+
+    # ---------------------------------------------------------------------------------------------------------
+    def _build(self):
+        model, B, dev = self.model, self.B, self.device
+        defs, mods, routs = model.module_defs, model.module_list, model.routs
+        n = len(defs)
+        shapes, prev = [], (self.Cin, self.H, self.W)
+        for i, (d, m) in enumerate(zip(defs, mods)):
+            t = d['type']
+            Cc, H, W = prev
+            if t == 'convolutional':
+                conv = _block_parts(m)[0]
+                H, W = ops.conv_out_hw(H, W, conv.kernel_size[0], conv.stride[0], conv.padding[0])
+                Cc = conv.out_channels
+            elif t == 'maxpool':
+                k, s = d['size'], d['stride']
+                if k == 2 and s == 1:
+                    H, W = (H + 1 - k) // s + 1, (W + 1 - k) // s + 1
+                else:
+                    pd = (k - 1) // 2
+                    H, W = (H + 2 * pd - k) // s + 1, (W + 2 * pd - k) // s + 1
+            elif t == 'upsample':
+                H, W = H * d['stride'], W * d['stride']
+            elif t == 'route':
+                srcs = [i + l if l < 0 else l for l in d['layers']]
+                Cc = sum(shapes[s][0] for s in srcs)
+                if 'groups' in d:
+                    Cc //= 2
+                H, W = shapes[srcs[0]][1], shapes[srcs[0]][2]
+            elif t in ('shortcut', 'yolo'):
+                pass
+            else:
+                raise NotImplementedError("layer type '%s' is not supported by the sm_100a training engine yet" % t)
+            prev = (Cc, H, W)
+            shapes.append(prev)
+
+        is_head = [False] * n
+        fused_into = [None] * n   # shortcut i folded into the bn+act apply of conv i-1
+        for i, d in enumerate(defs):
+            if d['type'] == 'yolo' and i > 0 and defs[i - 1]['type'] == 'convolutional':
+                is_head[i - 1] = True
+            if d['type'] == 'shortcut' and i > 1:
+                frm = [i + l if l < 0 else l for l in d['from']]
+                if (not self.keep_features
+                        and len(frm) == 1 and defs[i - 1]['type'] == 'convolutional' and not routs[i - 1]
+                        and not getattr(mods[i], 'weight', False) and shapes[frm[0]] == shapes[i - 1]
+                        and _block_parts(mods[i - 1])[1] is not None):
+                    fused_into[i] = i - 1
+
+        tens = [None] * n
+        for i, d in enumerate(defs):
+            t = d['type']
+            if t == 'yolo' or (t == 'route' and len(d['layers']) == 1 and 'groups' not in d):
+                continue
+            Cc, H, W = shapes[i]
+            tens[i] = _Tensor(Cc, H, W, torch.float32 if is_head[i] else torch.float16)
+        self.pre_add = {}
+        for i in range(n):
+            if fused_into[i] is not None:
+                tens[fused_into[i]] = tens[i]
+        for i, d in enumerate(defs):
+            if d['type'] == 'route' and len(d['layers']) == 1 and 'groups' not in d:
+                l = d['layers'][0]
+                src = i + l if l < 0 else l
+                tens[i] = tens[src]
+
+        # concat placement (same policy as the inference plan); gradients mirror the placement
+        placed, copies = set(), {}
+        self.bufs = []   # (activation buffer, gradient buffer) pairs to keep alive
+
+        def new_buf(Cc, H, W, dtype=torch.float16):
+            pitch = Cc if dtype == torch.float16 else _round_up(Cc, 4)
+            return torch.empty((B, H, W, pitch), dtype=dtype, device=dev)
+
+        self.grad_of = {}  # id(_Tensor) -> gradient _Tensor (fp16, same placement)
+
+        def make_grad(t, gbuf=None, c0=0):
+            g = _Tensor(t.C, t.H, t.W, torch.float16)
+            g.buf, g.c0 = gbuf, c0
+            self.grad_of[id(t)] = g
+            return g
+
+        for i, d in enumerate(defs):
+            if d['type'] != 'route' or len(d['layers']) == 1:
+                continue
+            srcs = [i + l if l < 0 else l for l in d['layers']]
+            dst = tens[i]
+            dst.buf = new_buf(dst.C, dst.H, dst.W)
+            gdst = make_grad(dst, torch.zeros_like(dst.buf))
+            off = 0
+            for s in srcs:
+                st = tens[s]
+                if id(st) not in placed and st.buf is None and off % 8 == 0 and st.dtype == torch.float16 \
+                        and st is not dst:
+                    st.buf, st.c0 = dst.buf, off
+                    make_grad(st, gdst.buf, off)
+                    placed.add(id(st))
+                else:
+                    copies.setdefault(i, []).append((st, off))
+                off += st.C
+
+        def alloc(t):
+            if t.buf is None:
+                t.buf = new_buf(t.C if t.dtype == torch.float16 else HEAD_PAD, t.H, t.W, t.dtype)
+                t.c0 = 0
+            if id(t) not in self.grad_of:
+                if t.dtype == torch.float16:
+                    make_grad(t, torch.zeros_like(t.buf))
+                else:  # head output: gradient is the fp16 d(raw) buffer, HEAD_PAD channels
+                    g = _Tensor(HEAD_PAD, t.H, t.W, torch.float16)
+                    g.buf = torch.zeros((B, t.H, t.W, HEAD_PAD), dtype=torch.float16, device=dev)
+                    self.grad_of[id(t)] = g
+            return t
+
+        self.yolo = []
+        self.feature_views = []
+        feat_idx = {}
+        for i, (d, m) in enumerate(zip(defs, mods)):
+            t = d['type']
+            if t == 'convolutional':
+                conv, bn, act, slope = _block_parts(m)
+                if conv.groups != 1:
+                    raise NotImplementedError("grouped convolution is not supported by the sm_100a engine yet")
+                r = _ConvRec()
+                r.i, r.conv, r.bn, r.act, r.slope = i, conv, bn, act, slope
+                r.k, r.s, r.p = conv.kernel_size[0], conv.stride[0], conv.padding[0]
+                r.head, r.stem = is_head[i], (i == 0)
+                if r.stem and conv.in_channels > 4:
+                    raise NotImplementedError("first layer with more than 4 input channels")
+                r.Cout = conv.out_channels
+                r.Cpad = HEAD_PAD if r.head else r.Cout
+                if r.head and (r.Cout > HEAD_PAD or bn is not None or act != 'linear'):
+                    raise NotImplementedError("unsupported YOLO head conv")
+                r.src = None if i == 0 else tens[i - 1]
+                r.y = alloc(tens[i])
+                if i + 1 < n and fused_into[i + 1] == i:
+                    l = defs[i + 1]['from'][0]
+                    r.res = tens[i + 1 + l if l < 0 else l]
+                if bn is not None:
+                    r.z = _Tensor(r.Cout, r.y.H, r.y.W)
+                    r.z.buf = new_buf(r.Cout, r.y.H, r.y.W)
+                    r.stats = torch.zeros((2, r.Cout), dtype=torch.float32, device=dev)
+                else:
+                    r.z = r.y   # no BN: the conv epilogue applies bias + activation directly
+                    r.ones = torch.ones(r.Cpad, dtype=torch.float32, device=dev)
+                    r.zeros = torch.zeros(r.Cpad, dtype=torch.float32, device=dev)
+                self.convs.append(r)
+                self.order.append(('conv', r))
+                if not is_head[i] and r.res is None:
+                    feat_idx[i] = r.y   # (a conv with a fused shortcut never materialises its pre-add output)
+            elif t == 'shortcut':
+                if fused_into[i] is not None:
+                    continue
+                frm = [i + l if l < 0 else l for l in d['from']]
+                if getattr(m, 'weight', False) or any(tens[s].C != tens[i - 1].C for s in frm):
+                    raise NotImplementedError("weighted / channel-sliced shortcut is not supported yet")
+                out = alloc(tens[i])
+                self.order.append(('add', tens[i - 1], [tens[s] for s in frm], out))
+            elif t == 'route':
+                if len(d['layers']) == 1:
+                    if 'groups' in d:
+                        src, g = tens[i - 1], tens[i]
+                        g.buf, g.c0 = src.buf, src.c0 + src.C // 2
+                        gs = self.grad_of[id(src)]
+                        make_grad(g, gs.buf, gs.c0 + src.C // 2)
+                    continue
+                for st, off in copies.get(i, []):
+                    self.order.append(('copy', st, tens[i], off))
+            elif t == 'upsample':
+                self.order.append(('upsample', tens[i - 1], alloc(tens[i]), d['stride']))
+            elif t == 'maxpool':
+                k, s = d['size'], d['stride']
+                self.order.append(('maxpool', tens[i - 1], alloc(tens[i]), k, s, k == 2 and s == 1))
+                if m.__class__.__name__ == 'Sequential':
+                    feat_idx[i] = tens[i]
+            elif t == 'yolo':
+                self.yolo.append((m, tens[i - 1]))
+        for i, m in enumerate(mods):
+            if m.__class__.__name__ == 'Sequential' and i + 1 < n and defs[i + 1]['type'] != 'yolo':
+                self.feature_views.append(feat_idx.get(i))
+        self.anchors_px = [m.anchors.to(dev).float().contiguous() for (m, _) in self.yolo]
+        self.bn_counters = [r.bn.num_batches_tracked for r in self.convs if r.bn is not None]
+        self.grad_bufs = []
+        seen = set()
+        for g in self.grad_of.values():
+            if g.buf is not None and g.buf.data_ptr() not in seen:
+                seen.add(g.buf.data_ptr())
+                self.grad_bufs.append(g.buf)
+        maxz = max(r.Cpad * r.y.H * r.y.W for r in self.convs)
+        self.dz_scratch = torch.empty(B * maxz, dtype=torch.float16, device=dev)
+        maxw = max(r.Cpad * r.conv.in_channels * r.k * r.k for r in self.convs)
+        self.dw_scratch = torch.empty(maxw, dtype=torch.float32, device=dev)
+        maxc = max(r.Cpad for r in self.convs)
+        self.dgb_scratch = torch.empty((2, maxc), dtype=torch.float32, device=dev)
+        self.params = [p for p in model.parameters()]
+
+    # ---------------------------------------------------------------------------------------------------------
+    def _params_version(self):
+        return sum(p._version for p in self.params)
+
+    def _pack(self):
+        for r in self.convs:
+            w = r.conv.weight.detach()
+            if r.head:
+                pad = torch.zeros((HEAD_PAD - r.Cout,) + tuple(w.shape[1:]), dtype=w.dtype, device=w.device)
+                w = torch.cat([w, pad], 0)
+            if r.stem:
+                r.w32 = w.float().contiguous()
+            else:
+                r.w16, _, _ = ops.pack_conv_weights(w)
+                hin, win = r.src.H, r.src.W
+                r.wT = ops.pack_dgrad_weights(w, r.s, r.p, (hin, win))
+
+    def _zview(self, r):
+        return r.z.buf[..., r.z.c0:r.z.c0 + r.Cpad] if r.head else r.z.view()
+
+    def forward(self, x):
+        model = self.model
+        ver = self._params_version()
+        if ver != self.param_version:
+            self._pack()
+            self.param_version = ver
+        x = x.contiguous().float()
+        self.x = x
+        for r in self.convs:
+            if r.stats is not None:
+                r.stats.zero_()
+        for st in self.order:
+            kind = st[0]
+            if kind == 'conv':
+                r = st[1]
+                self._conv_forward(r, x)
+            elif kind == 'add':
+                cur = st[1]
+                for s in st[2]:
+                    ops.add(cur.view(), s.view(), out=st[3].view())
+                    cur = st[3]
+            elif kind == 'copy':
+                _, srct, dst, off = st
+                ops.copy_channels(srct.view(), dst.buf[..., off:off + srct.C])
+            elif kind == 'upsample':
+                ops.upsample(st[1].view(), st[3], out=st[2].view())
+            elif kind == 'maxpool':
+                ops.maxpool(st[1].view(), st[3], st[4], tiny_pad=st[5], out=st[2].view())
+        if self.bn_counters:
+            torch._foreach_add_(self.bn_counters, 1)
+        outs = []
+        for (m, raw), anc in zip(self.yolo, self.anchors_px):
+            _, p = ops.yolo_decode(raw.buf, m.na, m.no, anc, m.stride, io=None)
+            m.nx, m.ny = raw.W, raw.H
+            outs.append(p)
+        return outs
+
+    def _conv_forward(self, r, x):
+        if r.bn is None:
+            bias = r.conv.bias.detach() if r.conv.bias is not None else None
+            if r.head and bias is not None:
+                bias = torch.cat([bias, bias.new_zeros(HEAD_PAD - r.Cout)])
+            out = self._zview(r)
+            if r.stem:
+                ops.stem_conv(x, r.w32, bias, r.k, r.s, r.p, act=r.act, slope=r.slope, out=out)
+            else:
+                ops.conv2d(r.src.view(), r.w16, bias, r.k, r.s, r.p, act=r.act, slope=r.slope, out=out)
+            return
+        z = r.z.view()
+        if r.stem:
+            ops.stem_conv(x, r.w32, None, r.k, r.s, r.p, act='linear', out=z)
+            # channel sums of the stem output: the reduce kernel with u = z, dy = z gives (sum z, sum z*z)
+            if r.ones is None:
+                r.ones = torch.ones(r.Cout, dtype=torch.float32, device=self.device)
+                r.zeros = torch.zeros(r.Cout, dtype=torch.float32, device=self.device)
+            B_, H_, W_, C_ = z.shape
+            call("b2y_bn_act_bwd_reduce", ptr(z), ops._pitch(z), ptr(z), ops._pitch(z), ptr(r.ones), ptr(r.zeros),
+                 ptr(r.zeros), ptr(r.ones), ptr(r.stats[1]), ptr(r.stats[0]), B_ * H_ * W_, C_, 0, 0.0, stream_ptr())
+        else:
+            ops.conv2d(r.src.view(), r.w16, None, r.k, r.s, r.p, out=z, stats=(r.stats[0], r.stats[1]))
+        bn = r.bn
+        count = z.shape[0] * z.shape[1] * z.shape[2]
+        r.mean, r.invstd, r.scale, r.shift = ops.bn_finalize(r.stats[0], r.stats[1], count, bn.weight.detach(),
+                                                             bn.bias.detach(), bn.eps, bn.momentum, bn.running_mean,
+                                                             bn.running_var)
+        ops.bn_act_fwd(z, r.scale, r.shift, r.act, r.slope, residual=r.res.view() if r.res is not None else None,
+                       out=r.y.view())
+
+    # ---------------------------------------------------------------------------------------------------------
+    def backward(self, dps):
+        """dps: gradients w.r.t. the yolo outputs p (fp32). Returns {param: grad} for every model parameter."""
+        S = float(getattr(self.model, 'grad_scale', 1024.0))
+        inv = 1.0 / S
+        for gb in self.grad_bufs:
+            gb.zero_()
+        grads = {}
+        for (m, raw), dp in zip(self.yolo, dps):
+            g = self.grad_of[id(raw)]
+            if dp is None:
+                continue
+            call("b2y_yolo_grad_to_raw", ptr(dp.contiguous().float()), ptr(g.buf), HEAD_PAD, self.B, m.na, m.no, raw.H,
+                 raw.W, S, stream_ptr())
+        G = lambda t: self.grad_of[id(t)]
+        for st in reversed(self.order):
+            kind = st[0]
+            if kind == 'conv':
+                self._conv_backward(st[1], grads, S, inv)
+            elif kind == 'add':
+                _, first, others, out = st
+                go = G(out).view()
+                for s in [first] + list(others):
+                    gs = G(s).view()
+                    ops.add(gs, go, out=gs)
+            elif kind == 'copy':
+                _, srct, dst, off = st
+                gd = G(dst)
+                gs = G(srct).view()
+                ops.add(gs, gd.buf[..., gd.c0 + off:gd.c0 + off + srct.C], out=gs)
+            elif kind == 'upsample':
+                _, src, out, s = st
+                gy, gx = G(out).view(), G(src).view()
+                call("b2y_upsample_nearest_bwd", ptr(gy), ops._pitch(gy), ptr(gx), ops._pitch(gx), self.B, src.H,
+                     src.W, src.C, int(s), stream_ptr())
+            elif kind == 'maxpool':
+                _, src, out, k, s, tiny = st
+                gy, gx, xv = G(out).view(), G(src).view(), src.view()
+                call("b2y_maxpool_bwd", ptr(xv), ops._pitch(xv), ptr(gy), ops._pitch(gy), ptr(gx), ops._pitch(gx),
+                     self.B, src.H, src.W, src.C, int(k), int(s), 1 if tiny else 0, stream_ptr())
+        return grads
+
+    def _conv_backward(self, r, grads, S, inv):
+        B = self.B
+        gy = self.grad_of[id(r.y)]
+        conv, bn = r.conv, r.bn
+        Ho, Wo = r.y.H, r.y.W
+        if bn is not None:
+            dy = gy.view()
+            if r.res is not None:   # fused shortcut: the same gradient also flows to the skip source
+                gs = self.grad_of[id(r.res)].view()
+                ops.add(gs, dy, out=gs)
+            dz = self.dz_scratch[:B * Ho * Wo * r.Cout].view(B, Ho, Wo, r.Cout)
+            dgb = self.dgb_scratch[:, :r.Cout]
+            dgb.zero_()
+            ops.bn_act_bwd(r.z.view(), dy, r.scale, r.shift, bn.weight.detach(), r.mean, r.invstd, r.act, r.slope,
+                           dx=dz, dgamma=dgb[0], dbeta=dgb[1])
+            grads[bn.weight] = dgb[0] * inv
+            grads[bn.bias] = dgb[1] * inv
+        else:
+            dz = gy.buf[..., :r.Cpad] if r.head else gy.view()
+            if r.act != 'linear':
+                raise NotImplementedError("activation without BatchNorm in training")
+            if conv.bias is not None:
+                db = self.dgb_scratch[1, :r.Cpad]
+                db.zero_()
+                ops.bias_act_bwd_reduce(dz, dz, r.ones, r.zeros, 'linear', dbeta=db)
+                grads[conv.bias] = db[:r.Cout] * inv
+        I = conv.in_channels
+        gw = torch.empty_like(conv.weight)
+        if r.stem:
+            gw.zero_()
+            d = ConvDesc(B, self.H, self.W, I, I, r.Cout, r.k, r.s, r.p, Ho, Wo, ops._pitch(dz), 0, 0.0, OUT_F16, 0)
+            call("b2y_stem_conv_bwd_weight", C.byref(d), ptr(self.x), ptr(dz), ptr(gw), inv, stream_ptr())
+        else:
+            dwp = self.dw_scratch[:r.Cpad * r.k * r.k * I].view(r.Cpad, r.k, r.k, I)
+            dwp.zero_()
+            ops.conv2d_bwd_weight(r.src.view(), dz, r.k, r.s, r.p, scale=inv, dw=dwp)
+            ops.unpack_wgrad(dwp[:r.Cout], gw)
+            gx = self.grad_of[id(r.src)]
+            ops.conv2d_bwd_data(dz, r.wT, (B, r.src.H, r.src.W, I), r.k, r.s, r.p, out=gx.view(), accumulate=True)
+        grads[conv.weight] = gw
+
+    # ---------------------------------------------------------------------------------------------------------
+    def run(self, x):
+        """autograd entry: returns (yolo_out list, feature_out)."""
+        outs = _DarknetTrain.apply(self, x, *self.params)
+        feats = LazyFeatures([None if t is None else t.view() for t in self.feature_views])
+        return list(outs), feats
+
+
+class _DarknetTrain(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, plan, x, *params):
+        ctx.plan = plan
+        ctx.params = params
+        with torch.no_grad():
+            outs = plan.forward(x)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *dps):
+        plan = ctx.plan
+        with torch.no_grad():
+            grads = plan.backward(dps)
+        out = []
+        for p in ctx.params:
+            g = grads.get(p)
+            out.append(g if (g is not None and p.requires_grad) else None)
+        return (None, None) + tuple(out)

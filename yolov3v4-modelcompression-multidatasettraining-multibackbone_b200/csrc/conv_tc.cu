@@ -94,7 +94,7 @@ static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const Conv
     }
     int tiles = p.num_m_tiles * p.num_n_tiles;
     int grid = tiles < g_num_sms ? tiles : g_num_sms;
-    kern<<<grid, 256, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p);
+    kern<<<grid, ConvTcEpi<BLOCK_N>::THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p);
     B2Y_CUDA_CHECK(cudaGetLastError());
     return B2Y_OK;
 }
@@ -407,6 +407,112 @@ extern "C" int b2y_conv2d_bwd_data(const b2y_conv_desc* d, const void* dy, const
 
 
 
+
+// ---- tensor-core stem ------------------------------------------------------------------------------------------
+// The image (NCHW fp32, Cin <= 4) is first re-laid as NHWC fp16 with the kw taps unrolled into the channel dim:
+//   packed[n][y][x][kw*Cin + c] = x[n][c][y][x + kw - pad]   (16 "channels", zero padded)
+// so that the conv becomes a k x 1 implicit GEMM with K = 16 per tap row on the same tcgen05 kernel.
+__global__ void stem_pack_kernel(const float* __restrict__ x, __half* __restrict__ out, int B, int Cin, int H, int W,
+                                 int k, int pad) {
+    const long long total = (long long)B * H * W;
+    for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < total;
+         pix += (long long)gridDim.x * blockDim.x) {
+        const int xo = (int)(pix % W);
+        const int yo = (int)((pix / W) % H);
+        const int n = (int)(pix / ((long long)W * H));
+        __align__(16) __half v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __float2half(0.f);
+        for (int kw = 0; kw < k; ++kw) {
+            const int xi = xo + kw - pad;
+            if (xi < 0 || xi >= W) continue;
+            for (int c = 0; c < Cin; ++c)
+                v[kw * Cin + c] = __float2half_rn(__ldg(x + (((long long)n * Cin + c) * H + yo) * W + xi));
+        }
+        uint4* op = reinterpret_cast<uint4*>(out + pix * 16);
+        op[0] = *reinterpret_cast<const uint4*>(&v[0]);
+        op[1] = *reinterpret_cast<const uint4*>(&v[8]);
+    }
+}
+
+// w (OIHW fp32, BN folded by the caller) -> [O][kh][16] fp16 with inner index kw*Cin + c
+__global__ void stem_pack_weights_kernel(const float* __restrict__ w, __half* __restrict__ out, int O, int Cin,
+                                         int k) {
+    const int total = O * k * 16;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int j = idx % 16;
+        const int r = (idx / 16) % k;
+        const int o = idx / (16 * k);
+        float v = 0.f;
+        if (j < k * Cin) {
+            const int kw = j / Cin, c = j % Cin;
+            v = w[(((long long)o * Cin + c) * k + r) * k + kw];
+        }
+        out[idx] = __float2half_rn(v);
+    }
+}
+
+extern "C" size_t b2y_stem_workspace_bytes(const b2y_conv_desc* d) {
+    if (!d) return 0;
+    return (size_t)d->batch * d->in_h * d->in_w * 16 * sizeof(__half);
+}
+
+extern "C" int b2y_pack_stem_weights(const float* w_oihw_folded, int out_c, int in_c, int ksize, void* w_stem,
+                                     void* stream) {
+    if (!w_oihw_folded || !w_stem || in_c * ksize > 16) return B2Y_ERR_INVALID;
+    stem_pack_weights_kernel<<<(out_c * ksize * 16 + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        w_oihw_folded, reinterpret_cast<__half*>(w_stem), out_c, in_c, ksize);
+    B2Y_CUDA_CHECK(cudaGetLastError());
+    return B2Y_OK;
+}
+
+extern "C" int b2y_stem_conv_fwd_tc(const b2y_conv_desc* d, const float* x_nchw, const void* w_stem, const float* bias,
+                                    void* workspace, void* y, float* stat_sum, float* stat_sqsum, void* stream) {
+    if (!d || !x_nchw || !w_stem || !workspace || !y) return B2Y_ERR_INVALID;
+    if (d->in_c * d->ksize > 16 || d->ksize > 16) return B2Y_ERR_UNSUPPORTED;
+    const int Ho = (d->in_h + 2 * d->pad - d->ksize) / d->stride + 1;
+    const int Wo = (d->in_w + 2 * d->pad - d->ksize) / d->stride + 1;
+    if (Ho != d->out_h || Wo != d->out_w) return B2Y_ERR_INVALID;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long pixels = (long long)d->batch * d->in_h * d->in_w;
+    int grid = (int)((pixels + 255) / 256);
+    if (grid > 148 * 32) grid = 148 * 32;
+    stem_pack_kernel<<<grid, 256, 0, st>>>(x_nchw, reinterpret_cast<__half*>(workspace), d->batch, d->in_c, d->in_h,
+                                           d->in_w, d->ksize, d->pad);
+    B2Y_CUDA_CHECK(cudaGetLastError());
+    GemmConvSpec g;
+    g.kind = CONV_KIND_F16;
+    g.a = workspace;
+    g.N = d->batch;
+    g.H = d->in_h;
+    g.W = d->in_w;
+    g.C = 16;
+    g.a_pitch = 16;
+    g.MH = Ho;
+    g.MW = Wo;
+    g.stride = d->stride;
+    g.lower_w = 0;            // the kw window is already centred by the pack
+    g.upper_w = 0;
+    g.lower_h = -d->pad;
+    g.upper_h = d->pad - (d->ksize - 1);
+    g.ntaps = d->ksize;
+    for (int r = 0; r < d->ksize; ++r) {
+        g.tap_oh[r] = (unsigned char)r;
+        g.tap_ow[r] = 0;
+    }
+    g.w = w_stem;
+    g.Nout = d->out_c;
+    EpilogueArgs e;
+    e.bias = bias;
+    e.act = d->act;
+    e.slope = d->slope;
+    e.out = y;
+    e.out_pitch = d->out_pitch;
+    e.out_dtype = OUT_F16;
+    e.stat_sum = stat_sum;
+    e.stat_sqsum = stat_sqsum;
+    return gemm_conv_launch(g, e, st);
+}
 
 extern "C" int b2y_conv2d_fwd(const b2y_conv_desc* d, const void* x, const void* w_packed, const float* bias,
                               const void* residual, void* y, void* stream) {

@@ -78,8 +78,15 @@ __device__ __forceinline__ float round_half_away(float x) {
     return copysignf(floorf(fabsf(x) + 0.5f), x);
 }
 
+template <int BLOCK_N>
+struct ConvTcEpi {
+    // two column groups of epilogue warps for wide tiles: more loads/stores in flight per SM
+    static constexpr int WARPS = BLOCK_N >= 128 ? 8 : 4;
+    static constexpr int THREADS = 128 + 32 * WARPS;
+};
+
 template <int BLOCK_N, int KBYTES, int KIND>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(ConvTcEpi<BLOCK_N>::THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const ConvTcParams p) {
     using Cfg = ConvTcCfg<BLOCK_N, KBYTES>;
@@ -115,7 +122,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full_bar[i], 1);
-            mbar_init(&tmem_empty_bar[i], 4);  // one arrive per epilogue warp
+            mbar_init(&tmem_empty_bar[i], ConvTcEpi<BLOCK_N>::WARPS);  // one arrive per epilogue warp
         }
         fence_barrier_init();
     }
@@ -213,8 +220,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else if (warp >= 4) {
         // ===================== epilogue =====================
-        const int ew = warp - 4;            // TMEM lanes [32*ew, 32*ew+32)
-        const int et = threadIdx.x - 128;   // 0..127
+        constexpr int EPI_WARPS = ConvTcEpi<BLOCK_N>::WARPS;
+        constexpr int EPI_THREADS = 32 * EPI_WARPS;
+        constexpr int COLS_PER_GROUP = BLOCK_N / (EPI_WARPS / 4);
+        const int ew = (warp - 4) & 3;          // TMEM lane quarter == warp_id % 4
+        const int cg = (warp - 4) >> 2;         // column group
+        const int et = threadIdx.x - 128;       // 0..EPI_THREADS-1
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -232,23 +243,41 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 row = ((long long)n_ * p.out_OH + (long long)p_ * p.out_ys + p.out_y0) * p.out_OW +
                       (long long)q_ * p.out_xs + p.out_x0;
             }
+            const int c_begin = cg * COLS_PER_GROUP;
+            const int c_end = c_begin + COLS_PER_GROUP;
+            // residual prefetch (one 32-column chunk ahead; the first chunk is issued before the accumulator wait)
+            const __half* res_row = (p.res != nullptr && row_ok) ? p.res + row * p.res_pitch + n0 : nullptr;
+            const bool res_vec = res_row != nullptr && ((reinterpret_cast<uintptr_t>(res_row) & 15) == 0);
+            uint4 rnext[4];
+            if (res_vec && n0 + c_begin + 32 <= p.Cout) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) rnext[q] = __ldg(reinterpret_cast<const uint4*>(res_row + c_begin) + q);
+            }
 
             // stage the bias slice for this tile
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            for (int i = et; i < BLOCK_N; i += 128) {
+            asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+            for (int i = et; i < BLOCK_N; i += EPI_THREADS) {
                 const int n = n0 + i;
                 sbias[i] = (p.bias != nullptr && n < p.Cout) ? __ldg(p.bias + n) : 0.f;
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
 
             mbar_wait(&tmem_full_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BLOCK_N);
 
 #pragma unroll 1
-            for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+            for (int c0 = c_begin; c0 < c_end; c0 += 32) {
                 uint32_t raw[32];
                 tmem_ld_32x32(taddr_row + (uint32_t)c0, raw);
+                uint4 rcur[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) rcur[q] = rnext[q];
+                if (res_vec && c0 + 32 < c_end && n0 + c0 + 64 <= p.Cout) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        rnext[q] = __ldg(reinterpret_cast<const uint4*>(res_row + c0 + 32) + q);
+                }
                 tc_wait_ld();
                 if (n0 + c0 >= p.Cout) continue;  // warp-uniform
 
@@ -315,10 +344,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (row_ok) {
                     if (p.res != nullptr) {
                         const __half* rp = p.res + row * p.res_pitch + n0 + c0;
-                        if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
+                        if (nvalid == 32 && res_vec) {
 #pragma unroll
                             for (int q = 0; q < 4; ++q) {
-                                uint4 u = __ldg(reinterpret_cast<const uint4*>(rp) + q);
+                                const uint4 u = rcur[q];
                                 const __half2* h2 = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
                                 for (int t = 0; t < 4; ++t) {

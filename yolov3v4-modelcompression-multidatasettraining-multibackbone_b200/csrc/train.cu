@@ -274,3 +274,214 @@ extern "C" int b2y_sgd_nesterov(float* param, const float* grad, float* momentum
     B2Y_CUDA_CHECK(cudaGetLastError());
     return B2Y_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// backward of the data-movement layers (gradients are NHWC fp16, accumulated in place)
+// ------------------------------------------------------------------------------------------------
+// YOLO head: dp fp32 [B][na][ny][nx][no] -> d(raw) fp16 [B][ny][nx][pitch] (channel a*no+o), times `scale`
+__global__ void yolo_grad_to_raw_kernel(const float* __restrict__ dp, __half* __restrict__ draw, long long pitch,
+                                        int B, int na, int no, int ny, int nx, float scale) {
+    const long long total = (long long)B * ny * nx * pitch;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % pitch);
+        long long t = idx / pitch;
+        const int x = (int)(t % nx);
+        t /= nx;
+        const int y = (int)(t % ny);
+        const int b = (int)(t / ny);
+        float v = 0.f;
+        if (c < na * no) {
+            const int a = c / no, o = c - a * no;
+            v = dp[((((long long)b * na + a) * ny + y) * nx + x) * no + o] * scale;
+        }
+        draw[idx] = __float2half_rn(v);
+    }
+}
+extern "C" int b2y_yolo_grad_to_raw(const float* dp, void* draw, long long raw_pitch, int batch, int na, int no,
+                                    int ny, int nx, float scale, void* stream) {
+    if (!dp || !draw || raw_pitch < (long long)na * no) return B2Y_ERR_INVALID;
+    const long long total = (long long)batch * ny * nx * raw_pitch;
+    yolo_grad_to_raw_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        dp, reinterpret_cast<__half*>(draw), raw_pitch, batch, na, no, ny, nx, scale);
+    B2Y_CUDA_CHECK(cudaGetLastError());
+    return B2Y_OK;
+}
+
+// nearest upsample backward: dx[n,y,x,:] += sum_{dy,dx<s} dup[n, y*s+dy, x*s+dx, :]
+__global__ void upsample_bwd_kernel(const __half* __restrict__ dy, long long dyp, __half* __restrict__ dx,
+                                    long long dxp, int B, int H, int W, int C, int s) {
+    const int CV = C / 8;
+    const long long total = (long long)B * H * W * CV;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int cv = (int)(idx % CV);
+        long long pix = idx / CV;
+        const int x = (int)(pix % W);
+        const int y = (int)((pix / W) % H);
+        const int n = (int)(pix / ((long long)W * H));
+        float acc[8];
+        {
+            const uint4 v = *(reinterpret_cast<const uint4*>(dx + pix * dxp) + cv);
+            const __half* h = reinterpret_cast<const __half*>(&v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = __half2float(h[j]);
+        }
+        for (int a = 0; a < s; ++a)
+            for (int b = 0; b < s; ++b) {
+                const long long op = ((long long)n * H * s + (y * s + a)) * (W * s) + (x * s + b);
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(dy + op * dyp) + cv);
+                const __half* h = reinterpret_cast<const __half*>(&v);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] += __half2float(h[j]);
+            }
+        uint4 o;
+        __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) oh[j] = __floats2half2_rn(acc[2 * j], acc[2 * j + 1]);
+        reinterpret_cast<uint4*>(dx + pix * dxp)[cv] = o;
+    }
+}
+extern "C" int b2y_upsample_nearest_bwd(const void* dy, long long dy_pitch, void* dx, long long dx_pitch, int batch,
+                                        int in_h, int in_w, int c, int scale, void* stream) {
+    if (!dy || !dx || c % 8 != 0 || dy_pitch % 8 != 0 || dx_pitch % 8 != 0 || scale < 1) return B2Y_ERR_INVALID;
+    const long long total = (long long)batch * in_h * in_w * (c / 8);
+    upsample_bwd_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const __half*>(dy), dy_pitch, reinterpret_cast<__half*>(dx), dx_pitch, batch, in_h, in_w, c,
+        scale);
+    B2Y_CUDA_CHECK(cudaGetLastError());
+    return B2Y_OK;
+}
+
+// maxpool backward: every output pixel re-finds its arg-max (first maximum in row-major window order, as
+// torch's max_pool2d does) and adds its gradient there (windows overlap for stride 1 -> fp16x2 atomics).
+__global__ void maxpool_bwd_kernel(const __half* __restrict__ x, long long xp, const __half* __restrict__ dy,
+                                   long long dyp, __half* __restrict__ dx, long long dxp, int B, int H, int W, int C,
+                                   int k, int stride, int pad, int Ho, int Wo, int zero_pad) {
+    const int CV = C / 2;
+    const long long total = (long long)B * Ho * Wo * CV;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int cv = (int)(idx % CV);
+        long long pix = idx / CV;
+        const int xo = (int)(pix % Wo);
+        const int yo = (int)((pix / Wo) % Ho);
+        const int n = (int)(pix / ((long long)Wo * Ho));
+        float best0 = -INFINITY, best1 = -INFINITY;
+        long long arg0 = -1, arg1 = -1;
+        for (int kh = 0; kh < k; ++kh) {
+            const int yi = yo * stride - pad + kh;
+            for (int kw = 0; kw < k; ++kw) {
+                const int xi = xo * stride - pad + kw;
+                if (yi < 0 || yi >= H || xi < 0 || xi >= W) {
+                    if (zero_pad) {  // the zero padding competes (and swallows the gradient when it wins)
+                        if (0.f > best0) { best0 = 0.f; arg0 = -1; }
+                        if (0.f > best1) { best1 = 0.f; arg1 = -1; }
+                    }
+                    continue;
+                }
+                const long long ip = ((long long)n * H + yi) * W + xi;
+                const __half2 v = *reinterpret_cast<const __half2*>(x + ip * xp + cv * 2);
+                const float a = __low2float(v), b = __high2float(v);
+                if (a > best0) { best0 = a; arg0 = ip; }
+                if (b > best1) { best1 = b; arg1 = ip; }
+            }
+        }
+        const __half2 g = *reinterpret_cast<const __half2*>(dy + pix * dyp + cv * 2);
+        const __half zero = __float2half(0.f);
+        if (arg0 >= 0 && arg0 == arg1) {
+            atomicAdd(reinterpret_cast<__half2*>(dx + arg0 * dxp + cv * 2), g);
+        } else {
+            if (arg0 >= 0) atomicAdd(reinterpret_cast<__half2*>(dx + arg0 * dxp + cv * 2), __halves2half2(__low2half(g), zero));
+            if (arg1 >= 0) atomicAdd(reinterpret_cast<__half2*>(dx + arg1 * dxp + cv * 2), __halves2half2(zero, __high2half(g)));
+        }
+    }
+}
+extern "C" int b2y_maxpool_bwd(const void* x, long long x_pitch, const void* dy, long long dy_pitch, void* dx,
+                               long long dx_pitch, int batch, int in_h, int in_w, int c, int ksize, int stride,
+                               int pad_mode, void* stream) {
+    if (!x || !dy || !dx || c % 2 != 0 || x_pitch % 2 != 0 || dy_pitch % 2 != 0 || dx_pitch % 2 != 0)
+        return B2Y_ERR_INVALID;
+    int pad, Ho, Wo;
+    if (pad_mode == 1) {
+        pad = 0;
+        Ho = (in_h + 1 - ksize) / stride + 1;
+        Wo = (in_w + 1 - ksize) / stride + 1;
+    } else {
+        pad = (ksize - 1) / 2;
+        Ho = (in_h + 2 * pad - ksize) / stride + 1;
+        Wo = (in_w + 2 * pad - ksize) / stride + 1;
+    }
+    const long long total = (long long)batch * Ho * Wo * (c / 2);
+    maxpool_bwd_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const __half*>(x), x_pitch, reinterpret_cast<const __half*>(dy), dy_pitch,
+        reinterpret_cast<__half*>(dx), dx_pitch, batch, in_h, in_w, c, ksize, stride, pad, Ho, Wo, pad_mode == 1);
+    B2Y_CUDA_CHECK(cudaGetLastError());
+    return B2Y_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stem weight gradient (Cin <= 4, NCHW fp32 image): dW[co][ci][kh][kw] += scale * sum_pix dz[pix][co] * x[...]
+// CTA = 32 output channels x 8 tap groups; each thread keeps <= TPG taps of one output channel in registers.
+// ------------------------------------------------------------------------------------------------
+template <int TPG>
+__global__ void __launch_bounds__(256)
+stem_wgrad_kernel(const float* __restrict__ x, const __half* __restrict__ dz, long long dzp, float* __restrict__ dw,
+                  int B, int Cin, int H, int W, int Cout, int k, int stride, int pad, int Ho, int Wo, float scale) {
+    const int taps = Cin * k * k;
+    const int co_l = threadIdx.x & 31;
+    const int grp = threadIdx.x >> 5;  // 0..7
+    const long long M = (long long)B * Ho * Wo;
+    for (int co0 = 0; co0 < Cout; co0 += 32) {
+        const int co = co0 + co_l;
+        float acc[TPG];
+        int t_ci[TPG], t_kh[TPG], t_kw[TPG];
+#pragma unroll
+        for (int j = 0; j < TPG; ++j) {
+            acc[j] = 0.f;
+            const int t = grp * TPG + j;
+            t_ci[j] = t / (k * k);
+            t_kh[j] = (t / k) % k;
+            t_kw[j] = t % k;
+        }
+        const long long per = (M + gridDim.x - 1) / gridDim.x;
+        const long long m0 = (long long)blockIdx.x * per;
+        const long long m1 = m0 + per < M ? m0 + per : M;
+        for (long long m = m0; m < m1; ++m) {
+            const int xo = (int)(m % Wo);
+            const int yo = (int)((m / Wo) % Ho);
+            const int n = (int)(m / ((long long)Wo * Ho));
+            const float g = co < Cout ? __half2float(dz[m * dzp + co]) : 0.f;
+#pragma unroll
+            for (int j = 0; j < TPG; ++j) {
+                if (grp * TPG + j < taps) {
+                    const int yi = yo * stride - pad + t_kh[j], xi = xo * stride - pad + t_kw[j];
+                    float v = 0.f;
+                    if (yi >= 0 && yi < H && xi >= 0 && xi < W)
+                        v = __ldg(x + (((long long)n * Cin + t_ci[j]) * H + yi) * W + xi);
+                    acc[j] = fmaf(g, v, acc[j]);
+                }
+            }
+        }
+        if (co < Cout) {
+#pragma unroll
+            for (int j = 0; j < TPG; ++j)
+                if (grp * TPG + j < taps) atomicAdd(dw + (long long)co * taps + grp * TPG + j, acc[j] * scale);
+        }
+    }
+}
+extern "C" int b2y_stem_conv_bwd_weight(const b2y_conv_desc* d, const float* x_nchw, const void* dz, float* dw_oihw,
+                                        float scale, void* stream) {
+    if (!d || !x_nchw || !dz || !dw_oihw) return B2Y_ERR_INVALID;
+    const int taps = d->in_c * d->ksize * d->ksize;
+    if (d->in_c > 4 || taps > 8 * 5) return B2Y_ERR_UNSUPPORTED;
+    const long long M = (long long)d->batch * d->out_h * d->out_w;
+    int grid = (int)((M + 1023) / 1024);
+    if (grid > 148 * 8) grid = 148 * 8;
+    if (grid < 1) grid = 1;
+    stem_wgrad_kernel<5><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        x_nchw, reinterpret_cast<const __half*>(dz), d->out_pitch, dw_oihw, d->batch, d->in_c, d->in_h, d->in_w,
+        d->out_c, d->ksize, d->stride, d->pad, d->out_h, d->out_w, scale);
+    B2Y_CUDA_CHECK(cudaGetLastError());
+    return B2Y_OK;
+}
