@@ -1,0 +1,83 @@
+"""CPU, world_size 2, gloo: host logic of the data-parallel path (b200yolo/parallel.py): parameter flattening,
+rank-0 broadcast of parameters and BN buffers, the single gradient all-reduce and its mean-over-ranks semantics
+(the same formula DDP(reference) produces)."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+import torch.nn as nn
+
+import helpers  # noqa: F401  (sys.path)
+
+
+class Toy(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.module_list = nn.ModuleList([nn.Sequential()])
+        self.module_list[0].add_module('Conv2d', nn.Conv2d(3, 4, 3, bias=False))
+        self.module_list[0].add_module('BatchNorm2d', nn.BatchNorm2d(4))
+        self.head = nn.Conv2d(4, 2, 1, bias=True)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from b200yolo.parallel import FlatDataParallel, _is_decay_param
+    torch.manual_seed(100 + rank)               # ranks start from different weights / buffers
+    m = Toy()
+    with torch.no_grad():
+        m.module_list[0][1].running_mean.fill_(float(rank + 1))
+    dp = FlatDataParallel(m)
+    res = {}
+    res["params"] = dp.flat_param.clone()
+    res["names"] = list(dp.names)
+    res["n_decay"] = dp.n_decay
+    # params are views of the flat buffer
+    dp.flat_param.mul_(1.0)
+    res["views"] = all(p.data_ptr() >= dp.flat_param.data_ptr() for p in dp.params)
+    # per-rank gradients written through the .grad views (what the training plan does through the sink)
+    g = torch.Generator().manual_seed(7 + rank)
+    local = []
+    for p in dp.params:
+        v = torch.randn(p.shape, generator=g)
+        dp.grad_views[id(p)].copy_(v)
+        local.append(v.reshape(-1))
+    res["local_grad"] = torch.cat(local)
+    dp.reduce_gradients()
+    res["avg"] = dp.averaged_gradients().clone()
+    # buffer broadcast: rank 0's running stats win
+    m.train()
+    dp._broadcast_buffers()
+    res["rm"] = m.module_list[0][1].running_mean.clone()
+    res["decay_flags"] = [_is_decay_param(n) for n in dp.names]
+    out[rank] = res
+    dist.destroy_process_group()
+
+
+def test_flat_data_parallel_gloo():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    r0, r1 = out[0], out[1]
+    assert torch.equal(r0["params"], r1["params"]), "parameters must be broadcast from rank 0"
+    assert r0["views"] and r1["views"]
+    # one all-reduce == mean of the per-rank gradients, bit exact for 2 ranks
+    expect = (r0["local_grad"] + r1["local_grad"]) / 2
+    assert torch.equal(r0["avg"], expect) and torch.equal(r1["avg"], expect)
+    assert torch.equal(r0["rm"], torch.ones(4)) and torch.equal(r1["rm"], torch.ones(4))
+    # optimiser grouping of the reference: weight decay only on '...Conv2d.weight'
+    names, flags = r0["names"], r0["decay_flags"]
+    assert flags == [("Conv2d.weight" in n and ".bias" not in n) for n in names]
+    assert r0["n_decay"] == 4 * 3 * 3 * 3 and names[0] == "module_list.0.Conv2d.weight"

@@ -1,0 +1,113 @@
+"""Data parallelism for the Darknet hot path: one process per GPU, ONE gradient all-reduce per step.
+
+Reference: train.py:93-107 (NCCL process group), :219-221 (DistributedDataParallel, find_unused_parameters=True),
+DDP's bucketed all-reduce (SUM, then / world) overlapped with backward, rank-0 buffer broadcast every forward
+(broadcast_buffers=True), optimiser groups train.py:125-144 (weight decay on 'Conv2d.weight' only).
+
+Here all parameters live in one flat fp32 buffer and all gradients in another (the training plan writes weight
+gradients straight into their slice), so the exchange step is exactly one `all_reduce(flat_grad, SUM)` over
+NCCL/NVLink and the 1/world factor is folded into the fused SGD-Nesterov kernel.  Semantics kept from DDP:
+  * reduced gradient = mean over ranks of the per-rank gradients (each rank's loss uses its own shard),
+  * BatchNorm statistics are per replica; running buffers follow rank 0 (broadcast before each forward),
+  * parameters are broadcast from rank 0 at construction.
+`torch.distributed` provides the communicator (backend "nccl" on GPUs, "gloo" in the CPU tests).
+"""
+import torch
+import torch.distributed as dist
+
+
+def _is_decay_param(name):
+    """train.py:126-133: pg1 (weight decay) = names containing 'Conv2d.weight'; '.bias' -> pg2; rest -> pg0."""
+    return ('.bias' not in name) and ('Conv2d.weight' in name)
+
+
+class FlatDataParallel:
+    def __init__(self, model, process_group=None, broadcast_buffers=True):
+        self.module = model
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(process_group) if dist.is_initialized() else 0
+        self.broadcast_buffers = broadcast_buffers
+        named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+        decay = [(n, p) for n, p in named if _is_decay_param(n)]
+        other = [(n, p) for n, p in named if not _is_decay_param(n)]
+        self.names = [n for n, _ in decay + other]
+        self.params = [p for _, p in decay + other]
+        self.n_decay = sum(p.numel() for _, p in decay)
+        total = sum(p.numel() for p in self.params)
+        dev = self.params[0].device
+        self.flat_param = torch.empty(total, dtype=torch.float32, device=dev)
+        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_mom = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.grad_views = {}
+        off = 0
+        with torch.no_grad():
+            for p in self.params:
+                n = p.numel()
+                self.flat_param[off:off + n].copy_(p.detach().reshape(-1))
+                p.data = self.flat_param[off:off + n].view_as(p)          # parameters become views of the flat buffer
+                gv = self.flat_grad[off:off + n].view_as(p)
+                p.grad = gv
+                self.grad_views[id(p)] = gv
+                off += n
+        self.buffers = [b for b in model.buffers() if b.dtype.is_floating_point]
+        self.steps = 0
+        if self.world > 1:
+            dist.broadcast(self.flat_param, src=0, group=self.pg)           # N2: parameters from rank 0
+            self._broadcast_buffers()
+        eng = getattr(model, 'engine', None)
+        if callable(eng):
+            model.engine().invalidate()
+        model._b2y_grad_sink = self.grad_views     # the training plan writes gradients straight into flat_grad
+
+    # DDP-like attribute forwarding so that utils.utils.compute_loss(model=wrapper) keeps working
+    def __getattr__(self, name):
+        return getattr(self.__dict__['module'], name)
+
+    def _broadcast_buffers(self):
+        if not self.buffers:
+            return
+        flat = torch.cat([b.reshape(-1) for b in self.buffers])
+        dist.broadcast(flat, src=0, group=self.pg)
+        off = 0
+        for b in self.buffers:
+            n = b.numel()
+            b.copy_(flat[off:off + n].view_as(b))
+            off += n
+
+    def __call__(self, x, *a, **k):
+        if self.world > 1 and self.broadcast_buffers and self.module.training:
+            self._broadcast_buffers()                                       # N3: rank-0 running stats win
+        return self.module(x, *a, **k)
+
+    def zero_grad(self):
+        self.flat_grad.zero_()
+
+    def reduce_gradients(self, async_op=False):
+        """The single exchange step of the data-parallel path (N4): SUM over ranks; the mean is taken in step()."""
+        if self.world > 1:
+            return dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.pg, async_op=async_op)
+        return None
+
+    def averaged_gradients(self):
+        """flat gradient divided by world (what DDP leaves in .grad) -- used by the tests."""
+        return self.flat_grad / float(self.world)
+
+    def step(self, lr, momentum=0.937, weight_decay=0.000484, nesterov=True):
+        """Fused SGD-Nesterov over the flat buffers (two launches: decayed conv weights, everything else)."""
+        from . import ops
+        assert nesterov, "the fused kernel implements the reference's nesterov=True configuration"
+        first = self.steps == 0
+        gs = 1.0 / float(self.world)
+        nd = self.n_decay
+        if nd:
+            ops.sgd_nesterov(self.flat_param[:nd], self.flat_grad[:nd], self.flat_mom[:nd], lr, momentum, weight_decay,
+                             grad_scale=gs, first_step=first)
+        if nd < self.flat_param.numel():
+            ops.sgd_nesterov(self.flat_param[nd:], self.flat_grad[nd:], self.flat_mom[nd:], lr, momentum, 0.0,
+                             grad_scale=gs, first_step=first)
+        self.steps += 1
+        eng = self.module.__dict__.get('_engine')
+        if eng is not None:
+            for plan in eng.plans.values():
+                plan.param_version = None    # weights changed through the flat buffer: re-pack on the next forward

@@ -334,6 +334,7 @@ class TrainPlan:
         """dps: gradients w.r.t. the yolo outputs p (fp32). Returns {param: grad} for every model parameter."""
         S = float(getattr(self.model, 'grad_scale', 1024.0))
         inv = 1.0 / S
+        self.sink = getattr(self.model, '_b2y_grad_sink', None)   # FlatDataParallel: write into the flat buffer
         for gb in self.grad_bufs:
             gb.zero_()
         grads = {}
@@ -386,8 +387,8 @@ class TrainPlan:
             dgb.zero_()
             ops.bn_act_bwd(r.z.view(), dy, r.scale, r.shift, bn.weight.detach(), r.mean, r.invstd, r.act, r.slope,
                            dx=dz, dgamma=dgb[0], dbeta=dgb[1])
-            grads[bn.weight] = dgb[0] * inv
-            grads[bn.bias] = dgb[1] * inv
+            self._emit(grads, bn.weight, dgb[0], inv)
+            self._emit(grads, bn.bias, dgb[1], inv)
         else:
             dz = gy.buf[..., :r.Cpad] if r.head else gy.view()
             if r.act != 'linear':
@@ -396,9 +397,12 @@ class TrainPlan:
                 db = self.dgb_scratch[1, :r.Cpad]
                 db.zero_()
                 ops.bias_act_bwd_reduce(dz, dz, r.ones, r.zeros, 'linear', dbeta=db)
-                grads[conv.bias] = db[:r.Cout] * inv
+                self._emit(grads, conv.bias, db[:r.Cout], inv)
         I = conv.in_channels
-        gw = torch.empty_like(conv.weight)
+        gw = self.sink.get(id(conv.weight)) if self.sink is not None else None
+        if gw is None:
+            gw = torch.empty_like(conv.weight)
+            grads[conv.weight] = gw
         if r.stem:
             gw.zero_()
             d = ConvDesc(B, self.H, self.W, I, I, r.Cout, r.k, r.s, r.p, Ho, Wo, ops._pitch(dz), 0, 0.0, OUT_F16, 0)
@@ -410,7 +414,13 @@ class TrainPlan:
             ops.unpack_wgrad(dwp[:r.Cout], gw)
             gx = self.grad_of[id(r.src)]
             ops.conv2d_bwd_data(dz, r.wT, (B, r.src.H, r.src.W, I), r.k, r.s, r.p, out=gx.view(), accumulate=True)
-        grads[conv.weight] = gw
+
+    def _emit(self, grads, param, src, alpha):
+        dst = self.sink.get(id(param)) if self.sink is not None else None
+        if dst is None:
+            grads[param] = src * alpha
+        else:
+            ops.axpby(src.contiguous(), dst, alpha, 0.0)
 
     # ---------------------------------------------------------------------------------------------------------
     def run(self, x):

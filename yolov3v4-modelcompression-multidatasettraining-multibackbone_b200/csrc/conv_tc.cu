@@ -412,26 +412,36 @@ extern "C" int b2y_conv2d_bwd_data(const b2y_conv_desc* d, const void* dy, const
 // The image (NCHW fp32, Cin <= 4) is first re-laid as NHWC fp16 with the kw taps unrolled into the channel dim:
 //   packed[n][y][x][kw*Cin + c] = x[n][c][y][x + kw - pad]   (16 "channels", zero padded)
 // so that the conv becomes a k x 1 implicit GEMM with K = 16 per tap row on the same tcgen05 kernel.
-__global__ void stem_pack_kernel(const float* __restrict__ x, __half* __restrict__ out, int B, int Cin, int H, int W,
-                                 int k, int pad) {
+template <int CIN, int K>
+__global__ void stem_pack_kernel(const float* __restrict__ x, __half* __restrict__ out, int B, int H, int W,
+                                 int pad) {
+    // one thread per pixel; all indices static so the 16-entry row lives in registers
     const long long total = (long long)B * H * W;
+    const long long plane = (long long)H * W;
     for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < total;
          pix += (long long)gridDim.x * blockDim.x) {
         const int xo = (int)(pix % W);
-        const int yo = (int)((pix / W) % H);
-        const int n = (int)(pix / ((long long)W * H));
-        __align__(16) __half v[16];
+        const long long n = pix / plane;
+        const long long in_plane = pix - n * plane;     // yo*W + xo
+        const float* xb = x + n * CIN * plane + in_plane;
+        float v[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = __float2half(0.f);
-        for (int kw = 0; kw < k; ++kw) {
+        for (int j = 0; j < 16; ++j) v[j] = 0.f;
+#pragma unroll
+        for (int kw = 0; kw < K; ++kw) {
             const int xi = xo + kw - pad;
-            if (xi < 0 || xi >= W) continue;
-            for (int c = 0; c < Cin; ++c)
-                v[kw * Cin + c] = __float2half_rn(__ldg(x + (((long long)n * Cin + c) * H + yo) * W + xi));
+            if (xi >= 0 && xi < W) {
+#pragma unroll
+                for (int c = 0; c < CIN; ++c) v[kw * CIN + c] = __ldg(xb + c * plane + (kw - pad));
+            }
         }
+        uint4 o[2];
+        __half2* oh = reinterpret_cast<__half2*>(o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) oh[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
         uint4* op = reinterpret_cast<uint4*>(out + pix * 16);
-        op[0] = *reinterpret_cast<const uint4*>(&v[0]);
-        op[1] = *reinterpret_cast<const uint4*>(&v[8]);
+        op[0] = o[0];
+        op[1] = o[1];
     }
 }
 
@@ -477,8 +487,14 @@ extern "C" int b2y_stem_conv_fwd_tc(const b2y_conv_desc* d, const float* x_nchw,
     const long long pixels = (long long)d->batch * d->in_h * d->in_w;
     int grid = (int)((pixels + 255) / 256);
     if (grid > 148 * 32) grid = 148 * 32;
-    stem_pack_kernel<<<grid, 256, 0, st>>>(x_nchw, reinterpret_cast<__half*>(workspace), d->batch, d->in_c, d->in_h,
-                                           d->in_w, d->ksize, d->pad);
+    __half* ws = reinterpret_cast<__half*>(workspace);
+#define B2Y_STEM_PACK(CI, KK)                                                                             \
+    if (d->in_c == CI && d->ksize == KK) {                                                                \
+        stem_pack_kernel<CI, KK><<<grid, 256, 0, st>>>(x_nchw, ws, d->batch, d->in_h, d->in_w, d->pad);   \
+    } else
+    B2Y_STEM_PACK(3, 3) B2Y_STEM_PACK(1, 3) B2Y_STEM_PACK(3, 5) B2Y_STEM_PACK(1, 5) B2Y_STEM_PACK(4, 3)
+    B2Y_STEM_PACK(3, 1) B2Y_STEM_PACK(1, 1) B2Y_STEM_PACK(2, 3) { return B2Y_ERR_UNSUPPORTED; }
+#undef B2Y_STEM_PACK
     B2Y_CUDA_CHECK(cudaGetLastError());
     GemmConvSpec g;
     g.kind = CONV_KIND_F16;
