@@ -199,6 +199,18 @@ int b2y_qconv2d_fwd(const b2y_qconv_desc* d, const void* x_i8, const void* w_i8,
 int b2y_pack_qconv_weights(const float* w_oihw_folded, int out_c, int in_c, int ksize, float w_scale, float lo,
                            float hi, void* w_i8, void* stream);
 
+/* int8 graph glue (eval): quantised shortcut (ptq_cos.py:876-884, 931-933), concat requantisation (ptq_cos.py:1540-1546),
+ * nearest upsample of codes, and the fp32 first layer with int8 output (the image is not on an int8 grid) */
+int b2y_qshortcut_i8(const void* x, long long x_pitch, const void* a, long long a_pitch, void* out, long long out_pitch,
+                     long long pixels, int c, float sx_in, float scale_x, float sa_in, float scale_a, float scale_sum,
+                     float lo, float hi, void* stream);
+int b2y_requant_i8(const void* x, long long x_pitch, void* out, long long out_pitch, long long pixels, int c,
+                   float s_in, float s_out, float lo, float hi, void* stream);
+int b2y_upsample_nearest_i8(const void* x, long long x_pitch, void* y, long long y_pitch, int batch, int in_h,
+                            int in_w, int c, int scale, void* stream);
+int b2y_stem_conv_fwd_q(const b2y_conv_desc* d, const float* x_nchw, const float* w_q, const float* bias_q, void* y_i8,
+                        float out_scale, float lo, float hi, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Training: BatchNorm (batch statistics), backward convolutions, optimiser
  * models.py:92-113 under autograd; train.py:135-151,437-459

@@ -18,10 +18,10 @@ GRAD_ELEM_TOL = 8e-2    # max |d| relative to the tensor's max |grad|
 @pytest.mark.parametrize("name", ["yolov3-tiny", "yolov3", "yolov4"])
 def test_train_step_parity(name):
     from utils import utils as my_utils
-    g = golden("%s_64_train" % name)
+    g = golden("%s_128_train" % name)
     model = attach_hyp(build_model(name, device="cuda")).train()
-    x = orc.synth_images(2, 64, 64, seed=0).cuda()
-    t = orc.synth_targets(2, 6, 80, seed=1).cuda()
+    x = orc.synth_images(4, 128, 128, seed=0).cuda()
+    t = orc.synth_targets(4, 6, 80, seed=1).cuda()
     pred, feats = model(x)
     loss, items = my_utils.compute_loss(pred, t, model)
     loss.backward()
@@ -64,8 +64,8 @@ def test_train_step_then_optimizer_changes_output():
     from utils import utils as my_utils
     model = attach_hyp(build_model("yolov3-tiny", device="cuda")).train()
     opt = torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.9, nesterov=True)
-    x = orc.synth_images(2, 64, 64, seed=0).cuda()
-    t = orc.synth_targets(2, 6, 80, seed=1).cuda()
+    x = orc.synth_images(4, 128, 128, seed=0).cuda()
+    t = orc.synth_targets(4, 6, 80, seed=1).cuda()
     losses = []
     for _ in range(4):
         opt.zero_grad()

@@ -34,10 +34,10 @@ def test_eval_forward_matches_reference(name, B, S, seed):
 
 @pytest.mark.parametrize("name", ["yolov3-tiny", "yolov3", "yolov4"])
 def test_train_forward_loss_backward_matches_reference(name):
-    g = golden("%s_64_train" % name)
+    g = golden("%s_128_train" % name)
     sd = _state(name, requires_grad=True)
-    x = orc.synth_images(2, 64, 64, seed=0)
-    t = orc.synth_targets(2, 6, 80, seed=1)
+    x = orc.synth_images(4, 128, 128, seed=0)
+    t = orc.synth_targets(4, 6, 80, seed=1)
     p, stats = orc.darknet_forward(module_defs(name), sd, x, name, training=True)
     for i, pi in enumerate(p):
         np.testing.assert_allclose(pi.detach().numpy(), g["p%d" % i], rtol=1e-3, atol=1e-3)

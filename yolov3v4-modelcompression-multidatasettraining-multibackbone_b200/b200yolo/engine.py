@@ -439,6 +439,23 @@ class Engine:
     def invalidate(self):
         self.plans.clear()
 
+    def _forward_quantized(self, x):
+        model = self.model
+        if model.quantized != 3:
+            raise NotImplementedError("quantized=%d: only the PTQ graph (quantized=3) has an INT8 engine in this "
+                                      "round (DESIGN.md)" % model.quantized)
+        if model.training:
+            raise NotImplementedError(
+                "PTQ calibration forwards (q_model.train(), PTQ.py:76-88) are not executed natively yet: load a "
+                "calibrated state_dict (PTQ.pt) and run q_model.eval() -- see INTEGRATION.md")
+        key = (tuple(x.shape), 'q3', x.device.index)
+        plan = self.plans.get(key)
+        if plan is None:
+            from .qengine import QPlan
+            plan = QPlan(model, tuple(x.shape), x.device)
+            self.plans[key] = plan
+        return plan.forward(x)
+
     def plan_for(self, x):
         self.forward(x)
         model = self.model
@@ -448,7 +465,7 @@ class Engine:
     def forward(self, x):
         model = self.model
         if model.quantized != -1:
-            raise NotImplementedError("quantized execution goes through b200yolo.qengine")
+            return self._forward_quantized(x)
         keep = bool(model.keep_features)
         key = (tuple(x.shape), bool(model.training), x.device.index, keep)
         plan = self.plans.get(key)

@@ -1,0 +1,201 @@
+"""INT8 graph executor for a PTQ-calibrated Darknet (quantized=3, reference PTQ.py:92-102 eval path).
+
+The reference *simulates* int8 in fp32: every tensor is a float on a power-of-two grid, convs are F.conv2d on those
+floats (utils/quantized/quantized_ptq_cos.py:288-296).  Because all scales are powers of two the products are exact
+integers times a power of two, so the same arithmetic runs here on the real int8 codes:
+
+   conv      int8 x int8 -> int32 on tcgen05 kind::i8, epilogue  acc*(s_in*s_w) + q_bias -> act -> requant(s_act)
+   shortcut  b2y_qshortcut_i8 (both addends rounded onto scale_x / scale_a, sum requantised to scale_sum)
+   concat    b2y_requant_i8 of every source onto the concat scale, written into its channel slot
+   upsample  nearest copy of codes
+   layer 0   fp32 direct conv of the float image on the fake-quantised weights (as the reference), int8 out
+   heads     fp32 fake-quant values for the (fp32) YOLO decode kernel
+"""
+import ctypes as C
+
+import torch
+
+from . import ops
+from .engine import _Tensor
+from .lib import OUT_F32, OUT_I8, call, ptr, stream_ptr
+
+_ACT_NAME = {'leaky': 'leaky', 'relu6': 'relu6', 'h_swish': 'h_swish', 'relu': 'relu', 'mish': 'mish',
+             'linear': 'linear'}
+
+
+def _s(t):
+    return float(t.reshape(-1)[0])
+
+
+class QPlan:
+    def __init__(self, model, x_shape, device):
+        self.model, self.device = model, device
+        self.B, self.Cin, self.H, self.W = x_shape
+        self.steps = []
+        self.prepared = False
+        self._build()
+
+    def _build(self):
+        model, B, dev = self.model, self.B, self.device
+        defs, mods = model.module_defs, model.module_list
+        n = len(defs)
+        shapes, prev = [], (self.Cin, self.H, self.W)
+        tens = [None] * n
+        self.yolo = []
+        row_off = 0
+        for i, (d, m) in enumerate(zip(defs, mods)):
+            t = d['type']
+            Cc, H, W = prev
+            if t == 'convolutional':
+                conv = m[0]
+                k, s, p = conv.kernel_size[0], conv.stride[0], conv.padding[0]
+                H, W = ops.conv_out_hw(H, W, k, s, p)
+                Cc = conv.out_channels
+                head = i + 1 < n and defs[i + 1]['type'] == 'yolo'
+                out = _Tensor(Cc, H, W, torch.float32 if head else torch.int8)
+                pitch = 256 if head else Cc
+                out.buf = torch.empty((B, H, W, pitch), dtype=out.dtype, device=dev)
+                if not head and Cc % 16 != 0:
+                    raise NotImplementedError("int8 graph needs channel counts that are multiples of 16")
+                self.steps.append(('conv', i, None if i == 0 else tens[i - 1], out, conv, head))
+                tens[i] = out
+            elif t == 'shortcut':
+                if m.__class__.__name__ not in ('COSPTQuantizedShortcut_min', 'COSPTQuantizedShortcut_max'):
+                    raise RuntimeError("quantized=3 needs shortcut_way 1 or 2 (the reference silently drops the "
+                                       "residual adds otherwise, models.py:275-305)")
+                if len(d['from']) != 1 or getattr(m, 'weight', False):
+                    raise NotImplementedError("weighted / multi-source quantised shortcut")
+                l = d['from'][0]
+                src = tens[i + l if l < 0 else l]
+                out = _Tensor(Cc, H, W, torch.int8)
+                out.buf = torch.empty((B, H, W, Cc), dtype=torch.int8, device=dev)
+                self.steps.append(('shortcut', i, tens[i - 1], src, out, m))
+                tens[i] = out
+            elif t == 'route':
+                srcs = [i + l if l < 0 else l for l in d['layers']]
+                if len(srcs) == 1:
+                    if 'groups' in d:
+                        raise NotImplementedError("grouped route in the int8 graph")
+                    tens[i] = tens[srcs[0]]
+                    Cc, H, W = tens[i].C, tens[i].H, tens[i].W
+                else:
+                    Cc = sum(tens[s].C for s in srcs)
+                    H, W = tens[srcs[0]].H, tens[srcs[0]].W
+                    out = _Tensor(Cc, H, W, torch.int8)
+                    out.buf = torch.empty((B, H, W, Cc), dtype=torch.int8, device=dev)
+                    self.steps.append(('concat', i, [tens[s] for s in srcs], out, m))
+                    tens[i] = out
+            elif t == 'upsample':
+                s = d['stride']
+                H, W = H * s, W * s
+                out = _Tensor(Cc, H, W, torch.int8)
+                out.buf = torch.empty((B, H, W, Cc), dtype=torch.int8, device=dev)
+                self.steps.append(('upsample', i, tens[i - 1], out, s))
+                tens[i] = out
+            elif t == 'yolo':
+                raw = tens[i - 1]
+                rows = m.na * raw.H * raw.W
+                self.yolo.append((m, raw, row_off, rows))
+                row_off += rows
+            else:
+                raise NotImplementedError("layer type '%s' in the int8 graph (the reference cannot PTQ-calibrate "
+                                          "maxpool cfgs either, models.py:537-539)" % t)
+            prev = (Cc, H, W)
+            shapes.append(prev)
+        self.total_rows = row_off
+        self.anchors_px = [m.anchors.to(dev).float().contiguous() for (m, _, _, _) in self.yolo]
+
+    def prepare(self):
+        """fold BN + quantise weights (reference first-call behaviour), pack int8 weights, resolve tensor scales."""
+        scale_of = {}
+        self.packed = {}
+        for st in self.steps:
+            kind = st[0]
+            if kind == 'conv':
+                _, i, src, out, conv, head = st
+                conv.fold_and_quantize()
+                s_w, s_a = _s(conv.weight_quantizer.scale), _s(conv.activation_quantizer.scale)
+                if s_w <= 0 or s_a <= 0:
+                    raise RuntimeError("layer %d is not calibrated (scale == 0): load a calibrated state_dict" % i)
+                bits_w, bits_a = conv.w_bits, conv.a_bits
+                if bits_w > 8 or bits_a > 8:
+                    raise NotImplementedError("the tcgen05 kind::i8 path covers <= 8 bit weights and activations")
+                act = _ACT_NAME[conv.activate]
+                slope = 0.25 if conv.maxabsscaler else 0.1
+                if src is None:
+                    self.packed[i] = (conv.q_weight.detach().float().contiguous(), conv.q_bias.detach().float(), s_a,
+                                      act, slope, bits_a)
+                else:
+                    w8 = ops.pack_qconv_weights(conv.q_weight.detach(), s_w, bits_w)
+                    self.packed[i] = (w8, conv.q_bias.detach().float().contiguous(), scale_of[id(src)] * s_w, s_a, act,
+                                      slope, bits_a)
+                scale_of[id(out)] = s_a
+            elif kind == 'shortcut':
+                _, i, x, a, out, m = st
+                scale_of[id(out)] = _s(m.scale_sum)
+            elif kind == 'concat':
+                scale_of[id(st[3])] = _s(st[4].scale)
+            elif kind == 'upsample':
+                scale_of[id(st[3])] = scale_of[id(st[2])]
+        self.scale_of = scale_of
+        self.prepared = True
+
+    def forward(self, x):
+        if not self.prepared:
+            self.prepare()
+        x = x.contiguous().float()
+        B = self.B
+        sc = self.scale_of
+        for st in self.steps:
+            kind = st[0]
+            if kind == 'conv':
+                _, i, src, out, conv, head = st
+                k, s, p = conv.kernel_size[0], conv.stride[0], conv.padding[0]
+                if src is None:
+                    wq, bq, s_a, act, slope, bits = self.packed[i]
+                    lo, hi = -(1 << (bits - 1)), (1 << (bits - 1)) - 1
+                    d = ops.make_conv_desc((B, self.H, self.W, self.Cin), self.Cin, conv.out_channels, k, s, p,
+                                           ops._pitch(out.view()), act, slope, OUT_I8)
+                    call("b2y_stem_conv_fwd_q", C.byref(d), ptr(x), ptr(wq), ptr(bq), ptr(out.buf), s_a, float(lo),
+                         float(hi), stream_ptr())
+                else:
+                    w8, bq, acc_scale, s_a, act, slope, bits = self.packed[i]
+                    if head:
+                        ops.qconv2d(src.view(), w8, bq, k, s, p, acc_scale, s_a, act=act, slope=slope, bits=bits,
+                                    out=out.buf[..., :conv.out_channels], out_kind=OUT_F32, requant=True)
+                    else:
+                        ops.qconv2d(src.view(), w8, bq, k, s, p, acc_scale, s_a, act=act, slope=slope, bits=bits,
+                                    out=out.view(), out_kind=OUT_I8)
+            elif kind == 'shortcut':
+                _, i, xt, at, out, m = st
+                lo, hi = -(1 << (m.bits - 1)), (1 << (m.bits - 1)) - 1
+                xv, av, ov = xt.view(), at.view(), out.view()
+                call("b2y_qshortcut_i8", ptr(xv), ops._pitch(xv), ptr(av), ops._pitch(av), ptr(ov), ops._pitch(ov),
+                     B * out.H * out.W, out.C, sc[id(xt)], _s(m.scale_x), sc[id(at)], _s(m.scale_a), _s(m.scale_sum),
+                     float(lo), float(hi), stream_ptr())
+            elif kind == 'concat':
+                _, i, srcs, out, m = st
+                lo, hi = -(1 << (m.bits - 1)), (1 << (m.bits - 1)) - 1
+                off = 0
+                for t in srcs:
+                    tv = t.view()
+                    ov = out.buf[..., off:off + t.C]
+                    call("b2y_requant_i8", ptr(tv), ops._pitch(tv), ptr(ov), ops._pitch(ov), B * t.H * t.W, t.C,
+                         sc[id(t)], _s(m.scale), float(lo), float(hi), stream_ptr())
+                    off += t.C
+            elif kind == 'upsample':
+                _, i, src, out, s = st
+                sv, ov = src.view(), out.view()
+                call("b2y_upsample_nearest_i8", ptr(sv), ops._pitch(sv), ptr(ov), ops._pitch(ov), B, src.H, src.W,
+                     src.C, int(s), stream_ptr())
+        no = self.yolo[0][0].no
+        io = torch.empty((B, self.total_rows, no), dtype=torch.float32, device=self.device)
+        p_out = []
+        for (m, raw, row_off, rows), anc in zip(self.yolo, self.anchors_px):
+            _, p = ops.yolo_decode(raw.buf, m.na, m.no, anc, m.stride, io=io, row_offset=row_off)
+            m.nx, m.ny = raw.W, raw.H
+            p_out.append(p)
+        return io, tuple(p_out), []
+
+    def launches_per_forward(self):
+        return sum(len(st[2]) if st[0] == 'concat' else 1 for st in self.steps) + len(self.yolo)

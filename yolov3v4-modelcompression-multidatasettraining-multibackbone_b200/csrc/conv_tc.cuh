@@ -64,7 +64,10 @@ struct ConvTcCfg {
     static constexpr int MAX_STAGE_SMEM = 196 * 1024;
     static constexpr int NUM_STAGES_RAW = MAX_STAGE_SMEM / STAGE_BYTES;
     static constexpr int NUM_STAGES = NUM_STAGES_RAW > 8 ? 8 : NUM_STAGES_RAW;
-    static constexpr int TMEM_COLS = (2 * BLOCK_N) < 32 ? 32 : (2 * BLOCK_N);
+    // accumulator ring in TMEM: narrow tiles get a deeper ring so the MMA warp can run several tiles ahead of
+    // the (latency-bound) epilogue; 256-wide tiles use the whole 512-column TMEM with 2 stages
+    static constexpr int ACC_STAGES = BLOCK_N >= 256 ? 2 : (BLOCK_N == 128 ? 4 : 8);
+    static constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;   // 512, 512, 512, 256 columns
     static constexpr int AUX_BYTES = 1024;  // barriers + tmem ptr + bias staging
     static constexpr int BIAS_BYTES = BLOCK_N * 4;
     static constexpr int SMEM_BYTES = 1024 /*align slack*/ + NUM_STAGES * STAGE_BYTES + AUX_BYTES + BIAS_BYTES;
@@ -103,9 +106,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint8_t* aux = smem + NS * Cfg::STAGE_BYTES;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);           // [NS]
     uint64_t* empty_bar = full_bar + NS;                             // [NS]
-    uint64_t* tmem_full_bar = empty_bar + NS;                        // [2]
-    uint64_t* tmem_empty_bar = tmem_full_bar + 2;                    // [2]
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+    constexpr int AS = Cfg::ACC_STAGES;
+    uint64_t* tmem_full_bar = empty_bar + NS;                        // [AS]
+    uint64_t* tmem_empty_bar = tmem_full_bar + AS;                   // [AS]
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + AS);
     float* sbias = reinterpret_cast<float*>(aux + Cfg::AUX_BYTES);   // [BLOCK_N]
 
     const int warp = threadIdx.x >> 5;
@@ -120,7 +124,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_init(&full_bar[i], 1);
             mbar_init(&empty_bar[i], 1);
         }
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < AS; ++i) {
             mbar_init(&tmem_full_bar[i], 1);
             mbar_init(&tmem_empty_bar[i], ConvTcEpi<BLOCK_N>::WARPS);  // one arrive per epilogue warp
         }
@@ -212,7 +216,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                 }
                 tc_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
-                if (++acc == 2) {
+                if (++acc == AS) {
                     acc = 0;
                     acc_phase ^= 1;
                 }
@@ -255,12 +259,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
 
             // stage the bias slice for this tile
-            asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
-            for (int i = et; i < BLOCK_N; i += EPI_THREADS) {
-                const int n = n0 + i;
-                sbias[i] = (p.bias != nullptr && n < p.Cout) ? __ldg(p.bias + n) : 0.f;
+            if (p.num_n_tiles > 1 || tile == (int)blockIdx.x) {   // a single N tile: the bias slice never changes
+                asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+                for (int i = et; i < BLOCK_N; i += EPI_THREADS) {
+                    const int n = n0 + i;
+                    sbias[i] = (p.bias != nullptr && n < p.Cout) ? __ldg(p.bias + n) : 0.f;
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
             }
-            asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
 
             mbar_wait(&tmem_full_bar[acc], acc_phase);
             tc_fence_after();
@@ -430,7 +436,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
-            if (++acc == 2) {
+            if (++acc == AS) {
                 acc = 0;
                 acc_phase ^= 1;
             }

@@ -238,3 +238,182 @@ extern "C" int b2y_pack_qconv_weights(const float* w_oihw_folded, int out_c, int
     B2Y_CUDA_CHECK(cudaGetLastError());
     return B2Y_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// int8 data-movement layers of the quantised graph (eval): shortcut and concat requantisation
+// reference: COSPTQuantizedShortcut_min.forward (ptq_cos.py:876-884, 931-933, 1031) and
+//            COSPTQuantizedFeatureConcat.forward eval branch (ptq_cos.py:1540-1546)
+// ------------------------------------------------------------------------------------------------
+// out = clamp(round((round(x*sx_in/scale_x)*scale_x + round(a*sa_in/scale_a)*scale_a) / scale_sum))
+__global__ void qshortcut_kernel(const int8_t* __restrict__ x, long long xp, const int8_t* __restrict__ a,
+                                 long long ap, int8_t* __restrict__ out, long long op, long long pixels, int C,
+                                 float sx_in, float scale_x, float sa_in, float scale_a, float scale_sum, float lo,
+                                 float hi) {
+    const int CV = C / 16;
+    const long long total = pixels * CV;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int cv = (int)(idx % CV);
+        const long long pix = idx / CV;
+        const uint4 xv = __ldg(reinterpret_cast<const uint4*>(x + pix * xp) + cv);
+        const uint4 av = __ldg(reinterpret_cast<const uint4*>(a + pix * ap) + cv);
+        const int8_t* xb = reinterpret_cast<const int8_t*>(&xv);
+        const int8_t* ab = reinterpret_cast<const int8_t*>(&av);
+        uint4 ov;
+        int8_t* ob = reinterpret_cast<int8_t*>(&ov);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const float xf = rha(((float)xb[j] * sx_in) / scale_x) * scale_x;   // rounded, NOT clamped
+            const float af = rha(((float)ab[j] * sa_in) / scale_a) * scale_a;
+            const float q = rha((xf + af) / scale_sum);
+            ob[j] = (int8_t)(int)fminf(fmaxf(q, lo), hi);
+        }
+        reinterpret_cast<uint4*>(out + pix * op)[cv] = ov;
+    }
+}
+extern "C" int b2y_qshortcut_i8(const void* x, long long x_pitch, const void* a, long long a_pitch, void* out,
+                                long long out_pitch, long long pixels, int c, float sx_in, float scale_x,
+                                float sa_in, float scale_a, float scale_sum, float lo, float hi, void* stream) {
+    if (!x || !a || !out || c % 16 != 0 || x_pitch % 16 != 0 || a_pitch % 16 != 0 || out_pitch % 16 != 0)
+        return B2Y_ERR_INVALID;
+    qshortcut_kernel<<<grid_for(pixels * (c / 16), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const int8_t*>(x), x_pitch, reinterpret_cast<const int8_t*>(a), a_pitch,
+        reinterpret_cast<int8_t*>(out), out_pitch, pixels, c, sx_in, scale_x, sa_in, scale_a, scale_sum, lo, hi);
+    B2Y_CUDA_CHECK(cudaGetLastError());
+    return B2Y_OK;
+}
+
+// out = clamp(round(x * s_in / s_out))   (channel-slice copy with requantisation; s_in == s_out is a plain copy)
+__global__ void requant_kernel(const int8_t* __restrict__ x, long long xp, int8_t* __restrict__ out, long long op,
+                               long long pixels, int C, float s_in, float s_out, float lo, float hi) {
+    const int CV = C / 16;
+    const long long total = pixels * CV;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int cv = (int)(idx % CV);
+        const long long pix = idx / CV;
+        const uint4 xv = __ldg(reinterpret_cast<const uint4*>(x + pix * xp) + cv);
+        const int8_t* xb = reinterpret_cast<const int8_t*>(&xv);
+        uint4 ov;
+        int8_t* ob = reinterpret_cast<int8_t*>(&ov);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const float q = rha(((float)xb[j] * s_in) / s_out);
+            ob[j] = (int8_t)(int)fminf(fmaxf(q, lo), hi);
+        }
+        reinterpret_cast<uint4*>(out + pix * op)[cv] = ov;
+    }
+}
+extern "C" int b2y_requant_i8(const void* x, long long x_pitch, void* out, long long out_pitch, long long pixels,
+                              int c, float s_in, float s_out, float lo, float hi, void* stream) {
+    if (!x || !out || c % 16 != 0 || x_pitch % 16 != 0 || out_pitch % 16 != 0) return B2Y_ERR_INVALID;
+    requant_kernel<<<grid_for(pixels * (c / 16), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const int8_t*>(x), x_pitch, reinterpret_cast<int8_t*>(out), out_pitch, pixels, c, s_in, s_out,
+        lo, hi);
+    B2Y_CUDA_CHECK(cudaGetLastError());
+    return B2Y_OK;
+}
+
+// nearest upsample of int8 NHWC codes (scale unchanged)
+__global__ void upsample_i8_kernel(const int8_t* __restrict__ x, long long xp, int8_t* __restrict__ y, long long yp,
+                                   int B, int H, int W, int C, int s) {
+    const int CV = C / 16;
+    const int Ho = H * s, Wo = W * s;
+    const long long total = (long long)B * Ho * Wo * CV;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int cv = (int)(idx % CV);
+        long long pix = idx / CV;
+        const int xo = (int)(pix % Wo);
+        const int yo = (int)((pix / Wo) % Ho);
+        const int n = (int)(pix / ((long long)Wo * Ho));
+        const long long ipix = ((long long)n * H + yo / s) * W + xo / s;
+        reinterpret_cast<uint4*>(y + pix * yp)[cv] = __ldg(reinterpret_cast<const uint4*>(x + ipix * xp) + cv);
+    }
+}
+extern "C" int b2y_upsample_nearest_i8(const void* x, long long x_pitch, void* y, long long y_pitch, int batch,
+                                       int in_h, int in_w, int c, int scale, void* stream) {
+    if (!x || !y || c % 16 != 0 || x_pitch % 16 != 0 || y_pitch % 16 != 0 || scale < 1) return B2Y_ERR_INVALID;
+    const long long total = (long long)batch * in_h * scale * in_w * scale * (c / 16);
+    upsample_i8_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const int8_t*>(x), x_pitch, reinterpret_cast<int8_t*>(y), y_pitch, batch, in_h, in_w, c,
+        scale);
+    B2Y_CUDA_CHECK(cudaGetLastError());
+    return B2Y_OK;
+}
+
+// First quantised layer: the image is float (not on an int8 grid), so conv 0 runs in fp32 on the fake-quantised
+// weights (exactly what the reference does, ptq_cos.py:288-296) and only its output is requantised to int8.
+__global__ void __launch_bounds__(128)
+stem_conv_q_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                   int8_t* __restrict__ y, int B, int Cin, int H, int W, int Cout, int k, int stride, int pad, int Ho,
+                   int Wo, long long out_pitch, int act, float slope, float out_scale, float lo, float hi) {
+    constexpr int CO = 32;
+    extern __shared__ float sw[];
+    const int taps = Cin * k * k;
+    const long long M = (long long)B * Ho * Wo;
+    for (int co0 = 0; co0 < Cout; co0 += CO) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < taps * CO; i += blockDim.x) {
+            int t = i / CO, c = i - t * CO;
+            sw[i] = (co0 + c < Cout) ? w[(long long)(co0 + c) * taps + t] : 0.f;
+        }
+        for (int i = threadIdx.x; i < CO; i += blockDim.x)
+            sw[taps * CO + i] = (bias != nullptr && co0 + i < Cout) ? bias[co0 + i] : 0.f;
+        __syncthreads();
+        for (long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x; m < M;
+             m += (long long)gridDim.x * blockDim.x) {
+            const int xo = (int)(m % Wo);
+            const int yo = (int)((m / Wo) % Ho);
+            const int n = (int)(m / ((long long)Wo * Ho));
+            float acc[CO];
+#pragma unroll
+            for (int c = 0; c < CO; ++c) acc[c] = 0.f;
+            int t = 0;
+            for (int ci = 0; ci < Cin; ++ci) {
+                const float* xp = x + ((long long)n * Cin + ci) * H * W;
+                for (int kh = 0; kh < k; ++kh) {
+                    const int yi = yo * stride - pad + kh;
+                    for (int kw = 0; kw < k; ++kw, ++t) {
+                        const int xi = xo * stride - pad + kw;
+                        float v = 0.f;
+                        if (yi >= 0 && yi < H && xi >= 0 && xi < W) v = __ldg(xp + (long long)yi * W + xi);
+                        const float4* wp = reinterpret_cast<const float4*>(sw + t * CO);
+#pragma unroll
+                        for (int c4 = 0; c4 < CO / 4; ++c4) {
+                            float4 ww = wp[c4];
+                            acc[c4 * 4 + 0] = fmaf(v, ww.x, acc[c4 * 4 + 0]);
+                            acc[c4 * 4 + 1] = fmaf(v, ww.y, acc[c4 * 4 + 1]);
+                            acc[c4 * 4 + 2] = fmaf(v, ww.z, acc[c4 * 4 + 2]);
+                            acc[c4 * 4 + 3] = fmaf(v, ww.w, acc[c4 * 4 + 3]);
+                        }
+                    }
+                }
+            }
+            int8_t* op = y + m * out_pitch + co0;
+#pragma unroll
+            for (int c = 0; c < CO; ++c) {
+                if (co0 + c < Cout) {
+                    const float v = apply_act(acc[c] + sw[taps * CO + c], act, slope);
+                    op[c] = (int8_t)(int)fminf(fmaxf(rha(v / out_scale), lo), hi);
+                }
+            }
+        }
+    }
+}
+extern "C" int b2y_stem_conv_fwd_q(const b2y_conv_desc* d, const float* x_nchw, const float* w_q, const float* bias_q,
+                                   void* y_i8, float out_scale, float lo, float hi, void* stream) {
+    if (!d || !x_nchw || !w_q || !y_i8 || !(out_scale > 0.f)) return B2Y_ERR_INVALID;
+    if (d->in_c < 1 || d->in_c > 4) return B2Y_ERR_UNSUPPORTED;
+    const long long M = (long long)d->batch * d->out_h * d->out_w;
+    const int taps = d->in_c * d->ksize * d->ksize;
+    const size_t smem = (size_t)(taps * 32 + 32) * sizeof(float);
+    if (smem > 48 * 1024) return B2Y_ERR_UNSUPPORTED;
+    int grid = (int)((M + 127) / 128);
+    if (grid > 148 * 16) grid = 148 * 16;
+    stem_conv_q_kernel<<<grid, 128, smem, static_cast<cudaStream_t>(stream)>>>(
+        x_nchw, w_q, bias_q, reinterpret_cast<int8_t*>(y_i8), d->batch, d->in_c, d->in_h, d->in_w, d->out_c, d->ksize,
+        d->stride, d->pad, d->out_h, d->out_w, d->out_pitch, d->act, d->slope, out_scale, lo, hi);
+    B2Y_CUDA_CHECK(cudaGetLastError());
+    return B2Y_OK;
+}
