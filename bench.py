@@ -114,7 +114,7 @@ def build_model(device):
     return m
 
 
-def cpu_reference_rate(max_seconds=20.0, threads=None):
+def cpu_reference_rate(max_seconds=20.0, threads=None, batch=2, max_iters=10):
     """The reference's CPU PyTorch path, restated in oracle/ (pinned to the reference by tests/golden):
     yolov3 eval forward at 640x640 on the host cores, bounded sample."""
     sys.path.insert(0, ROOT)
@@ -122,18 +122,22 @@ def cpu_reference_rate(max_seconds=20.0, threads=None):
     import models
     from b200yolo import cfggen
     from utils.parse_config import parse_model_cfg_text
-    threads = threads or os.cpu_count()
+    try:
+        avail = len(os.sched_getaffinity(0))      # cores this process may actually use (cgroup / affinity aware)
+    except AttributeError:
+        avail = os.cpu_count()
+    threads = threads or avail
     torch.set_num_threads(threads)
     defs = parse_model_cfg_text(cfggen.cfg_text(MODEL))[1:]
     path = cfggen.write_cfg(MODEL, "/tmp/b2y_cfg_cpu")
     sd = orc.synth_state_dict(models.Darknet(path).state_dict(), 0)
-    bs = 2
+    bs = batch
     x = orc.synth_images(bs, SIZE, SIZE, seed=0)
     with torch.no_grad():
         t0 = time.time()
         orc.darknet_forward(defs, sd, x, MODEL)          # warm-up (also sizes the sample)
         warm = time.time() - t0
-        iters = max(1, min(10, int(max_seconds / max(warm, 1e-3))))
+        iters = max(1, min(max_iters, int(max_seconds / max(warm, 1e-3))))
         t0 = time.time()
         for _ in range(iters):
             orc.darknet_forward(defs, sd, x, MODEL)
@@ -146,8 +150,9 @@ def cpu_reference_rate(max_seconds=20.0, threads=None):
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
-    per = max(5.0, min(25.0, 90.0 / max(1, args.steps + args.warmup)))
-    base, bs = cpu_reference_rate(max_seconds=per * max(1, args.steps))
+    # a "step" of the reference arm = one yolov3 640x640 eval forward of ONE image on all host cores; the number of
+    # timed steps is capped so that the whole run stays within ~2 minutes (stated in cpu_baseline.sample)
+    base, bs = cpu_reference_rate(max_seconds=100.0, batch=1, max_iters=max(1, args.steps))
     line = {"impl": "reference", "metric": "images/sec (640x640) yolov3 inference", "value": base["value"],
             "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": base["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

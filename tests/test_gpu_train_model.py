@@ -47,8 +47,8 @@ def test_train_step_parity(name):
     for k in g.files:
         if k.startswith("stat::"):
             stat_err = max(stat_err, float((sd[k[6:]].cpu() - torch.from_numpy(g[k])).abs().max()))
-    print("\n[%s train] max|dp|=%.3g items_rel=%s worst grad-norm rel=%.3g (%s) median=%.3g elem=%s stat=%.3g"
-          % (name, worst_p, np.round(rel_items, 5), rel[worst_k], worst_k, float(np.median(list(rel.values()))),
+    print("\n[%s train] grad_scale=%g max|dp|=%.3g items_rel=%s worst grad-norm rel=%.3g (%s) median=%.3g elem=%s stat=%.3g"
+          % (name, model.engine().last_plan.last_grad_scale, worst_p, np.round(rel_items, 5), rel[worst_k], worst_k, float(np.median(list(rel.values()))),
              {k.split('.')[1] + k[-12:]: round(v, 4) for k, v in elem.items()}, stat_err))
     assert worst_p < P_ABS_TOL
     assert rel_items.max() < LOSS_REL_TOL

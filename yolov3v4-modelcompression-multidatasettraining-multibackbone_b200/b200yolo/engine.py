@@ -476,6 +476,7 @@ class Engine:
             else:
                 plan = Plan(model, tuple(x.shape), x.device, False, keep)
             self.plans[key] = plan
+        self.last_plan = plan
         if model.training:
             return plan.run(x)
         return plan.forward(x)

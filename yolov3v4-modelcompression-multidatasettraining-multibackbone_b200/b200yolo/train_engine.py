@@ -6,7 +6,8 @@ Replaces autograd over ~500 ATen/cuDNN calls (reference train.py:380-441 -> mode
   backward  yolo permute^T -> [bn+act backward reduce / apply -> wgrad (tcgen05, pixel-K GEMM) -> dgrad (tcgen05)]
 
 Activations z (raw conv output) and y (post activation) are kept in NHWC fp16; gradients flow in fp16 multiplied by
-a static loss scale (model.grad_scale, default 1024) and are un-scaled when written to the fp32 parameter gradients.
+a power-of-two loss scale (chosen per step from the largest head gradient, or model.grad_scale if set) and are
+un-scaled when written to the fp32 parameter gradients.
 The plan plugs into autograd as ONE torch.autograd.Function whose inputs are the model parameters, so
 loss.backward(), DistributedDataParallel hooks and torch optimisers work unchanged.
 """
@@ -332,7 +333,17 @@ class TrainPlan:
     # ---------------------------------------------------------------------------------------------------------
     def backward(self, dps):
         """dps: gradients w.r.t. the yolo outputs p (fp32). Returns {param: grad} for every model parameter."""
-        S = float(getattr(self.model, 'grad_scale', 1024.0))
+        # loss scale for the fp16 gradient flow: model.grad_scale if set, else a power of two chosen from the largest
+        # head gradient so that it lands near 2^13 (one host read of a scalar per step, like GradScaler's inf check)
+        S = getattr(self.model, 'grad_scale', None)
+        if S is None:
+            amax = max(float(dp.detach().abs().max()) for dp in dps if dp is not None)
+            S = 1.0
+            if amax > 0 and amax == amax and amax != float('inf'):
+                import math
+                S = 2.0 ** max(0, min(40, math.floor(math.log2(8192.0 / amax))))
+        S = float(S)
+        self.last_grad_scale = S
         inv = 1.0 / S
         self.sink = getattr(self.model, '_b2y_grad_sink', None)   # FlatDataParallel: write into the flat buffer
         for gb in self.grad_bufs:

@@ -63,7 +63,9 @@ struct ConvTcCfg {
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;  // always a multiple of 1024
     static constexpr int MAX_STAGE_SMEM = 196 * 1024;
     static constexpr int NUM_STAGES_RAW = MAX_STAGE_SMEM / STAGE_BYTES;
-    static constexpr int NUM_STAGES = NUM_STAGES_RAW > 8 ? 8 : NUM_STAGES_RAW;
+    // small-K layers have small stages: keep up to 32 of them in flight so that enough bytes are outstanding per SM
+    // to cover HBM latency (Little's law: 148 SMs x ~190 KB / ~2 us)
+    static constexpr int NUM_STAGES = NUM_STAGES_RAW > 32 ? 32 : NUM_STAGES_RAW;
     // accumulator ring in TMEM: narrow tiles get a deeper ring so the MMA warp can run several tiles ahead of
     // the (latency-bound) epilogue; 256-wide tiles use the whole 512-column TMEM with 2 stages
     static constexpr int ACC_STAGES = BLOCK_N >= 256 ? 2 : (BLOCK_N == 128 ? 4 : 8);
