@@ -43,6 +43,11 @@ extern "C" {
 #define B2Y_ACT_HSWISH 5
 #define B2Y_ACT_SWISH 6
 
+/* 16-bit tensor dtypes (gradient tensors of the training path flow in bf16: fp16 overflows/underflows across the
+ * ~100 BatchNorm layers of a Darknet; activations stay fp16) */
+#define B2Y_DT_F16 0
+#define B2Y_DT_BF16 1
+
 /* output dtypes of the conv epilogue */
 #define B2Y_OUT_F16 0
 #define B2Y_OUT_F32 1
@@ -126,7 +131,7 @@ int b2y_copy_channels(const void* x, long long x_pitch, void* y, long long y_pit
                       void* stream);
 /* y = a + b (Shortcut fallback when the add is not fused in the conv epilogue), utils/layers.py:43-72 */
 int b2y_add(const void* a, long long a_pitch, const void* b, long long b_pitch, void* y, long long y_pitch,
-            long long pixels, int c, void* stream);
+            long long pixels, int c, int dtype /* B2Y_DT_* */, void* stream);
 /* standalone activation fwd/bwd on fp32 (Mish: utils/layers.py:117-128,146-148) */
 int b2y_act_fwd_f32(const float* x, float* y, long long n, int act, float slope, void* stream);
 int b2y_act_bwd_f32(const float* x, const float* dy, float* dx, long long n, int act, float slope, void* stream);
@@ -229,21 +234,22 @@ int b2y_bn_act_fwd(const void* x, long long x_pitch, const float* scale, const f
  * dx = (gamma*invstd) * (dz - dbeta/N - xhat*dgamma/N)                            (pass 2). */
 int b2y_bn_act_bwd_reduce(const void* x, long long x_pitch, const void* dy, long long dy_pitch, const float* scale,
                           const float* shift, const float* save_mean, const float* save_invstd, float* dgamma,
-                          float* dbeta, long long pixels, int c, int act, float slope, void* stream);
+                          float* dbeta, long long pixels, int c, int act, float slope, int grad_dtype, void* stream);
 int b2y_bn_act_bwd_apply(const void* x, long long x_pitch, const void* dy, long long dy_pitch, const float* scale,
                          const float* shift, const float* gamma, const float* save_mean, const float* save_invstd,
                          const float* dgamma, const float* dbeta, void* dx, long long dx_pitch, long long pixels,
-                         int c, int act, float slope, void* stream);
+                         int c, int act, float slope, int grad_dtype, void* stream);
 /* dX = conv_transpose(dY, W)   (data gradient; implicit GEMM on tcgen05) */
 int b2y_conv2d_bwd_data(const b2y_conv_desc* d, const void* dy, const void* w_packed_t, void* dx, int accumulate,
-                        void* stream);
+                        int grad_dtype, void* stream);
 /* weights for b2y_conv2d_bwd_data: OIHW fp32 -> per output-phase slabs [phase][in_c][tap][out_c] fp16
  * (stride-s data gradients are decomposed into s*s stride-1 implicit GEMMs over dY; out_c*ksize^2*in_c elements) */
-int b2y_pack_dgrad_weights(const b2y_conv_desc* d, const float* w_oihw, void* w_packed_t, void* stream);
+int b2y_pack_dgrad_weights(const b2y_conv_desc* d, const float* w_oihw, void* w_packed_t, int grad_dtype,
+                           void* stream);
 /* dW[o][kh][kw][i] += scale * sum_pixels dY[p][o] * X[p@(kh,kw)][i]  (weight gradient, tcgen05 GEMM over the pixel
  * dimension with MN-major operands; dw fp32 [O][kh][kw][I], caller zeroes it; split-K reduced with red.global.add) */
 int b2y_conv2d_bwd_weight(const b2y_conv_desc* d, const void* x, const void* dy, float* dw, float scale,
-                          void* stream);
+                          int grad_dtype, void* stream);
 /* [O][kh][kw][I] fp32 -> OIHW fp32 parameter-gradient layout: dst = alpha*src (+ dst if accumulate) */
 int b2y_unpack_wgrad(const float* dw_packed, float* dw_oihw, int out_c, int in_c, int ksize, float alpha,
                      int accumulate, void* stream);
@@ -251,17 +257,17 @@ int b2y_unpack_wgrad(const float* dw_packed, float* dw_oihw, int out_c, int in_c
 int b2y_axpby_f32(const float* src, float* dst, long long n, float alpha, float beta, void* stream);
 /* backward of the YOLO permute: dp fp32 [B][na][ny][nx][no] -> d(raw) fp16 [B][ny][nx][raw_pitch] * scale (models.py:406) */
 int b2y_yolo_grad_to_raw(const float* dp, void* draw, long long raw_pitch, int batch, int na, int no, int ny, int nx,
-                         float scale, void* stream);
+                         float scale, int grad_dtype, void* stream);
 /* backward of nn.Upsample (nearest): dx += window sums of dy (in place accumulate) */
 int b2y_upsample_nearest_bwd(const void* dy, long long dy_pitch, void* dx, long long dx_pitch, int batch, int in_h,
-                             int in_w, int c, int scale, void* stream);
+                             int in_w, int c, int scale, int grad_dtype, void* stream);
 /* backward of nn.MaxPool2d: dx[argmax] += dy (arg-max recomputed from x; first maximum wins like torch) */
 int b2y_maxpool_bwd(const void* x, long long x_pitch, const void* dy, long long dy_pitch, void* dx,
                     long long dx_pitch, int batch, int in_h, int in_w, int c, int ksize, int stride, int pad_mode,
-                    void* stream);
+                    int grad_dtype, void* stream);
 /* weight gradient of the stem (in_c <= 4): x fp32 NCHW, dz fp16 NHWC -> dw OIHW fp32 (+= scale * ...) */
 int b2y_stem_conv_bwd_weight(const b2y_conv_desc* d, const float* x_nchw, const void* dz, float* dw_oihw,
-                             float scale, void* stream);
+                             float scale, int grad_dtype, void* stream);
 /* SGD + Nesterov momentum + weight decay over a flat fp32 buffer (train.py:135-144), grads pre-scaled by
  * grad_scale (1/world_size after the NCCL sum) */
 int b2y_sgd_nesterov(float* param, const float* grad, float* momentum_buf, long long n, float lr, float momentum,

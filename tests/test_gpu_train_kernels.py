@@ -17,29 +17,35 @@ def _ops():
     return ops
 
 
-def _nhwc(t):
-    return t.permute(0, 2, 3, 1).contiguous().half().cuda()
+def _nhwc(t, dtype=torch.float16):
+    return t.permute(0, 2, 3, 1).contiguous().to(dtype).cuda()
 
 
 def _nchw(t):
     return t.float().permute(0, 3, 1, 2).cpu()
 
 
-def conv_grads_case(B, H, W, Cin, Cout, k, stride, seed=0, accumulate=False):
+def conv_grads_case(B, H, W, Cin, Cout, k, stride, seed=0, accumulate=False, gdt=torch.float16):
     ops = _ops()
     g = torch.Generator().manual_seed(seed)
     pad = (k - 1) // 2
     x = torch.randn(B, Cin, H, W, generator=g).half().double().requires_grad_(True)
     w = (torch.randn(Cout, Cin, k, k, generator=g) / math.sqrt(Cin * k * k)).half().double().requires_grad_(True)
     y = F.conv2d(x, w, None, stride=stride, padding=pad)
-    dy = torch.randn(y.shape, generator=g).half().double()
+    dy = torch.randn(y.shape, generator=g).to(gdt).double()
     y.backward(dy)
     dxr, dwr = x.grad.float(), w.grad.float()
-    wt = ops.pack_dgrad_weights(w.detach().float().cuda(), stride, pad, (H, W))
-    dyn = _nhwc(dy.float())
+    if gdt == torch.bfloat16:   # dgrad multiplies bf16-rounded weights; wgrad keeps the fp16 activations
+        wb = w.detach().float().bfloat16().double().requires_grad_(True)
+        F.conv2d(x.detach().double().requires_grad_(True), wb, None, stride=stride, padding=pad)
+        xx = x.detach().clone().requires_grad_(True)
+        F.conv2d(xx, wb, None, stride=stride, padding=pad).backward(dy)
+        dxr = xx.grad.float()
+    wt = ops.pack_dgrad_weights(w.detach().float().cuda(), stride, pad, (H, W), dtype=gdt)
+    dyn = _nhwc(dy.float(), gdt)
     if accumulate:
-        base = torch.randn(B, Cin, H, W, generator=g).half()
-        out = _nhwc(base.float())
+        base = torch.randn(B, Cin, H, W, generator=g).to(gdt)
+        out = _nhwc(base.float(), gdt)
         dx = ops.conv2d_bwd_data(dyn, wt, (B, H, W, Cin), k, stride, pad, out=out, accumulate=True)
         dxr = dxr + base.float()
     else:
@@ -75,13 +81,24 @@ def test_conv_bwd_data_and_weight(case):
     assert e_dw < 2e-4      # fp32 accumulate + fp32 atomics
 
 
+@pytest.mark.parametrize("case", [GRAD_CASES[1], GRAD_CASES[3], GRAD_CASES[6], GRAD_CASES[9]],
+                         ids=lambda c: "bf16-" + str(c))
+def test_conv_bwd_bf16_gradients(case):
+    """the training path: dY in bf16 (dgrad bf16 x bf16, wgrad bf16 dY x fp16 X -- mixed operand formats)."""
+    e_dx, e_dw = conv_grads_case(*case, gdt=torch.bfloat16)
+    print("\nbf16 %s dx err/rms=%.3g dw err/rms=%.3g" % (case, e_dx, e_dw))
+    assert e_dx < 3e-2      # bf16 store of dx (8-bit mantissa)
+    assert e_dw < 2e-4      # exact products of the bf16/fp16 operands, fp32 accumulate
+
+
 def test_conv_bwd_data_accumulate():
     e_dx, _ = conv_grads_case(2, 16, 16, 64, 128, 3, 2, accumulate=True)
     assert e_dx < 8e-3
 
 
+@pytest.mark.parametrize("gdt", [torch.float16, torch.bfloat16], ids=["f16", "bf16"])
 @pytest.mark.parametrize("act", ["leaky", "mish", "linear"])
-def test_bn_act_fwd_bwd(act):
+def test_bn_act_fwd_bwd(act, gdt):
     ops = _ops()
     g = torch.Generator().manual_seed(3)
     B, C, H, W = 4, 64, 12, 10
@@ -89,7 +106,7 @@ def test_bn_act_fwd_bwd(act):
     gamma = torch.rand(C, generator=g) + 0.5
     beta = torch.randn(C, generator=g) * 0.2
     res = torch.randn(B, C, H, W, generator=g).half().float()
-    dy = torch.randn(B, C, H, W, generator=g).half().float()
+    dy = torch.randn(B, C, H, W, generator=g).to(gdt).float()
     rm, rv = torch.zeros(C), torch.ones(C)
     # reference: torch BN (training) + activation + residual, autograd
     zr = z.clone().double().requires_grad_(True)
@@ -105,7 +122,7 @@ def test_bn_act_fwd_bwd(act):
     rmc, rvc = rm.cuda(), rv.cuda()
     mean, invstd, scale, shift = ops.bn_finalize(s1, s2, B * H * W, gamma.cuda(), beta.cuda(), 1e-5, 0.1, rmc, rvc)
     out = ops.bn_act_fwd(zn, scale, shift, act, residual=_nhwc(res))
-    dz, dgamma, dbeta = ops.bn_act_bwd(zn, _nhwc(dy), scale, shift, gamma.cuda(), mean, invstd, act)
+    dz, dgamma, dbeta = ops.bn_act_bwd(zn, _nhwc(dy, gdt), scale, shift, gamma.cuda(), mean, invstd, act)
     torch.cuda.synchronize()
     assert (_nchw(out) - y.detach().float()).abs().max() < 6e-3
     np.testing.assert_allclose(rmc.cpu().numpy(), rm_r.float().numpy(), rtol=1e-4, atol=1e-5)
@@ -113,7 +130,8 @@ def test_bn_act_fwd_bwd(act):
     np.testing.assert_allclose(dgamma.cpu().numpy(), gr.grad.float().numpy(), rtol=2e-3, atol=2e-3)
     np.testing.assert_allclose(dbeta.cpu().numpy(), br.grad.float().numpy(), rtol=2e-3, atol=2e-3)
     ref_dz = zr.grad.float()
-    assert (_nchw(dz) - ref_dz).abs().max() < 4e-3 * max(1.0, ref_dz.abs().max().item())
+    tol = 4e-3 if gdt == torch.float16 else 2e-2
+    assert (_nchw(dz) - ref_dz).abs().max() < tol * max(1.0, ref_dz.abs().max().item())
 
 
 def test_sgd_nesterov_matches_torch():

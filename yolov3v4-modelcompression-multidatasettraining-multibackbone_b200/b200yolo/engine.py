@@ -10,6 +10,8 @@ by a static plan over NHWC fp16 buffers:
 
 Parameters stay in the nn.Module tree (fp32, NCHW) and are folded/packed on the device whenever they change.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -399,7 +401,7 @@ class Plan:
             self.graph = None
         x = x.contiguous().float()
         no = self.yolo[0][0].no
-        use_graph = getattr(model, 'use_cuda_graph', True)
+        use_graph = getattr(model, 'use_cuda_graph', os.environ.get('B2Y_NO_GRAPH', '0') != '1')
         if not use_graph or self.runs < 1:
             self.io = torch.empty((self.B, self.total_rows, no), dtype=torch.float32, device=self.device)
             self.p_out = []

@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_PKG, "libb200yolo.so")
 
 ACT = {"linear": 0, "leaky": 1, "mish": 2, "relu": 3, "relu6": 4, "h_swish": 5, "swish": 6}
 OUT_F16, OUT_F32, OUT_I8 = 0, 1, 2
+DT_F16, DT_BF16 = 0, 1
 
 
 class ConvDesc(C.Structure):
@@ -63,7 +64,7 @@ _PROTOS = {
     "b2y_upsample_nearest": (i32, [vp, ll, vp, ll, i32, i32, i32, i32, i32, vp]),
     "b2y_maxpool": (i32, [vp, ll, vp, ll, i32, i32, i32, i32, i32, i32, i32, vp]),
     "b2y_copy_channels": (i32, [vp, ll, vp, ll, ll, i32, vp]),
-    "b2y_add": (i32, [vp, ll, vp, ll, vp, ll, ll, i32, vp]),
+    "b2y_add": (i32, [vp, ll, vp, ll, vp, ll, ll, i32, i32, vp]),
     "b2y_act_fwd_f32": (i32, [vp, vp, ll, i32, f32, vp]),
     "b2y_act_bwd_f32": (i32, [vp, vp, vp, ll, i32, f32, vp]),
     "b2y_nchw_f32_to_nhwc_f16": (i32, [vp, vp, ll, i32, i32, i32, i32, vp]),
@@ -85,17 +86,17 @@ _PROTOS = {
     "b2y_stem_conv_fwd_q": (i32, [C.POINTER(ConvDesc), vp, vp, vp, vp, f32, f32, f32, vp]),
     "b2y_bn_finalize": (i32, [vp, vp, ll, vp, vp, f32, f32, vp, vp, vp, vp, vp, vp, i32, vp]),
     "b2y_bn_act_fwd": (i32, [vp, ll, vp, vp, vp, ll, vp, ll, ll, i32, i32, f32, vp]),
-    "b2y_bn_act_bwd_reduce": (i32, [vp, ll, vp, ll, vp, vp, vp, vp, vp, vp, ll, i32, i32, f32, vp]),
-    "b2y_bn_act_bwd_apply": (i32, [vp, ll, vp, ll, vp, vp, vp, vp, vp, vp, vp, vp, ll, ll, i32, i32, f32, vp]),
-    "b2y_conv2d_bwd_data": (i32, [C.POINTER(ConvDesc), vp, vp, vp, i32, vp]),
-    "b2y_pack_dgrad_weights": (i32, [C.POINTER(ConvDesc), vp, vp, vp]),
-    "b2y_conv2d_bwd_weight": (i32, [C.POINTER(ConvDesc), vp, vp, vp, f32, vp]),
+    "b2y_bn_act_bwd_reduce": (i32, [vp, ll, vp, ll, vp, vp, vp, vp, vp, vp, ll, i32, i32, f32, i32, vp]),
+    "b2y_bn_act_bwd_apply": (i32, [vp, ll, vp, ll, vp, vp, vp, vp, vp, vp, vp, vp, ll, ll, i32, i32, f32, i32, vp]),
+    "b2y_conv2d_bwd_data": (i32, [C.POINTER(ConvDesc), vp, vp, vp, i32, i32, vp]),
+    "b2y_pack_dgrad_weights": (i32, [C.POINTER(ConvDesc), vp, vp, i32, vp]),
+    "b2y_conv2d_bwd_weight": (i32, [C.POINTER(ConvDesc), vp, vp, vp, f32, i32, vp]),
     "b2y_unpack_wgrad": (i32, [vp, vp, i32, i32, i32, f32, i32, vp]),
     "b2y_axpby_f32": (i32, [vp, vp, ll, f32, f32, vp]),
-    "b2y_yolo_grad_to_raw": (i32, [vp, vp, ll, i32, i32, i32, i32, i32, f32, vp]),
-    "b2y_upsample_nearest_bwd": (i32, [vp, ll, vp, ll, i32, i32, i32, i32, i32, vp]),
-    "b2y_maxpool_bwd": (i32, [vp, ll, vp, ll, vp, ll, i32, i32, i32, i32, i32, i32, i32, vp]),
-    "b2y_stem_conv_bwd_weight": (i32, [C.POINTER(ConvDesc), vp, vp, vp, f32, vp]),
+    "b2y_yolo_grad_to_raw": (i32, [vp, vp, ll, i32, i32, i32, i32, i32, f32, i32, vp]),
+    "b2y_upsample_nearest_bwd": (i32, [vp, ll, vp, ll, i32, i32, i32, i32, i32, i32, vp]),
+    "b2y_maxpool_bwd": (i32, [vp, ll, vp, ll, vp, ll, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
+    "b2y_stem_conv_bwd_weight": (i32, [C.POINTER(ConvDesc), vp, vp, vp, f32, i32, vp]),
     "b2y_sgd_nesterov": (i32, [vp, vp, vp, ll, f32, f32, f32, f32, i32, vp]),
 }
 

@@ -8,7 +8,12 @@ import ctypes as C
 import torch
 
 from . import lib
-from .lib import ACT, ConvDesc, QConvDesc, OUT_F16, OUT_F32, OUT_I8, call, ptr, stream_ptr
+from .lib import ACT, ConvDesc, QConvDesc, OUT_F16, OUT_F32, OUT_I8, DT_F16, DT_BF16, call, ptr, stream_ptr
+
+
+def _gdt(t):
+    """16-bit dtype code of a tensor (gradients may be bf16)."""
+    return DT_BF16 if t.dtype == torch.bfloat16 else DT_F16
 
 
 def _pitch(t):
@@ -148,7 +153,8 @@ def add(a, b, out=None):
     B, H, W, Cc = a.shape
     if out is None:
         out = torch.empty((B, H, W, Cc), dtype=a.dtype, device=a.device)
-    call("b2y_add", ptr(a), _pitch(a), ptr(b), _pitch(b), ptr(out), _pitch(out), B * H * W, Cc, stream_ptr())
+    assert a.dtype == b.dtype == out.dtype
+    call("b2y_add", ptr(a), _pitch(a), ptr(b), _pitch(b), ptr(out), _pitch(out), B * H * W, Cc, _gdt(a), stream_ptr())
     return out
 
 
@@ -232,14 +238,14 @@ def dgrad_weight_numel(out_c, in_c, k):
     return out_c * in_c * k * k
 
 
-def pack_dgrad_weights(w_oihw, stride, pad, in_hw):
+def pack_dgrad_weights(w_oihw, stride, pad, in_hw, dtype=torch.float16):
     """OIHW fp32 -> phase-decomposed dgrad weights (fp16) for b2y_conv2d_bwd_data."""
     O, I, k, _ = w_oihw.shape
     H, W = in_hw
     Ho, Wo = conv_out_hw(H, W, k, stride, pad)
-    out = torch.empty(O * I * k * k, dtype=torch.float16, device=w_oihw.device)
+    out = torch.empty(O * I * k * k, dtype=dtype, device=w_oihw.device)
     d = ConvDesc(1, H, W, I, I, O, k, stride, pad, Ho, Wo, O, 0, 0.0, OUT_F16, 0)
-    call("b2y_pack_dgrad_weights", C.byref(d), ptr(w_oihw.contiguous().float()), ptr(out), stream_ptr())
+    call("b2y_pack_dgrad_weights", C.byref(d), ptr(w_oihw.contiguous().float()), ptr(out), _gdt(out), stream_ptr())
     return out
 
 
@@ -248,10 +254,12 @@ def conv2d_bwd_data(dy, w_packed_t, in_shape, k, stride, pad, out=None, accumula
     B, H, W, I = in_shape
     _, Ho, Wo, O = dy.shape
     if out is None:
-        out = torch.empty((B, H, W, I), dtype=torch.float16, device=dy.device)
+        out = torch.empty((B, H, W, I), dtype=dy.dtype, device=dy.device)
         assert not accumulate
+    assert out.dtype == dy.dtype == w_packed_t.dtype
     d = ConvDesc(B, H, W, I, _pitch(out), O, k, stride, pad, Ho, Wo, _pitch(dy), 0, 0.0, OUT_F16, 0)
-    call("b2y_conv2d_bwd_data", C.byref(d), ptr(dy), ptr(w_packed_t), ptr(out), 1 if accumulate else 0, stream_ptr())
+    call("b2y_conv2d_bwd_data", C.byref(d), ptr(dy), ptr(w_packed_t), ptr(out), 1 if accumulate else 0, _gdt(dy),
+         stream_ptr())
     return out
 
 
@@ -262,7 +270,7 @@ def conv2d_bwd_weight(x, dy, k, stride, pad, scale=1.0, dw=None):
     if dw is None:
         dw = torch.zeros((O, k, k, I), dtype=torch.float32, device=x.device)
     d = ConvDesc(B, H, W, I, _pitch(x), O, k, stride, pad, Ho, Wo, _pitch(dy), 0, 0.0, OUT_F16, 0)
-    call("b2y_conv2d_bwd_weight", C.byref(d), ptr(x), ptr(dy), ptr(dw), float(scale), stream_ptr())
+    call("b2y_conv2d_bwd_weight", C.byref(d), ptr(x), ptr(dy), ptr(dw), float(scale), _gdt(dy), stream_ptr())
     return dw
 
 
@@ -306,11 +314,13 @@ def bn_act_bwd(x, dy, scale, shift, gamma, mean, invstd, act, slope=0.1, dx=None
         dbeta = torch.zeros(Cc, dtype=torch.float32, device=dev)
     a = ACT[act] if isinstance(act, str) else int(act)
     call("b2y_bn_act_bwd_reduce", ptr(x), _pitch(x), ptr(dy), _pitch(dy), ptr(scale), ptr(shift), ptr(mean),
-         ptr(invstd), ptr(dgamma), ptr(dbeta), B * H * W, Cc, a, float(slope), stream_ptr())
+         ptr(invstd), ptr(dgamma), ptr(dbeta), B * H * W, Cc, a, float(slope), _gdt(dy), stream_ptr())
     if dx is None:
-        dx = torch.empty((B, H, W, Cc), dtype=torch.float16, device=dev)
+        dx = torch.empty((B, H, W, Cc), dtype=dy.dtype, device=dev)
+    assert dx.dtype == dy.dtype
     call("b2y_bn_act_bwd_apply", ptr(x), _pitch(x), ptr(dy), _pitch(dy), ptr(scale), ptr(shift), ptr(gamma), ptr(mean),
-         ptr(invstd), ptr(dgamma), ptr(dbeta), ptr(dx), _pitch(dx), B * H * W, Cc, a, float(slope), stream_ptr())
+         ptr(invstd), ptr(dgamma), ptr(dbeta), ptr(dx), _pitch(dx), B * H * W, Cc, a, float(slope), _gdt(dy),
+         stream_ptr())
     return dx, dgamma, dbeta
 
 
@@ -320,7 +330,8 @@ def bias_act_bwd_reduce(x, dy, scale, shift, act, slope=0.1, dbeta=None):
     if dbeta is None:
         dbeta = torch.zeros(Cc, dtype=torch.float32, device=x.device)
     call("b2y_bn_act_bwd_reduce", ptr(x), _pitch(x), ptr(dy), _pitch(dy), ptr(scale), ptr(shift), None, None, None,
-         ptr(dbeta), B * H * W, Cc, ACT[act] if isinstance(act, str) else int(act), float(slope), stream_ptr())
+         ptr(dbeta), B * H * W, Cc, ACT[act] if isinstance(act, str) else int(act), float(slope), _gdt(dy),
+         stream_ptr())
     return dbeta
 
 

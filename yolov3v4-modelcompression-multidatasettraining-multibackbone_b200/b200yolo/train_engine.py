@@ -5,9 +5,10 @@ Replaces autograd over ~500 ATen/cuDNN calls (reference train.py:380-441 -> mode
   forward   conv (tcgen05, per-channel sum / sum^2 from the epilogue) -> bn_finalize -> bn+act(+shortcut) apply
   backward  yolo permute^T -> [bn+act backward reduce / apply -> wgrad (tcgen05, pixel-K GEMM) -> dgrad (tcgen05)]
 
-Activations z (raw conv output) and y (post activation) are kept in NHWC fp16; gradients flow in fp16 multiplied by
-a power-of-two loss scale (chosen per step from the largest head gradient, or model.grad_scale if set) and are
-un-scaled when written to the fp32 parameter gradients.
+Activations z (raw conv output) and y (post activation) are kept in NHWC fp16 (accurate forward); gradient tensors
+flow in **bf16** (fp32 range: the gradient magnitude drifts by orders of magnitude across ~100 BatchNorm layers, which
+fp16 cannot hold with one loss scale), weight / BN gradients are accumulated and stored in fp32.  The dgrad GEMM is
+bf16 x bf16, the wgrad GEMM bf16 (dY) x fp16 (X) -- tcgen05 kind::f16 takes the two operand formats independently.
 The plan plugs into autograd as ONE torch.autograd.Function whose inputs are the model parameters, so
 loss.backward(), DistributedDataParallel hooks and torch optimisers work unchanged.
 """
@@ -20,6 +21,7 @@ from . import ops
 from .engine import LazyFeatures, _Tensor, _block_parts
 from .lib import ConvDesc, OUT_F16, call, ptr, stream_ptr
 
+GDT = torch.bfloat16   # gradient tensors: bf16 (range of fp32) -- fp16 over/underflows across ~100 BN layers
 HEAD_PAD = 256  # head convs (255 filters) are run with 256 output channels (zero row) so that K % 16 == 0 in dgrad
 
 
@@ -123,7 +125,7 @@ class TrainPlan:
         self.grad_of = {}  # id(_Tensor) -> gradient _Tensor (fp16, same placement)
 
         def make_grad(t, gbuf=None, c0=0):
-            g = _Tensor(t.C, t.H, t.W, torch.float16)
+            g = _Tensor(t.C, t.H, t.W, GDT)
             g.buf, g.c0 = gbuf, c0
             self.grad_of[id(t)] = g
             return g
@@ -134,7 +136,7 @@ class TrainPlan:
             srcs = [i + l if l < 0 else l for l in d['layers']]
             dst = tens[i]
             dst.buf = new_buf(dst.C, dst.H, dst.W)
-            gdst = make_grad(dst, torch.zeros_like(dst.buf))
+            gdst = make_grad(dst, torch.zeros(dst.buf.shape, dtype=GDT, device=dev))
             off = 0
             for s in srcs:
                 st = tens[s]
@@ -153,10 +155,10 @@ class TrainPlan:
                 t.c0 = 0
             if id(t) not in self.grad_of:
                 if t.dtype == torch.float16:
-                    make_grad(t, torch.zeros_like(t.buf))
-                else:  # head output: gradient is the fp16 d(raw) buffer, HEAD_PAD channels
-                    g = _Tensor(HEAD_PAD, t.H, t.W, torch.float16)
-                    g.buf = torch.zeros((B, t.H, t.W, HEAD_PAD), dtype=torch.float16, device=dev)
+                    make_grad(t, torch.zeros(t.buf.shape, dtype=GDT, device=dev))
+                else:  # head output: gradient is the 16-bit d(raw) buffer, HEAD_PAD channels
+                    g = _Tensor(HEAD_PAD, t.H, t.W, GDT)
+                    g.buf = torch.zeros((B, t.H, t.W, HEAD_PAD), dtype=GDT, device=dev)
                     self.grad_of[id(t)] = g
             return t
 
@@ -235,7 +237,7 @@ class TrainPlan:
                 seen.add(g.buf.data_ptr())
                 self.grad_bufs.append(g.buf)
         maxz = max(r.Cpad * r.y.H * r.y.W for r in self.convs)
-        self.dz_scratch = torch.empty(B * maxz, dtype=torch.float16, device=dev)
+        self.dz_scratch = torch.empty(B * maxz, dtype=GDT, device=dev)
         maxw = max(r.Cpad * r.conv.in_channels * r.k * r.k for r in self.convs)
         self.dw_scratch = torch.empty(maxw, dtype=torch.float32, device=dev)
         maxc = max(r.Cpad for r in self.convs)
@@ -257,7 +259,7 @@ class TrainPlan:
             else:
                 r.w16, _, _ = ops.pack_conv_weights(w)
                 hin, win = r.src.H, r.src.W
-                r.wT = ops.pack_dgrad_weights(w, r.s, r.p, (hin, win))
+                r.wT = ops.pack_dgrad_weights(w, r.s, r.p, (hin, win), dtype=GDT)
 
     def _zview(self, r):
         return r.z.buf[..., r.z.c0:r.z.c0 + r.Cpad] if r.head else r.z.view()
@@ -319,7 +321,8 @@ class TrainPlan:
                 r.zeros = torch.zeros(r.Cout, dtype=torch.float32, device=self.device)
             B_, H_, W_, C_ = z.shape
             call("b2y_bn_act_bwd_reduce", ptr(z), ops._pitch(z), ptr(z), ops._pitch(z), ptr(r.ones), ptr(r.zeros),
-                 ptr(r.zeros), ptr(r.ones), ptr(r.stats[1]), ptr(r.stats[0]), B_ * H_ * W_, C_, 0, 0.0, stream_ptr())
+                 ptr(r.zeros), ptr(r.ones), ptr(r.stats[1]), ptr(r.stats[0]), B_ * H_ * W_, C_, 0, 0.0, 0,
+                 stream_ptr())
         else:
             ops.conv2d(r.src.view(), r.w16, None, r.k, r.s, r.p, out=z, stats=(r.stats[0], r.stats[1]))
         bn = r.bn
@@ -333,16 +336,8 @@ class TrainPlan:
     # ---------------------------------------------------------------------------------------------------------
     def backward(self, dps):
         """dps: gradients w.r.t. the yolo outputs p (fp32). Returns {param: grad} for every model parameter."""
-        # loss scale for the fp16 gradient flow: model.grad_scale if set, else a power of two chosen from the largest
-        # head gradient so that it lands near 2^13 (one host read of a scalar per step, like GradScaler's inf check)
-        S = getattr(self.model, 'grad_scale', None)
-        if S is None:
-            amax = max(float(dp.detach().abs().max()) for dp in dps if dp is not None)
-            S = 1.0
-            if amax > 0 and amax == amax and amax != float('inf'):
-                import math
-                S = 2.0 ** max(0, min(40, math.floor(math.log2(8192.0 / amax))))
-        S = float(S)
+        # gradients flow in bf16, so no loss scaling is needed; model.grad_scale (power of two) is still honoured
+        S = float(getattr(self.model, 'grad_scale', None) or 1.0)
         self.last_grad_scale = S
         inv = 1.0 / S
         self.sink = getattr(self.model, '_b2y_grad_sink', None)   # FlatDataParallel: write into the flat buffer
@@ -354,7 +349,7 @@ class TrainPlan:
             if dp is None:
                 continue
             call("b2y_yolo_grad_to_raw", ptr(dp.contiguous().float()), ptr(g.buf), HEAD_PAD, self.B, m.na, m.no, raw.H,
-                 raw.W, S, stream_ptr())
+                 raw.W, S, ops._gdt(g.buf), stream_ptr())
         G = lambda t: self.grad_of[id(t)]
         for st in reversed(self.order):
             kind = st[0]
@@ -375,12 +370,12 @@ class TrainPlan:
                 _, src, out, s = st
                 gy, gx = G(out).view(), G(src).view()
                 call("b2y_upsample_nearest_bwd", ptr(gy), ops._pitch(gy), ptr(gx), ops._pitch(gx), self.B, src.H,
-                     src.W, src.C, int(s), stream_ptr())
+                     src.W, src.C, int(s), ops._gdt(gy), stream_ptr())
             elif kind == 'maxpool':
                 _, src, out, k, s, tiny = st
                 gy, gx, xv = G(out).view(), G(src).view(), src.view()
                 call("b2y_maxpool_bwd", ptr(xv), ops._pitch(xv), ptr(gy), ops._pitch(gy), ptr(gx), ops._pitch(gx),
-                     self.B, src.H, src.W, src.C, int(k), int(s), 1 if tiny else 0, stream_ptr())
+                     self.B, src.H, src.W, src.C, int(k), int(s), 1 if tiny else 0, ops._gdt(gy), stream_ptr())
         return grads
 
     def _conv_backward(self, r, grads, S, inv):
@@ -417,7 +412,7 @@ class TrainPlan:
         if r.stem:
             gw.zero_()
             d = ConvDesc(B, self.H, self.W, I, I, r.Cout, r.k, r.s, r.p, Ho, Wo, ops._pitch(dz), 0, 0.0, OUT_F16, 0)
-            call("b2y_stem_conv_bwd_weight", C.byref(d), ptr(self.x), ptr(dz), ptr(gw), inv, stream_ptr())
+            call("b2y_stem_conv_bwd_weight", C.byref(d), ptr(self.x), ptr(dz), ptr(gw), inv, ops._gdt(dz), stream_ptr())
         else:
             dwp = self.dw_scratch[:r.Cpad * r.k * r.k * I].view(r.Cpad, r.k, r.k, I)
             dwp.zero_()

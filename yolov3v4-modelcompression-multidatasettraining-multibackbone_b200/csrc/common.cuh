@@ -2,6 +2,7 @@
 // Thin inline-PTX wrappers around mbarrier / TMA / tcgen05 / TMEM.
 #pragma once
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -207,6 +208,53 @@ __device__ __forceinline__ float act_grad(float v, int act, float slope) {
     }
 }
 
+}  // namespace b2y
+
+namespace b2y {
+// 16-bit storage helpers so that gradient kernels can be instantiated for fp16 or bf16 tensors
+template <typename T> struct Half8;
+template <> struct Half8<__half> {
+    __device__ static void load(const __half* p, float (&f)[8]) {
+        const uint4 u = *reinterpret_cast<const uint4*>(p);
+        const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 t = __half22float2(h[j]);
+            f[2 * j] = t.x;
+            f[2 * j + 1] = t.y;
+        }
+    }
+    __device__ static void store(__half* p, const float (&f)[8]) {
+        uint4 u;
+        __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
+        *reinterpret_cast<uint4*>(p) = u;
+    }
+    __device__ static float to_f(__half v) { return __half2float(v); }
+    __device__ static __half from_f(float v) { return __float2half_rn(v); }
+};
+template <> struct Half8<__nv_bfloat16> {
+    __device__ static void load(const __nv_bfloat16* p, float (&f)[8]) {
+        const uint4 u = *reinterpret_cast<const uint4*>(p);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 t = __bfloat1622float2(h[j]);
+            f[2 * j] = t.x;
+            f[2 * j + 1] = t.y;
+        }
+    }
+    __device__ static void store(__nv_bfloat16* p, const float (&f)[8]) {
+        uint4 u;
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+        *reinterpret_cast<uint4*>(p) = u;
+    }
+    __device__ static float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
+    __device__ static __nv_bfloat16 from_f(float v) { return __float2bfloat16_rn(v); }
+};
 }  // namespace b2y
 
 // host-side helpers ---------------------------------------------------------

@@ -44,14 +44,19 @@ static CUtensorMapSwizzle swizzle_enum(int kbytes) {
 }
 
 // 2-D tiled map over a row-major [rows][cols] matrix with row pitch `pitch_elems`.
+static CUtensorMapDataType tm_dtype(int esize, bool bf16) {
+    if (esize == 1) return CU_TENSOR_MAP_DATA_TYPE_UINT8;
+    return bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+}
+
 static int make_map_2d(CUtensorMap* m, const void* base, int esize, long long rows, long long cols,
-                       long long pitch_elems, int box_cols, int box_rows, int kbytes) {
+                       long long pitch_elems, int box_cols, int box_rows, int kbytes, bool bf16 = false) {
     if (!g_encodeTiled) return B2Y_ERR_DRIVER;
     cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t gstride[1] = {(cuuint64_t)(pitch_elems * esize)};
     cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = g_encodeTiled(m, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2,
+    CUresult r = g_encodeTiled(m, tm_dtype(esize, bf16), 2,
                                const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                swizzle_enum(kbytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -61,7 +66,7 @@ static int make_map_2d(CUtensorMap* m, const void* base, int esize, long long ro
 // im2col map over an NHWC activation tensor (dims C,W,H,N) for an RxS / stride / pad convolution.
 static int make_map_im2col(CUtensorMap* m, const void* base, int esize, int N, int H, int W, int C,
                            long long pitch_elems, int lower_w, int lower_h, int upper_w, int upper_h, int stride,
-                           int block_k, int kbytes, int pixels_per_column = 128) {
+                           int block_k, int kbytes, int pixels_per_column = 128, bool bf16 = false) {
     if (!g_encodeIm2col) return B2Y_ERR_DRIVER;
     cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     cuuint64_t gstride[3] = {(cuuint64_t)(pitch_elems * esize), (cuuint64_t)(pitch_elems * esize * W),
@@ -70,7 +75,7 @@ static int make_map_im2col(CUtensorMap* m, const void* base, int esize, int N, i
     int lower[2] = {lower_w, lower_h};
     int upper[2] = {upper_w, upper_h};
     cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
-    CUresult r = g_encodeIm2col(m, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 4,
+    CUresult r = g_encodeIm2col(m, tm_dtype(esize, bf16), 4,
                                 const_cast<void*>(base), gdim, gstride, lower, upper, (cuuint32_t)block_k,
                                 (cuuint32_t)pixels_per_column, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_enum(kbytes),
                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -127,6 +132,7 @@ struct EpilogueArgs {
     float q_lo = -128.f, q_hi = 127.f;
     float* stat_sum = nullptr;
     float* stat_sqsum = nullptr;
+    int res_bf16 = 0;
 };
 
 // Generic implicit-GEMM launch description: A = NHWC activation-like tensor gathered tap by tap, B = [Nout][ntaps*C].
@@ -141,6 +147,7 @@ struct GemmConvSpec {
     int ntaps = 1;
     unsigned char tap_ow[16] = {0}, tap_oh[16] = {0};
     bool pointwise = false;      // plain GEMM over [N*H*W][C] (2-D tiled TMA)
+    bool a_bf16 = false, b_bf16 = false;   // 16-bit operand formats of the kind::f16 MMA
     const void* w = nullptr;
     int Nout = 0;
     int out_identity = 1, out_OH = 0, out_OW = 0, out_ys = 1, out_xs = 1, out_y0 = 0, out_x0 = 0;
@@ -189,6 +196,8 @@ int gemm_conv_launch(const GemmConvSpec& g, const EpilogueArgs& e, cudaStream_t 
     p.act = e.act;
     p.slope = e.slope;
     p.acc_scale = e.acc_scale;
+    p.idesc_ab = (g.a_bf16 ? (1u << 7) : 0u) | (g.b_bf16 ? (1u << 10) : 0u);
+    p.res_bf16 = e.res_bf16;
     p.res = reinterpret_cast<const __half*>(e.res);
     p.res_pitch = e.res_pitch;
     p.out = e.out;
@@ -206,15 +215,15 @@ int gemm_conv_launch(const GemmConvSpec& g, const EpilogueArgs& e, cudaStream_t 
     int rc;
     if (g.pointwise) {
         p.a_mode = A_MODE_TILED2D;
-        rc = make_map_2d(&tmA, g.a, esize, M, g.C, g.a_pitch, block_k, 128, kbytes);
+        rc = make_map_2d(&tmA, g.a, esize, M, g.C, g.a_pitch, block_k, 128, kbytes, g.a_bf16);
     } else {
         p.a_mode = A_MODE_IM2COL;
         rc = make_map_im2col(&tmA, g.a, esize, g.N, g.H, g.W, g.C, g.a_pitch, g.lower_w, g.lower_h, g.upper_w,
-                             g.upper_h, g.stride, block_k, kbytes);
+                             g.upper_h, g.stride, block_k, kbytes, 128, g.a_bf16);
     }
     if (rc != B2Y_OK) return rc;
     const long long Ktot = (long long)g.ntaps * g.C;
-    rc = make_map_2d(&tmB, g.w, esize, g.Nout, Ktot, Ktot, block_k, block_n, kbytes);
+    rc = make_map_2d(&tmB, g.w, esize, g.Nout, Ktot, Ktot, block_k, block_n, kbytes, g.b_bf16);
     if (rc != B2Y_OK) return rc;
 
     if (g.kind == CONV_KIND_F16) return dispatch<CONV_KIND_F16>(block_n, kbytes, tmA, tmB, p, st);
@@ -311,7 +320,8 @@ static int enumerate_dgrad_phases(const b2y_conv_desc* d, DgradPhase* ph) {
 using namespace b2y;
 
 // pack W (OIHW fp32) into the per-phase dgrad layout [phase][Cin][tap][Cout] fp16
-__global__ void pack_dgrad_kernel(const float* __restrict__ w, __half* __restrict__ out, int O, int I, int k, int nh,
+template <typename T>
+__global__ void pack_dgrad_kernel(const float* __restrict__ w, T* __restrict__ out, int O, int I, int k, int nh,
                                   int nw, int r0, int r1, int r2, int r3, int s0, int s1, int s2, int s3) {
     const int rr[4] = {r0, r1, r2, r3}, ss[4] = {s0, s1, s2, s3};
     const int ntaps = nh * nw;
@@ -323,11 +333,12 @@ __global__ void pack_dgrad_kernel(const float* __restrict__ w, __half* __restric
         const int tap = (int)(t % ntaps);
         const int ci = (int)(t / ntaps);
         const int r = rr[tap / nw], s = ss[tap % nw];
-        out[idx] = __float2half_rn(w[(((long long)co * I + ci) * k + r) * k + s]);
+        out[idx] = Half8<T>::from_f(w[(((long long)co * I + ci) * k + r) * k + s]);
     }
 }
 
-extern "C" int b2y_pack_dgrad_weights(const b2y_conv_desc* d, const float* w_oihw, void* w_packed_t, void* stream) {
+extern "C" int b2y_pack_dgrad_weights(const b2y_conv_desc* d, const float* w_oihw, void* w_packed_t, int grad_dtype,
+                                      void* stream) {
     if (!d || !w_oihw || !w_packed_t) return B2Y_ERR_INVALID;
     DgradPhase ph[16];
     if (d->stride > 4) return B2Y_ERR_UNSUPPORTED;
@@ -339,16 +350,22 @@ extern "C" int b2y_pack_dgrad_weights(const b2y_conv_desc* d, const float* w_oih
         const long long total = (long long)d->in_c * P.nh * P.nw * d->out_c;
         int grid = (int)((total + 255) / 256);
         if (grid > 148 * 16) grid = 148 * 16;
-        pack_dgrad_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-            w_oihw, reinterpret_cast<__half*>(w_packed_t) + P.w_offset, d->out_c, d->in_c, d->ksize, P.nh, P.nw,
-            P.r[0], P.r[1], P.r[2], P.r[3], P.s[0], P.s[1], P.s[2], P.s[3]);
+        if (grad_dtype == B2Y_DT_BF16)
+            pack_dgrad_kernel<__nv_bfloat16><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+                w_oihw, reinterpret_cast<__nv_bfloat16*>(w_packed_t) + P.w_offset, d->out_c, d->in_c, d->ksize, P.nh,
+                P.nw, P.r[0], P.r[1], P.r[2], P.r[3], P.s[0], P.s[1], P.s[2], P.s[3]);
+        else
+            pack_dgrad_kernel<__half><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+                w_oihw, reinterpret_cast<__half*>(w_packed_t) + P.w_offset, d->out_c, d->in_c, d->ksize, P.nh, P.nw,
+                P.r[0], P.r[1], P.r[2], P.r[3], P.s[0], P.s[1], P.s[2], P.s[3]);
     }
     B2Y_CUDA_CHECK(cudaGetLastError());
     return B2Y_OK;
 }
 
 extern "C" int b2y_conv2d_bwd_data(const b2y_conv_desc* d, const void* dy, const void* w_packed_t, void* dx,
-                                   int accumulate, void* stream) {
+                                   int accumulate, int grad_dtype, void* stream) {
+    const bool gbf = grad_dtype == B2Y_DT_BF16;
     if (!d || !dy || !w_packed_t || !dx) return B2Y_ERR_INVALID;
     if (d->stride > 4) return B2Y_ERR_UNSUPPORTED;
     DgradPhase ph[16];
@@ -363,6 +380,7 @@ extern "C" int b2y_conv2d_bwd_data(const b2y_conv_desc* d, const void* dy, const
         }
         GemmConvSpec g;
         g.kind = CONV_KIND_F16;
+        g.a_bf16 = g.b_bf16 = gbf;
         g.a = dy;
         g.N = d->batch;
         g.H = d->out_h;
@@ -394,10 +412,11 @@ extern "C" int b2y_conv2d_bwd_data(const b2y_conv_desc* d, const void* dy, const
         EpilogueArgs e;
         e.out = dx;
         e.out_pitch = d->in_pitch;
-        e.out_dtype = OUT_F16;
+        e.out_dtype = gbf ? OUT_BF16 : OUT_F16;
         if (accumulate) {
             e.res = dx;
             e.res_pitch = d->in_pitch;
+            e.res_bf16 = gbf ? 1 : 0;
         }
         int rc = gemm_conv_launch(g, e, static_cast<cudaStream_t>(stream));
         if (rc != B2Y_OK) return rc;

@@ -17,7 +17,7 @@ namespace b2y {
 
 enum { CONV_KIND_F16 = 0, CONV_KIND_I8 = 1 };
 enum { A_MODE_IM2COL = 0, A_MODE_TILED2D = 1 };
-enum { OUT_F16 = 0, OUT_F32 = 1, OUT_I8 = 2 };
+enum { OUT_F16 = 0, OUT_F32 = 1, OUT_I8 = 2, OUT_BF16 = 3 };
 
 struct ConvTcParams {
     int M_total;      // B*Ho*Wo
@@ -41,7 +41,9 @@ struct ConvTcParams {
     int act;
     float slope;
     float acc_scale;        // multiplies the accumulator (1 for fp16; s_a*s_w for int8)
-    const __half* res;      // optional residual (fp16, NHWC) added after the activation
+    unsigned idesc_ab;      // a_format<<7 | b_format<<10 for kind::f16 (0 = f16, 1 = bf16 per operand)
+    int res_bf16;           // residual / accumulate tensor is bf16 instead of fp16
+    const __half* res;      // optional residual (16-bit, NHWC) added after the activation
     long long res_pitch;    // elements per pixel row
     void* out;
     long long out_pitch;    // elements per pixel row
@@ -207,7 +209,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int k = 0; k < KBYTES / 32; ++k) {
                         const uint32_t accum = (ks > 0 || k > 0) ? 1u : 0u;
                         if (KIND == CONV_KIND_F16)
-                            mma_f16_ss(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC, accum);
+                            mma_f16_ss(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC | p.idesc_ab,
+                                       accum);
                         else
                             mma_i8_ss(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC, accum);
                     }
@@ -356,18 +359,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                             for (int q = 0; q < 4; ++q) {
                                 const uint4 u = rcur[q];
-                                const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+                                if (p.res_bf16) {
+                                    const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
-                                for (int t = 0; t < 4; ++t) {
-                                    float2 f = __half22float2(h2[t]);
-                                    v[q * 8 + t * 2] += f.x;
-                                    v[q * 8 + t * 2 + 1] += f.y;
+                                    for (int t = 0; t < 4; ++t) {
+                                        float2 f = __bfloat1622float2(b2[t]);
+                                        v[q * 8 + t * 2] += f.x;
+                                        v[q * 8 + t * 2 + 1] += f.y;
+                                    }
+                                } else {
+                                    const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+                                    for (int t = 0; t < 4; ++t) {
+                                        float2 f = __half22float2(h2[t]);
+                                        v[q * 8 + t * 2] += f.x;
+                                        v[q * 8 + t * 2 + 1] += f.y;
+                                    }
                                 }
                             }
                         } else {
 #pragma unroll
                             for (int j = 0; j < 32; ++j)
-                                if (j < nvalid) v[j] += __half2float(rp[j]);
+                                if (j < nvalid)
+                                    v[j] += p.res_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(rp)[j])
+                                                       : __half2float(rp[j]);
                         }
                     }
 
@@ -380,7 +395,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                     }
 
-                    if (p.out_dtype == OUT_F16) {
+                    if (p.out_dtype == OUT_BF16) {
+                        __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.out_pitch + n0 + c0;
+                        if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                uint4 u;
+                                __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+                                for (int t = 0; t < 4; ++t)
+                                    h2[t] = __floats2bfloat162_rn(v[q * 8 + t * 2], v[q * 8 + t * 2 + 1]);
+                                reinterpret_cast<uint4*>(op)[q] = u;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (j < nvalid) op[j] = __float2bfloat16_rn(v[j]);
+                        }
+                    } else if (p.out_dtype == OUT_F16) {
                         __half* op = reinterpret_cast<__half*>(p.out) + row * p.out_pitch + n0 + c0;
                         if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
 #pragma unroll

@@ -284,37 +284,37 @@ extern "C" int b2y_copy_channels(const void* x, long long x_pitch, void* y, long
     return B2Y_OK;
 }
 
-__global__ void add_kernel(const __half* __restrict__ a, long long ap, const __half* __restrict__ b, long long bp,
-                           __half* __restrict__ y, long long yp, long long pixels, int C) {
+template <typename T>
+__global__ void add_kernel(const T* __restrict__ a, long long ap, const T* __restrict__ b, long long bp,
+                           T* __restrict__ y, long long yp, long long pixels, int C) {
     const int CV = C / 8;
     const long long total = pixels * CV;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
         const int cv = (int)(idx % CV);
         const long long pix = idx / CV;
-        const uint4 va = __ldg(reinterpret_cast<const uint4*>(a + pix * ap) + cv);
-        const uint4 vb = __ldg(reinterpret_cast<const uint4*>(b + pix * bp) + cv);
-        const __half2* ha = reinterpret_cast<const __half2*>(&va);
-        const __half2* hb = reinterpret_cast<const __half2*>(&vb);
-        uint4 o;
-        __half2* ho = reinterpret_cast<__half2*>(&o);
+        // fp32 add then a single rounding (the reference adds fp32 tensors)
+        float fa[8], fb[8];
+        Half8<T>::load(a + pix * ap + cv * 8, fa);
+        Half8<T>::load(b + pix * bp + cv * 8, fb);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            // fp32 add then a single rounding (the reference adds fp32 tensors)
-            float2 fa = __half22float2(ha[j]), fb = __half22float2(hb[j]);
-            ho[j] = __floats2half2_rn(fa.x + fb.x, fa.y + fb.y);
-        }
-        reinterpret_cast<uint4*>(y + pix * yp)[cv] = o;
+        for (int j = 0; j < 8; ++j) fa[j] += fb[j];
+        Half8<T>::store(y + pix * yp + cv * 8, fa);
     }
 }
 
 extern "C" int b2y_add(const void* a, long long a_pitch, const void* b, long long b_pitch, void* y, long long y_pitch,
-                       long long pixels, int c, void* stream) {
+                       long long pixels, int c, int dtype, void* stream) {
     if (!a || !b || !y || c % 8 != 0 || a_pitch % 8 != 0 || b_pitch % 8 != 0 || y_pitch % 8 != 0)
         return B2Y_ERR_INVALID;
-    add_kernel<<<grid_for(pixels * (c / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        reinterpret_cast<const __half*>(a), a_pitch, reinterpret_cast<const __half*>(b), b_pitch,
-        reinterpret_cast<__half*>(y), y_pitch, pixels, c);
+    if (dtype == B2Y_DT_BF16)
+        add_kernel<__nv_bfloat16><<<grid_for(pixels * (c / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+            reinterpret_cast<const __nv_bfloat16*>(a), a_pitch, reinterpret_cast<const __nv_bfloat16*>(b), b_pitch,
+            reinterpret_cast<__nv_bfloat16*>(y), y_pitch, pixels, c);
+    else
+        add_kernel<__half><<<grid_for(pixels * (c / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+            reinterpret_cast<const __half*>(a), a_pitch, reinterpret_cast<const __half*>(b), b_pitch,
+            reinterpret_cast<__half*>(y), y_pitch, pixels, c);
     B2Y_CUDA_CHECK(cudaGetLastError());
     return B2Y_OK;
 }

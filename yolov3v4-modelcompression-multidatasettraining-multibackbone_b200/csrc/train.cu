@@ -104,8 +104,9 @@ extern "C" int b2y_bn_act_fwd(const void* x, long long x_pitch, const float* sca
 // backward pass 1: dbeta[c] = sum du, dgamma[c] = sum du * xhat   with  u = x*scale+shift, du = dy*act'(u)
 // grid.y tiles the channels in slabs of 256 (32 lanes x 8 channels); each warp walks a strip of pixels.
 // ------------------------------------------------------------------------------------------------
+template <typename GT>
 __global__ void __launch_bounds__(256)
-bn_act_bwd_reduce_kernel(const __half* __restrict__ x, long long xp, const __half* __restrict__ dy, long long dp,
+bn_act_bwd_reduce_kernel(const __half* __restrict__ x, long long xp, const GT* __restrict__ dy, long long dp,
                          const float* __restrict__ scale, const float* __restrict__ shift,
                          const float* __restrict__ mean, const float* __restrict__ invstd,
                          float* __restrict__ dgamma, float* __restrict__ dbeta, long long pixels, int C, int act,
@@ -137,15 +138,14 @@ bn_act_bwd_reduce_kernel(const __half* __restrict__ x, long long xp, const __hal
     for (long long p0 = wid * ppw; p0 < pixels; p0 += warps_total * ppw) {
         const long long pix = p0 + lp;
         if (active && pix < pixels) {
-            const uint4 xv = __ldg(reinterpret_cast<const uint4*>(x + pix * xp) + cv);
-            const uint4 gv = __ldg(reinterpret_cast<const uint4*>(dy + pix * dp) + cv);
-            const __half* xh = reinterpret_cast<const __half*>(&xv);
-            const __half* gh = reinterpret_cast<const __half*>(&gv);
+            float xf8[8], g8[8];
+            Half8<__half>::load(x + pix * xp + cv * 8, xf8);
+            Half8<GT>::load(dy + pix * dp + cv * 8, g8);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const float xf = __half2float(xh[j]);
+                const float xf = xf8[j];
                 const float u = fmaf(xf, sc[j], sh[j]);
-                const float du = __half2float(gh[j]) * act_grad(u, act, slope);
+                const float du = g8[j] * act_grad(u, act, slope);
                 gb[j] += du;
                 gg[j] += du * ((xf - mu[j]) * is[j]);
             }
@@ -185,26 +185,32 @@ bn_act_bwd_reduce_kernel(const __half* __restrict__ x, long long xp, const __hal
 extern "C" int b2y_bn_act_bwd_reduce(const void* x, long long x_pitch, const void* dy, long long dy_pitch,
                                      const float* scale, const float* shift, const float* save_mean,
                                      const float* save_invstd, float* dgamma, float* dbeta, long long pixels, int c,
-                                     int act, float slope, void* stream) {
+                                     int act, float slope, int grad_dtype, void* stream) {
     if (!x || !dy || !scale || !shift || !dbeta || c % 8 != 0 || x_pitch % 8 != 0 || dy_pitch % 8 != 0)
         return B2Y_ERR_INVALID;
     const int CV = c / 8;
     dim3 grid(1, (CV + 31) / 32);
     long long want = (pixels + 63) / 64;
     grid.x = (unsigned)(want < 1 ? 1 : (want > 148 * 4 ? 148 * 4 : want));
-    bn_act_bwd_reduce_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        reinterpret_cast<const __half*>(x), x_pitch, reinterpret_cast<const __half*>(dy), dy_pitch, scale, shift,
-        save_mean, save_invstd, dgamma, dbeta, pixels, c, act, slope);
+    if (grad_dtype == B2Y_DT_BF16)
+        bn_act_bwd_reduce_kernel<__nv_bfloat16><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+            reinterpret_cast<const __half*>(x), x_pitch, reinterpret_cast<const __nv_bfloat16*>(dy), dy_pitch, scale,
+            shift, save_mean, save_invstd, dgamma, dbeta, pixels, c, act, slope);
+    else
+        bn_act_bwd_reduce_kernel<__half><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+            reinterpret_cast<const __half*>(x), x_pitch, reinterpret_cast<const __half*>(dy), dy_pitch, scale, shift,
+            save_mean, save_invstd, dgamma, dbeta, pixels, c, act, slope);
     B2Y_CUDA_CHECK(cudaGetLastError());
     return B2Y_OK;
 }
 
 // backward pass 2: dx = gamma*invstd * (du - dbeta/N - xhat*dgamma/N)
-__global__ void bn_act_bwd_apply_kernel(const __half* __restrict__ x, long long xp, const __half* __restrict__ dy,
+template <typename GT>
+__global__ void bn_act_bwd_apply_kernel(const __half* __restrict__ x, long long xp, const GT* __restrict__ dy,
                                         long long dp, const float* __restrict__ scale, const float* __restrict__ shift,
                                         const float* __restrict__ gamma, const float* __restrict__ mean,
                                         const float* __restrict__ invstd, const float* __restrict__ dgamma,
-                                        const float* __restrict__ dbeta, __half* __restrict__ dx, long long dxp,
+                                        const float* __restrict__ dbeta, GT* __restrict__ dx, long long dxp,
                                         long long pixels, int C, int act, float slope) {
     const int CV = C / 8;
     const long long total = pixels * CV;
@@ -213,26 +219,21 @@ __global__ void bn_act_bwd_apply_kernel(const __half* __restrict__ x, long long 
          idx += (long long)gridDim.x * blockDim.x) {
         const int cv = (int)(idx % CV);
         const long long pix = idx / CV;
-        const uint4 xv = __ldg(reinterpret_cast<const uint4*>(x + pix * xp) + cv);
-        const uint4 gv = __ldg(reinterpret_cast<const uint4*>(dy + pix * dp) + cv);
-        const __half* xh = reinterpret_cast<const __half*>(&xv);
-        const __half* gh = reinterpret_cast<const __half*>(&gv);
+        float xf8[8], g8[8];
+        Half8<__half>::load(x + pix * xp + cv * 8, xf8);
+        Half8<GT>::load(dy + pix * dp + cv * 8, g8);
         float r[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int c = cv * 8 + j;
-            const float xf = __half2float(xh[j]);
+            const float xf = xf8[j];
             const float u = fmaf(xf, scale[c], shift[c]);
-            const float du = __half2float(gh[j]) * act_grad(u, act, slope);
+            const float du = g8[j] * act_grad(u, act, slope);
             const float xhat = (xf - mean[c]) * invstd[c];
             const float g = gamma != nullptr ? gamma[c] : 1.f;
             r[j] = g * invstd[c] * (du - dbeta[c] * inv_n - xhat * dgamma[c] * inv_n);
         }
-        uint4 o;
-        __half2* oh = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) oh[j] = __floats2half2_rn(r[2 * j], r[2 * j + 1]);
-        reinterpret_cast<uint4*>(dx + pix * dxp)[cv] = o;
+        Half8<GT>::store(dx + pix * dxp + cv * 8, r);
     }
 }
 
@@ -240,12 +241,20 @@ extern "C" int b2y_bn_act_bwd_apply(const void* x, long long x_pitch, const void
                                     const float* scale, const float* shift, const float* gamma,
                                     const float* save_mean, const float* save_invstd, const float* dgamma,
                                     const float* dbeta, void* dx, long long dx_pitch, long long pixels, int c, int act,
-                                    float slope, void* stream) {
+                                    float slope, int grad_dtype, void* stream) {
     if (!x || !dy || !scale || !shift || !save_mean || !save_invstd || !dgamma || !dbeta || !dx || c % 8 != 0)
         return B2Y_ERR_INVALID;
-    bn_act_bwd_apply_kernel<<<grid_for(pixels * (c / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        reinterpret_cast<const __half*>(x), x_pitch, reinterpret_cast<const __half*>(dy), dy_pitch, scale, shift, gamma,
-        save_mean, save_invstd, dgamma, dbeta, reinterpret_cast<__half*>(dx), dx_pitch, pixels, c, act, slope);
+    if (grad_dtype == B2Y_DT_BF16)
+        bn_act_bwd_apply_kernel<__nv_bfloat16><<<grid_for(pixels * (c / 8), 256), 256, 0,
+                                                 static_cast<cudaStream_t>(stream)>>>(
+            reinterpret_cast<const __half*>(x), x_pitch, reinterpret_cast<const __nv_bfloat16*>(dy), dy_pitch, scale,
+            shift, gamma, save_mean, save_invstd, dgamma, dbeta, reinterpret_cast<__nv_bfloat16*>(dx), dx_pitch, pixels,
+            c, act, slope);
+    else
+        bn_act_bwd_apply_kernel<__half><<<grid_for(pixels * (c / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+            reinterpret_cast<const __half*>(x), x_pitch, reinterpret_cast<const __half*>(dy), dy_pitch, scale, shift,
+            gamma, save_mean, save_invstd, dgamma, dbeta, reinterpret_cast<__half*>(dx), dx_pitch, pixels, c, act,
+            slope);
     B2Y_CUDA_CHECK(cudaGetLastError());
     return B2Y_OK;
 }
@@ -279,7 +288,8 @@ extern "C" int b2y_sgd_nesterov(float* param, const float* grad, float* momentum
 // backward of the data-movement layers (gradients are NHWC fp16, accumulated in place)
 // ------------------------------------------------------------------------------------------------
 // YOLO head: dp fp32 [B][na][ny][nx][no] -> d(raw) fp16 [B][ny][nx][pitch] (channel a*no+o), times `scale`
-__global__ void yolo_grad_to_raw_kernel(const float* __restrict__ dp, __half* __restrict__ draw, long long pitch,
+template <typename GT>
+__global__ void yolo_grad_to_raw_kernel(const float* __restrict__ dp, GT* __restrict__ draw, long long pitch,
                                         int B, int na, int no, int ny, int nx, float scale) {
     const long long total = (long long)B * ny * nx * pitch;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -295,21 +305,26 @@ __global__ void yolo_grad_to_raw_kernel(const float* __restrict__ dp, __half* __
             const int a = c / no, o = c - a * no;
             v = dp[((((long long)b * na + a) * ny + y) * nx + x) * no + o] * scale;
         }
-        draw[idx] = __float2half_rn(v);
+        draw[idx] = Half8<GT>::from_f(v);
     }
 }
 extern "C" int b2y_yolo_grad_to_raw(const float* dp, void* draw, long long raw_pitch, int batch, int na, int no,
-                                    int ny, int nx, float scale, void* stream) {
+                                    int ny, int nx, float scale, int grad_dtype, void* stream) {
     if (!dp || !draw || raw_pitch < (long long)na * no) return B2Y_ERR_INVALID;
     const long long total = (long long)batch * ny * nx * raw_pitch;
-    yolo_grad_to_raw_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        dp, reinterpret_cast<__half*>(draw), raw_pitch, batch, na, no, ny, nx, scale);
+    if (grad_dtype == B2Y_DT_BF16)
+        yolo_grad_to_raw_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+            dp, reinterpret_cast<__nv_bfloat16*>(draw), raw_pitch, batch, na, no, ny, nx, scale);
+    else
+        yolo_grad_to_raw_kernel<__half><<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+            dp, reinterpret_cast<__half*>(draw), raw_pitch, batch, na, no, ny, nx, scale);
     B2Y_CUDA_CHECK(cudaGetLastError());
     return B2Y_OK;
 }
 
 // nearest upsample backward: dx[n,y,x,:] += sum_{dy,dx<s} dup[n, y*s+dy, x*s+dx, :]
-__global__ void upsample_bwd_kernel(const __half* __restrict__ dy, long long dyp, __half* __restrict__ dx,
+template <typename GT>
+__global__ void upsample_bwd_kernel(const GT* __restrict__ dy, long long dyp, GT* __restrict__ dx,
                                     long long dxp, int B, int H, int W, int C, int s) {
     const int CV = C / 8;
     const long long total = (long long)B * H * W * CV;
@@ -320,30 +335,20 @@ __global__ void upsample_bwd_kernel(const __half* __restrict__ dy, long long dyp
         const int x = (int)(pix % W);
         const int y = (int)((pix / W) % H);
         const int n = (int)(pix / ((long long)W * H));
-        float acc[8];
-        {
-            const uint4 v = *(reinterpret_cast<const uint4*>(dx + pix * dxp) + cv);
-            const __half* h = reinterpret_cast<const __half*>(&v);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] = __half2float(h[j]);
-        }
+        float acc[8], t8[8];
+        Half8<GT>::load(dx + pix * dxp + cv * 8, acc);
         for (int a = 0; a < s; ++a)
             for (int b = 0; b < s; ++b) {
                 const long long op = ((long long)n * H * s + (y * s + a)) * (W * s) + (x * s + b);
-                const uint4 v = __ldg(reinterpret_cast<const uint4*>(dy + op * dyp) + cv);
-                const __half* h = reinterpret_cast<const __half*>(&v);
+                Half8<GT>::load(dy + op * dyp + cv * 8, t8);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[j] += __half2float(h[j]);
+                for (int j = 0; j < 8; ++j) acc[j] += t8[j];
             }
-        uint4 o;
-        __half2* oh = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) oh[j] = __floats2half2_rn(acc[2 * j], acc[2 * j + 1]);
-        reinterpret_cast<uint4*>(dx + pix * dxp)[cv] = o;
+        Half8<GT>::store(dx + pix * dxp + cv * 8, acc);
     }
 }
 extern "C" int b2y_upsample_nearest_bwd(const void* dy, long long dy_pitch, void* dx, long long dx_pitch, int batch,
-                                        int in_h, int in_w, int c, int scale, void* stream) {
+                                        int in_h, int in_w, int c, int scale, int grad_dtype, void* stream) {
     if (!dy || !dx || c % 8 != 0 || dy_pitch % 8 != 0 || dx_pitch % 8 != 0 || scale < 1) return B2Y_ERR_INVALID;
     const long long total = (long long)batch * in_h * in_w * (c / 8);
     upsample_bwd_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
@@ -355,8 +360,9 @@ extern "C" int b2y_upsample_nearest_bwd(const void* dy, long long dy_pitch, void
 
 // maxpool backward: every output pixel re-finds its arg-max (first maximum in row-major window order, as
 // torch's max_pool2d does) and adds its gradient there (windows overlap for stride 1 -> fp16x2 atomics).
-__global__ void maxpool_bwd_kernel(const __half* __restrict__ x, long long xp, const __half* __restrict__ dy,
-                                   long long dyp, __half* __restrict__ dx, long long dxp, int B, int H, int W, int C,
+template <typename GT, typename GT2>
+__global__ void maxpool_bwd_kernel(const __half* __restrict__ x, long long xp, const GT* __restrict__ dy,
+                                   long long dyp, GT* __restrict__ dx, long long dxp, int B, int H, int W, int C,
                                    int k, int stride, int pad, int Ho, int Wo, int zero_pad) {
     const int CV = C / 2;
     const long long total = (long long)B * Ho * Wo * CV;
@@ -387,19 +393,30 @@ __global__ void maxpool_bwd_kernel(const __half* __restrict__ x, long long xp, c
                 if (b > best1) { best1 = b; arg1 = ip; }
             }
         }
-        const __half2 g = *reinterpret_cast<const __half2*>(dy + pix * dyp + cv * 2);
-        const __half zero = __float2half(0.f);
+        const GT g0 = dy[pix * dyp + cv * 2], g1 = dy[pix * dyp + cv * 2 + 1];
+        const GT zero = Half8<GT>::from_f(0.f);
+        GT2 v;
         if (arg0 >= 0 && arg0 == arg1) {
-            atomicAdd(reinterpret_cast<__half2*>(dx + arg0 * dxp + cv * 2), g);
+            v.x = g0;
+            v.y = g1;
+            atomicAdd(reinterpret_cast<GT2*>(dx + arg0 * dxp + cv * 2), v);
         } else {
-            if (arg0 >= 0) atomicAdd(reinterpret_cast<__half2*>(dx + arg0 * dxp + cv * 2), __halves2half2(__low2half(g), zero));
-            if (arg1 >= 0) atomicAdd(reinterpret_cast<__half2*>(dx + arg1 * dxp + cv * 2), __halves2half2(zero, __high2half(g)));
+            if (arg0 >= 0) {
+                v.x = g0;
+                v.y = zero;
+                atomicAdd(reinterpret_cast<GT2*>(dx + arg0 * dxp + cv * 2), v);
+            }
+            if (arg1 >= 0) {
+                v.x = zero;
+                v.y = g1;
+                atomicAdd(reinterpret_cast<GT2*>(dx + arg1 * dxp + cv * 2), v);
+            }
         }
     }
 }
 extern "C" int b2y_maxpool_bwd(const void* x, long long x_pitch, const void* dy, long long dy_pitch, void* dx,
                                long long dx_pitch, int batch, int in_h, int in_w, int c, int ksize, int stride,
-                               int pad_mode, void* stream) {
+                               int pad_mode, int grad_dtype, void* stream) {
     if (!x || !dy || !dx || c % 2 != 0 || x_pitch % 2 != 0 || dy_pitch % 2 != 0 || dx_pitch % 2 != 0)
         return B2Y_ERR_INVALID;
     int pad, Ho, Wo;
@@ -413,9 +430,16 @@ extern "C" int b2y_maxpool_bwd(const void* x, long long x_pitch, const void* dy,
         Wo = (in_w + 2 * pad - ksize) / stride + 1;
     }
     const long long total = (long long)batch * Ho * Wo * (c / 2);
-    maxpool_bwd_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        reinterpret_cast<const __half*>(x), x_pitch, reinterpret_cast<const __half*>(dy), dy_pitch,
-        reinterpret_cast<__half*>(dx), dx_pitch, batch, in_h, in_w, c, ksize, stride, pad, Ho, Wo, pad_mode == 1);
+    if (grad_dtype == B2Y_DT_BF16)
+        maxpool_bwd_kernel<__nv_bfloat16, __nv_bfloat162><<<grid_for(total, 256), 256, 0,
+                                                            static_cast<cudaStream_t>(stream)>>>(
+            reinterpret_cast<const __half*>(x), x_pitch, reinterpret_cast<const __nv_bfloat16*>(dy), dy_pitch,
+            reinterpret_cast<__nv_bfloat16*>(dx), dx_pitch, batch, in_h, in_w, c, ksize, stride, pad, Ho, Wo,
+            pad_mode == 1);
+    else
+        maxpool_bwd_kernel<__half, __half2><<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+            reinterpret_cast<const __half*>(x), x_pitch, reinterpret_cast<const __half*>(dy), dy_pitch,
+            reinterpret_cast<__half*>(dx), dx_pitch, batch, in_h, in_w, c, ksize, stride, pad, Ho, Wo, pad_mode == 1);
     B2Y_CUDA_CHECK(cudaGetLastError());
     return B2Y_OK;
 }
@@ -424,9 +448,9 @@ extern "C" int b2y_maxpool_bwd(const void* x, long long x_pitch, const void* dy,
 // stem weight gradient (Cin <= 4, NCHW fp32 image): dW[co][ci][kh][kw] += scale * sum_pix dz[pix][co] * x[...]
 // CTA = 32 output channels x 8 tap groups; each thread keeps <= TPG taps of one output channel in registers.
 // ------------------------------------------------------------------------------------------------
-template <int TPG>
+template <int TPG, typename GT>
 __global__ void __launch_bounds__(256)
-stem_wgrad_kernel(const float* __restrict__ x, const __half* __restrict__ dz, long long dzp, float* __restrict__ dw,
+stem_wgrad_kernel(const float* __restrict__ x, const GT* __restrict__ dz, long long dzp, float* __restrict__ dw,
                   int B, int Cin, int H, int W, int Cout, int k, int stride, int pad, int Ho, int Wo, float scale) {
     const int taps = Cin * k * k;
     const int co_l = threadIdx.x & 31;
@@ -451,7 +475,7 @@ stem_wgrad_kernel(const float* __restrict__ x, const __half* __restrict__ dz, lo
             const int xo = (int)(m % Wo);
             const int yo = (int)((m / Wo) % Ho);
             const int n = (int)(m / ((long long)Wo * Ho));
-            const float g = co < Cout ? __half2float(dz[m * dzp + co]) : 0.f;
+            const float g = co < Cout ? Half8<GT>::to_f(dz[m * dzp + co]) : 0.f;
 #pragma unroll
             for (int j = 0; j < TPG; ++j) {
                 if (grp * TPG + j < taps) {
@@ -471,7 +495,7 @@ stem_wgrad_kernel(const float* __restrict__ x, const __half* __restrict__ dz, lo
     }
 }
 extern "C" int b2y_stem_conv_bwd_weight(const b2y_conv_desc* d, const float* x_nchw, const void* dz, float* dw_oihw,
-                                        float scale, void* stream) {
+                                        float scale, int grad_dtype, void* stream) {
     if (!d || !x_nchw || !dz || !dw_oihw) return B2Y_ERR_INVALID;
     const int taps = d->in_c * d->ksize * d->ksize;
     if (d->in_c > 4 || taps > 8 * 5) return B2Y_ERR_UNSUPPORTED;
@@ -479,9 +503,14 @@ extern "C" int b2y_stem_conv_bwd_weight(const b2y_conv_desc* d, const float* x_n
     int grid = (int)((M + 1023) / 1024);
     if (grid > 148 * 8) grid = 148 * 8;
     if (grid < 1) grid = 1;
-    stem_wgrad_kernel<5><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        x_nchw, reinterpret_cast<const __half*>(dz), d->out_pitch, dw_oihw, d->batch, d->in_c, d->in_h, d->in_w,
-        d->out_c, d->ksize, d->stride, d->pad, d->out_h, d->out_w, scale);
+    if (grad_dtype == B2Y_DT_BF16)
+        stem_wgrad_kernel<5, __nv_bfloat16><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+            x_nchw, reinterpret_cast<const __nv_bfloat16*>(dz), d->out_pitch, dw_oihw, d->batch, d->in_c, d->in_h,
+            d->in_w, d->out_c, d->ksize, d->stride, d->pad, d->out_h, d->out_w, scale);
+    else
+        stem_wgrad_kernel<5, __half><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+            x_nchw, reinterpret_cast<const __half*>(dz), d->out_pitch, dw_oihw, d->batch, d->in_c, d->in_h, d->in_w,
+            d->out_c, d->ksize, d->stride, d->pad, d->out_h, d->out_w, scale);
     B2Y_CUDA_CHECK(cudaGetLastError());
     return B2Y_OK;
 }

@@ -23,6 +23,7 @@ struct WgradParams {
     int ksteps_total;         // ceil(K_total / BK)
     int ksteps_per_split;
     float scale;              // multiplies the accumulator (1 / loss-scale)
+    unsigned idesc_ab;        // operand formats: dY (A) may be bf16 while X (B) stays fp16
     float* dw;                // fp32 [Cout][k][k][Cin], accumulated with atomics
 };
 
@@ -160,7 +161,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant_
                     for (int k = 0; k < BK / 16; ++k) {
                         const uint64_t adesc = smem_desc_at(adesc_base, a_addr + k * 16 * 128);
                         const uint64_t bdesc = smem_desc_at(bdesc_base, b_addr + k * 16 * NB_ROW_BYTES);
-                        mma_f16_ss(tmem_base, adesc, bdesc, IDESC, (ks > ks0 || k > 0) ? 1u : 0u);
+                        mma_f16_ss(tmem_base, adesc, bdesc, IDESC | p.idesc_ab, (ks > ks0 || k > 0) ? 1u : 0u);
                     }
                     tc_commit(&empty_bar[stage]);
                     if (++stage == NS) {
@@ -282,7 +283,7 @@ static int wgrad_launch_cfg(const CUtensorMap& a, const CUtensorMap& b, const Wg
 using namespace b2y;
 
 extern "C" int b2y_conv2d_bwd_weight(const b2y_conv_desc* d, const void* x, const void* dy, float* dw, float scale,
-                                     void* stream) {
+                                     int grad_dtype, void* stream) {
     std::call_once(w_once, w_resolve);
     if (!d || !x || !dy || !dw) return B2Y_ERR_INVALID;
     if (!w_encodeTiled || !w_encodeIm2col) return B2Y_ERR_DRIVER;
@@ -330,6 +331,7 @@ extern "C" int b2y_conv2d_bwd_weight(const b2y_conv_desc* d, const void* x, cons
     p.ksplits = (p.ksteps_total + p.ksteps_per_split - 1) / p.ksteps_per_split;
     p.scale = scale;
     p.dw = dw;
+    p.idesc_ab = grad_dtype == B2Y_DT_BF16 ? (1u << 7) : 0u;
 
     CUtensorMap tmDy, tmX;
     {
@@ -337,7 +339,8 @@ extern "C" int b2y_conv2d_bwd_weight(const b2y_conv_desc* d, const void* x, cons
         cuuint64_t gstride[1] = {(cuuint64_t)(d->out_pitch * 2)};
         cuuint32_t box[2] = {64, 64};
         cuuint32_t estr[2] = {1, 1};
-        if (w_encodeTiled(&tmDy, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(dy), gdim, gstride, box, estr,
+        if (w_encodeTiled(&tmDy, grad_dtype == B2Y_DT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                                           : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(dy), gdim, gstride, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return B2Y_ERR_DRIVER;
