@@ -43,8 +43,9 @@ extern "C" {
 #define B2Y_ACT_HSWISH 5
 #define B2Y_ACT_SWISH 6
 
-/* 16-bit tensor dtypes (gradient tensors of the training path flow in bf16: fp16 overflows/underflows across the
- * ~100 BatchNorm layers of a Darknet; activations stay fp16) */
+/* 16-bit tensor dtypes.  Training: activation gradients (dY) are stored in bf16 (fp16 over/underflows across the ~100
+ * BatchNorm layers of a Darknet); the conv data gradient dZ that feeds the tensor-core GEMMs is fp16 times a per-layer
+ * power-of-two scale picked on the device (tcgen05 kind::f16 faults on mixed f16/bf16 operands) */
 #define B2Y_DT_F16 0
 #define B2Y_DT_BF16 1
 
@@ -234,14 +235,18 @@ int b2y_bn_act_fwd(const void* x, long long x_pitch, const float* scale, const f
  * dx = (gamma*invstd) * (dz - dbeta/N - xhat*dgamma/N)                            (pass 2). */
 int b2y_bn_act_bwd_reduce(const void* x, long long x_pitch, const void* dy, long long dy_pitch, const float* scale,
                           const float* shift, const float* save_mean, const float* save_invstd, float* dgamma,
-                          float* dbeta, long long pixels, int c, int act, float slope, int grad_dtype, void* stream);
+                          float* dbeta, float* du_absmax /* optional: atomicMax of |du|, caller zeroes */,
+                          long long pixels, int c, int act, float slope, int grad_dtype, void* stream);
 int b2y_bn_act_bwd_apply(const void* x, long long x_pitch, const void* dy, long long dy_pitch, const float* scale,
                          const float* shift, const float* gamma, const float* save_mean, const float* save_invstd,
-                         const float* dgamma, const float* dbeta, void* dx, long long dx_pitch, long long pixels,
-                         int c, int act, float slope, int grad_dtype, void* stream);
+                         const float* dgamma, const float* dbeta, void* dx /* fp16, times s */, long long dx_pitch,
+                         long long pixels, int c, int act, float slope, int grad_dtype /* of dy */,
+                         const float* du_absmax, float* scale_out /* [s, 1/s] chosen on the device, power of two */,
+                         void* stream);
 /* dX = conv_transpose(dY, W)   (data gradient; implicit GEMM on tcgen05) */
 int b2y_conv2d_bwd_data(const b2y_conv_desc* d, const void* dy, const void* w_packed_t, void* dx, int accumulate,
-                        int grad_dtype, void* stream);
+                        int operand_dtype /* dY and weights */, int out_dtype /* dX */,
+                        const float* inv_scale_ptr /* optional device scalar multiplied into dX */, void* stream);
 /* weights for b2y_conv2d_bwd_data: OIHW fp32 -> per output-phase slabs [phase][in_c][tap][out_c] fp16
  * (stride-s data gradients are decomposed into s*s stride-1 implicit GEMMs over dY; out_c*ksize^2*in_c elements) */
 int b2y_pack_dgrad_weights(const b2y_conv_desc* d, const float* w_oihw, void* w_packed_t, int grad_dtype,
@@ -249,7 +254,7 @@ int b2y_pack_dgrad_weights(const b2y_conv_desc* d, const float* w_oihw, void* w_
 /* dW[o][kh][kw][i] += scale * sum_pixels dY[p][o] * X[p@(kh,kw)][i]  (weight gradient, tcgen05 GEMM over the pixel
  * dimension with MN-major operands; dw fp32 [O][kh][kw][I], caller zeroes it; split-K reduced with red.global.add) */
 int b2y_conv2d_bwd_weight(const b2y_conv_desc* d, const void* x, const void* dy, float* dw, float scale,
-                          int grad_dtype, void* stream);
+                          int operand_dtype /* X and dY */, const float* inv_scale_ptr, void* stream);
 /* [O][kh][kw][I] fp32 -> OIHW fp32 parameter-gradient layout: dst = alpha*src (+ dst if accumulate) */
 int b2y_unpack_wgrad(const float* dw_packed, float* dw_oihw, int out_c, int in_c, int ksize, float alpha,
                      int accumulate, void* stream);
@@ -257,7 +262,8 @@ int b2y_unpack_wgrad(const float* dw_packed, float* dw_oihw, int out_c, int in_c
 int b2y_axpby_f32(const float* src, float* dst, long long n, float alpha, float beta, void* stream);
 /* backward of the YOLO permute: dp fp32 [B][na][ny][nx][no] -> d(raw) fp16 [B][ny][nx][raw_pitch] * scale (models.py:406) */
 int b2y_yolo_grad_to_raw(const float* dp, void* draw, long long raw_pitch, int batch, int na, int no, int ny, int nx,
-                         float scale, int grad_dtype, void* stream);
+                         float scale, const float* scale_ptr /* optional device scalar */, int grad_dtype,
+                         void* stream);
 /* backward of nn.Upsample (nearest): dx += window sums of dy (in place accumulate) */
 int b2y_upsample_nearest_bwd(const void* dy, long long dy_pitch, void* dx, long long dx_pitch, int batch, int in_h,
                              int in_w, int c, int scale, int grad_dtype, void* stream);

@@ -81,14 +81,36 @@ def test_conv_bwd_data_and_weight(case):
     assert e_dw < 2e-4      # fp32 accumulate + fp32 atomics
 
 
-@pytest.mark.parametrize("case", [GRAD_CASES[1], GRAD_CASES[3], GRAD_CASES[6], GRAD_CASES[9]],
-                         ids=lambda c: "bf16-" + str(c))
-def test_conv_bwd_bf16_gradients(case):
-    """the training path: dY in bf16 (dgrad bf16 x bf16, wgrad bf16 dY x fp16 X -- mixed operand formats)."""
-    e_dx, e_dw = conv_grads_case(*case, gdt=torch.bfloat16)
-    print("\nbf16 %s dx err/rms=%.3g dw err/rms=%.3g" % (case, e_dx, e_dw))
-    assert e_dx < 3e-2      # bf16 store of dx (8-bit mantissa)
-    assert e_dw < 2e-4      # exact products of the bf16/fp16 operands, fp32 accumulate
+def test_dgrad_fp16_operands_bf16_output_with_device_scale():
+    """the training configuration: dZ fp16 (scaled by s), weights fp16, dX accumulated in bf16, 1/s read on device."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(12)
+    B, H, W, Cin, Cout, k, stride, pad = 2, 16, 16, 64, 128, 3, 2, 1
+    w = (torch.randn(Cout, Cin, k, k, generator=g) / 24).half().double()
+    sc = 64.0
+    dz_true = (torch.randn(B, Cout, 8, 8, generator=g) * 1e-3)
+    dz16 = (dz_true * sc).half()
+    x = torch.zeros(B, Cin, H, W, dtype=torch.double, requires_grad=True)
+    F.conv2d(x, w, None, stride=stride, padding=pad).backward(dz16.double() / sc)
+    base = (torch.randn(B, Cin, H, W, generator=g) * 1e-2).bfloat16()
+    ref = x.grad.float() + base.float()
+    wt = ops.pack_dgrad_weights(w.float().cuda(), stride, pad, (H, W))
+    out = _nhwc(base.float(), torch.bfloat16)
+    inv = torch.tensor([1.0 / sc], device="cuda")
+    ops.conv2d_bwd_data(_nhwc(dz16.float()), wt, (B, H, W, Cin), k, stride, pad, out=out, accumulate=True, inv_scale=inv)
+    got = _nchw(out)
+    assert (got - ref).abs().max() <= 1.5e-2 * ref.abs().max()      # bf16 store
+    dw = ops.conv2d_bwd_weight(_nhwc(torch.randn(B, Cin, H, W, generator=g)), _nhwc(dz16.float()), k, stride, pad,
+                               inv_scale=inv)
+    assert torch.isfinite(dw).all()
+
+
+def test_mixed_f16_bf16_operands_are_rejected():
+    ops = _ops()
+    x = torch.zeros(1, 8, 8, 64, dtype=torch.float16, device="cuda")
+    dy = torch.zeros(1, 8, 8, 64, dtype=torch.bfloat16, device="cuda")
+    with pytest.raises(AssertionError):
+        ops.conv2d_bwd_weight(x, dy, 3, 1, 1)
 
 
 def test_conv_bwd_data_accumulate():
@@ -122,7 +144,11 @@ def test_bn_act_fwd_bwd(act, gdt):
     rmc, rvc = rm.cuda(), rv.cuda()
     mean, invstd, scale, shift = ops.bn_finalize(s1, s2, B * H * W, gamma.cuda(), beta.cuda(), 1e-5, 0.1, rmc, rvc)
     out = ops.bn_act_fwd(zn, scale, shift, act, residual=_nhwc(res))
-    dz, dgamma, dbeta = ops.bn_act_bwd(zn, _nhwc(dy, gdt), scale, shift, gamma.cuda(), mean, invstd, act)
+    dz, dgamma, dbeta, aux = ops.bn_act_bwd(zn, _nhwc(dy, gdt), scale, shift, gamma.cuda(), mean, invstd, act)
+    s_dev, inv_dev = float(aux[1]), float(aux[2])
+    assert s_dev > 0 and abs(s_dev * inv_dev - 1.0) < 1e-6 and float(torch.log2(aux[1])) % 1.0 == 0.0
+    assert float(dz.float().abs().max()) <= 8192.0          # scaled into the fp16 sweet spot
+    dz = dz.float() * inv_dev
     torch.cuda.synchronize()
     assert (_nchw(out) - y.detach().float()).abs().max() < 6e-3
     np.testing.assert_allclose(rmc.cpu().numpy(), rm_r.float().numpy(), rtol=1e-4, atol=1e-5)
@@ -131,7 +157,7 @@ def test_bn_act_fwd_bwd(act, gdt):
     np.testing.assert_allclose(dbeta.cpu().numpy(), br.grad.float().numpy(), rtol=2e-3, atol=2e-3)
     ref_dz = zr.grad.float()
     tol = 4e-3 if gdt == torch.float16 else 2e-2
-    assert (_nchw(dz) - ref_dz).abs().max() < tol * max(1.0, ref_dz.abs().max().item())
+    assert (dz.permute(0, 3, 1, 2).cpu() - ref_dz).abs().max() < tol * max(1.0, ref_dz.abs().max().item())
 
 
 def test_sgd_nesterov_matches_torch():

@@ -249,28 +249,31 @@ def pack_dgrad_weights(w_oihw, stride, pad, in_hw, dtype=torch.float16):
     return out
 
 
-def conv2d_bwd_data(dy, w_packed_t, in_shape, k, stride, pad, out=None, accumulate=False):
-    """dx = conv^T(dy, W): dy NHWC fp16 [B,Ho,Wo,O] -> dx NHWC fp16 [B,H,W,I]."""
+def conv2d_bwd_data(dy, w_packed_t, in_shape, k, stride, pad, out=None, accumulate=False, inv_scale=None):
+    """dx (+)= conv^T(dy, W) [* inv_scale]: dy NHWC 16-bit [B,Ho,Wo,O] (same format as the packed weights) -> dx NHWC
+    fp16 or bf16 [B,H,W,I]; inv_scale: optional device scalar multiplied into the result."""
     B, H, W, I = in_shape
     _, Ho, Wo, O = dy.shape
     if out is None:
         out = torch.empty((B, H, W, I), dtype=dy.dtype, device=dy.device)
         assert not accumulate
-    assert out.dtype == dy.dtype == w_packed_t.dtype
+    assert dy.dtype == w_packed_t.dtype, "dY and the packed weights must share one 16-bit format"
     d = ConvDesc(B, H, W, I, _pitch(out), O, k, stride, pad, Ho, Wo, _pitch(dy), 0, 0.0, OUT_F16, 0)
     call("b2y_conv2d_bwd_data", C.byref(d), ptr(dy), ptr(w_packed_t), ptr(out), 1 if accumulate else 0, _gdt(dy),
-         stream_ptr())
+         _gdt(out), ptr(inv_scale), stream_ptr())
     return out
 
 
-def conv2d_bwd_weight(x, dy, k, stride, pad, scale=1.0, dw=None):
-    """dW [O][k][k][I] fp32 (+)= scale * sum_pixels dy (x) x."""
+def conv2d_bwd_weight(x, dy, k, stride, pad, scale=1.0, dw=None, inv_scale=None):
+    """dW [O][k][k][I] fp32 (+)= scale [* inv_scale] * sum_pixels dy (x) x   (x and dy share one 16-bit format)."""
     B, H, W, I = x.shape
     _, Ho, Wo, O = dy.shape
     if dw is None:
         dw = torch.zeros((O, k, k, I), dtype=torch.float32, device=x.device)
     d = ConvDesc(B, H, W, I, _pitch(x), O, k, stride, pad, Ho, Wo, _pitch(dy), 0, 0.0, OUT_F16, 0)
-    call("b2y_conv2d_bwd_weight", C.byref(d), ptr(x), ptr(dy), ptr(dw), float(scale), _gdt(dy), stream_ptr())
+    assert x.dtype == dy.dtype, "tcgen05 kind::f16 needs both operands in the same 16-bit format"
+    call("b2y_conv2d_bwd_weight", C.byref(d), ptr(x), ptr(dy), ptr(dw), float(scale), _gdt(dy), ptr(inv_scale),
+         stream_ptr())
     return dw
 
 
@@ -305,23 +308,27 @@ def bn_act_fwd(x, scale, shift, act, slope=0.1, residual=None, out=None):
     return out
 
 
-def bn_act_bwd(x, dy, scale, shift, gamma, mean, invstd, act, slope=0.1, dx=None, dgamma=None, dbeta=None):
-    """Returns (dx fp16, dgamma fp32, dbeta fp32) for y = act(x*scale+shift) with batch statistics."""
+def bn_act_bwd(x, dy, scale, shift, gamma, mean, invstd, act, slope=0.1, dx=None, dgamma=None, dbeta=None, aux=None):
+    """Backward of y = act(x*scale+shift) with batch statistics.
+    Returns (dz fp16 = s * true gradient, dgamma fp32, dbeta fp32, aux) where aux = device float[3]
+    [max|du|, s, 1/s]: the power-of-two scale s is chosen inside the kernel (no host sync)."""
     B, H, W, Cc = x.shape
     dev = x.device
     if dgamma is None:
         dgamma = torch.zeros(Cc, dtype=torch.float32, device=dev)
         dbeta = torch.zeros(Cc, dtype=torch.float32, device=dev)
+    if aux is None:
+        aux = torch.zeros(3, dtype=torch.float32, device=dev)
     a = ACT[act] if isinstance(act, str) else int(act)
     call("b2y_bn_act_bwd_reduce", ptr(x), _pitch(x), ptr(dy), _pitch(dy), ptr(scale), ptr(shift), ptr(mean),
-         ptr(invstd), ptr(dgamma), ptr(dbeta), B * H * W, Cc, a, float(slope), _gdt(dy), stream_ptr())
+         ptr(invstd), ptr(dgamma), ptr(dbeta), ptr(aux), B * H * W, Cc, a, float(slope), _gdt(dy), stream_ptr())
     if dx is None:
-        dx = torch.empty((B, H, W, Cc), dtype=dy.dtype, device=dev)
-    assert dx.dtype == dy.dtype
+        dx = torch.empty((B, H, W, Cc), dtype=torch.float16, device=dev)
+    assert dx.dtype == torch.float16
     call("b2y_bn_act_bwd_apply", ptr(x), _pitch(x), ptr(dy), _pitch(dy), ptr(scale), ptr(shift), ptr(gamma), ptr(mean),
          ptr(invstd), ptr(dgamma), ptr(dbeta), ptr(dx), _pitch(dx), B * H * W, Cc, a, float(slope), _gdt(dy),
-         stream_ptr())
-    return dx, dgamma, dbeta
+         ptr(aux), C.c_void_p(aux.data_ptr() + 4), stream_ptr())
+    return dx, dgamma, dbeta, aux
 
 
 def bias_act_bwd_reduce(x, dy, scale, shift, act, slope=0.1, dbeta=None):
@@ -330,7 +337,7 @@ def bias_act_bwd_reduce(x, dy, scale, shift, act, slope=0.1, dbeta=None):
     if dbeta is None:
         dbeta = torch.zeros(Cc, dtype=torch.float32, device=x.device)
     call("b2y_bn_act_bwd_reduce", ptr(x), _pitch(x), ptr(dy), _pitch(dy), ptr(scale), ptr(shift), None, None, None,
-         ptr(dbeta), B * H * W, Cc, ACT[act] if isinstance(act, str) else int(act), float(slope), _gdt(dy),
+         ptr(dbeta), None, B * H * W, Cc, ACT[act] if isinstance(act, str) else int(act), float(slope), _gdt(dy),
          stream_ptr())
     return dbeta
 

@@ -5,10 +5,13 @@ Replaces autograd over ~500 ATen/cuDNN calls (reference train.py:380-441 -> mode
   forward   conv (tcgen05, per-channel sum / sum^2 from the epilogue) -> bn_finalize -> bn+act(+shortcut) apply
   backward  yolo permute^T -> [bn+act backward reduce / apply -> wgrad (tcgen05, pixel-K GEMM) -> dgrad (tcgen05)]
 
-Activations z (raw conv output) and y (post activation) are kept in NHWC fp16 (accurate forward); gradient tensors
-flow in **bf16** (fp32 range: the gradient magnitude drifts by orders of magnitude across ~100 BatchNorm layers, which
-fp16 cannot hold with one loss scale), weight / BN gradients are accumulated and stored in fp32.  The dgrad GEMM is
-bf16 x bf16, the wgrad GEMM bf16 (dY) x fp16 (X) -- tcgen05 kind::f16 takes the two operand formats independently.
+Activations z (raw conv output) and y (post activation) are kept in NHWC fp16 (accurate forward).  Gradients w.r.t.
+activations (dY) are stored in **bf16** (fp32 range: their magnitude drifts by orders of magnitude across ~100
+BatchNorm layers, which fp16 cannot hold with one loss scale).  The conv data gradient dZ, which is an operand of the
+two tensor-core GEMMs (dgrad with the fp16 weights, wgrad with the fp16 activations), is written in fp16 times a
+per-layer power-of-two scale chosen inside the BN-backward kernel from a bound on max|dZ| (tcgen05 kind::f16 faults on
+mixed f16/bf16 operands); the GEMM epilogues read 1/scale from device memory, so there is no host synchronisation.
+Weight / BN gradients are accumulated and stored in fp32.
 The plan plugs into autograd as ONE torch.autograd.Function whose inputs are the model parameters, so
 loss.backward(), DistributedDataParallel hooks and torch optimisers work unchanged.
 """
@@ -31,7 +34,7 @@ def _round_up(v, m):
 
 class _ConvRec:
     __slots__ = ('i', 'conv', 'bn', 'act', 'slope', 'src', 'z', 'y', 'res', 'head', 'stem', 'k', 's', 'p', 'Cout',
-                 'Cpad', 'w16', 'wT', 'stats', 'mean', 'invstd', 'scale', 'shift', 'ones', 'zeros', 'w32')
+                 'Cpad', 'w16', 'wT', 'stats', 'mean', 'invstd', 'scale', 'shift', 'ones', 'zeros', 'w32', 'aux_row')
 
     def __init__(self):
         for k in self.__slots__:
@@ -156,9 +159,9 @@ class TrainPlan:
             if id(t) not in self.grad_of:
                 if t.dtype == torch.float16:
                     make_grad(t, torch.zeros(t.buf.shape, dtype=GDT, device=dev))
-                else:  # head output: gradient is the 16-bit d(raw) buffer, HEAD_PAD channels
-                    g = _Tensor(HEAD_PAD, t.H, t.W, GDT)
-                    g.buf = torch.zeros((B, t.H, t.W, HEAD_PAD), dtype=GDT, device=dev)
+                else:  # head output: its gradient is directly the GEMM operand dZ -> fp16 (times a device-side scale)
+                    g = _Tensor(HEAD_PAD, t.H, t.W, torch.float16)
+                    g.buf = torch.zeros((B, t.H, t.W, HEAD_PAD), dtype=torch.float16, device=dev)
                     self.grad_of[id(t)] = g
             return t
 
@@ -194,6 +197,7 @@ class TrainPlan:
                     r.z = r.y   # no BN: the conv epilogue applies bias + activation directly
                     r.ones = torch.ones(r.Cpad, dtype=torch.float32, device=dev)
                     r.zeros = torch.zeros(r.Cpad, dtype=torch.float32, device=dev)
+                r.aux_row = len(self.convs)
                 self.convs.append(r)
                 self.order.append(('conv', r))
                 if not is_head[i] and r.res is None:
@@ -237,7 +241,8 @@ class TrainPlan:
                 seen.add(g.buf.data_ptr())
                 self.grad_bufs.append(g.buf)
         maxz = max(r.Cpad * r.y.H * r.y.W for r in self.convs)
-        self.dz_scratch = torch.empty(B * maxz, dtype=GDT, device=dev)
+        self.dz_scratch = torch.empty(B * maxz, dtype=torch.float16, device=dev)
+        self.dz_aux = torch.zeros((len(self.convs) + 1, 4), dtype=torch.float32, device=dev)  # [max|du|, s, 1/s, -]
         maxw = max(r.Cpad * r.conv.in_channels * r.k * r.k for r in self.convs)
         self.dw_scratch = torch.empty(maxw, dtype=torch.float32, device=dev)
         maxc = max(r.Cpad for r in self.convs)
@@ -259,7 +264,7 @@ class TrainPlan:
             else:
                 r.w16, _, _ = ops.pack_conv_weights(w)
                 hin, win = r.src.H, r.src.W
-                r.wT = ops.pack_dgrad_weights(w, r.s, r.p, (hin, win), dtype=GDT)
+                r.wT = ops.pack_dgrad_weights(w, r.s, r.p, (hin, win), dtype=torch.float16)
 
     def _zview(self, r):
         return r.z.buf[..., r.z.c0:r.z.c0 + r.Cpad] if r.head else r.z.view()
@@ -321,7 +326,7 @@ class TrainPlan:
                 r.zeros = torch.zeros(r.Cout, dtype=torch.float32, device=self.device)
             B_, H_, W_, C_ = z.shape
             call("b2y_bn_act_bwd_reduce", ptr(z), ops._pitch(z), ptr(z), ops._pitch(z), ptr(r.ones), ptr(r.zeros),
-                 ptr(r.zeros), ptr(r.ones), ptr(r.stats[1]), ptr(r.stats[0]), B_ * H_ * W_, C_, 0, 0.0, 0,
+                 ptr(r.zeros), ptr(r.ones), ptr(r.stats[1]), ptr(r.stats[0]), None, B_ * H_ * W_, C_, 0, 0.0, 0,
                  stream_ptr())
         else:
             ops.conv2d(r.src.view(), r.w16, None, r.k, r.s, r.p, out=z, stats=(r.stats[0], r.stats[1]))
@@ -343,13 +348,19 @@ class TrainPlan:
         self.sink = getattr(self.model, '_b2y_grad_sink', None)   # FlatDataParallel: write into the flat buffer
         for gb in self.grad_bufs:
             gb.zero_()
+        self.dz_aux.zero_()
         grads = {}
+        # head gradients are GEMM operands (fp16): scale them by a power of two derived on the device from max|dp|
+        live = [dp for dp in dps if dp is not None]
+        amax = torch.stack([dp.detach().abs().max() for dp in live]).max().clamp(min=1e-30)
+        hs = torch.exp2(torch.floor(torch.log2(4096.0 / amax))).clamp(1e-30, 1e30).float()
+        self.head_scale = torch.stack([hs, 1.0 / hs]).contiguous()           # device [s, 1/s]
         for (m, raw), dp in zip(self.yolo, dps):
             g = self.grad_of[id(raw)]
             if dp is None:
                 continue
             call("b2y_yolo_grad_to_raw", ptr(dp.contiguous().float()), ptr(g.buf), HEAD_PAD, self.B, m.na, m.no, raw.H,
-                 raw.W, S, ops._gdt(g.buf), stream_ptr())
+                 raw.W, S, ptr(self.head_scale), ops._gdt(g.buf), stream_ptr())
         G = lambda t: self.grad_of[id(t)]
         for st in reversed(self.order):
             kind = st[0]
@@ -391,19 +402,22 @@ class TrainPlan:
             dz = self.dz_scratch[:B * Ho * Wo * r.Cout].view(B, Ho, Wo, r.Cout)
             dgb = self.dgb_scratch[:, :r.Cout]
             dgb.zero_()
+            aux = self.dz_aux[self.convs.index(r)] if r.aux_row is None else self.dz_aux[r.aux_row]
             ops.bn_act_bwd(r.z.view(), dy, r.scale, r.shift, bn.weight.detach(), r.mean, r.invstd, r.act, r.slope,
-                           dx=dz, dgamma=dgb[0], dbeta=dgb[1])
+                           dx=dz, dgamma=dgb[0], dbeta=dgb[1], aux=aux)
+            inv_s = aux[2:3]                                   # device scalar 1/s of this layer's dz
             self._emit(grads, bn.weight, dgb[0], inv)
             self._emit(grads, bn.bias, dgb[1], inv)
         else:
             dz = gy.buf[..., :r.Cpad] if r.head else gy.view()
+            inv_s = self.head_scale[1:2]
             if r.act != 'linear':
                 raise NotImplementedError("activation without BatchNorm in training")
             if conv.bias is not None:
                 db = self.dgb_scratch[1, :r.Cpad]
                 db.zero_()
                 ops.bias_act_bwd_reduce(dz, dz, r.ones, r.zeros, 'linear', dbeta=db)
-                self._emit(grads, conv.bias, db[:r.Cout], inv)
+                self._emit(grads, conv.bias, db[:r.Cout] * inv_s, inv)
         I = conv.in_channels
         gw = self.sink.get(id(conv.weight)) if self.sink is not None else None
         if gw is None:
@@ -413,13 +427,15 @@ class TrainPlan:
             gw.zero_()
             d = ConvDesc(B, self.H, self.W, I, I, r.Cout, r.k, r.s, r.p, Ho, Wo, ops._pitch(dz), 0, 0.0, OUT_F16, 0)
             call("b2y_stem_conv_bwd_weight", C.byref(d), ptr(self.x), ptr(dz), ptr(gw), inv, ops._gdt(dz), stream_ptr())
+            gw.mul_(inv_s)
         else:
             dwp = self.dw_scratch[:r.Cpad * r.k * r.k * I].view(r.Cpad, r.k, r.k, I)
             dwp.zero_()
-            ops.conv2d_bwd_weight(r.src.view(), dz, r.k, r.s, r.p, scale=inv, dw=dwp)
+            ops.conv2d_bwd_weight(r.src.view(), dz, r.k, r.s, r.p, scale=inv, dw=dwp, inv_scale=inv_s)
             ops.unpack_wgrad(dwp[:r.Cout], gw)
             gx = self.grad_of[id(r.src)]
-            ops.conv2d_bwd_data(dz, r.wT, (B, r.src.H, r.src.W, I), r.k, r.s, r.p, out=gx.view(), accumulate=True)
+            ops.conv2d_bwd_data(dz, r.wT, (B, r.src.H, r.src.W, I), r.k, r.s, r.p, out=gx.view(), accumulate=True,
+                                inv_scale=inv_s)
 
     def _emit(self, grads, param, src, alpha):
         dst = self.sink.get(id(param)) if self.sink is not None else None

@@ -133,6 +133,7 @@ struct EpilogueArgs {
     float* stat_sum = nullptr;
     float* stat_sqsum = nullptr;
     int res_bf16 = 0;
+    const float* acc_scale_ptr = nullptr;
 };
 
 // Generic implicit-GEMM launch description: A = NHWC activation-like tensor gathered tap by tap, B = [Nout][ntaps*C].
@@ -196,6 +197,7 @@ int gemm_conv_launch(const GemmConvSpec& g, const EpilogueArgs& e, cudaStream_t 
     p.act = e.act;
     p.slope = e.slope;
     p.acc_scale = e.acc_scale;
+    p.acc_scale_ptr = e.acc_scale_ptr;
     p.idesc_ab = (g.a_bf16 ? (1u << 7) : 0u) | (g.b_bf16 ? (1u << 10) : 0u);
     p.res_bf16 = e.res_bf16;
     p.res = reinterpret_cast<const __half*>(e.res);
@@ -364,8 +366,11 @@ extern "C" int b2y_pack_dgrad_weights(const b2y_conv_desc* d, const float* w_oih
 }
 
 extern "C" int b2y_conv2d_bwd_data(const b2y_conv_desc* d, const void* dy, const void* w_packed_t, void* dx,
-                                   int accumulate, int grad_dtype, void* stream) {
-    const bool gbf = grad_dtype == B2Y_DT_BF16;
+                                   int accumulate, int operand_dtype, int out_dtype, const float* inv_scale_ptr,
+                                   void* stream) {
+    const bool gbf = operand_dtype == B2Y_DT_BF16;     // dY and the packed weights (must match: tcgen05 kind::f16
+                                                       // raises an illegal-instruction fault for mixed f16/bf16)
+    const bool obf = out_dtype == B2Y_DT_BF16;         // dX (and the accumulate source)
     if (!d || !dy || !w_packed_t || !dx) return B2Y_ERR_INVALID;
     if (d->stride > 4) return B2Y_ERR_UNSUPPORTED;
     DgradPhase ph[16];
@@ -412,11 +417,12 @@ extern "C" int b2y_conv2d_bwd_data(const b2y_conv_desc* d, const void* dy, const
         EpilogueArgs e;
         e.out = dx;
         e.out_pitch = d->in_pitch;
-        e.out_dtype = gbf ? OUT_BF16 : OUT_F16;
+        e.out_dtype = obf ? OUT_BF16 : OUT_F16;
+        e.acc_scale_ptr = inv_scale_ptr;
         if (accumulate) {
             e.res = dx;
             e.res_pitch = d->in_pitch;
-            e.res_bf16 = gbf ? 1 : 0;
+            e.res_bf16 = obf ? 1 : 0;
         }
         int rc = gemm_conv_launch(g, e, static_cast<cudaStream_t>(stream));
         if (rc != B2Y_OK) return rc;

@@ -41,6 +41,7 @@ struct ConvTcParams {
     int act;
     float slope;
     float acc_scale;        // multiplies the accumulator (1 for fp16; s_a*s_w for int8)
+    const float* acc_scale_ptr;  // optional device scalar multiplied in as well (per-layer gradient un-scaling)
     unsigned idesc_ab;      // a_format<<7 | b_format<<10 for kind::f16 (0 = f16, 1 = bf16 per operand)
     int res_bf16;           // residual / accumulate tensor is bf16 instead of fp16
     const __half* res;      // optional residual (16-bit, NHWC) added after the activation
@@ -232,6 +233,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         constexpr int EPI_WARPS = ConvTcEpi<BLOCK_N>::WARPS;
         constexpr int EPI_THREADS = 32 * EPI_WARPS;
         constexpr int COLS_PER_GROUP = BLOCK_N / (EPI_WARPS / 4);
+        const float acc_mul = p.acc_scale * (p.acc_scale_ptr != nullptr ? __ldg(p.acc_scale_ptr) : 1.f);
         const int ew = (warp - 4) & 3;          // TMEM lane quarter == warp_id % 4
         const int cg = (warp - 4) >> 2;         // column group
         const int et = threadIdx.x - 128;       // 0..EPI_THREADS-1
@@ -296,7 +298,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     float a = (KIND == CONV_KIND_F16) ? __uint_as_float(raw[j]) : (float)(int)raw[j];
-                    v[j] = a * p.acc_scale;
+                    v[j] = a * acc_mul;
                 }
 
                 if (p.stat_sum != nullptr) {

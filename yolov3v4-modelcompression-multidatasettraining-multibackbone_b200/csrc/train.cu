@@ -109,9 +109,10 @@ __global__ void __launch_bounds__(256)
 bn_act_bwd_reduce_kernel(const __half* __restrict__ x, long long xp, const GT* __restrict__ dy, long long dp,
                          const float* __restrict__ scale, const float* __restrict__ shift,
                          const float* __restrict__ mean, const float* __restrict__ invstd,
-                         float* __restrict__ dgamma, float* __restrict__ dbeta, long long pixels, int C, int act,
-                         float slope) {
+                         float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ du_absmax,
+                         long long pixels, int C, int act, float slope) {
     __shared__ float red[8][32][17];
+    float amax = 0.f;
     const int CV = C / 8;
     const int cv0 = blockIdx.y * 32;
     const int cvn = min(32, CV - cv0);                 // channel vectors in this slab
@@ -148,8 +149,14 @@ bn_act_bwd_reduce_kernel(const __half* __restrict__ x, long long xp, const GT* _
                 const float du = g8[j] * act_grad(u, act, slope);
                 gb[j] += du;
                 gg[j] += du * ((xf - mu[j]) * is[j]);
+                amax = fmaxf(amax, fabsf(du));
             }
         }
+    }
+    if (du_absmax != nullptr) {   // max |du| over the tensor (non-negative floats order like their bit patterns)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+        if (lane == 0 && amax > 0.f) atomicMax(reinterpret_cast<unsigned int*>(du_absmax), __float_as_uint(amax));
     }
     // combine the pixel sub-lanes of a warp, then the 8 warps of the CTA, then one atomic per channel
 #pragma unroll
@@ -184,8 +191,8 @@ bn_act_bwd_reduce_kernel(const __half* __restrict__ x, long long xp, const GT* _
 
 extern "C" int b2y_bn_act_bwd_reduce(const void* x, long long x_pitch, const void* dy, long long dy_pitch,
                                      const float* scale, const float* shift, const float* save_mean,
-                                     const float* save_invstd, float* dgamma, float* dbeta, long long pixels, int c,
-                                     int act, float slope, int grad_dtype, void* stream) {
+                                     const float* save_invstd, float* dgamma, float* dbeta, float* du_absmax,
+                                     long long pixels, int c, int act, float slope, int grad_dtype, void* stream) {
     if (!x || !dy || !scale || !shift || !dbeta || c % 8 != 0 || x_pitch % 8 != 0 || dy_pitch % 8 != 0)
         return B2Y_ERR_INVALID;
     const int CV = c / 8;
@@ -195,26 +202,60 @@ extern "C" int b2y_bn_act_bwd_reduce(const void* x, long long x_pitch, const voi
     if (grad_dtype == B2Y_DT_BF16)
         bn_act_bwd_reduce_kernel<__nv_bfloat16><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
             reinterpret_cast<const __half*>(x), x_pitch, reinterpret_cast<const __nv_bfloat16*>(dy), dy_pitch, scale,
-            shift, save_mean, save_invstd, dgamma, dbeta, pixels, c, act, slope);
+            shift, save_mean, save_invstd, dgamma, dbeta, du_absmax, pixels, c, act, slope);
     else
         bn_act_bwd_reduce_kernel<__half><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
             reinterpret_cast<const __half*>(x), x_pitch, reinterpret_cast<const __half*>(dy), dy_pitch, scale, shift,
-            save_mean, save_invstd, dgamma, dbeta, pixels, c, act, slope);
+            save_mean, save_invstd, dgamma, dbeta, du_absmax, pixels, c, act, slope);
     B2Y_CUDA_CHECK(cudaGetLastError());
     return B2Y_OK;
 }
 
 // backward pass 2: dx = gamma*invstd * (du - dbeta/N - xhat*dgamma/N)
+// The data gradient dz feeds two tensor-core GEMMs whose operands must share one 16-bit format with the fp16
+// activations / weights, so dz is written in fp16 multiplied by a per-layer power of two s chosen on the device from
+// a bound of max|dz| (no host sync); the GEMM epilogues multiply by 1/s (scale_out[1]) read from device memory.
 template <typename GT>
 __global__ void bn_act_bwd_apply_kernel(const __half* __restrict__ x, long long xp, const GT* __restrict__ dy,
                                         long long dp, const float* __restrict__ scale, const float* __restrict__ shift,
                                         const float* __restrict__ gamma, const float* __restrict__ mean,
                                         const float* __restrict__ invstd, const float* __restrict__ dgamma,
-                                        const float* __restrict__ dbeta, GT* __restrict__ dx, long long dxp,
-                                        long long pixels, int C, int act, float slope) {
+                                        const float* __restrict__ dbeta, __half* __restrict__ dx, long long dxp,
+                                        long long pixels, int C, int act, float slope,
+                                        const float* __restrict__ du_absmax, float* __restrict__ scale_out) {
     const int CV = C / 8;
     const long long total = pixels * CV;
     const float inv_n = 1.f / (float)pixels;
+    // every CTA derives the same scale: bound = max_c |gamma_c*invstd_c| * (max|du| + |dbeta_c|/N + 16*|dgamma_c|/N)
+    __shared__ float s_red[32];
+    __shared__ float s_scale;
+    float bound = 0.f;
+    {
+        const float dumax = du_absmax != nullptr ? *du_absmax : 1.f;
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            const float g = gamma != nullptr ? gamma[c] : 1.f;
+            const float b = fabsf(g * invstd[c]) * (dumax + fabsf(dbeta[c]) * inv_n + 16.f * fabsf(dgamma[c]) * inv_n);
+            bound = fmaxf(bound, b);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) bound = fmaxf(bound, __shfl_xor_sync(0xffffffffu, bound, o));
+        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = bound;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float m = 0.f;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, s_red[w]);
+            float sc = 1.f;
+            if (m > 0.f && m < 3.0e38f) sc = exp2f(floorf(log2f(4096.f / m)));   // target max |dz|*s <= 2^12
+            sc = fminf(fmaxf(sc, 1.0e-30f), 1.0e30f);
+            s_scale = sc;
+            if (blockIdx.x == 0 && scale_out != nullptr) {
+                scale_out[0] = sc;
+                scale_out[1] = 1.f / sc;
+            }
+        }
+        __syncthreads();
+    }
+    const float sc = s_scale;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
         const int cv = (int)(idx % CV);
@@ -231,9 +272,9 @@ __global__ void bn_act_bwd_apply_kernel(const __half* __restrict__ x, long long 
             const float du = g8[j] * act_grad(u, act, slope);
             const float xhat = (xf - mean[c]) * invstd[c];
             const float g = gamma != nullptr ? gamma[c] : 1.f;
-            r[j] = g * invstd[c] * (du - dbeta[c] * inv_n - xhat * dgamma[c] * inv_n);
+            r[j] = sc * (g * invstd[c] * (du - dbeta[c] * inv_n - xhat * dgamma[c] * inv_n));
         }
-        Half8<GT>::store(dx + pix * dxp + cv * 8, r);
+        Half8<__half>::store(dx + pix * dxp + cv * 8, r);
     }
 }
 
@@ -241,20 +282,21 @@ extern "C" int b2y_bn_act_bwd_apply(const void* x, long long x_pitch, const void
                                     const float* scale, const float* shift, const float* gamma,
                                     const float* save_mean, const float* save_invstd, const float* dgamma,
                                     const float* dbeta, void* dx, long long dx_pitch, long long pixels, int c, int act,
-                                    float slope, int grad_dtype, void* stream) {
+                                    float slope, int grad_dtype, const float* du_absmax, float* scale_out,
+                                    void* stream) {
     if (!x || !dy || !scale || !shift || !save_mean || !save_invstd || !dgamma || !dbeta || !dx || c % 8 != 0)
         return B2Y_ERR_INVALID;
     if (grad_dtype == B2Y_DT_BF16)
         bn_act_bwd_apply_kernel<__nv_bfloat16><<<grid_for(pixels * (c / 8), 256), 256, 0,
                                                  static_cast<cudaStream_t>(stream)>>>(
             reinterpret_cast<const __half*>(x), x_pitch, reinterpret_cast<const __nv_bfloat16*>(dy), dy_pitch, scale,
-            shift, gamma, save_mean, save_invstd, dgamma, dbeta, reinterpret_cast<__nv_bfloat16*>(dx), dx_pitch, pixels,
-            c, act, slope);
+            shift, gamma, save_mean, save_invstd, dgamma, dbeta, reinterpret_cast<__half*>(dx), dx_pitch, pixels, c,
+            act, slope, du_absmax, scale_out);
     else
         bn_act_bwd_apply_kernel<__half><<<grid_for(pixels * (c / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
             reinterpret_cast<const __half*>(x), x_pitch, reinterpret_cast<const __half*>(dy), dy_pitch, scale, shift,
             gamma, save_mean, save_invstd, dgamma, dbeta, reinterpret_cast<__half*>(dx), dx_pitch, pixels, c, act,
-            slope);
+            slope, du_absmax, scale_out);
     B2Y_CUDA_CHECK(cudaGetLastError());
     return B2Y_OK;
 }
@@ -290,7 +332,9 @@ extern "C" int b2y_sgd_nesterov(float* param, const float* grad, float* momentum
 // YOLO head: dp fp32 [B][na][ny][nx][no] -> d(raw) fp16 [B][ny][nx][pitch] (channel a*no+o), times `scale`
 template <typename GT>
 __global__ void yolo_grad_to_raw_kernel(const float* __restrict__ dp, GT* __restrict__ draw, long long pitch,
-                                        int B, int na, int no, int ny, int nx, float scale) {
+                                        int B, int na, int no, int ny, int nx, float scale,
+                                        const float* __restrict__ scale_ptr) {
+    if (scale_ptr != nullptr) scale *= __ldg(scale_ptr);
     const long long total = (long long)B * ny * nx * pitch;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
@@ -309,15 +353,16 @@ __global__ void yolo_grad_to_raw_kernel(const float* __restrict__ dp, GT* __rest
     }
 }
 extern "C" int b2y_yolo_grad_to_raw(const float* dp, void* draw, long long raw_pitch, int batch, int na, int no,
-                                    int ny, int nx, float scale, int grad_dtype, void* stream) {
+                                    int ny, int nx, float scale, const float* scale_ptr, int grad_dtype,
+                                    void* stream) {
     if (!dp || !draw || raw_pitch < (long long)na * no) return B2Y_ERR_INVALID;
     const long long total = (long long)batch * ny * nx * raw_pitch;
     if (grad_dtype == B2Y_DT_BF16)
         yolo_grad_to_raw_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-            dp, reinterpret_cast<__nv_bfloat16*>(draw), raw_pitch, batch, na, no, ny, nx, scale);
+            dp, reinterpret_cast<__nv_bfloat16*>(draw), raw_pitch, batch, na, no, ny, nx, scale, scale_ptr);
     else
         yolo_grad_to_raw_kernel<__half><<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-            dp, reinterpret_cast<__half*>(draw), raw_pitch, batch, na, no, ny, nx, scale);
+            dp, reinterpret_cast<__half*>(draw), raw_pitch, batch, na, no, ny, nx, scale, scale_ptr);
     B2Y_CUDA_CHECK(cudaGetLastError());
     return B2Y_OK;
 }

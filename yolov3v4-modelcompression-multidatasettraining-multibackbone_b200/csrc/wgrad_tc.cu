@@ -23,7 +23,8 @@ struct WgradParams {
     int ksteps_total;         // ceil(K_total / BK)
     int ksteps_per_split;
     float scale;              // multiplies the accumulator (1 / loss-scale)
-    unsigned idesc_ab;        // operand formats: dY (A) may be bf16 while X (B) stays fp16
+    unsigned idesc_ab;        // operand formats (both operands must share it: mixed f16/bf16 faults in hardware)
+    const float* scale_ptr;   // optional device scalar multiplied into `scale` (per-layer gradient un-scaling)
     float* dw;                // fp32 [Cout][k][k][Cin], accumulated with atomics
 };
 
@@ -176,6 +177,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant_
     } else if (warp >= 4) {
         const int ew = warp - 4;
         uint32_t acc_phase = 0;
+        const float wscale = p.scale * (p.scale_ptr != nullptr ? __ldg(p.scale_ptr) : 1.f);
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             int m_tile, n_tile, tap, split;
             decode(tile, m_tile, n_tile, tap, split);
@@ -202,16 +204,16 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant_
                     if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
-                            float4 v = make_float4(__uint_as_float(raw[q * 4]) * p.scale,
-                                                   __uint_as_float(raw[q * 4 + 1]) * p.scale,
-                                                   __uint_as_float(raw[q * 4 + 2]) * p.scale,
-                                                   __uint_as_float(raw[q * 4 + 3]) * p.scale);
+                            float4 v = make_float4(__uint_as_float(raw[q * 4]) * wscale,
+                                                   __uint_as_float(raw[q * 4 + 1]) * wscale,
+                                                   __uint_as_float(raw[q * 4 + 2]) * wscale,
+                                                   __uint_as_float(raw[q * 4 + 3]) * wscale);
                             atomicAdd(reinterpret_cast<float4*>(dst) + q, v);
                         }
                     } else {
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
-                            if (j < nvalid) atomicAdd(dst + j, __uint_as_float(raw[j]) * p.scale);
+                            if (j < nvalid) atomicAdd(dst + j, __uint_as_float(raw[j]) * wscale);
                     }
                 }
                 __syncwarp();
@@ -283,7 +285,8 @@ static int wgrad_launch_cfg(const CUtensorMap& a, const CUtensorMap& b, const Wg
 using namespace b2y;
 
 extern "C" int b2y_conv2d_bwd_weight(const b2y_conv_desc* d, const void* x, const void* dy, float* dw, float scale,
-                                     int grad_dtype, void* stream) {
+                                     int operand_dtype, const float* inv_scale_ptr, void* stream) {
+    const int grad_dtype = operand_dtype;   // X and dY share one 16-bit format
     std::call_once(w_once, w_resolve);
     if (!d || !x || !dy || !dw) return B2Y_ERR_INVALID;
     if (!w_encodeTiled || !w_encodeIm2col) return B2Y_ERR_DRIVER;
@@ -331,7 +334,8 @@ extern "C" int b2y_conv2d_bwd_weight(const b2y_conv_desc* d, const void* x, cons
     p.ksplits = (p.ksteps_total + p.ksteps_per_split - 1) / p.ksteps_per_split;
     p.scale = scale;
     p.dw = dw;
-    p.idesc_ab = grad_dtype == B2Y_DT_BF16 ? (1u << 7) : 0u;
+    p.idesc_ab = grad_dtype == B2Y_DT_BF16 ? ((1u << 7) | (1u << 10)) : 0u;
+    p.scale_ptr = inv_scale_ptr;
 
     CUtensorMap tmDy, tmX;
     {
@@ -355,7 +359,8 @@ extern "C" int b2y_conv2d_bwd_weight(const b2y_conv_desc* d, const void* x, cons
         CUtensorMapSwizzle sw = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                                                  : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
                                                                     : CU_TENSOR_MAP_SWIZZLE_32B);
-        if (w_encodeIm2col(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(x), gdim, gstride, lower, upper,
+        if (w_encodeIm2col(&tmX, grad_dtype == B2Y_DT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                                            : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(x), gdim, gstride, lower, upper,
                            (cuuint32_t)(row_bytes / 2), 64, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return B2Y_ERR_DRIVER;
