@@ -209,6 +209,8 @@ def darknet_forward(module_defs, state, x, cfg_name, training=False, emulate_fp1
         else:
             raise NotImplementedError(t)
         outs.append(x)
+    if return_layers == 'both':
+        return yolo_out, outs
     if return_layers:
         return outs
     if training:

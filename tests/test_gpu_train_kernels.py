@@ -218,3 +218,50 @@ def test_int8_conv_bit_exact(case):
     got = out.permute(0, 3, 1, 2).cpu().float()
     mism = (got != ref_q).float().mean().item()
     assert mism == 0.0, "int8 conv differs from fake-quant fp32 reference on %.4g of outputs" % mism
+
+
+@pytest.mark.parametrize("gdt", [torch.float16, torch.bfloat16], ids=["f16", "bf16"])
+def test_data_movement_backward_kernels(gdt):
+    """upsample / maxpool / add backward on 16-bit gradient tensors (channel-slice views included)."""
+    import ctypes as C
+    from b200yolo.lib import call, ptr, stream_ptr
+    ops = _ops()
+    g = torch.Generator().manual_seed(21)
+    B, Cc, H, W = 2, 32, 6, 5
+    # upsample x2: dx += window sums of dy, dy living in a wider (concat) buffer
+    dyf = torch.randn(B, Cc, 2 * H, 2 * W, generator=g).to(gdt).float()
+    basef = torch.randn(B, Cc, H, W, generator=g).to(gdt).float()
+    wide = torch.zeros(B, 2 * H, 2 * W, Cc + 64, dtype=gdt, device="cuda")
+    gy = wide[..., :Cc]
+    gy.copy_(dyf.permute(0, 2, 3, 1).to(gdt))
+    gx = _nhwc(basef, gdt)
+    call("b2y_upsample_nearest_bwd", ptr(gy), ops._pitch(gy), ptr(gx), ops._pitch(gx), B, H, W, Cc, 2, ops._gdt(gy),
+         stream_ptr())
+    ref = basef + F.avg_pool2d(dyf, 2) * 4
+    tol = 2e-3 if gdt == torch.float16 else 1.6e-2
+    assert (_nchw(gx) - ref).abs().max() <= tol * ref.abs().max()
+    # maxpool 2x2 s2 and the SPP-style 5x5 s1
+    for k, s in ((2, 2), (5, 1)):
+        x = torch.randn(B, Cc, 8, 8, generator=g).half().float().requires_grad_(True)
+        y = F.max_pool2d(x, k, s, (k - 1) // 2)
+        dy = torch.randn(y.shape, generator=g).to(gdt).float()
+        y.backward(dy)
+        gxm = torch.zeros(B, 8, 8, Cc, dtype=gdt, device="cuda")
+        xn, dyn = _nhwc(x.detach()), _nhwc(dy, gdt)
+        call("b2y_maxpool_bwd", ptr(xn), ops._pitch(xn), ptr(dyn), ops._pitch(dyn), ptr(gxm), ops._pitch(gxm), B, 8, 8,
+             Cc, k, s, 0, ops._gdt(dyn), stream_ptr())
+        assert (_nchw(gxm) - x.grad).abs().max() <= 4 * tol * max(1.0, x.grad.abs().max().item())
+    # add (gradient accumulation into a slice)
+    a = torch.randn(B, Cc, H, W, generator=g).to(gdt)
+    b = torch.randn(B, Cc, H, W, generator=g).to(gdt)
+    an, bn = _nhwc(a.float(), gdt), _nhwc(b.float(), gdt)
+    ops.add(an, bn, out=an)
+    assert torch.equal(_nchw(an), (a.float() + b.float()).to(gdt).float())
+    # yolo permute^T with a device-side scale
+    dp = torch.randn(B, 3, 4, 5, 85, generator=g)
+    raw = torch.zeros(B, 4, 5, 256, dtype=gdt, device="cuda")
+    sc = torch.tensor([8.0, 0.125], device="cuda")
+    call("b2y_yolo_grad_to_raw", ptr(dp.cuda()), ptr(raw), 256, B, 3, 85, 4, 5, 1.0, ptr(sc), ops._gdt(raw),
+         stream_ptr())
+    want = (dp.permute(0, 2, 3, 1, 4).reshape(B, 4, 5, 255) * 8.0).to(gdt)
+    assert torch.equal(raw[..., :255].cpu(), want) and float(raw[..., 255].abs().max()) == 0.0

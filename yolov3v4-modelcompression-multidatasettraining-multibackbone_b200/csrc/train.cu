@@ -396,9 +396,14 @@ extern "C" int b2y_upsample_nearest_bwd(const void* dy, long long dy_pitch, void
                                         int in_h, int in_w, int c, int scale, int grad_dtype, void* stream) {
     if (!dy || !dx || c % 8 != 0 || dy_pitch % 8 != 0 || dx_pitch % 8 != 0 || scale < 1) return B2Y_ERR_INVALID;
     const long long total = (long long)batch * in_h * in_w * (c / 8);
-    upsample_bwd_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        reinterpret_cast<const __half*>(dy), dy_pitch, reinterpret_cast<__half*>(dx), dx_pitch, batch, in_h, in_w, c,
-        scale);
+    if (grad_dtype == B2Y_DT_BF16)
+        upsample_bwd_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+            reinterpret_cast<const __nv_bfloat16*>(dy), dy_pitch, reinterpret_cast<__nv_bfloat16*>(dx), dx_pitch, batch,
+            in_h, in_w, c, scale);
+    else
+        upsample_bwd_kernel<__half><<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+            reinterpret_cast<const __half*>(dy), dy_pitch, reinterpret_cast<__half*>(dx), dx_pitch, batch, in_h, in_w,
+            c, scale);
     B2Y_CUDA_CHECK(cudaGetLastError());
     return B2Y_OK;
 }
