@@ -162,11 +162,24 @@ def darknet_forward(module_defs, state, x, cfg_name, training=False, emulate_fp1
                     wf = wf.half().float()
                 y = F.conv2d(x, wf, bf, stride=int(d['stride']), padding=pad)
             elif int(d['batch_normalize']):
-                y = F.conv2d(x, w, None, stride=int(d['stride']), padding=pad)
+                wq = w.half().float() if (emulate_fp16 and i > 0) else w
+                y = F.conv2d(x, wq, None, stride=int(d['stride']), padding=pad)
                 g_, b_ = state[pre + 'BatchNorm2d.weight'], state[pre + 'BatchNorm2d.bias']
                 rm = state[pre + 'BatchNorm2d.running_mean'].clone()
                 rv = state[pre + 'BatchNorm2d.running_var'].clone()
-                y = F.batch_norm(y, rm, rv, g_, b_, True, bn_momentum, 1e-5)        # models.py:100
+                if emulate_fp16:
+                    # engine policy: statistics from the fp32 accumulators, normalisation applied to the fp16-stored z
+                    mean = y.mean(dim=(0, 2, 3))
+                    var = y.var(dim=(0, 2, 3), unbiased=False)
+                    n_ = y.numel() / y.shape[1]
+                    with torch.no_grad():
+                        rm.mul_(1 - bn_momentum).add_(bn_momentum * mean)
+                        rv.mul_(1 - bn_momentum).add_(bn_momentum * var * n_ / max(n_ - 1, 1))
+                    z16 = y.half().float()
+                    y = (z16 - mean.view(1, -1, 1, 1)) / torch.sqrt(var.view(1, -1, 1, 1) + 1e-5) \
+                        * g_.view(1, -1, 1, 1) + b_.view(1, -1, 1, 1)
+                else:
+                    y = F.batch_norm(y, rm, rv, g_, b_, True, bn_momentum, 1e-5)    # models.py:100
                 new_stats[pre + 'BatchNorm2d.running_mean'] = rm
                 new_stats[pre + 'BatchNorm2d.running_var'] = rv
             else:
