@@ -2,6 +2,7 @@
 // C-ABI entry points (include/b200yolo.h).
 #include "conv_tc.cuh"
 
+#include <cstdlib>
 #include <mutex>
 
 #include "b200yolo.h"
@@ -88,33 +89,70 @@ static int make_map_im2col(CUtensorMap* m, const void* base, int esize, int N, i
     return B2Y_OK;
 }
 
-template <int BLOCK_N, int KBYTES, int KIND>
+template <int BLOCK_N, int KBYTES, int KIND, int CLUSTER>
 static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvTcParams& p, cudaStream_t st) {
     using Cfg = ConvTcCfg<BLOCK_N, KBYTES>;
-    auto kern = conv_tc_kernel<BLOCK_N, KBYTES, KIND>;
+    auto kern = conv_tc_kernel<BLOCK_N, KBYTES, KIND, CLUSTER>;
     static bool attr_set = false;
     if (!attr_set) {
         B2Y_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         attr_set = true;
     }
-    int tiles = p.num_m_tiles * p.num_n_tiles;
-    int grid = tiles < g_num_sms ? tiles : g_num_sms;
-    kern<<<grid, ConvTcEpi<BLOCK_N>::THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p);
+    const int items = ((p.num_m_tiles + CLUSTER - 1) / CLUSTER) * p.num_n_tiles;
+    const int max_clusters = g_num_sms / CLUSTER;
+    const int clusters = items < max_clusters ? items : max_clusters;
+    if (CLUSTER == 1) {
+        kern<<<clusters, ConvTcEpi<BLOCK_N>::THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p);
+    } else {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(clusters * CLUSTER);
+        cfg.blockDim = dim3(ConvTcEpi<BLOCK_N>::THREADS);
+        cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = CLUSTER;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        B2Y_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
+    }
     B2Y_CUDA_CHECK(cudaGetLastError());
     return B2Y_OK;
 }
 
 template <int KIND>
-static int dispatch(int block_n, int kbytes, const CUtensorMap& a, const CUtensorMap& b, const ConvTcParams& p,
-                    cudaStream_t st) {
+static int dispatch(int block_n, int kbytes, int cluster, const CUtensorMap& a, const CUtensorMap& b,
+                    const ConvTcParams& p, cudaStream_t st) {
 #define B2Y_CASE(BN, KB) \
-    if (block_n == BN && kbytes == KB) return launch_cfg<BN, KB, KIND>(a, b, p, st);
+    if (block_n == BN && kbytes == KB && cluster == 1) return launch_cfg<BN, KB, KIND, 1>(a, b, p, st);
     B2Y_CASE(32, 32) B2Y_CASE(32, 64) B2Y_CASE(32, 128)
     B2Y_CASE(64, 32) B2Y_CASE(64, 64) B2Y_CASE(64, 128)
     B2Y_CASE(128, 32) B2Y_CASE(128, 64) B2Y_CASE(128, 128)
     B2Y_CASE(256, 32) B2Y_CASE(256, 64) B2Y_CASE(256, 128)
 #undef B2Y_CASE
+    // weight-multicast clusters exist for the wide, deep tiles only (KBYTES = 128)
+    if (kbytes == 128 && block_n == 128 && cluster == 2) return launch_cfg<128, 128, KIND, 2>(a, b, p, st);
+    if (kbytes == 128 && block_n == 256 && cluster == 2) return launch_cfg<256, 128, KIND, 2>(a, b, p, st);
+    if (kbytes == 128 && block_n == 256 && cluster == 4) return launch_cfg<256, 128, KIND, 4>(a, b, p, st);
     return B2Y_ERR_UNSUPPORTED;
+}
+
+// cluster size for a launch: B2Y_CLUSTER env (1 = off, 2 default, 4) when the tile shape supports multicast and
+// there is more than one M tile per cluster to share the weights across
+static int pick_cluster(int block_n, int kbytes, int num_m_tiles) {
+    static int want = -1;
+    if (want < 0) {
+        const char* e = getenv("B2Y_CLUSTER");
+        want = e ? atoi(e) : 2;
+        if (want != 1 && want != 2 && want != 4) want = 2;
+    }
+    if (kbytes != 128 || block_n < 128) return 1;
+    int c = want;
+    if (c == 4 && block_n != 256) c = 2;
+    if (num_m_tiles < 2 * c) return 1;
+    return c;
 }
 
 struct EpilogueArgs {
@@ -225,11 +263,12 @@ int gemm_conv_launch(const GemmConvSpec& g, const EpilogueArgs& e, cudaStream_t 
     }
     if (rc != B2Y_OK) return rc;
     const long long Ktot = (long long)g.ntaps * g.C;
-    rc = make_map_2d(&tmB, g.w, esize, g.Nout, Ktot, Ktot, block_k, block_n, kbytes, g.b_bf16);
+    const int cluster = pick_cluster(block_n, kbytes, p.num_m_tiles);
+    rc = make_map_2d(&tmB, g.w, esize, g.Nout, Ktot, Ktot, block_k, block_n / cluster, kbytes, g.b_bf16);
     if (rc != B2Y_OK) return rc;
 
-    if (g.kind == CONV_KIND_F16) return dispatch<CONV_KIND_F16>(block_n, kbytes, tmA, tmB, p, st);
-    return dispatch<CONV_KIND_I8>(block_n, kbytes, tmA, tmB, p, st);
+    if (g.kind == CONV_KIND_F16) return dispatch<CONV_KIND_F16>(block_n, kbytes, cluster, tmA, tmB, p, st);
+    return dispatch<CONV_KIND_I8>(block_n, kbytes, cluster, tmA, tmB, p, st);
 }
 
 // Forward convolution: x NHWC (fp16 or int8), w [Cout][R][S][Cin].

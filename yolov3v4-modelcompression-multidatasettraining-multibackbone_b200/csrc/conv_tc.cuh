@@ -93,7 +93,9 @@ struct ConvTcEpi {
     static constexpr int THREADS = 128 + 32 * WARPS;
 };
 
-template <int BLOCK_N, int KBYTES, int KIND>
+// CLUSTER > 1: the CTAs of a cluster work on CLUSTER consecutive M tiles of the same N tile; each loads 1/CLUSTER of
+// the weight tile and TMA-multicasts it to all of them, so the (dominant) weight re-reads from L2 drop by CLUSTER x.
+template <int BLOCK_N, int KBYTES, int KIND, int CLUSTER>
 __global__ void __launch_bounds__(ConvTcEpi<BLOCK_N>::THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const ConvTcParams p) {
@@ -127,7 +129,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < NS; ++i) {
             mbar_init(&full_bar[i], 1);
-            mbar_init(&empty_bar[i], 1);
+            mbar_init(&empty_bar[i], CLUSTER);   // every CTA that multicasts into this stage must see it released
         }
         for (int i = 0; i < AS; ++i) {
             mbar_init(&tmem_full_bar[i], 1);
@@ -141,10 +143,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     tc_fence_before();
     __syncthreads();
+    if (CLUSTER > 1) cluster_sync_all();   // barriers of every CTA are initialised before any remote arrive / multicast
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
-    const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+    // work items: (group of CLUSTER consecutive M tiles, N tile); this CTA takes M tile group*CLUSTER + rank.
+    // A "ghost" M tile past the end still runs the pipeline (TMA zero fill) but stores nothing.
+    const int cta_rank = CLUSTER > 1 ? (int)cluster_ctarank() : 0;
+    const int cluster_id = (int)blockIdx.x / CLUSTER;
+    const int num_clusters = (int)gridDim.x / CLUSTER;
+    const int num_mgroups = (p.num_m_tiles + CLUSTER - 1) / CLUSTER;
+    const int num_items = num_mgroups * p.num_n_tiles;
+    constexpr uint16_t MC_MASK = (uint16_t)((1u << CLUSTER) - 1u);
     const int taps = p.ntaps;
     const int k_steps = taps * p.k_chunks;
 
@@ -154,9 +164,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int stage = 0;
             uint32_t phase = 0;
             const int HoWo = p.MH * p.MW;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m_tile = tile / p.num_n_tiles;
-                const int n_tile = tile - m_tile * p.num_n_tiles;
+            for (int item = cluster_id; item < num_items; item += num_clusters) {
+                const int mgroup = item / p.num_n_tiles;
+                const int n_tile = item - mgroup * p.num_n_tiles;
+                const int m_tile = mgroup * CLUSTER + cta_rank;
                 const int m0 = m_tile * 128;
                 const int img = m0 / HoWo;
                 const int rem = m0 - img * HoWo;
@@ -178,7 +189,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         } else {
                             tma_load_2d(a_dst, &tmA, &full_bar[stage], kc * BLOCK_K, m0);
                         }
-                        tma_load_2d(b_dst, &tmB, &full_bar[stage], tap * p.Cin + kc * BLOCK_K, n_tile * BLOCK_N);
+                        if (CLUSTER > 1) {
+                            constexpr int SLICE_ROWS = BLOCK_N / CLUSTER;
+                            tma_load_2d_multicast(b_dst + cta_rank * SLICE_ROWS * KBYTES, &tmB, &full_bar[stage],
+                                                  tap * p.Cin + kc * BLOCK_K, n_tile * BLOCK_N + cta_rank * SLICE_ROWS,
+                                                  MC_MASK);
+                        } else {
+                            tma_load_2d(b_dst, &tmB, &full_bar[stage], tap * p.Cin + kc * BLOCK_K, n_tile * BLOCK_N);
+                        }
                         if (++stage == NS) {
                             stage = 0;
                             phase ^= 1;
@@ -195,7 +213,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int acc = 0;
             uint32_t acc_phase = 0;
             const uint64_t desc_base = smem_desc_base(16, 8 * KBYTES, LAYOUT);
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int item = cluster_id; item < num_items; item += num_clusters) {
                 mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
@@ -215,7 +233,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         else
                             mma_i8_ss(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC, accum);
                     }
-                    tc_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+                    if (CLUSTER > 1)
+                        tc_commit_multicast(&empty_bar[stage], MC_MASK);  // release the slot in every CTA of the cluster
+                    else
+                        tc_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
                     if (++stage == NS) {
                         stage = 0;
                         phase ^= 1;
@@ -239,9 +260,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int et = threadIdx.x - 128;       // 0..EPI_THREADS-1
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int m_tile = tile / p.num_n_tiles;
-            const int n_tile = tile - m_tile * p.num_n_tiles;
+        bool first_item = true;
+        for (int item = cluster_id; item < num_items; item += num_clusters) {
+            const int mgroup = item / p.num_n_tiles;
+            const int n_tile = item - mgroup * p.num_n_tiles;
+            const int m_tile = mgroup * CLUSTER + cta_rank;
             const int n0 = n_tile * BLOCK_N;
             const long long grow = (long long)m_tile * 128 + ew * 32 + lane;   // GEMM row
             const bool row_ok = grow < p.M_total;
@@ -266,7 +289,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
 
             // stage the bias slice for this tile
-            if (p.num_n_tiles > 1 || tile == (int)blockIdx.x) {   // a single N tile: the bias slice never changes
+            if (p.num_n_tiles > 1 || first_item) {   // a single N tile: the bias slice never changes
+                first_item = false;
                 asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
                 for (int i = et; i < BLOCK_N; i += EPI_THREADS) {
                     const int n = n0 + i;
@@ -481,6 +505,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     tc_fence_before();
     __syncthreads();
+    if (CLUSTER > 1) cluster_sync_all();   // nobody leaves while a peer may still multicast / arrive into its smem
     if (warp == 2) {
         tc_fence_after();
         tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
