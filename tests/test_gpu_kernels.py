@@ -140,6 +140,23 @@ def test_stem_conv():
     assert (y.float().permute(0, 3, 1, 2).cpu() - ref).abs().max() <= 2e-3 * max(1.0, ref.abs().max().item())
 
 
+@pytest.mark.parametrize("cin,k,stride,cout", [(3, 3, 1, 32), (3, 3, 2, 32), (3, 3, 1, 16), (1, 5, 1, 32), (3, 5, 1, 32)])
+def test_stem_conv_tensor_core(cin, k, stride, cout):
+    """Both tensor-core stem layouts: full im2col row (cin*k*k <= 32) and one row per kernel row (cin*k <= 16)."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(11)
+    x = torch.rand(2, cin, 40, 56, generator=g)
+    w = torch.randn(cout, cin, k, k, generator=g) / (cin * k)
+    b = torch.randn(cout, generator=g)
+    ref = F.leaky_relu(F.conv2d(x.half().float(), w.half().float(), b, stride=stride, padding=k // 2), 0.1)
+    ws = ops.pack_stem_weights(w.cuda())
+    y, _ = ops.stem_conv_tc(x.cuda(), ws, b.cuda(), cin, k, stride, k // 2, act="leaky")
+    torch.cuda.synchronize()
+    got = y.float().permute(0, 3, 1, 2).cpu()
+    assert got.shape == ref.shape
+    assert (got - ref).abs().max() <= 2e-3 * max(1.0, ref.abs().max().item())
+
+
 def test_pack_weights_bn_fold():
     ops = _ops()
     g = torch.Generator().manual_seed(2)

@@ -267,7 +267,8 @@ class Plan:
             wp, bias, w32 = ops.pack_conv_weights(conv.weight.detach(), conv.bias.detach() if conv.bias is not None
                                                   else None, bnp, eps, want_fp32=stem)
             wstem = None
-            if stem and conv.in_channels * conv.kernel_size[0] <= 16:
+            if stem and (conv.in_channels * conv.kernel_size[0] <= 16 or
+                         conv.in_channels * conv.kernel_size[0] ** 2 <= 32):
                 wstem = ops.pack_stem_weights(w32)
             self.weights[i] = (wp, bias, w32, wstem)
 
@@ -283,8 +284,9 @@ class Plan:
                         raise NotImplementedError("first layer with more than 4 input channels")
                     if wstem is not None:
                         if getattr(self, 'stem_ws', None) is None:
-                            self.stem_ws = torch.empty((self.B, self.H, self.W, 16), dtype=torch.float16,
-                                                       device=self.device)
+                            self.stem_ws = ops.stem_workspace(
+                                ops.make_conv_desc((self.B, self.H, self.W, conv.in_channels), conv.in_channels,
+                                                   conv.out_channels, k, s, p, conv.out_channels), self.device)
                         ops.stem_conv_tc(x, wstem, bias, conv.in_channels, k, s, p, act=act, slope=slope,
                                          out=out.view(), workspace=self.stem_ws)
                     else:

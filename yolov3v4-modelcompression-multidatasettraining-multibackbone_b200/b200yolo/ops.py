@@ -100,22 +100,29 @@ def stem_conv(x_nchw, w_oihw, bias, k, stride, pad, act="linear", slope=0.1, out
 
 def pack_stem_weights(w_oihw_folded):
     O, I, k, _ = w_oihw_folded.shape
-    out = torch.empty((O, k, 16), dtype=torch.float16, device=w_oihw_folded.device)
+    shape = (O, 32) if I * k * k <= 32 else (O, k, 16)     # full-im2col row vs one row per kernel row (conv_tc.cu)
+    out = torch.empty(shape, dtype=torch.float16, device=w_oihw_folded.device)
     call("b2y_pack_stem_weights", ptr(w_oihw_folded.contiguous().float()), O, I, k, ptr(out), stream_ptr())
     return out
 
 
+def stem_workspace(desc, device):
+    from .lib import raw
+    nbytes = int(raw().b2y_stem_workspace_bytes(C.byref(desc)))
+    return torch.empty((nbytes // 2,), dtype=torch.float16, device=device)
+
+
 def stem_conv_tc(x_nchw, w_stem, bias, in_c, k, stride, pad, act="linear", slope=0.1, out=None, workspace=None,
                  stats=None):
-    """Tensor-core stem: NCHW fp32 image -> NHWC fp16 (k*in_c <= 16). Returns (out, workspace)."""
+    """Tensor-core stem: NCHW fp32 image -> NHWC fp16 (in_c*k*k <= 32 or k*in_c <= 16). Returns (out, workspace)."""
     B, Cin, H, W = x_nchw.shape
     O = w_stem.shape[0]
     Ho, Wo = conv_out_hw(H, W, k, stride, pad)
     if out is None:
         out = torch.empty((B, Ho, Wo, O), dtype=torch.float16, device=x_nchw.device)
-    if workspace is None:
-        workspace = torch.empty((B, H, W, 16), dtype=torch.float16, device=x_nchw.device)
     d = make_conv_desc((B, H, W, Cin), Cin, O, k, stride, pad, _pitch(out), act, slope, OUT_F16)
+    if workspace is None:
+        workspace = stem_workspace(d, x_nchw.device)
     call("b2y_stem_conv_fwd_tc", C.byref(d), ptr(x_nchw), ptr(w_stem), ptr(bias), ptr(workspace), ptr(out),
          ptr(stats[0]) if stats is not None else None, ptr(stats[1]) if stats is not None else None, stream_ptr())
     return out, workspace

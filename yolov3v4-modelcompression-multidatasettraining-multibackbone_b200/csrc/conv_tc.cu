@@ -221,8 +221,11 @@ int gemm_conv_launch(const GemmConvSpec& g, const EpilogueArgs& e, cudaStream_t 
     p.lower_w = g.lower_w;
     p.lower_h = g.lower_h;
     for (int t = 0; t < 16; ++t) {
+        if (g.tap_ow[t] > 15 || g.tap_oh[t] > 15) return B2Y_ERR_UNSUPPORTED;
         p.tap_ow[t] = g.tap_ow[t];
         p.tap_oh[t] = g.tap_oh[t];
+        p.tap_w_packed |= (unsigned long long)g.tap_ow[t] << (4 * t);
+        p.tap_h_packed |= (unsigned long long)g.tap_oh[t] << (4 * t);
     }
     p.out_identity = g.out_identity;
     p.out_OH = g.out_OH;
@@ -250,6 +253,16 @@ int gemm_conv_launch(const GemmConvSpec& g, const EpilogueArgs& e, cudaStream_t 
     p.q_hi = e.q_hi;
     p.stat_sum = e.stat_sum;
     p.stat_sqsum = e.stat_sqsum;
+    {
+        // the short epilogue: fp16/bf16 output, no partial channel tile, everything 16-byte addressable
+        auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+        const bool act_ok = e.act == B2Y_ACT_LINEAR || e.act == B2Y_ACT_MISH ||
+                            (e.act == B2Y_ACT_LEAKY && e.slope >= 0.f && e.slope <= 1.f);
+        p.epi_fast = g.kind == CONV_KIND_F16 && (e.out_dtype == OUT_F16 || e.out_dtype == OUT_BF16) &&
+                     !e.out_fakequant && e.stat_sum == nullptr && g.Nout % block_n == 0 && act_ok && al16(e.out) &&
+                     e.out_pitch % 8 == 0 && (e.bias == nullptr || al16(e.bias)) &&
+                     (e.res == nullptr || (al16(e.res) && e.res_pitch % 8 == 0));
+    }
 
     CUtensorMap tmA, tmB;
     int rc;
@@ -526,14 +539,84 @@ __global__ void stem_pack_weights_kernel(const float* __restrict__ w, __half* __
     }
 }
 
+// Small stems (Cin*k*k <= 32, e.g. 3x3 on RGB = 27): the whole receptive field of one output pixel fits one 64-byte
+// GEMM row, so the pack writes the im2col matrix itself,
+//   packed[n][yo][xo][(kh*K + kw)*Cin + c] = x[n][c][yo*s + kh - pad][xo*s + kw - pad]   (32 columns, zero padded)
+// and the conv is ONE k-step of a plain [M][32] x [32][Cout] GEMM (the 3-tap variant above costs three 32-byte-row
+// TMA gathers per tile and is bound by L2 request rate, not bytes).
+template <int CIN, int K>
+__global__ void stem_fullpack_kernel(const float* __restrict__ x, __half* __restrict__ out, int B, int H, int W,
+                                     int Ho, int Wo, int stride, int pad) {
+    const long long total = (long long)B * Ho * Wo;
+    const long long plane = (long long)H * W;
+    for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < total;
+         pix += (long long)gridDim.x * blockDim.x) {
+        const int xo = (int)(pix % Wo);
+        const long long t = pix / Wo;
+        const int yo = (int)(t % Ho);
+        const long long n = t / Ho;
+        const float* xb = x + n * CIN * plane;
+        const int y0 = yo * stride - pad, x0 = xo * stride - pad;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+#pragma unroll
+        for (int kh = 0; kh < K; ++kh) {
+            const int yi = y0 + kh;
+            if (yi < 0 || yi >= H) continue;
+#pragma unroll
+            for (int kw = 0; kw < K; ++kw) {
+                const int xi = x0 + kw;
+                if (xi >= 0 && xi < W) {
+#pragma unroll
+                    for (int c = 0; c < CIN; ++c) v[(kh * K + kw) * CIN + c] = __ldg(xb + c * plane + (long long)yi * W + xi);
+                }
+            }
+        }
+        uint4 o[4];
+        __half2* oh = reinterpret_cast<__half2*>(o);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) oh[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+        uint4* op = reinterpret_cast<uint4*>(out + pix * 32);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) op[q] = o[q];
+    }
+}
+
+// w (OIHW fp32, BN folded) -> [O][32] fp16 with inner index (kh*k + kw)*Cin + c
+__global__ void stem_fullpack_weights_kernel(const float* __restrict__ w, __half* __restrict__ out, int O, int Cin,
+                                             int k) {
+    const int total = O * 32;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int j = idx % 32;
+        const int o = idx / 32;
+        float v = 0.f;
+        if (j < k * k * Cin) {
+            const int c = j % Cin, kw = (j / Cin) % k, kh = j / (Cin * k);
+            v = w[(((long long)o * Cin + c) * k + kh) * k + kw];
+        }
+        out[idx] = __float2half_rn(v);
+    }
+}
+
+static inline bool stem_is_full(int in_c, int ksize) { return in_c * ksize * ksize <= 32; }
+
 extern "C" size_t b2y_stem_workspace_bytes(const b2y_conv_desc* d) {
     if (!d) return 0;
+    if (stem_is_full(d->in_c, d->ksize)) return (size_t)d->batch * d->out_h * d->out_w * 32 * sizeof(__half);
     return (size_t)d->batch * d->in_h * d->in_w * 16 * sizeof(__half);
 }
 
 extern "C" int b2y_pack_stem_weights(const float* w_oihw_folded, int out_c, int in_c, int ksize, void* w_stem,
                                      void* stream) {
-    if (!w_oihw_folded || !w_stem || in_c * ksize > 16) return B2Y_ERR_INVALID;
+    if (!w_oihw_folded || !w_stem) return B2Y_ERR_INVALID;
+    if (stem_is_full(in_c, ksize)) {
+        stem_fullpack_weights_kernel<<<(out_c * 32 + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+            w_oihw_folded, reinterpret_cast<__half*>(w_stem), out_c, in_c, ksize);
+        B2Y_CUDA_CHECK(cudaGetLastError());
+        return B2Y_OK;
+    }
+    if (in_c * ksize > 16) return B2Y_ERR_INVALID;
     stem_pack_weights_kernel<<<(out_c * ksize * 16 + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         w_oihw_folded, reinterpret_cast<__half*>(w_stem), out_c, in_c, ksize);
     B2Y_CUDA_CHECK(cudaGetLastError());
@@ -543,11 +626,50 @@ extern "C" int b2y_pack_stem_weights(const float* w_oihw_folded, int out_c, int 
 extern "C" int b2y_stem_conv_fwd_tc(const b2y_conv_desc* d, const float* x_nchw, const void* w_stem, const float* bias,
                                     void* workspace, void* y, float* stat_sum, float* stat_sqsum, void* stream) {
     if (!d || !x_nchw || !w_stem || !workspace || !y) return B2Y_ERR_INVALID;
-    if (d->in_c * d->ksize > 16 || d->ksize > 16) return B2Y_ERR_UNSUPPORTED;
     const int Ho = (d->in_h + 2 * d->pad - d->ksize) / d->stride + 1;
     const int Wo = (d->in_w + 2 * d->pad - d->ksize) / d->stride + 1;
     if (Ho != d->out_h || Wo != d->out_w) return B2Y_ERR_INVALID;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (stem_is_full(d->in_c, d->ksize)) {
+        const long long opix = (long long)d->batch * Ho * Wo;
+        int fgrid = (int)((opix + 127) / 128);
+        if (fgrid > 148 * 64) fgrid = 148 * 64;
+        __half* fws = reinterpret_cast<__half*>(workspace);
+#define B2Y_STEM_FULL(CI, KK)                                                                                       \
+    if (d->in_c == CI && d->ksize == KK) {                                                                          \
+        stem_fullpack_kernel<CI, KK><<<fgrid, 128, 0, st>>>(x_nchw, fws, d->batch, d->in_h, d->in_w, Ho, Wo,        \
+                                                            d->stride, d->pad);                                     \
+    } else
+        B2Y_STEM_FULL(3, 3) B2Y_STEM_FULL(1, 3) B2Y_STEM_FULL(2, 3) B2Y_STEM_FULL(1, 5) B2Y_STEM_FULL(3, 1)
+        B2Y_STEM_FULL(1, 1) B2Y_STEM_FULL(4, 1) B2Y_STEM_FULL(2, 1) { return B2Y_ERR_UNSUPPORTED; }
+#undef B2Y_STEM_FULL
+        B2Y_CUDA_CHECK(cudaGetLastError());
+        GemmConvSpec g;
+        g.kind = CONV_KIND_F16;
+        g.a = workspace;
+        g.N = d->batch;
+        g.H = Ho;
+        g.W = Wo;
+        g.C = 32;
+        g.a_pitch = 32;
+        g.MH = Ho;
+        g.MW = Wo;
+        g.pointwise = true;
+        g.ntaps = 1;
+        g.w = w_stem;
+        g.Nout = d->out_c;
+        EpilogueArgs e;
+        e.bias = bias;
+        e.act = d->act;
+        e.slope = d->slope;
+        e.out = y;
+        e.out_pitch = d->out_pitch;
+        e.out_dtype = OUT_F16;
+        e.stat_sum = stat_sum;
+        e.stat_sqsum = stat_sqsum;
+        return gemm_conv_launch(g, e, st);
+    }
+    if (d->in_c * d->ksize > 16 || d->ksize > 16) return B2Y_ERR_UNSUPPORTED;
     const long long pixels = (long long)d->batch * d->in_h * d->in_w;
     int grid = (int)((pixels + 255) / 256);
     if (grid > 148 * 32) grid = 148 * 32;

@@ -9,7 +9,7 @@
 // * One elected thread issues tcgen05.mma (M=128, N=BLOCK_N, K=32 bytes) with the fp32/int32
 //   accumulator in TMEM, double-buffered so the epilogue of tile i overlaps the MMAs of tile i+1.
 // * Persistent grid (<= #SMs CTAs), warp-specialised: warp0 = TMA producer, warp1 = MMA issuer,
-//   warp2 = TMEM allocator, warps 4-7 = epilogue (TMEM -> regs -> bias/act/residual -> global).
+//   warp2 = TMEM allocator, warps 4-11 = epilogue (TMEM -> regs -> bias/act/residual -> global).
 #pragma once
 #include "common.cuh"
 
@@ -32,6 +32,7 @@ struct ConvTcParams {
     int lower_w, lower_h;     // coordinate of base pixel (0,0): base = q*stride + lower
     unsigned char tap_ow[16]; // per-tap im2col offsets (>= 0)
     unsigned char tap_oh[16];
+    unsigned long long tap_w_packed, tap_h_packed;   // the same offsets, 4 bits per tap (what the producer reads)
     int a_mode;
     // row -> output pixel mapping: pixel(n,p,q) = ((n*out_OH + p*out_ys + out_y0)*out_OW + q*out_xs + out_x0)
     int out_identity;         // 1: output pixel index == GEMM row index
@@ -56,6 +57,7 @@ struct ConvTcParams {
     // training extras: per-channel sum / sum of squares of the raw (pre-bias) output, fp32 atomics
     float* stat_sum;
     float* stat_sqsum;
+    int epi_fast;           // host-checked: 16-bit out, whole channel tiles, 16-byte aligned bias/residual/output
 };
 
 template <int BLOCK_N, int KBYTES>
@@ -73,9 +75,8 @@ struct ConvTcCfg {
     // the (latency-bound) epilogue; 256-wide tiles use the whole 512-column TMEM with 2 stages
     static constexpr int ACC_STAGES = BLOCK_N >= 256 ? 2 : (BLOCK_N == 128 ? 4 : 8);
     static constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;   // 512, 512, 512, 256 columns
-    static constexpr int AUX_BYTES = 1024;  // barriers + tmem ptr + bias staging
-    static constexpr int BIAS_BYTES = BLOCK_N * 4;
-    static constexpr int SMEM_BYTES = 1024 /*align slack*/ + NUM_STAGES * STAGE_BYTES + AUX_BYTES + BIAS_BYTES;
+    static constexpr int AUX_BYTES = 1024;  // barriers + tmem ptr
+    static constexpr int SMEM_BYTES = 1024 /*align slack*/ + NUM_STAGES * STAGE_BYTES + AUX_BYTES;
 };
 
 __device__ __noinline__ float mish_noinline(float x) { return mish_f(x); }
@@ -88,18 +89,161 @@ __device__ __forceinline__ float round_half_away(float x) {
 
 template <int BLOCK_N>
 struct ConvTcEpi {
-    // two column groups of epilogue warps for wide tiles: more loads/stores in flight per SM
-    static constexpr int WARPS = BLOCK_N >= 128 ? 8 : 4;
+    // 8 epilogue warps (two groups of 4, one warp per TMEM lane quarter each):
+    //   wide tiles  (BLOCK_N >= 128): both groups work on the same tile, half of the columns each;
+    //   narrow tiles (BLOCK_N < 128): the groups take alternate tiles, so two accumulators drain concurrently.
+    static constexpr int WARPS = 8;
+    static constexpr bool SPLIT_TILES = BLOCK_N < 128;
+    static constexpr int ARRIVALS = SPLIT_TILES ? 4 : 8;    // epilogue warps that release one accumulator stage
     static constexpr int THREADS = 128 + 32 * WARPS;
 };
 
+// General (slow-path) epilogue for one 32-column chunk: every output type, partial channel tiles, batch statistics,
+// int8 requantisation.  `v` holds the scaled accumulators on entry.
+template <int KIND>
+__device__ __forceinline__ void epi_chunk_general(float (&v)[32], const ConvTcParams& p, int n0c0, long long row,
+                                               bool row_ok, int lane) {
+    if (p.stat_sum != nullptr) {
+        // per-channel batch statistics of the raw conv output (training BN): butterfly over the 32 rows of this warp
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            float s1 = row_ok ? v[j] : 0.f;
+            float s2 = s1 * s1;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+            }
+            if (lane == j && n0c0 + j < p.Cout) {
+                atomicAdd(p.stat_sum + n0c0 + j, s1);
+                atomicAdd(p.stat_sqsum + n0c0 + j, s2);
+            }
+        }
+    }
+    const int nvalid = min(32, p.Cout - n0c0);
+    if (p.bias != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (j < nvalid) v[j] += __ldg(p.bias + n0c0 + j);
+    }
+    switch (p.act) {
+        case B2Y_ACT_LEAKY:
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * p.slope;
+            break;
+        case B2Y_ACT_MISH:
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = mish_noinline(v[j]);
+            break;
+        case B2Y_ACT_RELU:
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            break;
+        case B2Y_ACT_RELU6:
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fminf(fmaxf(v[j], 0.f), 6.f);
+            break;
+        case B2Y_ACT_HSWISH:
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = v[j] * (fminf(fmaxf(v[j] + 3.f, 0.f), 6.f) / 6.f);
+            break;
+        case B2Y_ACT_SWISH:
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = swish_noinline(v[j]);
+            break;
+        default:
+            break;
+    }
+    if (!row_ok) return;
+    if (p.res != nullptr) {
+        const __half* rp = p.res + row * p.res_pitch + n0c0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (j < nvalid)
+                v[j] += p.res_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(rp)[j]) : __half2float(rp[j]);
+    }
+    if (p.out_fakequant || p.out_dtype == OUT_I8) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            float q = round_half_away(v[j] * p.out_inv_scale);
+            q = fminf(fmaxf(q, p.q_lo), p.q_hi);
+            v[j] = (p.out_dtype == OUT_I8) ? q : q * p.out_scale;
+        }
+    }
+    if (p.out_dtype == OUT_BF16) {
+        __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.out_pitch + n0c0;
+        if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint4 u;
+                __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) h2[t] = __floats2bfloat162_rn(v[q * 8 + t * 2], v[q * 8 + t * 2 + 1]);
+                reinterpret_cast<uint4*>(op)[q] = u;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (j < nvalid) op[j] = __float2bfloat16_rn(v[j]);
+        }
+    } else if (p.out_dtype == OUT_F16) {
+        __half* op = reinterpret_cast<__half*>(p.out) + row * p.out_pitch + n0c0;
+        if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint4 u;
+                __half2* h2 = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) h2[t] = __floats2half2_rn(v[q * 8 + t * 2], v[q * 8 + t * 2 + 1]);
+                reinterpret_cast<uint4*>(op)[q] = u;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (j < nvalid) op[j] = __float2half_rn(v[j]);
+        }
+    } else if (p.out_dtype == OUT_F32) {
+        float* op = reinterpret_cast<float*>(p.out) + row * p.out_pitch + n0c0;
+        if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                reinterpret_cast<float4*>(op)[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (j < nvalid) op[j] = v[j];
+        }
+    } else {  // OUT_I8
+        int8_t* op = reinterpret_cast<int8_t*>(p.out) + row * p.out_pitch + n0c0;
+        if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                uint32_t w[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const int b = q * 16 + t * 4;
+                    w[t] = ((uint32_t)(uint8_t)(int8_t)(int)v[b]) | ((uint32_t)(uint8_t)(int8_t)(int)v[b + 1] << 8) |
+                           ((uint32_t)(uint8_t)(int8_t)(int)v[b + 2] << 16) |
+                           ((uint32_t)(uint8_t)(int8_t)(int)v[b + 3] << 24);
+                }
+                reinterpret_cast<uint4*>(op)[q] = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (j < nvalid) op[j] = (int8_t)(int)v[j];
+        }
+    }
+}
+
 // CLUSTER > 1: the CTAs of a cluster work on CLUSTER consecutive M tiles of the same N tile; each loads 1/CLUSTER of
-// the weight tile and TMA-multicasts it to all of them, so the (dominant) weight re-reads from L2 drop by CLUSTER x.
+// the weight tile and TMA-multicasts it to all of them, so the weight re-reads from L2 drop by CLUSTER x.
 template <int BLOCK_N, int KBYTES, int KIND, int CLUSTER>
 __global__ void __launch_bounds__(ConvTcEpi<BLOCK_N>::THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const ConvTcParams p) {
+               const __grid_constant__ ConvTcParams p) {
     using Cfg = ConvTcCfg<BLOCK_N, KBYTES>;
+    using Epi = ConvTcEpi<BLOCK_N>;
     constexpr int NS = Cfg::NUM_STAGES;
     constexpr int ESIZE = (KIND == CONV_KIND_F16) ? 2 : 1;
     constexpr int BLOCK_K = KBYTES / ESIZE;  // elements per k-chunk
@@ -117,7 +261,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* tmem_full_bar = empty_bar + NS;                        // [AS]
     uint64_t* tmem_empty_bar = tmem_full_bar + AS;                   // [AS]
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + AS);
-    float* sbias = reinterpret_cast<float*>(aux + Cfg::AUX_BYTES);   // [BLOCK_N]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -133,7 +276,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int i = 0; i < AS; ++i) {
             mbar_init(&tmem_full_bar[i], 1);
-            mbar_init(&tmem_empty_bar[i], ConvTcEpi<BLOCK_N>::WARPS);  // one arrive per epilogue warp
+            mbar_init(&tmem_empty_bar[i], Epi::ARRIVALS);
         }
         fence_barrier_init();
     }
@@ -152,236 +295,205 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int cta_rank = CLUSTER > 1 ? (int)cluster_ctarank() : 0;
     const int cluster_id = (int)blockIdx.x / CLUSTER;
     const int num_clusters = (int)gridDim.x / CLUSTER;
+    const int num_n_tiles = p.num_n_tiles;
     const int num_mgroups = (p.num_m_tiles + CLUSTER - 1) / CLUSTER;
-    const int num_items = num_mgroups * p.num_n_tiles;
+    const int num_items = num_mgroups * num_n_tiles;
     constexpr uint16_t MC_MASK = (uint16_t)((1u << CLUSTER) - 1u);
     const int taps = p.ntaps;
-    const int k_steps = taps * p.k_chunks;
+    const int k_chunks = p.k_chunks;
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t full_base = smem_u32(full_bar);
+    const uint32_t empty_base = smem_u32(empty_bar);
 
+    // The two issue loops below are executed by the whole (converged) warp with one elected lane doing the issue:
+    // all loop state is then warp-uniform and lives in the uniform datapath.  (Run by a single divergent lane, each
+    // TMA / MMA issue cost ~10 extra R2UR/ELECT instructions and the loops, at ~8 cycles per dependent instruction,
+    // became the bottleneck of every layer whose k-step is shorter than ~800 cycles.)
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            const int HoWo = p.MH * p.MW;
-            for (int item = cluster_id; item < num_items; item += num_clusters) {
-                const int mgroup = item / p.num_n_tiles;
-                const int n_tile = item - mgroup * p.num_n_tiles;
-                const int m_tile = mgroup * CLUSTER + cta_rank;
-                const int m0 = m_tile * 128;
-                const int img = m0 / HoWo;
+        uint32_t stage = 0, phase = 0;
+        const int HoWo = p.MH * p.MW;
+        const int MW = p.MW;
+        const int cstride = p.stride, lower_w = p.lower_w, lower_h = p.lower_h, Cin = p.Cin;
+        const bool im2col = p.a_mode == A_MODE_IM2COL;
+        const unsigned long long tw = p.tap_w_packed, th = p.tap_h_packed;
+        for (int item = cluster_id; item < num_items; item += num_clusters) {
+            const int mgroup = item / num_n_tiles;
+            const int n_tile = item - mgroup * num_n_tiles;
+            const int m0 = (mgroup * CLUSTER + cta_rank) * 128;
+            int img = 0, base_w = 0, base_h = 0;
+            if (im2col) {
+                img = m0 / HoWo;
                 const int rem = m0 - img * HoWo;
-                const int po = rem / p.MW;
-                const int qo = rem - po * p.MW;
-                const int base_w = qo * p.stride + p.lower_w;
-                const int base_h = po * p.stride + p.lower_h;
-                for (int tap = 0; tap < taps; ++tap) {
-                    const int r = p.tap_oh[tap];
-                    const int s = p.tap_ow[tap];
-                    for (int kc = 0; kc < p.k_chunks; ++kc) {
-                        mbar_wait(&empty_bar[stage], phase ^ 1);
-                        uint8_t* a_dst = smem + stage * Cfg::STAGE_BYTES;
-                        uint8_t* b_dst = a_dst + Cfg::A_BYTES;
-                        mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-                        if (p.a_mode == A_MODE_IM2COL) {
-                            tma_load_im2col_4d(a_dst, &tmA, &full_bar[stage], kc * BLOCK_K, base_w, base_h, img,
-                                               (uint16_t)s, (uint16_t)r);
-                        } else {
-                            tma_load_2d(a_dst, &tmA, &full_bar[stage], kc * BLOCK_K, m0);
-                        }
-                        if (CLUSTER > 1) {
-                            constexpr int SLICE_ROWS = BLOCK_N / CLUSTER;
-                            tma_load_2d_multicast(b_dst + cta_rank * SLICE_ROWS * KBYTES, &tmB, &full_bar[stage],
-                                                  tap * p.Cin + kc * BLOCK_K, n_tile * BLOCK_N + cta_rank * SLICE_ROWS,
-                                                  MC_MASK);
-                        } else {
-                            tma_load_2d(b_dst, &tmB, &full_bar[stage], tap * p.Cin + kc * BLOCK_K, n_tile * BLOCK_N);
-                        }
-                        if (++stage == NS) {
-                            stage = 0;
-                            phase ^= 1;
-                        }
-                    }
-                }
+                const int po = rem / MW;
+                base_w = (rem - po * MW) * cstride + lower_w;
+                base_h = po * cstride + lower_h;
             }
-        }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            int acc = 0;
-            uint32_t acc_phase = 0;
-            const uint64_t desc_base = smem_desc_base(16, 8 * KBYTES, LAYOUT);
-            for (int item = cluster_id; item < num_items; item += num_clusters) {
-                mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
-                for (int ks = 0; ks < k_steps; ++ks) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
-                    const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-                    const uint32_t b_addr = a_addr + Cfg::A_BYTES;
-                    const uint64_t adesc = smem_desc_at(desc_base, a_addr);
-                    const uint64_t bdesc = smem_desc_at(desc_base, b_addr);
-#pragma unroll
-                    for (int k = 0; k < KBYTES / 32; ++k) {
-                        const uint32_t accum = (ks > 0 || k > 0) ? 1u : 0u;
-                        if (KIND == CONV_KIND_F16)
-                            mma_f16_ss(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC | p.idesc_ab,
-                                       accum);
+            const int b_row = n_tile * BLOCK_N + (CLUSTER > 1 ? cta_rank * (BLOCK_N / CLUSTER) : 0);
+            int b_k = 0;
+            for (int tap = 0; tap < taps; ++tap) {
+                const uint16_t s = (uint16_t)((tw >> (4 * tap)) & 15);
+                const uint16_t r = (uint16_t)((th >> (4 * tap)) & 15);
+                int a_c = 0;
+                for (int kc = 0; kc < k_chunks; ++kc) {
+                    mbar_wait_s(empty_base + stage * 8, phase ^ 1);
+                    if (elect_one()) {
+                        const uint32_t a_dst = smem_base + stage * Cfg::STAGE_BYTES;
+                        const uint32_t b_dst = a_dst + Cfg::A_BYTES;
+                        const uint32_t fb = full_base + stage * 8;
+                        mbar_expect_tx_s(fb, Cfg::STAGE_BYTES);
+                        if (im2col)
+                            tma_load_im2col_4d_s(a_dst, &tmA, fb, a_c, base_w, base_h, img, s, r);
                         else
-                            mma_i8_ss(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC, accum);
+                            tma_load_2d_s(a_dst, &tmA, fb, a_c, m0);
+                        if (CLUSTER > 1)
+                            tma_load_2d_multicast_s(b_dst + cta_rank * (BLOCK_N / CLUSTER) * KBYTES, &tmB, fb, b_k, b_row,
+                                                    MC_MASK);
+                        else
+                            tma_load_2d_s(b_dst, &tmB, fb, b_k, b_row);
                     }
-                    if (CLUSTER > 1)
-                        tc_commit_multicast(&empty_bar[stage], MC_MASK);  // release the slot in every CTA of the cluster
-                    else
-                        tc_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+                    a_c += BLOCK_K;
+                    b_k += BLOCK_K;
                     if (++stage == NS) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
-                tc_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
-                if (++acc == AS) {
-                    acc = 0;
-                    acc_phase ^= 1;
+                b_k += Cin - k_chunks * BLOCK_K;   // == 0 (Cin is a whole number of chunks); keeps the intent explicit
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+        const int k_steps = taps * k_chunks;
+        const uint32_t idesc = IDESC | (KIND == CONV_KIND_F16 ? p.idesc_ab : 0u);
+        const uint64_t desc_base = smem_desc_base(16, 8 * KBYTES, LAYOUT);
+        const uint32_t tfull_base = smem_u32(tmem_full_bar), tempty_base = smem_u32(tmem_empty_bar);
+        for (int item = cluster_id; item < num_items; item += num_clusters) {
+            mbar_wait_s(tempty_base + acc * 8, acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+            uint32_t accum = 0;
+            for (int ks = 0; ks < k_steps; ++ks) {
+                mbar_wait_s(full_base + stage * 8, phase);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t a_addr = smem_base + stage * Cfg::STAGE_BYTES;
+                    const uint64_t adesc = desc_base | (uint64_t)((a_addr >> 4) & 0x3FFF);
+                    const uint64_t bdesc = desc_base | (uint64_t)(((a_addr + Cfg::A_BYTES) >> 4) & 0x3FFF);
+#pragma unroll
+                    for (int k = 0; k < KBYTES / 32; ++k) {
+                        if (KIND == CONV_KIND_F16)
+                            mma_f16_ss(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                                       k > 0 ? 1u : accum);
+                        else
+                            mma_i8_ss(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                                      k > 0 ? 1u : accum);
+                    }
+                    if (CLUSTER > 1)
+                        tc_commit_multicast_s(empty_base + stage * 8, MC_MASK);  // release the slot in every CTA
+                    else
+                        tc_commit_s(empty_base + stage * 8);  // frees the smem slot when these MMAs retire
                 }
+                accum = 1;
+                if (++stage == NS) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+            if (elect_one()) tc_commit_s(tfull_base + acc * 8);  // accumulator complete -> epilogue
+            if (++acc == AS) {
+                acc = 0;
+                acc_phase ^= 1;
             }
         }
     } else if (warp >= 4) {
         // ===================== epilogue =====================
-        constexpr int EPI_WARPS = ConvTcEpi<BLOCK_N>::WARPS;
-        constexpr int EPI_THREADS = 32 * EPI_WARPS;
-        constexpr int COLS_PER_GROUP = BLOCK_N / (EPI_WARPS / 4);
+        constexpr int COLS_PER_GROUP = Epi::SPLIT_TILES ? BLOCK_N : BLOCK_N / 2;
         const float acc_mul = p.acc_scale * (p.acc_scale_ptr != nullptr ? __ldg(p.acc_scale_ptr) : 1.f);
         const int ew = (warp - 4) & 3;          // TMEM lane quarter == warp_id % 4
-        const int cg = (warp - 4) >> 2;         // column group
-        const int et = threadIdx.x - 128;       // 0..EPI_THREADS-1
-        int acc = 0;
-        uint32_t acc_phase = 0;
-        bool first_item = true;
-        for (int item = cluster_id; item < num_items; item += num_clusters) {
-            const int mgroup = item / p.num_n_tiles;
-            const int n_tile = item - mgroup * p.num_n_tiles;
+        const int cg = (warp - 4) >> 2;         // group
+        const bool fast = p.epi_fast != 0;
+        const int act = p.act;
+        const float slope = p.slope;
+        const int c_begin = Epi::SPLIT_TILES ? 0 : cg * COLS_PER_GROUP;
+        const int hw = p.MH * p.MW;
+        int it = 0;
+        for (int item = cluster_id; item < num_items; item += num_clusters, ++it) {
+            if (Epi::SPLIT_TILES && (it & 1) != cg) continue;
+            const int acc = it % AS;
+            const uint32_t acc_phase = (uint32_t)(it / AS) & 1u;
+            const int mgroup = item / num_n_tiles;
+            const int n_tile = item - mgroup * num_n_tiles;
             const int m_tile = mgroup * CLUSTER + cta_rank;
             const int n0 = n_tile * BLOCK_N;
             const long long grow = (long long)m_tile * 128 + ew * 32 + lane;   // GEMM row
             const bool row_ok = grow < p.M_total;
             long long row = grow;                                              // output pixel index
             if (!p.out_identity && row_ok) {
-                const int hw = p.MH * p.MW;
                 const int n_ = (int)(grow / hw);
                 const int r_ = (int)(grow - (long long)n_ * hw);
                 const int p_ = r_ / p.MW, q_ = r_ - p_ * p.MW;
                 row = ((long long)n_ * p.out_OH + (long long)p_ * p.out_ys + p.out_y0) * p.out_OW +
                       (long long)q_ * p.out_xs + p.out_x0;
             }
-            const int c_begin = cg * COLS_PER_GROUP;
-            const int c_end = c_begin + COLS_PER_GROUP;
-            // residual prefetch (one 32-column chunk ahead; the first chunk is issued before the accumulator wait)
-            const __half* res_row = (p.res != nullptr && row_ok) ? p.res + row * p.res_pitch + n0 : nullptr;
-            const bool res_vec = res_row != nullptr && ((reinterpret_cast<uintptr_t>(res_row) & 15) == 0);
-            uint4 rnext[4];
-            if (res_vec && n0 + c_begin + 32 <= p.Cout) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) rnext[q] = __ldg(reinterpret_cast<const uint4*>(res_row + c_begin) + q);
-            }
-
-            // stage the bias slice for this tile
-            if (p.num_n_tiles > 1 || first_item) {   // a single N tile: the bias slice never changes
-                first_item = false;
-                asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
-                for (int i = et; i < BLOCK_N; i += EPI_THREADS) {
-                    const int n = n0 + i;
-                    sbias[i] = (p.bias != nullptr && n < p.Cout) ? __ldg(p.bias + n) : 0.f;
-                }
-                asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
-            }
-
-            mbar_wait(&tmem_full_bar[acc], acc_phase);
-            tc_fence_after();
             const uint32_t taddr_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BLOCK_N);
 
+            if (fast) {
+                // 16-bit output, whole channel tile valid, vector-aligned bias / residual / output (checked on the host)
+                const float* bias_p = p.bias != nullptr ? p.bias + n0 + c_begin : nullptr;
+                const uint4* res_p = (p.res != nullptr && row_ok)
+                                         ? reinterpret_cast<const uint4*>(p.res + row * p.res_pitch + n0 + c_begin)
+                                         : nullptr;
+                uint4* out_p = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + row * p.out_pitch + n0 + c_begin);
+                uint4 rnext[4];
+                if (res_p != nullptr) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) rnext[q] = __ldg(res_p + q);
+                }
+                mbar_wait(&tmem_full_bar[acc], acc_phase);
+                tc_fence_after();
 #pragma unroll 1
-            for (int c0 = c_begin; c0 < c_end; c0 += 32) {
-                uint32_t raw[32];
-                tmem_ld_32x32(taddr_row + (uint32_t)c0, raw);
-                uint4 rcur[4];
+                for (int c = 0; c < COLS_PER_GROUP; c += 32) {
+                    uint32_t raw[32];
+                    tmem_ld_32x32(taddr_row + (uint32_t)(c_begin + c), raw);
+                    float4 bv[8];
+                    if (bias_p != nullptr) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) rcur[q] = rnext[q];
-                if (res_vec && c0 + 32 < c_end && n0 + c0 + 64 <= p.Cout) {
+                        for (int q = 0; q < 8; ++q) bv[q] = __ldg(reinterpret_cast<const float4*>(bias_p + c) + q);
+                    } else {
 #pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        rnext[q] = __ldg(reinterpret_cast<const uint4*>(res_row + c0 + 32) + q);
-                }
-                tc_wait_ld();
-                if (n0 + c0 >= p.Cout) continue;  // warp-uniform
-
-                float v[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float a = (KIND == CONV_KIND_F16) ? __uint_as_float(raw[j]) : (float)(int)raw[j];
-                    v[j] = a * acc_mul;
-                }
-
-                if (p.stat_sum != nullptr) {
-                    // per-channel batch statistics of the raw conv output (training BN):
-                    // butterfly-reduce each column over the 32 rows of this warp.
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        float s1 = row_ok ? v[j] : 0.f;
-                        float s2 = s1 * s1;
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) {
-                            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-                            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-                        }
-                        if (lane == j && n0 + c0 + j < p.Cout) {
-                            atomicAdd(p.stat_sum + n0 + c0 + j, s1);
-                            atomicAdd(p.stat_sqsum + n0 + c0 + j, s2);
-                        }
+                        for (int q = 0; q < 8; ++q) bv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
                     }
-                }
-
-                // bias + activation: the switch is hoisted out of the element loop so that the executed path is one
-                // short straight-line block (a per-element switch made the unrolled body ~64 KB and I-cache bound)
+                    uint4 rcur[4];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] += sbias[c0 + j];
-                switch (p.act) {
-                    case B2Y_ACT_LEAKY:
+                    for (int q = 0; q < 4; ++q) rcur[q] = rnext[q];
+                    if (res_p != nullptr && c + 32 < COLS_PER_GROUP) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * p.slope;
-                        break;
-                    case B2Y_ACT_MISH:
+                        for (int q = 0; q < 4; ++q) rnext[q] = __ldg(res_p + (c + 32) / 8 + q);
+                    }
+                    tc_wait_ld();
+                    float v[32];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float a0 = (KIND == CONV_KIND_F16) ? __uint_as_float(raw[4 * q]) : (float)(int)raw[4 * q];
+                        const float a1 = (KIND == CONV_KIND_F16) ? __uint_as_float(raw[4 * q + 1]) : (float)(int)raw[4 * q + 1];
+                        const float a2 = (KIND == CONV_KIND_F16) ? __uint_as_float(raw[4 * q + 2]) : (float)(int)raw[4 * q + 2];
+                        const float a3 = (KIND == CONV_KIND_F16) ? __uint_as_float(raw[4 * q + 3]) : (float)(int)raw[4 * q + 3];
+                        v[4 * q] = fmaf(a0, acc_mul, bv[q].x);
+                        v[4 * q + 1] = fmaf(a1, acc_mul, bv[q].y);
+                        v[4 * q + 2] = fmaf(a2, acc_mul, bv[q].z);
+                        v[4 * q + 3] = fmaf(a3, acc_mul, bv[q].w);
+                    }
+                    if (act == B2Y_ACT_LEAKY) {       // 0 <= slope <= 1 on this path: max(v, slope*v)
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], v[j] * slope);
+                    } else if (act == B2Y_ACT_MISH) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = mish_noinline(v[j]);
-                        break;
-                    case B2Y_ACT_RELU:
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-                        break;
-                    case B2Y_ACT_RELU6:
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = fminf(fmaxf(v[j], 0.f), 6.f);
-                        break;
-                    case B2Y_ACT_HSWISH:
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = v[j] * (fminf(fmaxf(v[j] + 3.f, 0.f), 6.f) / 6.f);
-                        break;
-                    case B2Y_ACT_SWISH:
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = swish_noinline(v[j]);
-                        break;
-                    default:
-                        break;
-                }
-
-                const int nvalid = min(32, p.Cout - (n0 + c0));
-                if (row_ok) {
-                    if (p.res != nullptr) {
-                        const __half* rp = p.res + row * p.res_pitch + n0 + c0;
-                        if (nvalid == 32 && res_vec) {
+                    }
+                    if (row_ok) {
+                        if (res_p != nullptr) {
 #pragma unroll
                             for (int q = 0; q < 4; ++q) {
                                 const uint4 u = rcur[q];
@@ -389,7 +501,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                     const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
                                     for (int t = 0; t < 4; ++t) {
-                                        float2 f = __bfloat1622float2(b2[t]);
+                                        const float2 f = __bfloat1622float2(b2[t]);
                                         v[q * 8 + t * 2] += f.x;
                                         v[q * 8 + t * 2 + 1] += f.y;
                                     }
@@ -397,33 +509,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                     const __half2* h2 = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
                                     for (int t = 0; t < 4; ++t) {
-                                        float2 f = __half22float2(h2[t]);
+                                        const float2 f = __half22float2(h2[t]);
                                         v[q * 8 + t * 2] += f.x;
                                         v[q * 8 + t * 2 + 1] += f.y;
                                     }
                                 }
                             }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (j < nvalid)
-                                    v[j] += p.res_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(rp)[j])
-                                                       : __half2float(rp[j]);
                         }
-                    }
-
-                    if (p.out_fakequant || p.out_dtype == OUT_I8) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            float q = round_half_away(v[j] * p.out_inv_scale);
-                            q = fminf(fmaxf(q, p.q_lo), p.q_hi);
-                            v[j] = (p.out_dtype == OUT_I8) ? q : q * p.out_scale;
-                        }
-                    }
-
-                    if (p.out_dtype == OUT_BF16) {
-                        __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.out_pitch + n0 + c0;
-                        if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+                        if (p.out_dtype == OUT_BF16) {
 #pragma unroll
                             for (int q = 0; q < 4; ++q) {
                                 uint4 u;
@@ -431,16 +524,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                                 for (int t = 0; t < 4; ++t)
                                     h2[t] = __floats2bfloat162_rn(v[q * 8 + t * 2], v[q * 8 + t * 2 + 1]);
-                                reinterpret_cast<uint4*>(op)[q] = u;
+                                out_p[c / 8 + q] = u;
                             }
                         } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (j < nvalid) op[j] = __float2bfloat16_rn(v[j]);
-                        }
-                    } else if (p.out_dtype == OUT_F16) {
-                        __half* op = reinterpret_cast<__half*>(p.out) + row * p.out_pitch + n0 + c0;
-                        if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
 #pragma unroll
                             for (int q = 0; q < 4; ++q) {
                                 uint4 u;
@@ -448,58 +534,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                                 for (int t = 0; t < 4; ++t)
                                     h2[t] = __floats2half2_rn(v[q * 8 + t * 2], v[q * 8 + t * 2 + 1]);
-                                reinterpret_cast<uint4*>(op)[q] = u;
+                                out_p[c / 8 + q] = u;
                             }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (j < nvalid) op[j] = __float2half_rn(v[j]);
-                        }
-                    } else if (p.out_dtype == OUT_F32) {
-                        float* op = reinterpret_cast<float*>(p.out) + row * p.out_pitch + n0 + c0;
-                        if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
-#pragma unroll
-                            for (int q = 0; q < 8; ++q)
-                                reinterpret_cast<float4*>(op)[q] =
-                                    make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (j < nvalid) op[j] = v[j];
-                        }
-                    } else {  // OUT_I8
-                        int8_t* op = reinterpret_cast<int8_t*>(p.out) + row * p.out_pitch + n0 + c0;
-                        if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
-#pragma unroll
-                            for (int q = 0; q < 2; ++q) {
-                                uint32_t w[4];
-#pragma unroll
-                                for (int t = 0; t < 4; ++t) {
-                                    const int b = q * 16 + t * 4;
-                                    w[t] = ((uint32_t)(uint8_t)(int8_t)(int)v[b]) |
-                                           ((uint32_t)(uint8_t)(int8_t)(int)v[b + 1] << 8) |
-                                           ((uint32_t)(uint8_t)(int8_t)(int)v[b + 2] << 16) |
-                                           ((uint32_t)(uint8_t)(int8_t)(int)v[b + 3] << 24);
-                                }
-                                reinterpret_cast<uint4*>(op)[q] = make_uint4(w[0], w[1], w[2], w[3]);
-                            }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (j < nvalid) op[j] = (int8_t)(int)v[j];
                         }
                     }
                 }
-                __syncwarp();
+            } else {
+                mbar_wait(&tmem_full_bar[acc], acc_phase);
+                tc_fence_after();
+#pragma unroll 1
+                for (int c = 0; c < COLS_PER_GROUP; c += 32) {
+                    const int c0 = c_begin + c;
+                    uint32_t raw[32];
+                    tmem_ld_32x32(taddr_row + (uint32_t)c0, raw);
+                    tc_wait_ld();
+                    if (n0 + c0 >= p.Cout) continue;  // warp-uniform
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        v[j] = ((KIND == CONV_KIND_F16) ? __uint_as_float(raw[j]) : (float)(int)raw[j]) * acc_mul;
+                    epi_chunk_general<KIND>(v, p, n0 + c0, row, row_ok, lane);
+                }
             }
             // release this accumulator stage back to the MMA warp
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
-            if (++acc == AS) {
-                acc = 0;
-                acc_phase ^= 1;
-            }
         }
     }
 
