@@ -108,6 +108,18 @@ int b2y_pack_stem_weights(const float* w_oihw_folded, int out_c, int in_c, int k
 int b2y_stem_conv_fwd_tc(const b2y_conv_desc* d, const float* x_nchw, const void* w_stem, const float* bias,
                          void* workspace, void* y, float* stat_sum, float* stat_sqsum, void* stream);
 
+/* Fused tensor-core stem (in_c*ksize*ksize <= 32, out_c <= 64): the CTA builds the im2col tile in shared memory
+ * straight from the image and feeds tcgen05.mma, so only the image is read and only y is written (no workspace).
+ *   x_nchw   NCHW image, x_dtype = B2Y_STEM_X_F32 / _F16 / _U8; value = raw / x_div
+ *            (x_div = 255 for uint8 images: reference test.py:97 / detect.py "img.float() / 255.0")
+ *   w_stem   fp16 [out_c][32] from b2y_pack_stem_weights (the layout it produces when in_c*k*k <= 32)
+ *   y        NHWC fp16 */
+#define B2Y_STEM_X_F32 0
+#define B2Y_STEM_X_F16 1
+#define B2Y_STEM_X_U8 2
+int b2y_stem_conv_fwd_fused(const b2y_conv_desc* d, const void* x_nchw, int x_dtype, float x_div, const void* w_stem,
+                            const float* bias, void* y, void* stream);
+
 /* Fold BatchNorm (running stats) into conv weights and repack OIHW fp32 -> [O][kh][kw][I] fp16.
  *   w_f = w * gamma/sqrt(var+eps);  b_f = beta - gamma*mean/sqrt(var+eps) (+ conv_bias*scale)
  * (utils/torch_utils.py:65-89, utils/quantized/quantized_ptq_cos.py:193-206).

@@ -157,6 +157,36 @@ def test_stem_conv_tensor_core(cin, k, stride, cout):
     assert (got - ref).abs().max() <= 2e-3 * max(1.0, ref.abs().max().item())
 
 
+@pytest.mark.parametrize("cin,k,stride,cout,dtype", [
+    (3, 3, 1, 32, "f32"), (3, 3, 2, 32, "f16"), (3, 3, 1, 16, "u8"), (1, 5, 1, 32, "f32"), (3, 3, 1, 64, "u8"),
+    (3, 3, 1, 48, "f32")])
+def test_stem_conv_fused(cin, k, stride, cout, dtype):
+    """Fused stem: the CTA builds the im2col tile in smem from the NCHW image (fp32 / fp16 / uint8 with /255)."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(12)
+    B, H, W = 3, 44, 72            # 3*44*72 = 9504 pixels: 74.25 tiles -> partial last tile, several tiles per CTA group
+    if dtype == "u8":
+        x = torch.randint(0, 256, (B, cin, H, W), generator=g, dtype=torch.uint8)
+        xf, div = x.float() / 255.0, 255.0
+    elif dtype == "f16":
+        x = torch.rand(B, cin, H, W, generator=g).half()
+        xf, div = x.float(), 1.0
+    else:
+        x = torch.rand(B, cin, H, W, generator=g)
+        xf, div = x, 1.0
+    w = torch.randn(cout, cin, k, k, generator=g) / (cin * k)
+    b = torch.randn(cout, generator=g)
+    for act, fn in (("leaky", lambda t: F.leaky_relu(t, 0.1)), ("mish", lambda t: t * torch.tanh(F.softplus(t)))):
+        ref = fn(F.conv2d(xf.half().float(), w.half().float(), b, stride=stride, padding=k // 2))
+        ws = ops.pack_stem_weights(w.cuda())
+        assert ws.dim() == 2
+        y = ops.stem_conv_fused(x.cuda(), ws, b.cuda(), k, stride, k // 2, act=act, x_div=div)
+        torch.cuda.synchronize()
+        got = y.float().permute(0, 3, 1, 2).cpu()
+        assert got.shape == ref.shape
+        assert (got - ref).abs().max() <= 2e-3 * max(1.0, ref.abs().max().item()), (act, (got - ref).abs().max())
+
+
 def test_pack_weights_bn_fold():
     ops = _ops()
     g = torch.Generator().manual_seed(2)

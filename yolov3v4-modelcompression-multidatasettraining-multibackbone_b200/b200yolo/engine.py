@@ -282,7 +282,14 @@ class Plan:
                 if src is None:
                     if conv.in_channels > 4:
                         raise NotImplementedError("first layer with more than 4 input channels")
-                    if wstem is not None:
+                    if wstem is not None and wstem.dim() == 2 and conv.out_channels <= 64 and \
+                            os.environ.get('B2Y_STEM', 'fused') == 'fused':
+                        # full-im2col weight layout: the fused kernel builds the A tile in smem (no workspace)
+                        ops.stem_conv_fused(x, wstem, bias, k, s, p, act=act, slope=slope, out=out.view(),
+                                            x_div=255.0 if x.dtype == torch.uint8 else 1.0)
+                    elif wstem is not None:
+                        if x.dtype != torch.float32:
+                            x = x.float() / 255.0 if x.dtype == torch.uint8 else x.float()
                         if getattr(self, 'stem_ws', None) is None:
                             self.stem_ws = ops.stem_workspace(
                                 ops.make_conv_desc((self.B, self.H, self.W, conv.in_channels), conv.in_channels,
@@ -290,6 +297,8 @@ class Plan:
                         ops.stem_conv_tc(x, wstem, bias, conv.in_channels, k, s, p, act=act, slope=slope,
                                          out=out.view(), workspace=self.stem_ws)
                     else:
+                        if x.dtype != torch.float32:
+                            x = x.float() / 255.0 if x.dtype == torch.uint8 else x.float()
                         ops.stem_conv(x, w32, bias, k, s, p, act=act, slope=slope, out=out.view())
                 else:
                     ops.conv2d(src.view(), wp, bias, k, s, p, act=act, slope=slope,
@@ -401,7 +410,11 @@ class Plan:
             self._pack_weights()
             self.param_version = ver
             self.graph = None
-        x = x.contiguous().float()
+        # fp32 / fp16 images go to the stem as they are; uint8 images (the reference's dataloader output before
+        # test.py:97 "imgs.float() / 255.0") are normalised inside the stem kernel
+        x = x.contiguous()
+        if x.dtype not in (torch.float32, torch.float16, torch.uint8):
+            x = x.float()
         no = self.yolo[0][0].no
         use_graph = getattr(model, 'use_cuda_graph', os.environ.get('B2Y_NO_GRAPH', '0') != '1')
         if not use_graph or self.runs < 1:
@@ -464,14 +477,14 @@ class Engine:
         self.forward(x)
         model = self.model
         keep = bool(model.keep_features)
-        return self.plans[(tuple(x.shape), bool(model.training), x.device.index, keep)]
+        return self.plans[(tuple(x.shape), bool(model.training), x.device.index, keep, x.dtype)]
 
     def forward(self, x):
         model = self.model
         if model.quantized != -1:
             return self._forward_quantized(x)
         keep = bool(model.keep_features)
-        key = (tuple(x.shape), bool(model.training), x.device.index, keep)
+        key = (tuple(x.shape), bool(model.training), x.device.index, keep, x.dtype)
         plan = self.plans.get(key)
         if plan is None:
             if model.training:

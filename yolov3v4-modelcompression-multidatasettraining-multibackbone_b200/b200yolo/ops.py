@@ -128,6 +128,24 @@ def stem_conv_tc(x_nchw, w_stem, bias, in_c, k, stride, pad, act="linear", slope
     return out, workspace
 
 
+STEM_X = {torch.float32: 0, torch.float16: 1, torch.uint8: 2}
+
+
+def stem_conv_fused(x_nchw, w_stem, bias, k, stride, pad, act="linear", slope=0.1, out=None, x_div=1.0):
+    """Fused tensor-core stem (in_c*k*k <= 32): NCHW fp32/fp16/uint8 image -> NHWC fp16, no workspace."""
+    _require_cuda(x_nchw)
+    B, Cin, H, W = x_nchw.shape
+    O = w_stem.shape[0]
+    Ho, Wo = conv_out_hw(H, W, k, stride, pad)
+    if out is None:
+        out = torch.empty((B, Ho, Wo, O), dtype=torch.float16, device=x_nchw.device)
+    x_nchw = x_nchw.contiguous()
+    d = make_conv_desc((B, H, W, Cin), Cin, O, k, stride, pad, _pitch(out), act, slope, OUT_F16)
+    call("b2y_stem_conv_fwd_fused", C.byref(d), ptr(x_nchw), STEM_X[x_nchw.dtype], float(x_div), ptr(w_stem), ptr(bias),
+         ptr(out), stream_ptr())
+    return out
+
+
 def upsample(x, scale, out=None):
     B, H, W, Cc = x.shape
     if out is None:
