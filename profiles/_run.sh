@@ -1,4 +1,5 @@
 cd /root/repo
-timeout 300 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x -k "stem" 2>&1 | tail -4
-python bench.py --steps 20 --warmup 5 --no-cpu-baseline --profile-layers gpurun_out/layers_r01j.json > gpurun_out/bench10.json 2> gpurun_out/bench10.err; tail -3 gpurun_out/bench10.err; head -c 250 gpurun_out/bench10.json; echo
-B2Y_STEM_NG=2 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --profile-layers gpurun_out/layers_r01k.json > gpurun_out/bench10_ng2.json 2>/dev/null; head -c 250 gpurun_out/bench10_ng2.json; echo
+timeout 300 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x 2>&1 | tail -12
+timeout 300 python -m pytest tests/test_gpu_model.py -m gpu -q -x 2>&1 | tail -5
+timeout 200 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --profile-layers gpurun_out/layers_pair.json 2>gpurun_out/bench12.err | head -c 250; echo; tail -3 gpurun_out/bench12.err
+B2Y_PAIR=0 B2Y_CLUSTER=1 timeout 200 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --profile-layers gpurun_out/layers_nopair.json 2>/dev/null | head -c 250; echo

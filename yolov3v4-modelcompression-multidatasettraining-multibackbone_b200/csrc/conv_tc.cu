@@ -89,10 +89,10 @@ static int make_map_im2col(CUtensorMap* m, const void* base, int esize, int N, i
     return B2Y_OK;
 }
 
-template <int BLOCK_N, int KBYTES, int KIND, int CLUSTER>
+template <int BLOCK_N, int KBYTES, int KIND, int CLUSTER, int PAIR = 0>
 static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvTcParams& p, cudaStream_t st) {
     using Cfg = ConvTcCfg<BLOCK_N, KBYTES>;
-    auto kern = conv_tc_kernel<BLOCK_N, KBYTES, KIND, CLUSTER>;
+    auto kern = conv_tc_kernel<BLOCK_N, KBYTES, KIND, CLUSTER, PAIR>;
     static bool attr_set = false;
     if (!attr_set) {
         B2Y_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -133,6 +133,11 @@ static int dispatch(int block_n, int kbytes, int cluster, const CUtensorMap& a, 
     B2Y_CASE(256, 32) B2Y_CASE(256, 64) B2Y_CASE(256, 128)
 #undef B2Y_CASE
     // weight-multicast clusters exist for the wide, deep tiles only (KBYTES = 128)
+    if (p.pair) {
+        if (kbytes == 128 && block_n == 128 && cluster == 2) return launch_cfg<128, 128, KIND, 2, 1>(a, b, p, st);
+        if (kbytes == 128 && block_n == 256 && cluster == 2) return launch_cfg<256, 128, KIND, 2, 1>(a, b, p, st);
+        return B2Y_ERR_UNSUPPORTED;
+    }
     if (kbytes == 128 && block_n == 128 && cluster == 2) return launch_cfg<128, 128, KIND, 2>(a, b, p, st);
     if (kbytes == 128 && block_n == 256 && cluster == 2) return launch_cfg<256, 128, KIND, 2>(a, b, p, st);
     if (kbytes == 128 && block_n == 256 && cluster == 4) return launch_cfg<256, 128, KIND, 4>(a, b, p, st);
@@ -280,6 +285,34 @@ int gemm_conv_launch(const GemmConvSpec& g, const EpilogueArgs& e, cudaStream_t 
     rc = make_map_2d(&tmB, g.w, esize, g.Nout, Ktot, Ktot, block_k, block_n / cluster, kbytes, g.b_bf16);
     if (rc != B2Y_OK) return rc;
 
+    {
+        // smem ring depth; weight-stationary mode when the whole weight panel of a single N tile fits beside >= min_stages
+        // A stages (B2Y_BRES=0 disables, B2Y_BRES_MIN_STAGES overrides the default of 6)
+        static int bres_on = -1, bres_min = 6;
+        if (bres_on < 0) {
+            const char* e = getenv("B2Y_BRES");
+            bres_on = (e && atoi(e) == 0) ? 0 : 1;
+            const char* m = getenv("B2Y_BRES_MIN_STAGES");
+            if (m && atoi(m) >= 2) bres_min = atoi(m);
+        }
+        const long long max_smem = 196 * 1024;
+        const long long a_bytes = 128LL * kbytes, b_bytes = (long long)block_n * kbytes;
+        const long long res_bytes = (long long)p.ntaps * p.k_chunks * b_bytes;
+        static int pair_on = -1;     // B2Y_PAIR=0: clusters of two use weight multicast instead of cta_group::2 MMA
+        if (pair_on < 0) {
+            const char* e = getenv("B2Y_PAIR");
+            pair_on = (e && atoi(e) == 0) ? 0 : 1;
+        }
+        p.pair = (cluster == 2 && pair_on) ? 1 : 0;
+        p.b_resident = 0;
+        long long ns = max_smem / (a_bytes + (p.pair ? b_bytes / 2 : b_bytes));
+        if (bres_on && cluster == 1 && p.num_n_tiles == 1 && p.num_m_tiles > g_num_sms &&
+            res_bytes + bres_min * a_bytes <= max_smem) {
+            p.b_resident = 1;
+            ns = (max_smem - res_bytes) / a_bytes;
+        }
+        p.num_stages = (int)(ns > 32 ? 32 : ns);
+    }
     if (g.kind == CONV_KIND_F16) return dispatch<CONV_KIND_F16>(block_n, kbytes, cluster, tmA, tmB, p, st);
     return dispatch<CONV_KIND_I8>(block_n, kbytes, cluster, tmA, tmB, p, st);
 }

@@ -57,6 +57,9 @@ struct ConvTcParams {
     // training extras: per-channel sum / sum of squares of the raw (pre-bias) output, fp32 atomics
     float* stat_sum;
     float* stat_sqsum;
+    int b_resident;         // 1: the whole weight panel of the (single) N tile stays in smem, loaded once per CTA
+    int num_stages;         // smem ring depth for this launch (<= 32)
+    int pair;               // host: launch the cta_group::2 variant (cluster of two)
     int epi_fast;           // host-checked: 16-bit out, whole channel tiles, 16-byte aligned bias/residual/output
 };
 
@@ -75,8 +78,8 @@ struct ConvTcCfg {
     // the (latency-bound) epilogue; 256-wide tiles use the whole 512-column TMEM with 2 stages
     static constexpr int ACC_STAGES = BLOCK_N >= 256 ? 2 : (BLOCK_N == 128 ? 4 : 8);
     static constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;   // 512, 512, 512, 256 columns
-    static constexpr int AUX_BYTES = 1024;  // barriers + tmem ptr
-    static constexpr int SMEM_BYTES = 1024 /*align slack*/ + NUM_STAGES * STAGE_BYTES + AUX_BYTES;
+    static constexpr int AUX_BYTES = 1024;  // barriers + tmem ptr, at a fixed offset behind the tile area
+    static constexpr int SMEM_BYTES = 1024 /*align slack*/ + MAX_STAGE_SMEM + AUX_BYTES;
 };
 
 __device__ __noinline__ float mish_noinline(float x) { return mish_f(x); }
@@ -238,29 +241,41 @@ __device__ __forceinline__ void epi_chunk_general(float (&v)[32], const ConvTcPa
 
 // CLUSTER > 1: the CTAs of a cluster work on CLUSTER consecutive M tiles of the same N tile; each loads 1/CLUSTER of
 // the weight tile and TMA-multicasts it to all of them, so the weight re-reads from L2 drop by CLUSTER x.
-template <int BLOCK_N, int KBYTES, int KIND, int CLUSTER>
+//
+// PAIR (CLUSTER == 2): the two CTAs of the cluster are one cta_group::2 MMA pair.  Each CTA loads its own 128-row A tile
+// and HALF of the weight tile; the leader CTA issues one M=256 tcgen05.mma per k-slice that reads both halves, each
+// CTA's TMEM receives its own 128 accumulator rows.  Per CTA the smem fill per k-step drops from A + B to A + B/2,
+// which is what bounds the wide layers (L2 -> SM bandwidth), with no extra instructions on the critical loops.
+template <int BLOCK_N, int KBYTES, int KIND, int CLUSTER, int PAIR = 0>
 __global__ void __launch_bounds__(ConvTcEpi<BLOCK_N>::THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ ConvTcParams p) {
     using Cfg = ConvTcCfg<BLOCK_N, KBYTES>;
     using Epi = ConvTcEpi<BLOCK_N>;
-    constexpr int NS = Cfg::NUM_STAGES;
+    constexpr int MAX_NS = 32;
     constexpr int ESIZE = (KIND == CONV_KIND_F16) ? 2 : 1;
     constexpr int BLOCK_K = KBYTES / ESIZE;  // elements per k-chunk
     constexpr uint32_t LAYOUT = swizzle_layout_type(KBYTES);
     constexpr uint32_t IDESC = (KIND == CONV_KIND_F16)
-                                   ? make_idesc(/*c=F32*/ 1, /*a=F16*/ 0, /*b=F16*/ 0, 0, 0, 128, BLOCK_N)
-                                   : make_idesc(/*c=S32*/ 2, /*a=S8*/ 1, /*b=S8*/ 1, 0, 0, 128, BLOCK_N);
+                                   ? make_idesc(/*c=F32*/ 1, /*a=F16*/ 0, /*b=F16*/ 0, 0, 0, PAIR ? 256 : 128, BLOCK_N)
+                                   : make_idesc(/*c=S32*/ 2, /*a=S8*/ 1, /*b=S8*/ 1, 0, 0, PAIR ? 256 : 128, BLOCK_N);
+    static_assert(!PAIR || CLUSTER == 2, "a CTA pair is a cluster of two");
 
+    // smem: [ns stages of A (+B)] [resident weight panel, if any] ... [aux at a fixed offset]
+    const bool b_res = CLUSTER == 1 && p.b_resident != 0;
+    const int ns = p.num_stages;
+    const uint32_t stage_bytes = b_res ? (uint32_t)Cfg::A_BYTES
+                                       : (PAIR ? (uint32_t)(Cfg::A_BYTES + Cfg::B_BYTES / 2) : (uint32_t)Cfg::STAGE_BYTES);
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* aux = smem + NS * Cfg::STAGE_BYTES;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);           // [NS]
-    uint64_t* empty_bar = full_bar + NS;                             // [NS]
+    uint8_t* aux = smem + Cfg::MAX_STAGE_SMEM;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);           // [MAX_NS]
+    uint64_t* empty_bar = full_bar + MAX_NS;                         // [MAX_NS]
     constexpr int AS = Cfg::ACC_STAGES;
-    uint64_t* tmem_full_bar = empty_bar + NS;                        // [AS]
+    uint64_t* tmem_full_bar = empty_bar + MAX_NS;                    // [AS]
     uint64_t* tmem_empty_bar = tmem_full_bar + AS;                   // [AS]
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + AS);
+    uint64_t* bres_bar = tmem_empty_bar + AS;                        // [1] resident weight panel landed
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bres_bar + 1);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -270,19 +285,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         prefetch_tmap(&tmB);
     }
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < NS; ++i) {
+        for (int i = 0; i < ns; ++i) {
             mbar_init(&full_bar[i], 1);
-            mbar_init(&empty_bar[i], CLUSTER);   // every CTA that multicasts into this stage must see it released
+            mbar_init(&empty_bar[i], PAIR ? 1 : CLUSTER);   // multicast: every CTA that writes this stage releases it
         }
+        mbar_init(bres_bar, 1);
         for (int i = 0; i < AS; ++i) {
             mbar_init(&tmem_full_bar[i], 1);
-            mbar_init(&tmem_empty_bar[i], Epi::ARRIVALS);
+            mbar_init(&tmem_empty_bar[i], PAIR ? 2 * Epi::ARRIVALS : Epi::ARRIVALS);   // pair: both CTAs' epilogues
         }
         fence_barrier_init();
     }
     if (warp == 2) {
-        tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
-        tmem_relinquish();
+        if (PAIR) {
+            tmem_alloc2(tmem_ptr_smem, Cfg::TMEM_COLS);
+            tmem_relinquish2();
+        } else {
+            tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
+            tmem_relinquish();
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -304,6 +325,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t full_base = smem_u32(full_bar);
     const uint32_t empty_base = smem_u32(empty_bar);
+    const uint32_t bres_base = smem_base + (uint32_t)ns * stage_bytes;     // resident weight panel (k_steps x B tile)
 
     // The two issue loops below are executed by the whole (converged) warp with one elected lane doing the issue:
     // all loop state is then warp-uniform and lives in the uniform datapath.  (Run by a single divergent lane, each
@@ -317,6 +339,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int cstride = p.stride, lower_w = p.lower_w, lower_h = p.lower_h, Cin = p.Cin;
         const bool im2col = p.a_mode == A_MODE_IM2COL;
         const unsigned long long tw = p.tap_w_packed, th = p.tap_h_packed;
+        if (b_res && elect_one()) {
+            // weight-stationary: all k-steps of the (only) N tile are fetched once; the ring then carries A alone
+            const int k_steps = taps * k_chunks;
+            mbar_expect_tx_s(smem_u32(bres_bar), (uint32_t)k_steps * Cfg::B_BYTES);
+            for (int ks = 0; ks < k_steps; ++ks)
+                tma_load_2d_s(bres_base + ks * Cfg::B_BYTES, &tmB, smem_u32(bres_bar), ks * BLOCK_K, 0);
+        }
+        __syncwarp();
         for (int item = cluster_id; item < num_items; item += num_clusters) {
             const int mgroup = item / num_n_tiles;
             const int n_tile = item - mgroup * num_n_tiles;
@@ -338,10 +368,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int kc = 0; kc < k_chunks; ++kc) {
                     mbar_wait_s(empty_base + stage * 8, phase ^ 1);
                     if (elect_one()) {
-                        const uint32_t a_dst = smem_base + stage * Cfg::STAGE_BYTES;
+                        const uint32_t a_dst = smem_base + stage * stage_bytes;
                         const uint32_t b_dst = a_dst + Cfg::A_BYTES;
                         const uint32_t fb = full_base + stage * 8;
-                        mbar_expect_tx_s(fb, Cfg::STAGE_BYTES);
+                        if (PAIR) {
+                            // all four loads of the pair complete on the leader's barrier, which expects both CTAs' bytes
+                            if (cta_rank == 0) mbar_expect_tx_s(fb, 2 * stage_bytes);
+                            const uint32_t lb = mapa_u32(fb, 0);
+                            if (im2col)
+                                tma2_load_im2col_4d(a_dst, &tmA, lb, a_c, base_w, base_h, img, s, r);
+                            else
+                                tma2_load_2d(a_dst, &tmA, lb, a_c, m0);
+                            tma2_load_2d(b_dst, &tmB, lb, b_k, b_row);
+                        } else {
+                        mbar_expect_tx_s(fb, stage_bytes);
                         if (im2col)
                             tma_load_im2col_4d_s(a_dst, &tmA, fb, a_c, base_w, base_h, img, s, r);
                         else
@@ -349,12 +389,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         if (CLUSTER > 1)
                             tma_load_2d_multicast_s(b_dst + cta_rank * (BLOCK_N / CLUSTER) * KBYTES, &tmB, fb, b_k, b_row,
                                                     MC_MASK);
-                        else
+                        else if (!b_res)
                             tma_load_2d_s(b_dst, &tmB, fb, b_k, b_row);
+                        }
                     }
                     a_c += BLOCK_K;
                     b_k += BLOCK_K;
-                    if (++stage == NS) {
+                    if (++stage == (uint32_t)ns) {
                         stage = 0;
                         phase ^= 1;
                     }
@@ -362,13 +403,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 b_k += Cin - k_chunks * BLOCK_K;   // == 0 (Cin is a whole number of chunks); keeps the intent explicit
             }
         }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
+    } else if (warp == 1 && (!PAIR || cta_rank == 0)) {
+        // ===================== MMA issuer (pair: the leader CTA issues for both) =====================
         uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
         const int k_steps = taps * k_chunks;
         const uint32_t idesc = IDESC | (KIND == CONV_KIND_F16 ? p.idesc_ab : 0u);
         const uint64_t desc_base = smem_desc_base(16, 8 * KBYTES, LAYOUT);
         const uint32_t tfull_base = smem_u32(tmem_full_bar), tempty_base = smem_u32(tmem_empty_bar);
+        if (b_res) {
+            mbar_wait_s(smem_u32(bres_bar), 0);
+            tc_fence_after();
+        }
         for (int item = cluster_id; item < num_items; item += num_clusters) {
             mbar_wait_s(tempty_base + acc * 8, acc_phase ^ 1);
             tc_fence_after();
@@ -378,30 +423,45 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mbar_wait_s(full_base + stage * 8, phase);
                 tc_fence_after();
                 if (elect_one()) {
-                    const uint32_t a_addr = smem_base + stage * Cfg::STAGE_BYTES;
+                    const uint32_t a_addr = smem_base + stage * stage_bytes;
+                    const uint32_t b_addr = b_res ? bres_base + ks * Cfg::B_BYTES : a_addr + Cfg::A_BYTES;
                     const uint64_t adesc = desc_base | (uint64_t)((a_addr >> 4) & 0x3FFF);
-                    const uint64_t bdesc = desc_base | (uint64_t)(((a_addr + Cfg::A_BYTES) >> 4) & 0x3FFF);
+                    const uint64_t bdesc = desc_base | (uint64_t)((b_addr >> 4) & 0x3FFF);
 #pragma unroll
                     for (int k = 0; k < KBYTES / 32; ++k) {
-                        if (KIND == CONV_KIND_F16)
+                        if (PAIR) {
+                            if (KIND == CONV_KIND_F16)
+                                mma2_f16_ss(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                                            k > 0 ? 1u : accum);
+                            else
+                                mma2_i8_ss(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                                           k > 0 ? 1u : accum);
+                        } else if (KIND == CONV_KIND_F16)
                             mma_f16_ss(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
                                        k > 0 ? 1u : accum);
                         else
                             mma_i8_ss(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
                                       k > 0 ? 1u : accum);
                     }
-                    if (CLUSTER > 1)
+                    if (PAIR)
+                        tc_commit2_multicast_s(empty_base + stage * 8, MC_MASK);   // frees the slot in both CTAs
+                    else if (CLUSTER > 1)
                         tc_commit_multicast_s(empty_base + stage * 8, MC_MASK);  // release the slot in every CTA
                     else
                         tc_commit_s(empty_base + stage * 8);  // frees the smem slot when these MMAs retire
                 }
                 accum = 1;
-                if (++stage == NS) {
+                if (++stage == (uint32_t)ns) {
                     stage = 0;
                     phase ^= 1;
                 }
             }
-            if (elect_one()) tc_commit_s(tfull_base + acc * 8);  // accumulator complete -> epilogue
+            if (elect_one()) {   // accumulator complete -> epilogue (of both CTAs for a pair)
+                if (PAIR)
+                    tc_commit2_multicast_s(tfull_base + acc * 8, MC_MASK);
+                else
+                    tc_commit_s(tfull_base + acc * 8);
+            }
             if (++acc == AS) {
                 acc = 0;
                 acc_phase ^= 1;
@@ -559,7 +619,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // release this accumulator stage back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+            if (lane == 0) {
+                if (PAIR)
+                    mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[acc]), 0));   // the leader's MMA warp waits on it
+                else
+                    mbar_arrive(&tmem_empty_bar[acc]);
+            }
         }
     }
 
@@ -568,7 +633,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (CLUSTER > 1) cluster_sync_all();   // nobody leaves while a peer may still multicast / arrive into its smem
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+        if (PAIR)
+            tmem_dealloc2(tmem_base, Cfg::TMEM_COLS);
+        else
+            tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
     }
 }
 
