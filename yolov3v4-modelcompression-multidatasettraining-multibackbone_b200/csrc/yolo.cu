@@ -13,37 +13,45 @@ static inline int grid_for(long long n, int block) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// decode: one thread per output element, index order == memory order of p / io (coalesced writes)
+// decode: one warp per (image, pixel, anchor) = one contiguous run of `no` floats in raw, p and io; lanes stride the run,
+// so every load / store instruction is one contiguous 128-byte segment and all index arithmetic is per warp.
 // ------------------------------------------------------------------------------------------------
-__global__ void yolo_decode_kernel(const float* __restrict__ raw, long long raw_pitch, float* __restrict__ p,
-                                   float* __restrict__ io, long long total_rows, long long row_offset, int B, int na,
-                                   int no, int ny, int nx, const float* __restrict__ anchors_px, float stride) {
-    const long long total = (long long)B * na * ny * nx * no;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        const int o = (int)(idx % no);
-        long long t = idx / no;
-        const int x = (int)(t % nx);
-        t /= nx;
-        const int y = (int)(t % ny);
-        t /= ny;
-        const int a = (int)(t % na);
-        const int b = (int)(t / na);
-        const float v = __ldg(raw + (((long long)b * ny + y) * nx + x) * raw_pitch + a * no + o);
-        if (p != nullptr) p[idx] = v;
-        if (io != nullptr) {
-            float r;
-            if (o < 2) {
-                const float g = (o == 0) ? (float)x : (float)y;  // grid[...,0]=x, grid[...,1]=y (models.py:373-374)
-                r = (sigmoid_f(v) + g) * stride;
-            } else if (o < 4) {
-                const float av = anchors_px[a * 2 + (o - 2)] / stride;  // anchor_vec (models.py:362)
-                r = (expf(v) * av) * stride;
-            } else {
-                r = sigmoid_f(v);
+__global__ void __launch_bounds__(256) yolo_decode_kernel(const float* __restrict__ raw, long long raw_pitch,
+                                                          float* __restrict__ p, float* __restrict__ io,
+                                                          long long total_rows, long long row_offset, int B, int na,
+                                                          int no, int ny, int nx, const float* __restrict__ anchors_px,
+                                                          float stride) {
+    const int lane = threadIdx.x & 31;
+    const unsigned plane = (unsigned)(ny * nx);
+    const unsigned runs = (unsigned)B * plane * (unsigned)na;          // host checks < 2^31
+    const unsigned warps = (gridDim.x * blockDim.x) >> 5;
+    for (unsigned run = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; run < runs; run += warps) {
+        // run order = raw memory order: (b, y, x, a)
+        const unsigned a = run % (unsigned)na;
+        const unsigned pix = run / (unsigned)na;                        // b*plane + y*nx + x
+        const unsigned b = pix / plane;
+        const unsigned yx = pix - b * plane;
+        const unsigned y = yx / (unsigned)nx, x = yx - y * (unsigned)nx;
+        const float* src = raw + (long long)pix * raw_pitch + a * no;
+        const long long prow = ((long long)b * na + a) * plane + yx;
+        float* pd = p != nullptr ? p + prow * no : nullptr;
+        float* iod = io != nullptr ? io + ((long long)b * total_rows + row_offset + (long long)a * plane + yx) * no : nullptr;
+        const float aw = __ldg(anchors_px + a * 2) / stride, ah = __ldg(anchors_px + a * 2 + 1) / stride;   // anchor_vec
+        for (int o = lane; o < no; o += 32) {
+            const float v = __ldg(src + o);
+            if (pd != nullptr) pd[o] = v;
+            if (iod != nullptr) {
+                float r;
+                if (o < 2) {
+                    const float g = (o == 0) ? (float)x : (float)y;  // grid[...,0]=x, grid[...,1]=y (models.py:373-374)
+                    r = (sigmoid_f(v) + g) * stride;
+                } else if (o < 4) {
+                    r = (expf(v) * (o == 2 ? aw : ah)) * stride;     // (models.py:362, 416-417)
+                } else {
+                    r = sigmoid_f(v);
+                }
+                iod[o] = r;
             }
-            const long long row = row_offset + ((long long)a * ny + y) * nx + x;
-            io[((long long)b * total_rows + row) * no + o] = r;
         }
     }
 }
@@ -53,8 +61,11 @@ extern "C" int b2y_yolo_decode(const float* raw, long long raw_pitch, float* p, 
                                const float* anchors_px, float stride, void* stream) {
     if (!raw || !anchors_px || batch <= 0 || na <= 0 || no < 5 || ny <= 0 || nx <= 0) return B2Y_ERR_INVALID;
     if (raw_pitch < (long long)na * no) return B2Y_ERR_INVALID;
-    const long long total = (long long)batch * na * ny * nx * no;
-    yolo_decode_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    const long long runs = (long long)batch * na * ny * nx;
+    if (runs > 0x7fffffffLL) return B2Y_ERR_UNSUPPORTED;
+    long long blocks = (runs + 7) / 8;                 // 8 warps per block
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    yolo_decode_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         raw, raw_pitch, p, io, total_rows, row_offset, batch, na, no, ny, nx, anchors_px, stride);
     B2Y_CUDA_CHECK(cudaGetLastError());
     return B2Y_OK;
