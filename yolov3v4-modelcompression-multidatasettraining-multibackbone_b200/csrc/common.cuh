@@ -77,6 +77,10 @@ __device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_expect_tx_s(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// programmatic dependent launch: wait for the upstream grid's memory / let the downstream grid start its prologue
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // one lane of a converged warp
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;

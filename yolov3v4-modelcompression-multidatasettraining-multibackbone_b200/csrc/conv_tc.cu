@@ -101,23 +101,35 @@ static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const Conv
     const int items = ((p.num_m_tiles + CLUSTER - 1) / CLUSTER) * p.num_n_tiles;
     const int max_clusters = g_num_sms / CLUSTER;
     const int clusters = items < max_clusters ? items : max_clusters;
-    if (CLUSTER == 1) {
-        kern<<<clusters, ConvTcEpi<BLOCK_N>::THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p);
-    } else {
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(clusters * CLUSTER);
-        cfg.blockDim = dim3(ConvTcEpi<BLOCK_N>::THREADS);
-        cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
-        cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = CLUSTER;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        B2Y_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
+    static int pdl = -1;        // B2Y_PDL=0: plain stream order (no programmatic dependent launch)
+    if (pdl < 0) {
+        const char* e = getenv("B2Y_PDL");
+        pdl = (e && atoi(e) == 0) ? 0 : 1;
     }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(clusters * CLUSTER);
+    cfg.blockDim = dim3(ConvTcEpi<BLOCK_N>::THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (CLUSTER > 1) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = CLUSTER;
+        attr[na].val.clusterDim.y = 1;
+        attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    if (pdl) {
+        // the kernel's prologue (and its static weight loads) may start while the previous kernel drains; it executes
+        // griddepcontrol.wait before touching activations
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    B2Y_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
     B2Y_CUDA_CHECK(cudaGetLastError());
     return B2Y_OK;
 }

@@ -347,6 +347,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tma_load_2d_s(bres_base + ks * Cfg::B_BYTES, &tmB, smem_u32(bres_bar), ks * BLOCK_K, 0);
         }
         __syncwarp();
+        // everything above (barriers, TMEM, the static weights) may overlap the tail of the previous layer's kernel;
+        // activations must not be touched before it has completed (programmatic dependent launch)
+        pdl_wait();
+        pdl_launch_dependents();
         for (int item = cluster_id; item < num_items; item += num_clusters) {
             const int mgroup = item / num_n_tiles;
             const int n_tile = item - mgroup * num_n_tiles;
@@ -470,6 +474,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else if (warp >= 4) {
         // ===================== epilogue =====================
         constexpr int COLS_PER_GROUP = Epi::SPLIT_TILES ? BLOCK_N : BLOCK_N / 2;
+        pdl_wait();
         const float acc_mul = p.acc_scale * (p.acc_scale_ptr != nullptr ? __ldg(p.acc_scale_ptr) : 1.f);
         const int ew = (warp - 4) & 3;          // TMEM lane quarter == warp_id % 4
         const int cg = (warp - 4) >> 2;         // group
