@@ -287,7 +287,7 @@ def main():
                     "algorithmic_flops_per_step": conv_flops}
 
         if args.profile_layers and rank == 0:
-            rows = plan.profile_layers(x_dev, reps=5)
+            rows = plan.profile_layers(x_dev, reps=10)
             os.makedirs(os.path.dirname(os.path.abspath(args.profile_layers)), exist_ok=True)
             with open(args.profile_layers, "w") as f:
                 json.dump({"batch": B, "size": SIZE, "ms_per_step": ms_step, "rows": rows}, f, indent=1)

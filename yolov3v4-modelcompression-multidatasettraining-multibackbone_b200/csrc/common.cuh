@@ -157,6 +157,19 @@ __device__ __forceinline__ void tma_load_im2col_4d_s(uint32_t dst, const CUtenso
         : "memory");
 }
 
+// TMA store of a smem box (written by generic stores + fence.proxy.async) to global; bulk-group completion
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(m)),
+                 "r"(src), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_cta() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // ---- CTA-pair (cta_group::2) variants: both CTAs of the pair issue their own loads, all of them complete on the
 // mbarrier of the leader CTA (rank 0), addressed through the shared::cluster window (mapa).
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t cta_rank) {

@@ -47,6 +47,7 @@ static CUtensorMapSwizzle swizzle_enum(int kbytes) {
 // 2-D tiled map over a row-major [rows][cols] matrix with row pitch `pitch_elems`.
 static CUtensorMapDataType tm_dtype(int esize, bool bf16) {
     if (esize == 1) return CU_TENSOR_MAP_DATA_TYPE_UINT8;
+    if (esize == 4) return CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
     return bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
 }
 
@@ -90,7 +91,8 @@ static int make_map_im2col(CUtensorMap* m, const void* base, int esize, int N, i
 }
 
 template <int BLOCK_N, int KBYTES, int KIND, int CLUSTER, int PAIR = 0>
-static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvTcParams& p, cudaStream_t st) {
+static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const ConvTcParams& p,
+                      cudaStream_t st) {
     using Cfg = ConvTcCfg<BLOCK_N, KBYTES>;
     auto kern = conv_tc_kernel<BLOCK_N, KBYTES, KIND, CLUSTER, PAIR>;
     static bool attr_set = false;
@@ -129,16 +131,16 @@ static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const Conv
     }
     cfg.attrs = attr;
     cfg.numAttrs = na;
-    B2Y_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
+    B2Y_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, p));
     B2Y_CUDA_CHECK(cudaGetLastError());
     return B2Y_OK;
 }
 
 template <int KIND>
 static int dispatch(int block_n, int kbytes, int cluster, const CUtensorMap& a, const CUtensorMap& b,
-                    const ConvTcParams& p, cudaStream_t st) {
+                    const CUtensorMap& c, const ConvTcParams& p, cudaStream_t st) {
 #define B2Y_CASE(BN, KB) \
-    if (block_n == BN && kbytes == KB && cluster == 1) return launch_cfg<BN, KB, KIND, 1>(a, b, p, st);
+    if (block_n == BN && kbytes == KB && cluster == 1) return launch_cfg<BN, KB, KIND, 1>(a, b, c, p, st);
     B2Y_CASE(32, 32) B2Y_CASE(32, 64) B2Y_CASE(32, 128)
     B2Y_CASE(64, 32) B2Y_CASE(64, 64) B2Y_CASE(64, 128)
     B2Y_CASE(128, 32) B2Y_CASE(128, 64) B2Y_CASE(128, 128)
@@ -146,13 +148,13 @@ static int dispatch(int block_n, int kbytes, int cluster, const CUtensorMap& a, 
 #undef B2Y_CASE
     // weight-multicast clusters exist for the wide, deep tiles only (KBYTES = 128)
     if (p.pair) {
-        if (kbytes == 128 && block_n == 128 && cluster == 2) return launch_cfg<128, 128, KIND, 2, 1>(a, b, p, st);
-        if (kbytes == 128 && block_n == 256 && cluster == 2) return launch_cfg<256, 128, KIND, 2, 1>(a, b, p, st);
+        if (kbytes == 128 && block_n == 128 && cluster == 2) return launch_cfg<128, 128, KIND, 2, 1>(a, b, c, p, st);
+        if (kbytes == 128 && block_n == 256 && cluster == 2) return launch_cfg<256, 128, KIND, 2, 1>(a, b, c, p, st);
         return B2Y_ERR_UNSUPPORTED;
     }
-    if (kbytes == 128 && block_n == 128 && cluster == 2) return launch_cfg<128, 128, KIND, 2>(a, b, p, st);
-    if (kbytes == 128 && block_n == 256 && cluster == 2) return launch_cfg<256, 128, KIND, 2>(a, b, p, st);
-    if (kbytes == 128 && block_n == 256 && cluster == 4) return launch_cfg<256, 128, KIND, 4>(a, b, p, st);
+    if (kbytes == 128 && block_n == 128 && cluster == 2) return launch_cfg<128, 128, KIND, 2>(a, b, c, p, st);
+    if (kbytes == 128 && block_n == 256 && cluster == 2) return launch_cfg<256, 128, KIND, 2>(a, b, c, p, st);
+    if (kbytes == 128 && block_n == 256 && cluster == 4) return launch_cfg<256, 128, KIND, 4>(a, b, c, p, st);
     return B2Y_ERR_UNSUPPORTED;
 }
 
@@ -307,7 +309,7 @@ int gemm_conv_launch(const GemmConvSpec& g, const EpilogueArgs& e, cudaStream_t 
             const char* m = getenv("B2Y_BRES_MIN_STAGES");
             if (m && atoi(m) >= 2) bres_min = atoi(m);
         }
-        const long long max_smem = 196 * 1024;
+        const long long max_smem = 192 * 1024;
         const long long a_bytes = 128LL * kbytes, b_bytes = (long long)block_n * kbytes;
         const long long res_bytes = (long long)p.ntaps * p.k_chunks * b_bytes;
         static int pair_on = -1;     // B2Y_PAIR=0: clusters of two use weight multicast instead of cta_group::2 MMA
@@ -325,8 +327,23 @@ int gemm_conv_launch(const GemmConvSpec& g, const EpilogueArgs& e, cudaStream_t 
         }
         p.num_stages = (int)(ns > 32 ? 32 : ns);
     }
-    if (g.kind == CONV_KIND_F16) return dispatch<CONV_KIND_F16>(block_n, kbytes, cluster, tmA, tmB, p, st);
-    return dispatch<CONV_KIND_I8>(block_n, kbytes, cluster, tmA, tmB, p, st);
+    // output map for the TMA-store epilogue (16-bit outputs on the short path with identity row mapping)
+    CUtensorMap tmC = tmB;
+    p.epi_tma = 0;
+    {
+        static int tma_on = -1;
+        if (tma_on < 0) {
+            const char* e = getenv("B2Y_EPI_TMA");
+            tma_on = (e && atoi(e) == 0) ? 0 : 1;
+        }
+        if (tma_on && p.epi_fast && p.out_identity) {
+            rc = make_map_2d(&tmC, e.out, 2, M, g.Nout, e.out_pitch, 32, 32, 64, e.out_dtype == OUT_BF16);
+            if (rc != B2Y_OK) return rc;
+            p.epi_tma = 1;
+        }
+    }
+    if (g.kind == CONV_KIND_F16) return dispatch<CONV_KIND_F16>(block_n, kbytes, cluster, tmA, tmB, tmC, p, st);
+    return dispatch<CONV_KIND_I8>(block_n, kbytes, cluster, tmA, tmB, tmC, p, st);
 }
 
 // Forward convolution: x NHWC (fp16 or int8), w [Cout][R][S][Cin].

@@ -60,6 +60,7 @@ struct ConvTcParams {
     int b_resident;         // 1: the whole weight panel of the (single) N tile stays in smem, loaded once per CTA
     int num_stages;         // smem ring depth for this launch (<= 32)
     int pair;               // host: launch the cta_group::2 variant (cluster of two)
+    int epi_tma;            // the short epilogue stores through smem + TMA (tmC valid); rows / columns clipped by the map
     int epi_fast;           // host-checked: 16-bit out, whole channel tiles, 16-byte aligned bias/residual/output
 };
 
@@ -69,7 +70,7 @@ struct ConvTcCfg {
     static constexpr int A_BYTES = BLOCK_M * KBYTES;
     static constexpr int B_BYTES = BLOCK_N * KBYTES;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;  // always a multiple of 1024
-    static constexpr int MAX_STAGE_SMEM = 196 * 1024;
+    static constexpr int MAX_STAGE_SMEM = 192 * 1024;
     static constexpr int NUM_STAGES_RAW = MAX_STAGE_SMEM / STAGE_BYTES;
     // small-K layers have small stages: keep up to 32 of them in flight so that enough bytes are outstanding per SM
     // to cover HBM latency (Little's law: 148 SMs x ~190 KB / ~2 us)
@@ -79,7 +80,8 @@ struct ConvTcCfg {
     static constexpr int ACC_STAGES = BLOCK_N >= 256 ? 2 : (BLOCK_N == 128 ? 4 : 8);
     static constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;   // 512, 512, 512, 256 columns
     static constexpr int AUX_BYTES = 1024;  // barriers + tmem ptr, at a fixed offset behind the tile area
-    static constexpr int SMEM_BYTES = 1024 /*align slack*/ + MAX_STAGE_SMEM + AUX_BYTES;
+    static constexpr int EPI_STAGE_BYTES = 8 * 4096;   // per epilogue warp: 2 x 2 KB output staging for TMA stores
+    static constexpr int SMEM_BYTES = 1024 /*align slack*/ + MAX_STAGE_SMEM + AUX_BYTES + EPI_STAGE_BYTES;
 };
 
 __device__ __noinline__ float mish_noinline(float x) { return mish_f(x); }
@@ -249,7 +251,7 @@ __device__ __forceinline__ void epi_chunk_general(float (&v)[32], const ConvTcPa
 template <int BLOCK_N, int KBYTES, int KIND, int CLUSTER, int PAIR = 0>
 __global__ void __launch_bounds__(ConvTcEpi<BLOCK_N>::THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ ConvTcParams p) {
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ ConvTcParams p) {
     using Cfg = ConvTcCfg<BLOCK_N, KBYTES>;
     using Epi = ConvTcEpi<BLOCK_N>;
     constexpr int MAX_NS = 32;
@@ -276,6 +278,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* tmem_empty_bar = tmem_full_bar + AS;                   // [AS]
     uint64_t* bres_bar = tmem_empty_bar + AS;                        // [1] resident weight panel landed
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bres_bar + 1);
+    uint8_t* epi_stage = aux + Cfg::AUX_BYTES;                       // [8 warps][4096] output staging for TMA stores
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -283,6 +286,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA);
         prefetch_tmap(&tmB);
+        prefetch_tmap(&tmC);
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < ns; ++i) {
@@ -483,6 +487,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const float slope = p.slope;
         const int c_begin = Epi::SPLIT_TILES ? 0 : cg * COLS_PER_GROUP;
         const int hw = p.MH * p.MW;
+        const bool epi_tma = p.epi_tma != 0;
+        uint8_t* my_stage = epi_stage + (warp - 4) * 4096;
+        int sbuf = 0;
         int it = 0;
         for (int item = cluster_id; item < num_items; item += num_clusters, ++it) {
             if (Epi::SPLIT_TILES && (it & 1) != cg) continue;
@@ -515,6 +522,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (res_p != nullptr) {
 #pragma unroll
                     for (int q = 0; q < 4; ++q) rnext[q] = __ldg(res_p + q);
+                }
+                if (p.res != nullptr) {
+                    // pull the residual rows of this warp's NEXT tile into L2 now: by the time its accumulator is ready
+                    // the loads above hit L2 instead of paying HBM latency inside the epilogue
+                    const int nitem = item + (Epi::SPLIT_TILES ? 2 : 1) * num_clusters;
+                    if (nitem < num_items) {
+                        const int nmg = nitem / num_n_tiles;
+                        const int nnt = nitem - nmg * num_n_tiles;
+                        const long long ngrow = (long long)(nmg * CLUSTER + cta_rank) * 128 + ew * 32 + lane;
+                        if (ngrow < p.M_total && p.out_identity) {
+                            const char* np_ = reinterpret_cast<const char*>(p.res + ngrow * p.res_pitch + nnt * BLOCK_N + c_begin);
+#pragma unroll
+                            for (int b = 0; b < COLS_PER_GROUP * 2; b += 128)
+                                asm volatile("prefetch.global.L2 [%0];" ::"l"(np_ + b));
+                        }
+                    }
                 }
                 mbar_wait(&tmem_full_bar[acc], acc_phase);
                 tc_fence_after();
@@ -557,51 +580,64 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = mish_noinline(v[j]);
                     }
-                    if (row_ok) {
-                        if (res_p != nullptr) {
+                    if (row_ok && res_p != nullptr) {
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const uint4 u = rcur[q];
-                                if (p.res_bf16) {
-                                    const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+                        for (int q = 0; q < 4; ++q) {
+                            const uint4 u = rcur[q];
+                            if (p.res_bf16) {
+                                const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
-                                    for (int t = 0; t < 4; ++t) {
-                                        const float2 f = __bfloat1622float2(b2[t]);
-                                        v[q * 8 + t * 2] += f.x;
-                                        v[q * 8 + t * 2 + 1] += f.y;
-                                    }
-                                } else {
-                                    const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+                                for (int t = 0; t < 4; ++t) {
+                                    const float2 f = __bfloat1622float2(b2[t]);
+                                    v[q * 8 + t * 2] += f.x;
+                                    v[q * 8 + t * 2 + 1] += f.y;
+                                }
+                            } else {
+                                const __half2* h2 = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
-                                    for (int t = 0; t < 4; ++t) {
-                                        const float2 f = __half22float2(h2[t]);
-                                        v[q * 8 + t * 2] += f.x;
-                                        v[q * 8 + t * 2 + 1] += f.y;
-                                    }
+                                for (int t = 0; t < 4; ++t) {
+                                    const float2 f = __half22float2(h2[t]);
+                                    v[q * 8 + t * 2] += f.x;
+                                    v[q * 8 + t * 2 + 1] += f.y;
                                 }
                             }
                         }
-                        if (p.out_dtype == OUT_BF16) {
+                    }
+                    uint4 ou[4];
+                    if (p.out_dtype == OUT_BF16) {
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                uint4 u;
-                                __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+                        for (int q = 0; q < 4; ++q) {
+                            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&ou[q]);
 #pragma unroll
-                                for (int t = 0; t < 4; ++t)
-                                    h2[t] = __floats2bfloat162_rn(v[q * 8 + t * 2], v[q * 8 + t * 2 + 1]);
-                                out_p[c / 8 + q] = u;
-                            }
-                        } else {
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                uint4 u;
-                                __half2* h2 = reinterpret_cast<__half2*>(&u);
-#pragma unroll
-                                for (int t = 0; t < 4; ++t)
-                                    h2[t] = __floats2half2_rn(v[q * 8 + t * 2], v[q * 8 + t * 2 + 1]);
-                                out_p[c / 8 + q] = u;
-                            }
+                            for (int t = 0; t < 4; ++t) h2[t] = __floats2bfloat162_rn(v[q * 8 + t * 2], v[q * 8 + t * 2 + 1]);
                         }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            __half2* h2 = reinterpret_cast<__half2*>(&ou[q]);
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) h2[t] = __floats2half2_rn(v[q * 8 + t * 2], v[q * 8 + t * 2 + 1]);
+                        }
+                    }
+                    if (epi_tma) {
+                        // 32 rows x 64 B through smem (SWIZZLE_64B image) and one TMA store: full 64-byte row segments reach
+                        // L2 instead of 32 scattered 16-byte pieces per store instruction; the map clips the M / Cout tails
+                        uint8_t* buf = my_stage + sbuf * 2048;
+                        if (lane == 0) bulk_wait_read<1>();      // the store that last read this buffer is done with it
+                        __syncwarp();
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            *reinterpret_cast<uint4*>(buf + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) = ou[q];
+                        fence_proxy_async_cta();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_2d(&tmC, smem_u32(buf), n0 + c_begin + c, m_tile * 128 + ew * 32);
+                            bulk_commit();
+                        }
+                        sbuf ^= 1;
+                    } else if (row_ok) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) out_p[c / 8 + q] = ou[q];
                     }
                 }
             } else {
@@ -631,6 +667,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mbar_arrive(&tmem_empty_bar[acc]);
             }
         }
+        if (epi_tma && lane == 0) bulk_wait_all();   // outstanding TMA stores complete before the CTA exits
     }
 
     tc_fence_before();
