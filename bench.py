@@ -254,10 +254,11 @@ def main():
         def e2e_step():
             j = state["i"] & 1
             main.wait_event(ready[j])
-            xd = dev_u8[j].float() / 256.0                                # train.py:348 / test.py:95
+            # uint8 batch straight into the model: the stem kernel applies the reference's "/ 256.0"
+            # (train.py:348 / test.py:95) while it builds its im2col tile, no fp32 image is materialised
+            out, _, _ = model(dev_u8[j])
             consumed[j].record(main)
             issue_copy(j ^ 1)                                             # prefetch the next batch
-            out, _, _ = model(xd)
             idx = out[..., 4].argmax(dim=1)                               # best-objectness row per image
             top = out[torch.arange(B, device=dev), idx]
             top_host.copy_(top, non_blocking=True)

@@ -111,7 +111,7 @@ int b2y_stem_conv_fwd_tc(const b2y_conv_desc* d, const float* x_nchw, const void
 /* Fused tensor-core stem (in_c*ksize*ksize <= 32, out_c <= 64): the CTA builds the im2col tile in shared memory
  * straight from the image and feeds tcgen05.mma, so only the image is read and only y is written (no workspace).
  *   x_nchw   NCHW image, x_dtype = B2Y_STEM_X_F32 / _F16 / _U8; value = raw / x_div
- *            (x_div = 255 for uint8 images: reference test.py:97 / detect.py "img.float() / 255.0")
+ *            (x_div = 256 for uint8 images: reference test.py:95, train.py:348, detect.py:101 "/ 256.0")
  *   w_stem   fp16 [out_c][32] from b2y_pack_stem_weights (the layout it produces when in_c*k*k <= 32)
  *   y        NHWC fp16 */
 #define B2Y_STEM_X_F32 0

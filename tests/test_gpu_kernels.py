@@ -158,16 +158,17 @@ def test_stem_conv_tensor_core(cin, k, stride, cout):
 
 
 @pytest.mark.parametrize("cin,k,stride,cout,dtype", [
-    (3, 3, 1, 32, "f32"), (3, 3, 2, 32, "f16"), (3, 3, 1, 16, "u8"), (1, 5, 1, 32, "f32"), (3, 3, 1, 64, "u8"),
+    (3, 3, 1, 32, "f32"), (3, 3, 2, 32, "f16"), (3, 3, 1, 16, "u8"), (1, 5, 1, 32, "f32"), (3, 3, 1, 64, "u8256"),
     (3, 3, 1, 48, "f32")])
 def test_stem_conv_fused(cin, k, stride, cout, dtype):
     """Fused stem: the CTA builds the im2col tile in smem from the NCHW image (fp32 / fp16 / uint8 with /255)."""
     ops = _ops()
     g = torch.Generator().manual_seed(12)
     B, H, W = 3, 44, 72            # 3*44*72 = 9504 pixels: 74.25 tiles -> partial last tile, several tiles per CTA group
-    if dtype == "u8":
+    if dtype in ("u8", "u8256"):
         x = torch.randint(0, 256, (B, cin, H, W), generator=g, dtype=torch.uint8)
-        xf, div = x.float() / 255.0, 255.0
+        div = 255.0 if dtype == "u8" else 256.0
+        xf = x.float() / div
     elif dtype == "f16":
         x = torch.rand(B, cin, H, W, generator=g).half()
         xf, div = x.float(), 1.0

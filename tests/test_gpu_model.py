@@ -130,3 +130,19 @@ def test_loss_edge_cases():
     np.testing.assert_allclose(items.cpu().numpy(), ritems.numpy(), rtol=1e-4)
     for a, b in zip(p, pr):
         np.testing.assert_allclose(a.grad.cpu().numpy(), b.grad.numpy(), rtol=1e-4, atol=1e-6)
+
+
+def test_uint8_and_fp16_images_match_the_reference_normalisation():
+    """uint8 batches are normalised inside the stem kernel with the reference's "/ 256.0" (test.py:95, train.py:348);
+    fp16 batches are consumed as they are.  Both must equal the explicit host-side conversion bit for bit."""
+    model = build_model("yolov3-tiny", device="cuda").eval()
+    g = torch.Generator().manual_seed(5)
+    u8 = torch.randint(0, 256, (2, 3, 96, 96), dtype=torch.uint8, generator=g).cuda()
+    with torch.no_grad():
+        ref_io, ref_p, _ = model(u8.float() / 256.0)
+        io, p, _ = model(u8)
+        io16, _, _ = model((u8.float() / 256.0).half())
+    torch.cuda.synchronize()
+    assert torch.equal(io, ref_io)
+    assert all(torch.equal(a, b) for a, b in zip(p, ref_p))
+    assert torch.equal(io16, ref_io)          # k/256 is exact in fp16

@@ -286,10 +286,10 @@ class Plan:
                             os.environ.get('B2Y_STEM', 'fused') == 'fused':
                         # full-im2col weight layout: the fused kernel builds the A tile in smem (no workspace)
                         ops.stem_conv_fused(x, wstem, bias, k, s, p, act=act, slope=slope, out=out.view(),
-                                            x_div=255.0 if x.dtype == torch.uint8 else 1.0)
+                                            x_div=256.0 if x.dtype == torch.uint8 else 1.0)
                     elif wstem is not None:
                         if x.dtype != torch.float32:
-                            x = x.float() / 255.0 if x.dtype == torch.uint8 else x.float()
+                            x = x.float() / 256.0 if x.dtype == torch.uint8 else x.float()
                         if getattr(self, 'stem_ws', None) is None:
                             self.stem_ws = ops.stem_workspace(
                                 ops.make_conv_desc((self.B, self.H, self.W, conv.in_channels), conv.in_channels,
@@ -298,7 +298,7 @@ class Plan:
                                          out=out.view(), workspace=self.stem_ws)
                     else:
                         if x.dtype != torch.float32:
-                            x = x.float() / 255.0 if x.dtype == torch.uint8 else x.float()
+                            x = x.float() / 256.0 if x.dtype == torch.uint8 else x.float()
                         ops.stem_conv(x, w32, bias, k, s, p, act=act, slope=slope, out=out.view())
                 else:
                     ops.conv2d(src.view(), wp, bias, k, s, p, act=act, slope=slope,
@@ -424,7 +424,7 @@ class Plan:
             self.param_version = ver
             self.graph = None
         # fp32 / fp16 images go to the stem as they are; uint8 images (the reference's dataloader output before
-        # test.py:97 "imgs.float() / 255.0") are normalised inside the stem kernel
+        # test.py:95 / train.py:348 "imgs.float() / 256.0") are normalised inside the stem kernel
         x = x.contiguous()
         if x.dtype not in (torch.float32, torch.float16, torch.uint8):
             x = x.float()

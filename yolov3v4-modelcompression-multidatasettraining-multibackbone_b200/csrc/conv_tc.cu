@@ -272,15 +272,25 @@ int gemm_conv_launch(const GemmConvSpec& g, const EpilogueArgs& e, cudaStream_t 
     p.q_hi = e.q_hi;
     p.stat_sum = e.stat_sum;
     p.stat_sqsum = e.stat_sqsum;
+    static int tma_on = -1;      // B2Y_EPI_TMA=0: direct 16-byte stores from registers instead of smem + TMA
+    if (tma_on < 0) {
+        const char* ev = getenv("B2Y_EPI_TMA");
+        tma_on = (ev && atoi(ev) == 0) ? 0 : 1;
+    }
     {
-        // the short epilogue: fp16/bf16 output, no partial channel tile, everything 16-byte addressable
+        // the short epilogue: fp16/bf16 output (fp32 only through TMA), everything 16-byte addressable; a clipped last
+        // N tile (Cout = 255 heads) needs the TMA store's clipping and has no residual
         auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
         const bool act_ok = e.act == B2Y_ACT_LINEAR || e.act == B2Y_ACT_MISH ||
                             (e.act == B2Y_ACT_LEAKY && e.slope >= 0.f && e.slope <= 1.f);
-        p.epi_fast = g.kind == CONV_KIND_F16 && (e.out_dtype == OUT_F16 || e.out_dtype == OUT_BF16) &&
-                     !e.out_fakequant && e.stat_sum == nullptr && g.Nout % block_n == 0 && act_ok && al16(e.out) &&
-                     e.out_pitch % 8 == 0 && (e.bias == nullptr || al16(e.bias)) &&
-                     (e.res == nullptr || (al16(e.res) && e.res_pitch % 8 == 0));
+        const bool out16 = e.out_dtype == OUT_F16 || e.out_dtype == OUT_BF16;
+        const bool out32 = e.out_dtype == OUT_F32;
+        const bool tma_ok = tma_on && g.out_identity;
+        const bool full = g.Nout % block_n == 0;
+        p.epi_fast = g.kind == CONV_KIND_F16 && (out16 || (out32 && tma_ok)) && !e.out_fakequant &&
+                     e.stat_sum == nullptr && act_ok && al16(e.out) && e.out_pitch % (out16 ? 8 : 4) == 0 &&
+                     (e.bias == nullptr || al16(e.bias)) && (e.res == nullptr || (al16(e.res) && e.res_pitch % 8 == 0)) &&
+                     (full || (tma_ok && e.res == nullptr));
     }
 
     CUtensorMap tmA, tmB;
@@ -330,17 +340,11 @@ int gemm_conv_launch(const GemmConvSpec& g, const EpilogueArgs& e, cudaStream_t 
     // output map for the TMA-store epilogue (16-bit outputs on the short path with identity row mapping)
     CUtensorMap tmC = tmB;
     p.epi_tma = 0;
-    {
-        static int tma_on = -1;
-        if (tma_on < 0) {
-            const char* e = getenv("B2Y_EPI_TMA");
-            tma_on = (e && atoi(e) == 0) ? 0 : 1;
-        }
-        if (tma_on && p.epi_fast && p.out_identity) {
-            rc = make_map_2d(&tmC, e.out, 2, M, g.Nout, e.out_pitch, 32, 32, 64, e.out_dtype == OUT_BF16);
-            if (rc != B2Y_OK) return rc;
-            p.epi_tma = 1;
-        }
+    if (tma_on && p.epi_fast && p.out_identity) {
+        const bool o32 = e.out_dtype == OUT_F32;
+        rc = make_map_2d(&tmC, e.out, o32 ? 4 : 2, M, g.Nout, e.out_pitch, 32, 32, o32 ? 128 : 64, e.out_dtype == OUT_BF16);
+        if (rc != B2Y_OK) return rc;
+        p.epi_tma = 1;
     }
     if (g.kind == CONV_KIND_F16) return dispatch<CONV_KIND_F16>(block_n, kbytes, cluster, tmA, tmB, tmC, p, st);
     return dispatch<CONV_KIND_I8>(block_n, kbytes, cluster, tmA, tmB, tmC, p, st);

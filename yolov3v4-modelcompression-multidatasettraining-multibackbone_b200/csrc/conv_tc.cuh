@@ -512,7 +512,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t taddr_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BLOCK_N);
 
             if (fast) {
-                // 16-bit output, whole channel tile valid, vector-aligned bias / residual / output (checked on the host)
+                // short path: 16-bit output (or fp32 through TMA), vector-aligned bias / residual / output (checked on the host);
+                // a clipped last N tile is allowed on TMA-store launches
                 const float* bias_p = p.bias != nullptr ? p.bias + n0 + c_begin : nullptr;
                 const uint4* res_p = (p.res != nullptr && row_ok)
                                          ? reinterpret_cast<const uint4*>(p.res + row * p.res_pitch + n0 + c_begin)
@@ -543,12 +544,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tc_fence_after();
 #pragma unroll 1
                 for (int c = 0; c < COLS_PER_GROUP; c += 32) {
+                    const int cvalid = p.Cout - (n0 + c_begin + c);     // < 32 only in the last chunk of a clipped N tile
+                    if (cvalid <= 0) break;                              // (TMA-store launches only; warp-uniform)
                     uint32_t raw[32];
                     tmem_ld_32x32(taddr_row + (uint32_t)(c_begin + c), raw);
                     float4 bv[8];
-                    if (bias_p != nullptr) {
+                    if (bias_p != nullptr && cvalid >= 32) {
 #pragma unroll
                         for (int q = 0; q < 8; ++q) bv[q] = __ldg(reinterpret_cast<const float4*>(bias_p + c) + q);
+                    } else if (bias_p != nullptr) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            bv[q].x = 4 * q < cvalid ? __ldg(bias_p + c + 4 * q) : 0.f;
+                            bv[q].y = 4 * q + 1 < cvalid ? __ldg(bias_p + c + 4 * q + 1) : 0.f;
+                            bv[q].z = 4 * q + 2 < cvalid ? __ldg(bias_p + c + 4 * q + 2) : 0.f;
+                            bv[q].w = 4 * q + 3 < cvalid ? __ldg(bias_p + c + 4 * q + 3) : 0.f;
+                        }
                     } else {
 #pragma unroll
                         for (int q = 0; q < 8; ++q) bv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -602,6 +613,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 }
                             }
                         }
+                    }
+                    if (p.out_dtype == OUT_F32) {
+                        // fp32 rows (YOLO head): 32 rows x 128 B, SWIZZLE_128B image, one TMA store; the map clips column 255
+                        uint8_t* buf = my_stage;
+                        if (lane == 0) bulk_wait_read<0>();
+                        __syncwarp();
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            *reinterpret_cast<float4*>(buf + lane * 128 + ((q ^ (lane & 7)) << 4)) =
+                                make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                        fence_proxy_async_cta();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_2d(&tmC, smem_u32(buf), n0 + c_begin + c, m_tile * 128 + ew * 32);
+                            bulk_commit();
+                        }
+                        continue;
                     }
                     uint4 ou[4];
                     if (p.out_dtype == OUT_BF16) {

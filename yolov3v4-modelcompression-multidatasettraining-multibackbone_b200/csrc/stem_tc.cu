@@ -17,6 +17,7 @@
 //     convert + store the A row of tile j  -> fence.proxy.async -> mbarrier arrive -> MMA warp issues tile j
 // Two smem/TMEM stages per group (tile parity); the accumulator-full barrier of tile j-2 doubles as the "stage free"
 // signal, so no empty barriers are needed.
+#include <cmath>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -27,7 +28,8 @@ enum { STEM_X_F32 = 0, STEM_X_F16 = 1, STEM_X_U8 = 2 };
 
 struct StemParams {
     const void* x;        // NCHW image
-    float x_div;          // value = raw / x_div  (255 for uint8 images, 1 otherwise; reference test.py:97)
+    float x_div;          // value = raw / x_div  (256 for uint8 images: reference test.py:95, train.py:348; 1 otherwise)
+    float x_mul;          // host: 1/x_div when that multiplication gives the same fp16 as the division, else 0
     int B, H, W, Ho, Wo, stride, pad;
     const __half* w;      // [BLOCK_N][32] fp16, column (kh*K + kw)*Cin + c  (b2y_pack_stem_weights, full layout)
     const float* bias;    // [Cout] or null
@@ -122,10 +124,9 @@ __global__ void __launch_bounds__(128 * NG + 64, 1) stem_fused_kernel(const __gr
         const XT* xin = reinterpret_cast<const XT*>(p.x);
         const int plane = p.H * p.W;             // 32-bit image indexing (host checks B*Cin*H*W < 2^31)
         const int W = p.W, H = p.H;
-        // uint8 images: raw * (1/255) and raw / 255 round to the same fp16 for all 256 codes
-        const bool use_mul = p.x_div == 255.f && sizeof(XT) == 1;
-        const float mul = use_mul ? (1.f / 255.f) : 1.f;
-        const bool exact_div = p.x_div != 1.f && !use_mul;
+        const bool use_mul = p.x_mul != 0.f && p.x_mul != 1.f;
+        const float mul = p.x_mul;
+        const bool exact_div = p.x_div != 1.f && p.x_mul == 0.f;
         const int act = p.act;
         const float slope = p.slope;
         const bool leaky_max = act == B2Y_ACT_LEAKY && slope >= 0.f && slope <= 1.f;
@@ -368,6 +369,13 @@ extern "C" int b2y_stem_conv_fwd_fused(const b2y_conv_desc* d, const void* x_nch
     StemParams p{};
     p.x = x_nchw;
     p.x_div = x_div;
+    {
+        // raw * (1/x_div) == raw / x_div exactly when x_div is a power of two; for uint8 codes / 255 the two round to the
+        // same fp16 for all 256 codes (checked exhaustively); anything else takes the IEEE division
+        int ex = 0;
+        const float mant = frexpf(fabsf(x_div), &ex);
+        if (mant == 0.5f || (x_dtype == STEM_X_U8 && x_div == 255.f)) p.x_mul = 1.f / x_div;
+    }
     p.B = d->batch;
     p.H = d->in_h;
     p.W = d->in_w;
