@@ -165,6 +165,36 @@ def run_reference_arm(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def ncu_conv_traffic():
+    """DRAM bytes (read + write) of the tcgen05 conv launches of ONE forward, from the committed ncu launch list
+    (profiles/r01c/launches_r01c.csv: `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` of this same
+    workload, eager launches).  Returns (bytes, n_launches) or (None, 0)."""
+    import csv
+    path = os.path.join(ROOT, "profiles", "r01c", "launches_r01c.csv")
+    if not os.path.exists(path):
+        return None, 0
+    rows = list(csv.reader(l for l in open(path) if l.startswith('"')))
+    if not rows:
+        return None, 0
+    hdr = rows[0]
+    ik, im, iv, iu = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    ii = hdr.index("ID")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    launches = {}
+    for r in rows[1:]:
+        d = launches.setdefault(int(r[ii]), {"name": r[ik]})
+        if r[im].startswith("dram__bytes"):
+            d[r[im]] = float(r[iv].replace(",", "")) * scale.get(r[iu], 1.0)
+    ids = sorted(launches)
+    stems = [i for i in ids if "stem_fused" in launches[i]["name"]]
+    if len(stems) < 2:
+        return None, 0
+    a, b = stems[-2], stems[-1]                       # one complete forward between two stem launches
+    convs = [launches[i] for i in ids if a <= i < b and ("conv_tc_kernel" in launches[i]["name"])]
+    total = sum(c.get("dram__bytes_read.sum", 0.0) + c.get("dram__bytes_write.sum", 0.0) for c in convs)
+    return total, len(convs)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -283,10 +313,14 @@ def main():
         achieved = conv_flops / (conv_ms / 1e3) / 1e12
         roofline = {"bound": "tensor", "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
                     "frac": achieved / pk["tflops"], "traffic": None, "peak_source": pk["source"] + " (sustained bf16)",
+                    "traffic_unit": "bytes per step, DRAM read+write of the conv launches (ncu, profiles/r01c)",
                     "kernel": "conv_tc_kernel (all %d tcgen05 conv launches of one step, back to back)" % n_convs,
                     "kernel_ms_per_step": conv_ms, "share_of_step": conv_ms / ms_step,
                     "algorithmic_flops_per_step": conv_flops}
 
+        tb, tn = ncu_conv_traffic()
+        if tb is not None and tn == n_convs and B == 32:
+            roofline["traffic"] = tb
         if args.profile_layers and rank == 0:
             rows = plan.profile_layers(x_dev, reps=10)
             os.makedirs(os.path.dirname(os.path.abspath(args.profile_layers)), exist_ok=True)
