@@ -123,14 +123,34 @@ def cpu_reference_rate(max_seconds=20.0, threads=None, batch=2, max_iters=10):
     from b200yolo import cfggen
     from utils.parse_config import parse_model_cfg_text
     try:
-        avail = len(os.sched_getaffinity(0))      # cores this process may actually use (cgroup / affinity aware)
+        avail = len(os.sched_getaffinity(0))      # cores this process may be scheduled on
     except AttributeError:
         avail = os.cpu_count()
-    threads = threads or avail
-    torch.set_num_threads(threads)
+    try:                                           # ... and the cgroup CPU quota, if any (cpu.max = "<quota> <period>")
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            avail = max(1, min(avail, int(float(q) / float(per) + 0.5)))
+    except (OSError, ValueError):
+        pass
     defs = parse_model_cfg_text(cfggen.cfg_text(MODEL))[1:]
     path = cfggen.write_cfg(MODEL, "/tmp/b2y_cfg_cpu")
     sd = orc.synth_state_dict(models.Darknet(path).state_dict(), 0)
+    if threads is None:
+        # "all the host threads it can use": more threads than physically free cores make torch's CPU convs slower,
+        # so take the fastest of a few thread counts on a small probe forward
+        best = None
+        probe = orc.synth_images(1, 256, 256, seed=1)
+        for t in sorted({avail, min(avail, 64), min(avail, 32), min(avail, 16), min(avail, 8)}, reverse=True):
+            torch.set_num_threads(t)
+            with torch.no_grad():
+                orc.darknet_forward(defs, sd, probe, MODEL)
+                t0 = time.time()
+                orc.darknet_forward(defs, sd, probe, MODEL)
+                dt = time.time() - t0
+            if best is None or dt < best[0]:
+                best = (dt, t)
+        threads = best[1]
+    torch.set_num_threads(threads)
     bs = batch
     x = orc.synth_images(bs, SIZE, SIZE, seed=0)
     with torch.no_grad():

@@ -1,3 +1,4 @@
 cd /root/repo
-timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -5
-timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --profile-layers gpurun_out/layers_h1.json > gpurun_out/bench17.json 2>gpurun_out/bench17.err; tail -2 gpurun_out/bench17.err; head -c 1500 gpurun_out/bench17.json
+timeout 600 python -c "import __graft_entry__ as g; g.build(); g.smoke(); print('SMOKE OK')" 2>&1 | tail -3
+timeout 600 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; tail -2 gpurun_out/bench_default.err; cat gpurun_out/bench_default.json | tail -1 | cut -c1-2500
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 2>/dev/null | tail -1 | cut -c1-900
