@@ -1,4 +1,2 @@
 cd /root/repo
-timeout 600 python -c "import __graft_entry__ as g; g.build(); g.smoke(); print('SMOKE OK')" 2>&1 | tail -3
-timeout 600 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; tail -2 gpurun_out/bench_default.err; cat gpurun_out/bench_default.json | tail -1 | cut -c1-2500
-timeout 600 python bench.py --impl reference --steps 3 --warmup 1 2>/dev/null | tail -1 | cut -c1-900
+timeout 900 python -m pytest tests/test_gpu_train_model.py -m gpu -q -x -s 2>&1 | grep -v "Warning\|^$" | tail -24

@@ -99,3 +99,43 @@ def test_train_step_then_optimizer_changes_output():
         opt.step()
         losses.append(float(loss))
     assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
+
+
+@pytest.mark.parametrize("name", ["yolov3-tiny", "yolov4"])
+def test_graph_replay_matches_eager_training(name):
+    """Steps 3+ replay the captured forward / backward CUDA graphs.  With frozen parameters every step computes the
+    same thing, so the replayed loss and gradients must equal the eagerly launched ones up to the fp32 reordering of
+    the atomics (split-K weight gradient, BN sums) -- no chaotic amplification across optimiser steps involved."""
+    from utils import utils as my_utils
+    x = orc.synth_images(4, 128, 128, seed=0).cuda()
+    t = orc.synth_targets(4, 6, 80, seed=1).cuda()
+    res = {}
+    for graphed in (False, True):
+        model = attach_hyp(build_model(name, device="cuda")).train()
+        model.use_cuda_graph = graphed
+        losses, grads = [], []
+        for _ in range(4):                       # eager, capture, replay, replay
+            model.zero_grad(set_to_none=True)
+            pred, _ = model(x)
+            loss, _ = my_utils.compute_loss(pred, t, model)
+            loss.backward()
+            losses.append(float(loss.detach()))
+            grads.append({k: p.grad.detach().clone() for k, p in model.named_parameters()})
+        res[graphed] = (losses, grads)
+    le, lg = res[False][0], res[True][0]
+    print("\n[%s] eager losses %s\n      graph losses %s" % (name, le, lg))
+    assert all(np.isfinite(lg))
+    ltol = 2e-3 if name == "yolov3-tiny" else 3e-2     # yolov4 at this size amplifies the atomics' fp32 reordering
+    assert max(abs(a - b) / abs(a) for a, b in zip(le, lg)) < ltol
+    assert max(abs(a - lg[0]) / abs(lg[0]) for a in lg) < ltol          # replays reproduce the eager step
+
+    def worst(ga, gb):
+        d = sorted(((float((ga[k] - gb[k]).norm() / (ga[k].norm() + 1e-12)), k, float(ga[k].norm())) for k in ga),
+                   reverse=True)
+        return d[:3]
+    noise = worst(res[False][1][0], res[False][1][3])         # eager step 1 vs eager step 4: atomics reordering only
+    replay = worst(res[True][1][0], res[True][1][3])          # same model: eager step 1 vs graph replay step 4
+    cross = worst(res[False][1][3], res[True][1][3])
+    print("      eager-vs-eager   ", noise, "\n      eager-vs-replay  ", replay, "\n      model-vs-model   ", cross)
+    assert replay[0][0] < max(5e-2, 3 * noise[0][0])
+    assert cross[0][0] < max(5e-2, 3 * noise[0][0])

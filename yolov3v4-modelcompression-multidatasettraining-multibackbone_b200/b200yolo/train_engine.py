@@ -17,6 +17,8 @@ loss.backward(), DistributedDataParallel hooks and torch optimisers work unchang
 """
 import ctypes as C
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -34,7 +36,7 @@ def _round_up(v, m):
 
 class _ConvRec:
     __slots__ = ('i', 'conv', 'bn', 'act', 'slope', 'src', 'z', 'y', 'res', 'head', 'stem', 'k', 's', 'p', 'Cout',
-                 'Cpad', 'w16', 'wT', 'stats', 'mean', 'invstd', 'scale', 'shift', 'ones', 'zeros', 'w32', 'aux_row')
+                 'Cpad', 'w16', 'wT', 'stats', 'mean', 'invstd', 'scale', 'shift', 'ones', 'zeros', 'w32', 'aux_row', 'wstem')
 
     def __init__(self):
         for k in self.__slots__:
@@ -248,6 +250,9 @@ class TrainPlan:
         maxc = max(r.Cpad for r in self.convs)
         self.dgb_scratch = torch.empty((2, maxc), dtype=torch.float32, device=dev)
         self.params = [p for p in model.parameters()]
+        self.runs = 0
+        self.fwd_graph = self.bwd_graph = None
+        self.bwd_key = None
 
     # ---------------------------------------------------------------------------------------------------------
     def _params_version(self):
@@ -261,6 +266,8 @@ class TrainPlan:
                 w = torch.cat([w, pad], 0)
             if r.stem:
                 r.w32 = w.float().contiguous()
+                # tensor-core stem: full-im2col weight layout when the receptive field fits one 64-byte GEMM row
+                r.wstem = ops.pack_stem_weights(r.w32) if w.shape[1] * r.k * r.k <= 32 and not r.head else None
             else:
                 r.w16, _, _ = ops.pack_conv_weights(w)
                 hin, win = r.src.H, r.src.W
@@ -269,12 +276,62 @@ class TrainPlan:
     def _zview(self, r):
         return r.z.buf[..., r.z.c0:r.z.c0 + r.Cpad] if r.head else r.z.view()
 
-    def forward(self, x):
+    # ---- CUDA-graph replay of the two static launch sequences (forward, backward) ------------------------------
+    # A training step is ~15 launches per conv layer; issued eagerly from Python the step is CPU-launch bound at 8
+    # images per GPU.  Shapes, buffers and the master parameters are static, the per-layer gradient scales live on the
+    # device, and the (dynamic) target list only enters the loss between the two graphs.
+    def _graphs_enabled(self):
+        return getattr(self.model, 'use_cuda_graph', os.environ.get('B2Y_NO_GRAPH', '0') != '1')
+
+    def forward_graphed(self, x):
+        if not self._graphs_enabled():
+            return self.forward(x)
+        if self.runs < 1:                      # first step eager: lazy allocations, warm caches
+            self.runs += 1
+            return self.forward(x)
+        if self.fwd_graph is None:
+            self.static_x = torch.empty((self.B, 3, self.H, self.W), dtype=torch.float32, device=self.device)
+            self.static_x.copy_(x)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.static_outs = self.forward(self.static_x, force_pack=True)
+            self.fwd_graph = g
+            self.bwd_graph = None
+        self.static_x.copy_(x)
+        self.fwd_graph.replay()
+        return [o.view_as(o) for o in self.static_outs]
+
+    def backward_graphed(self, dps):
+        if not self._graphs_enabled() or self.fwd_graph is None:
+            return self.backward(dps)
+        sink = getattr(self.model, '_b2y_grad_sink', None)
+        key = (id(sink), float(getattr(self.model, 'grad_scale', None) or 1.0))
+        if self.bwd_graph is None or key != self.bwd_key:
+            self.static_dps = [torch.zeros_like(o, dtype=torch.float32) for o in self.static_outs]
+            for sd, d in zip(self.static_dps, dps):
+                if d is not None:
+                    sd.copy_(d)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=self.fwd_graph.pool()):
+                self.static_grads = self.backward(self.static_dps)
+            self.bwd_graph, self.bwd_key = g, key
+        for sd, d in zip(self.static_dps, dps):
+            if d is None:
+                sd.zero_()
+            else:
+                sd.copy_(d)
+        self.bwd_graph.replay()
+        # gradients that are not written into a flat sink live in graph-owned memory: hand out copies
+        return {p: g.clone() for p, g in self.static_grads.items()}
+
+    def forward(self, x, force_pack=False):
         model = self.model
         ver = self._params_version()
-        if ver != self.param_version:
+        if force_pack or ver != self.param_version:
             self._pack()
-            self.param_version = ver
+            self.param_version = None if force_pack else ver
         x = x.contiguous().float()
         self.x = x
         for r in self.convs:
@@ -318,7 +375,16 @@ class TrainPlan:
                 ops.conv2d(r.src.view(), r.w16, bias, r.k, r.s, r.p, act=r.act, slope=r.slope, out=out)
             return
         z = r.z.view()
-        if r.stem:
+        if r.stem and getattr(r, 'wstem', None) is not None:
+            # im2col workspace [B*Ho*Wo][32] fp16 (kept for the weight gradient) + one-k-step GEMM with the BN sums
+            # coming out of its epilogue
+            d = ops.make_conv_desc((self.B, self.H, self.W, r.conv.in_channels), r.conv.in_channels, r.Cout, r.k, r.s,
+                                   r.p, r.Cout)
+            if getattr(self, 'stem_ws', None) is None:
+                self.stem_ws = ops.stem_workspace(d, self.device)
+            ops.stem_conv_tc(x, r.wstem, None, r.conv.in_channels, r.k, r.s, r.p, act='linear', out=z,
+                             workspace=self.stem_ws, stats=(r.stats[0], r.stats[1]))
+        elif r.stem:
             ops.stem_conv(x, r.w32, None, r.k, r.s, r.p, act='linear', out=z)
             # channel sums of the stem output: the reduce kernel with u = z, dy = z gives (sum z, sum z*z)
             if r.ones is None:
@@ -423,7 +489,15 @@ class TrainPlan:
         if gw is None:
             gw = torch.empty_like(conv.weight)
             grads[conv.weight] = gw
-        if r.stem:
+        if r.stem and getattr(r, 'wstem', None) is not None and getattr(self, 'stem_ws', None) is not None:
+            # dW = dz^T . im2col(x): the pixel-dimension GEMM on the tensor cores over the forward's workspace
+            kk = I * r.k * r.k
+            xcol = self.stem_ws[:B * Ho * Wo * 32].view(B, Ho, Wo, 32)
+            dwp = self.dw_scratch[:r.Cpad * 32].view(r.Cpad, 1, 1, 32)
+            dwp.zero_()
+            ops.conv2d_bwd_weight(xcol, dz, 1, 1, 0, scale=inv, dw=dwp, inv_scale=inv_s)
+            gw.copy_(dwp[:r.Cout, 0, 0, :kk].view(r.Cout, r.k, r.k, I).permute(0, 3, 1, 2))
+        elif r.stem:
             gw.zero_()
             d = ConvDesc(B, self.H, self.W, I, I, r.Cout, r.k, r.s, r.p, Ho, Wo, ops._pitch(dz), 0, 0.0, OUT_F16, 0)
             call("b2y_stem_conv_bwd_weight", C.byref(d), ptr(self.x), ptr(dz), ptr(gw), inv, ops._gdt(dz), stream_ptr())
@@ -458,14 +532,14 @@ class _DarknetTrain(torch.autograd.Function):
         ctx.plan = plan
         ctx.params = params
         with torch.no_grad():
-            outs = plan.forward(x)
+            outs = plan.forward_graphed(x)
         return tuple(outs)
 
     @staticmethod
     def backward(ctx, *dps):
         plan = ctx.plan
         with torch.no_grad():
-            grads = plan.backward(dps)
+            grads = plan.backward_graphed(dps)
         out = []
         for p in ctx.params:
             g = grads.get(p)

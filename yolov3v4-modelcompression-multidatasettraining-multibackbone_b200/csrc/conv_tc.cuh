@@ -107,22 +107,26 @@ struct ConvTcEpi {
 // int8 requantisation.  `v` holds the scaled accumulators on entry.
 template <int KIND>
 __device__ __forceinline__ void epi_chunk_general(float (&v)[32], const ConvTcParams& p, int n0c0, long long row,
-                                               bool row_ok, int lane) {
+                                               bool row_ok, int lane, uint8_t* stage) {
     if (p.stat_sum != nullptr) {
-        // per-channel batch statistics of the raw conv output (training BN): butterfly over the 32 rows of this warp
+        // per-channel batch statistics of the raw conv output (training BN): the warp's 32x32 chunk goes through its smem
+        // staging tile (rotated columns: conflict-free both ways), then lane j sums column j -- 32 STS + 32 LDS instead of
+        // 640 shuffles per chunk
+        float* tile = reinterpret_cast<float*>(stage);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            float s1 = row_ok ? v[j] : 0.f;
-            float s2 = s1 * s1;
+        for (int j = 0; j < 32; ++j) tile[lane * 32 + ((j + lane) & 31)] = row_ok ? v[j] : 0.f;
+        __syncwarp();
+        float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-                s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-            }
-            if (lane == j && n0c0 + j < p.Cout) {
-                atomicAdd(p.stat_sum + n0c0 + j, s1);
-                atomicAdd(p.stat_sqsum + n0c0 + j, s2);
-            }
+        for (int i = 0; i < 32; ++i) {
+            const float t = tile[i * 32 + ((lane + i) & 31)];
+            s1 += t;
+            s2 = fmaf(t, t, s2);
+        }
+        __syncwarp();
+        if (n0c0 + lane < p.Cout) {
+            atomicAdd(p.stat_sum + n0c0 + lane, s1);
+            atomicAdd(p.stat_sqsum + n0c0 + lane, s2);
         }
     }
     const int nvalid = min(32, p.Cout - n0c0);
@@ -682,7 +686,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
                         v[j] = ((KIND == CONV_KIND_F16) ? __uint_as_float(raw[j]) : (float)(int)raw[j]) * acc_mul;
-                    epi_chunk_general<KIND>(v, p, n0 + c0, row, row_ok, lane);
+                    epi_chunk_general<KIND>(v, p, n0 + c0, row, row_ok, lane, my_stage);
                 }
             }
             // release this accumulator stage back to the MMA warp

@@ -88,11 +88,70 @@ __global__ void bn_act_fwd_kernel(const __half* __restrict__ x, long long xp, co
     }
 }
 
+// v2 layout for the three BatchNorm passes: a thread owns ONE 8-channel vector (its per-channel coefficients live in
+// registers for the whole kernel) and walks the pixels with a fixed stride, so the loop body is loads + math + store:
+// no index divisions, no per-element coefficient loads, the activation resolved at compile time.  Needs 256 % (C/8) == 0.
+template <int ACT>
+__global__ void __launch_bounds__(256)
+bn_act_fwd_v2_kernel(const __half* __restrict__ x, long long xp, const float* __restrict__ scale,
+                     const float* __restrict__ shift, const __half* __restrict__ res, long long rp,
+                     __half* __restrict__ y, long long yp, long long pixels, int CV, float slope) {
+    const int cv = threadIdx.x % CV;
+    const int ppb = 256 / CV;
+    float sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        sc[j] = __ldg(scale + cv * 8 + j);
+        sh[j] = __ldg(shift + cv * 8 + j);
+    }
+    for (long long pix = (long long)blockIdx.x * ppb + threadIdx.x / CV; pix < pixels; pix += (long long)gridDim.x * ppb) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + pix * xp) + cv);
+        const __half* h = reinterpret_cast<const __half*>(&v);
+        float r[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = apply_act(fmaf(__half2float(h[j]), sc[j], sh[j]), ACT, slope);
+        if (res != nullptr) {
+            const uint4 rv = __ldg(reinterpret_cast<const uint4*>(res + pix * rp) + cv);
+            const __half* rh = reinterpret_cast<const __half*>(&rv);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] += __half2float(rh[j]);
+        }
+        uint4 o;
+        __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) oh[j] = __floats2half2_rn(r[2 * j], r[2 * j + 1]);
+        reinterpret_cast<uint4*>(y + pix * yp)[cv] = o;
+    }
+}
+
+static inline int v2_grid(long long pixels, int CV) {
+    const int ppb = 256 / CV;
+    long long g = (pixels + ppb - 1) / ppb;
+    const long long cap = 148 * 8;
+    return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+static inline bool v2_ok(int c) { return c % 8 == 0 && c / 8 <= 256 && 256 % (c / 8) == 0; }
+
 extern "C" int b2y_bn_act_fwd(const void* x, long long x_pitch, const float* scale, const float* shift,
                               const void* residual, long long res_pitch, void* y, long long y_pitch,
                               long long pixels, int c, int act, float slope, void* stream) {
     if (!x || !y || !scale || !shift || c % 8 != 0 || x_pitch % 8 != 0 || y_pitch % 8 != 0) return B2Y_ERR_INVALID;
     if (residual != nullptr && res_pitch % 8 != 0) return B2Y_ERR_INVALID;
+    if (v2_ok(c) && (act == B2Y_ACT_LEAKY || act == B2Y_ACT_MISH || act == B2Y_ACT_LINEAR)) {
+        const int CV = c / 8;
+        const int grid = v2_grid(pixels, CV);
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define B2Y_FWD_V2(A)                                                                                                  \
+    bn_act_fwd_v2_kernel<A><<<grid, 256, 0, st>>>(reinterpret_cast<const __half*>(x), x_pitch, scale, shift,           \
+                                                  reinterpret_cast<const __half*>(residual), res_pitch,               \
+                                                  reinterpret_cast<__half*>(y), y_pitch, pixels, CV, slope)
+        if (act == B2Y_ACT_LEAKY) B2Y_FWD_V2(B2Y_ACT_LEAKY);
+        else if (act == B2Y_ACT_MISH) B2Y_FWD_V2(B2Y_ACT_MISH);
+        else B2Y_FWD_V2(B2Y_ACT_LINEAR);
+#undef B2Y_FWD_V2
+        B2Y_CUDA_CHECK(cudaGetLastError());
+        return B2Y_OK;
+    }
     bn_act_fwd_kernel<<<grid_for(pixels * (c / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const __half*>(x), x_pitch, scale, shift, reinterpret_cast<const __half*>(residual), res_pitch,
         reinterpret_cast<__half*>(y), y_pitch, pixels, c, act, slope);
@@ -189,6 +248,64 @@ bn_act_bwd_reduce_kernel(const __half* __restrict__ x, long long xp, const GT* _
     }
 }
 
+template <typename GT, int ACT>
+__global__ void __launch_bounds__(256)
+bn_act_bwd_reduce_v2_kernel(const __half* __restrict__ x, long long xp, const GT* __restrict__ dy, long long dp,
+                            const float* __restrict__ scale, const float* __restrict__ shift,
+                            const float* __restrict__ mean, const float* __restrict__ invstd,
+                            float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ du_absmax,
+                            long long pixels, int CV, float slope) {
+    __shared__ float red[256][17];
+    const int cv = threadIdx.x % CV;
+    const int ppb = 256 / CV;
+    float sc[8], sh[8], mu[8], is[8], gb[8], gg[8];
+    float amax = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        gb[j] = gg[j] = 0.f;
+        const int c = cv * 8 + j;
+        sc[j] = __ldg(scale + c);
+        sh[j] = __ldg(shift + c);
+        mu[j] = mean ? __ldg(mean + c) : 0.f;
+        is[j] = invstd ? __ldg(invstd + c) : 1.f;
+    }
+    for (long long pix = (long long)blockIdx.x * ppb + threadIdx.x / CV; pix < pixels; pix += (long long)gridDim.x * ppb) {
+        float xf8[8], g8[8];
+        Half8<__half>::load(x + pix * xp + cv * 8, xf8);
+        Half8<GT>::load(dy + pix * dp + cv * 8, g8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float xf = xf8[j];
+            const float u = fmaf(xf, sc[j], sh[j]);
+            const float du = g8[j] * act_grad(u, ACT, slope);
+            gb[j] += du;
+            gg[j] += du * ((xf - mu[j]) * is[j]);
+            amax = fmaxf(amax, fabsf(du));
+        }
+    }
+    if (du_absmax != nullptr) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+        if ((threadIdx.x & 31) == 0 && amax > 0.f) atomicMax(reinterpret_cast<unsigned int*>(du_absmax), __float_as_uint(amax));
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        red[threadIdx.x][j] = gb[j];
+        red[threadIdx.x][8 + j] = gg[j];
+    }
+    __syncthreads();
+    // threads 0 .. CV*16-1: one (channel vector, component) each, summed over the 256/CV pixel sub-rows of the CTA
+    for (int i = threadIdx.x; i < CV * 16; i += 256) {
+        const int v = i / 16, comp = i % 16;
+        float sum = 0.f;
+        for (int k = 0; k < ppb; ++k) sum += red[v + k * CV][comp];
+        if (comp < 8)
+            atomicAdd(dbeta + v * 8 + comp, sum);
+        else if (dgamma != nullptr)
+            atomicAdd(dgamma + v * 8 + comp - 8, sum);
+    }
+}
+
 extern "C" int b2y_bn_act_bwd_reduce(const void* x, long long x_pitch, const void* dy, long long dy_pitch,
                                      const float* scale, const float* shift, const float* save_mean,
                                      const float* save_invstd, float* dgamma, float* dbeta, float* du_absmax,
@@ -196,6 +313,27 @@ extern "C" int b2y_bn_act_bwd_reduce(const void* x, long long x_pitch, const voi
     if (!x || !dy || !scale || !shift || !dbeta || c % 8 != 0 || x_pitch % 8 != 0 || dy_pitch % 8 != 0)
         return B2Y_ERR_INVALID;
     const int CV = c / 8;
+    if (v2_ok(c) && (act == B2Y_ACT_LEAKY || act == B2Y_ACT_MISH || act == B2Y_ACT_LINEAR)) {
+        const int g2 = v2_grid(pixels, CV);
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define B2Y_RED_V2(T, A)                                                                                               \
+    bn_act_bwd_reduce_v2_kernel<T, A><<<g2, 256, 0, st>>>(reinterpret_cast<const __half*>(x), x_pitch,                  \
+                                                          reinterpret_cast<const T*>(dy), dy_pitch, scale, shift,      \
+                                                          save_mean, save_invstd, dgamma, dbeta, du_absmax, pixels,   \
+                                                          CV, slope)
+        if (grad_dtype == B2Y_DT_BF16) {
+            if (act == B2Y_ACT_LEAKY) B2Y_RED_V2(__nv_bfloat16, B2Y_ACT_LEAKY);
+            else if (act == B2Y_ACT_MISH) B2Y_RED_V2(__nv_bfloat16, B2Y_ACT_MISH);
+            else B2Y_RED_V2(__nv_bfloat16, B2Y_ACT_LINEAR);
+        } else {
+            if (act == B2Y_ACT_LEAKY) B2Y_RED_V2(__half, B2Y_ACT_LEAKY);
+            else if (act == B2Y_ACT_MISH) B2Y_RED_V2(__half, B2Y_ACT_MISH);
+            else B2Y_RED_V2(__half, B2Y_ACT_LINEAR);
+        }
+#undef B2Y_RED_V2
+        B2Y_CUDA_CHECK(cudaGetLastError());
+        return B2Y_OK;
+    }
     dim3 grid(1, (CV + 31) / 32);
     long long want = (pixels + 63) / 64;
     grid.x = (unsigned)(want < 1 ? 1 : (want > 148 * 4 ? 148 * 4 : want));
@@ -278,6 +416,76 @@ __global__ void bn_act_bwd_apply_kernel(const __half* __restrict__ x, long long 
     }
 }
 
+template <typename GT, int ACT>
+__global__ void __launch_bounds__(256)
+bn_act_bwd_apply_v2_kernel(const __half* __restrict__ x, long long xp, const GT* __restrict__ dy, long long dp,
+                           const float* __restrict__ scale, const float* __restrict__ shift,
+                           const float* __restrict__ gamma, const float* __restrict__ mean,
+                           const float* __restrict__ invstd, const float* __restrict__ dgamma,
+                           const float* __restrict__ dbeta, __half* __restrict__ dx, long long dxp, long long pixels,
+                           int CV, float slope, const float* __restrict__ du_absmax, float* __restrict__ scale_out) {
+    const int C = CV * 8;
+    const float inv_n = 1.f / (float)pixels;
+    __shared__ float s_red[8];
+    __shared__ float s_scale;
+    float bound = 0.f;
+    {   // same bound / scale as bn_act_bwd_apply_kernel (every CTA derives it identically)
+        const float dumax = du_absmax != nullptr ? *du_absmax : 1.f;
+        for (int c = threadIdx.x; c < C; c += 256) {
+            const float g = gamma != nullptr ? gamma[c] : 1.f;
+            const float b = fabsf(g * invstd[c]) * (dumax + fabsf(dbeta[c]) * inv_n + 16.f * fabsf(dgamma[c]) * inv_n);
+            bound = fmaxf(bound, b);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) bound = fmaxf(bound, __shfl_xor_sync(0xffffffffu, bound, o));
+        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = bound;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float m = 0.f;
+            for (int w = 0; w < 8; ++w) m = fmaxf(m, s_red[w]);
+            float sc = 1.f;
+            if (m > 0.f && m < 3.0e38f) sc = exp2f(floorf(log2f(4096.f / m)));
+            sc = fminf(fmaxf(sc, 1.0e-30f), 1.0e30f);
+            s_scale = sc;
+            if (blockIdx.x == 0 && scale_out != nullptr) {
+                scale_out[0] = sc;
+                scale_out[1] = 1.f / sc;
+            }
+        }
+        __syncthreads();
+    }
+    const float scl = s_scale;
+    const int cv = threadIdx.x % CV;
+    const int ppb = 256 / CV;
+    float sc[8], sh[8], mu[8], is[8], gi[8], db[8], dg[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = cv * 8 + j;
+        sc[j] = __ldg(scale + c);
+        sh[j] = __ldg(shift + c);
+        mu[j] = __ldg(mean + c);
+        is[j] = __ldg(invstd + c);
+        gi[j] = (gamma != nullptr ? __ldg(gamma + c) : 1.f) * is[j];
+        db[j] = __ldg(dbeta + c) * inv_n;
+        dg[j] = __ldg(dgamma + c) * inv_n;
+    }
+    for (long long pix = (long long)blockIdx.x * ppb + threadIdx.x / CV; pix < pixels; pix += (long long)gridDim.x * ppb) {
+        float xf8[8], g8[8];
+        Half8<__half>::load(x + pix * xp + cv * 8, xf8);
+        Half8<GT>::load(dy + pix * dp + cv * 8, g8);
+        float r[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float xf = xf8[j];
+            const float u = fmaf(xf, sc[j], sh[j]);
+            const float du = g8[j] * act_grad(u, ACT, slope);
+            const float xhat = (xf - mu[j]) * is[j];
+            r[j] = scl * (gi[j] * (du - db[j] - xhat * dg[j]));
+        }
+        Half8<__half>::store(dx + pix * dxp + cv * 8, r);
+    }
+}
+
 extern "C" int b2y_bn_act_bwd_apply(const void* x, long long x_pitch, const void* dy, long long dy_pitch,
                                     const float* scale, const float* shift, const float* gamma,
                                     const float* save_mean, const float* save_invstd, const float* dgamma,
@@ -286,6 +494,28 @@ extern "C" int b2y_bn_act_bwd_apply(const void* x, long long x_pitch, const void
                                     void* stream) {
     if (!x || !dy || !scale || !shift || !save_mean || !save_invstd || !dgamma || !dbeta || !dx || c % 8 != 0)
         return B2Y_ERR_INVALID;
+    if (v2_ok(c) && (act == B2Y_ACT_LEAKY || act == B2Y_ACT_MISH || act == B2Y_ACT_LINEAR)) {
+        const int CV = c / 8;
+        const int g2 = v2_grid(pixels, CV);
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define B2Y_APP_V2(T, A)                                                                                               \
+    bn_act_bwd_apply_v2_kernel<T, A><<<g2, 256, 0, st>>>(                                                               \
+        reinterpret_cast<const __half*>(x), x_pitch, reinterpret_cast<const T*>(dy), dy_pitch, scale, shift, gamma,    \
+        save_mean, save_invstd, dgamma, dbeta, reinterpret_cast<__half*>(dx), dx_pitch, pixels, CV, slope, du_absmax,  \
+        scale_out)
+        if (grad_dtype == B2Y_DT_BF16) {
+            if (act == B2Y_ACT_LEAKY) B2Y_APP_V2(__nv_bfloat16, B2Y_ACT_LEAKY);
+            else if (act == B2Y_ACT_MISH) B2Y_APP_V2(__nv_bfloat16, B2Y_ACT_MISH);
+            else B2Y_APP_V2(__nv_bfloat16, B2Y_ACT_LINEAR);
+        } else {
+            if (act == B2Y_ACT_LEAKY) B2Y_APP_V2(__half, B2Y_ACT_LEAKY);
+            else if (act == B2Y_ACT_MISH) B2Y_APP_V2(__half, B2Y_ACT_MISH);
+            else B2Y_APP_V2(__half, B2Y_ACT_LINEAR);
+        }
+#undef B2Y_APP_V2
+        B2Y_CUDA_CHECK(cudaGetLastError());
+        return B2Y_OK;
+    }
     if (grad_dtype == B2Y_DT_BF16)
         bn_act_bwd_apply_kernel<__nv_bfloat16><<<grid_for(pixels * (c / 8), 256), 256, 0,
                                                  static_cast<cudaStream_t>(stream)>>>(
