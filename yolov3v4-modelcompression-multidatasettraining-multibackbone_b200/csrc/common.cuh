@@ -347,7 +347,20 @@ __device__ __forceinline__ float softplus_f(float x) {
     // torch F.softplus(beta=1, threshold=20)  (reference utils/layers.py:148)
     return x > 20.f ? x : log1pf(expf(x));
 }
-__device__ __forceinline__ float mish_f(float x) { return x * tanhf(softplus_f(x)); }
+// Mish (reference utils/layers.py:118-128, 146-148): tanh(softplus(x)) in closed form.  With e = exp(x):
+//   tanh(log(1+e)) = ((1+e)^2 - 1) / ((1+e)^2 + 1) = n / (n + 2),  n = e (e + 2)
+// one exponential and one division instead of exp + log1p + tanh; no cancellation for either sign of x (for x << 0 it
+// tends to e like the original).  x is clamped at 20, where torch's softplus switches to the identity and tanh is 1
+// in fp32 anyway.  Agreement with the literal formula: a few fp32 ulp.
+__device__ __forceinline__ float mish_tanh_softplus(float x, float& e) {
+    e = __expf(fminf(x, 20.f));
+    const float n = e * (e + 2.f);
+    return __fdividef(n, n + 2.f);
+}
+__device__ __forceinline__ float mish_f(float x) {
+    float e;
+    return x * mish_tanh_softplus(x, e);
+}
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
 
 __device__ __forceinline__ float apply_act(float v, int act, float slope) {
@@ -366,9 +379,10 @@ __device__ __forceinline__ float act_grad(float v, int act, float slope) {
     switch (act) {
         case B2Y_ACT_LEAKY: return v > 0.f ? 1.f : slope;
         case B2Y_ACT_MISH: {
-            // reference utils/layers.py:123-128
-            float sx = sigmoid_f(v);
-            float fx = tanhf(softplus_f(v));
+            // reference utils/layers.py:123-128: fx + x * sigmoid(x) * (1 - fx^2), fx = tanh(softplus(x))
+            float e;
+            const float fx = mish_tanh_softplus(v, e);
+            const float sx = __fdividef(e, 1.f + e);        // sigmoid(x) = e / (1 + e)  (-> 1 for the clamped large x)
             return fx + v * sx * (1.f - fx * fx);
         }
         case B2Y_ACT_RELU: return v > 0.f ? 1.f : 0.f;

@@ -101,35 +101,47 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant_
         m_tile = t / p.n_tiles;
     };
 
+    // Both issue loops run warp-uniform with one elected lane issuing (same reason as in conv_tc.cuh: a single divergent
+    // lane pays ~10 extra R2UR/ELECT instructions per TMA / MMA issue and the loop becomes the bottleneck).
     if (warp == 0) {
-        if (lane == 0) {
-            int stage = 0;
+        {
+            uint32_t stage = 0;
             uint32_t phase = 0;
             const int HoWo = p.MH * p.MW;
+            const uint32_t smem_base = smem_u32(smem), full_base = smem_u32(full_bar), empty_base = smem_u32(empty_bar);
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 int m_tile, n_tile, tap, split;
                 decode(tile, m_tile, n_tile, tap, split);
                 const int r = tap / p.ksize, s = tap - r * p.ksize;
                 const int ks0 = split * p.ksteps_per_split;
                 const int ks1 = min(ks0 + p.ksteps_per_split, p.ksteps_total);
+                // pixel coordinates of the k-step, advanced incrementally (BK pixels per step)
+                int k0 = ks0 * BK;
+                int img = k0 / HoWo;
+                int rem = k0 - img * HoWo;
                 for (int ks = ks0; ks < ks1; ++ks) {
-                    const int k0 = ks * BK;
-                    const int img = k0 / HoWo;
-                    const int rem = k0 - img * HoWo;
                     const int po = rem / p.MW, qo = rem - po * p.MW;
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
-                    uint8_t* a_dst = smem + stage * Cfg::STAGE_BYTES;
-                    uint8_t* b_dst = a_dst + Cfg::A_BYTES;
-                    mbar_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::B_BYTES);
+                    mbar_wait_s(empty_base + stage * 8, phase ^ 1);
+                    if (elect_one()) {
+                        const uint32_t a_dst = smem_base + stage * Cfg::STAGE_BYTES;
+                        const uint32_t b_dst = a_dst + Cfg::A_BYTES;
+                        const uint32_t fb = full_base + stage * 8;
+                        mbar_expect_tx_s(fb, Cfg::A_BYTES + Cfg::B_BYTES);
 #pragma unroll
-                    for (int at = 0; at < Cfg::A_ATOMS; ++at)
-                        tma_load_2d(a_dst + at * Cfg::A_ATOM_BYTES, &tmDy, &full_bar[stage], m_tile * 128 + at * 64,
-                                    k0);
+                        for (int at = 0; at < Cfg::A_ATOMS; ++at)
+                            tma_load_2d_s(a_dst + at * Cfg::A_ATOM_BYTES, &tmDy, fb, m_tile * 128 + at * 64, k0);
 #pragma unroll
-                    for (int at = 0; at < Cfg::B_ATOMS; ++at)
-                        tma_load_im2col_4d(b_dst + at * Cfg::B_ATOM_BYTES, &tmX, &full_bar[stage],
-                                           n_tile * BLOCK_N + at * Cfg::B_ATOM_CH, qo * p.stride - p.pad,
-                                           po * p.stride - p.pad, img, (uint16_t)s, (uint16_t)r);
+                        for (int at = 0; at < Cfg::B_ATOMS; ++at)
+                            tma_load_im2col_4d_s(b_dst + at * Cfg::B_ATOM_BYTES, &tmX, fb,
+                                                 n_tile * BLOCK_N + at * Cfg::B_ATOM_CH, qo * p.stride - p.pad,
+                                                 po * p.stride - p.pad, img, (uint16_t)s, (uint16_t)r);
+                    }
+                    k0 += BK;
+                    rem += BK;
+                    if (rem >= HoWo) {      // BK <= HoWo is not guaranteed for tiny maps: general wrap
+                        img += rem / HoWo;
+                        rem = rem % HoWo;
+                    }
                     if (++stage == NS) {
                         stage = 0;
                         phase ^= 1;
@@ -138,7 +150,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant_
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
             int stage = 0;
             uint32_t phase = 0;
             uint32_t acc_phase = 0;
@@ -146,6 +158,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant_
             const uint64_t adesc_base = smem_desc_base(Cfg::A_ATOM_BYTES, 8 * 128, swizzle_layout_type(128));
             const uint64_t bdesc_base =
                 smem_desc_base(Cfg::B_ATOM_BYTES, 8 * NB_ROW_BYTES, swizzle_layout_type(NB_ROW_BYTES));
+            const uint32_t idesc = IDESC | p.idesc_ab;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 int m_tile, n_tile, tap, split;
                 decode(tile, m_tile, n_tile, tap, split);
@@ -153,24 +166,28 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant_
                 const int ks1 = min(ks0 + p.ksteps_per_split, p.ksteps_total);
                 mbar_wait(tmem_empty_bar, acc_phase ^ 1);
                 tc_fence_after();
+                uint32_t accum = 0;
                 for (int ks = ks0; ks < ks1; ++ks) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-                    const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+                    if (elect_one()) {
+                        const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                        const uint32_t b_addr = a_addr + Cfg::A_BYTES;
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        const uint64_t adesc = smem_desc_at(adesc_base, a_addr + k * 16 * 128);
-                        const uint64_t bdesc = smem_desc_at(bdesc_base, b_addr + k * 16 * NB_ROW_BYTES);
-                        mma_f16_ss(tmem_base, adesc, bdesc, IDESC | p.idesc_ab, (ks > ks0 || k > 0) ? 1u : 0u);
+                        for (int k = 0; k < BK / 16; ++k) {
+                            const uint64_t adesc = smem_desc_at(adesc_base, a_addr + k * 16 * 128);
+                            const uint64_t bdesc = smem_desc_at(bdesc_base, b_addr + k * 16 * NB_ROW_BYTES);
+                            mma_f16_ss(tmem_base, adesc, bdesc, idesc, k > 0 ? 1u : accum);
+                        }
+                        tc_commit(&empty_bar[stage]);
                     }
-                    tc_commit(&empty_bar[stage]);
+                    accum = 1;
                     if (++stage == NS) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
-                tc_commit(tmem_full_bar);
+                if (elect_one()) tc_commit(tmem_full_bar);
                 acc_phase ^= 1;
             }
         }
