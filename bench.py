@@ -241,7 +241,7 @@ def main():
     dev = torch.device("cuda", local)
     import torch.distributed as dist
     if world > 1:
-        dist.init_process_group("nccl", init_method="env://")
+        dist.init_process_group("nccl", init_method="env://", device_id=dev)
 
     model = build_model(dev)
     B = args.batch

@@ -119,6 +119,11 @@ int b2y_stem_conv_fwd_tc(const b2y_conv_desc* d, const float* x_nchw, const void
 #define B2Y_STEM_X_U8 2
 int b2y_stem_conv_fwd_fused(const b2y_conv_desc* d, const void* x_nchw, int x_dtype, float x_div, const void* w_stem,
                             const float* bias, void* y, void* stream);
+/* Same kernel as the first layer of the INT8 graph (ptq_cos.py:288-296: fp32 conv of the float image with the
+ * fake-quantised weights, output requantised): w_stem = b2y_pack_stem_weights of the fake-quantised fp32 weights (exact
+ * in fp16), y_i8 = clamp(round_half_away(act(conv + bias_q) / out_scale)) int8 NHWC. */
+int b2y_stem_conv_fwd_fused_q(const b2y_conv_desc* d, const void* x_nchw, int x_dtype, float x_div, const void* w_stem,
+                              const float* bias_q, void* y_i8, float out_scale, float lo, float hi, void* stream);
 
 /* Fold BatchNorm (running stats) into conv weights and repack OIHW fp32 -> [O][kh][kw][I] fp16.
  *   w_f = w * gamma/sqrt(var+eps);  b_f = beta - gamma*mean/sqrt(var+eps) (+ conv_bias*scale)

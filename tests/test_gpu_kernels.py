@@ -188,6 +188,30 @@ def test_stem_conv_fused(cin, k, stride, cout, dtype):
         assert (got - ref).abs().max() <= 2e-3 * max(1.0, ref.abs().max().item()), (act, (got - ref).abs().max())
 
 
+@pytest.mark.parametrize("cin,cout,k,stride,res", [(32, 64, 3, 1, True), (32, 64, 3, 2, False), (64, 32, 1, 1, False),
+                                                  (128, 64, 1, 1, False)])
+def test_conv_weight_stationary_many_tiles(cin, cout, k, stride, res):
+    """More M tiles than SMs and a weight panel that fits in smem: the weight-stationary launch (whole panel loaded once
+    per CTA, the ring carries A only), 8 epilogue warps on alternate tiles, TMA-store epilogue with a partial last tile."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(21)
+    B, H, W = 2, 110, 100                       # 22000 pixels = 171.9 tiles > 148 SMs
+    x = torch.randn(B, H, W, cin, generator=g).half()
+    w = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).half()
+    b = torch.randn(cout, generator=g)
+    Ho, Wo = (H + 2 * (k // 2) - k) // stride + 1, (W + 2 * (k // 2) - k) // stride + 1
+    r = torch.randn(B, Ho, Wo, cout, generator=g).half() if res else None
+    ref = F.leaky_relu(F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b, stride=stride, padding=k // 2), 0.1)
+    if res:
+        ref = ref + r.float().permute(0, 3, 1, 2)
+    wp = w.permute(0, 2, 3, 1).contiguous().cuda()
+    y = ops.conv2d(x.cuda(), wp, b.cuda(), k, stride, k // 2, act="leaky", residual=r.cuda() if res else None)
+    torch.cuda.synchronize()
+    got = y.float().permute(0, 3, 1, 2).cpu()
+    assert got.shape == ref.shape
+    assert (got - ref).abs().max() <= 4e-3 * max(1.0, ref.abs().max().item())
+
+
 def test_pack_weights_bn_fold():
     ops = _ops()
     g = torch.Generator().manual_seed(2)

@@ -34,7 +34,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", init_method="env://")
+        dist.init_process_group("nccl", init_method="env://", device_id=dev)
     import models
     from b200yolo import cfggen
     from b200yolo.parallel import FlatDataParallel

@@ -60,6 +60,7 @@ _PROTOS = {
     "b2y_stem_workspace_bytes": (sz, [C.POINTER(ConvDesc)]),
     "b2y_pack_stem_weights": (i32, [vp, i32, i32, i32, vp, vp]),
     "b2y_stem_conv_fwd_fused": (i32, [C.POINTER(ConvDesc), vp, i32, f32, vp, vp, vp, vp]),
+    "b2y_stem_conv_fwd_fused_q": (i32, [C.POINTER(ConvDesc), vp, i32, f32, vp, vp, vp, f32, f32, f32, vp]),
     "b2y_stem_conv_fwd_tc": (i32, [C.POINTER(ConvDesc), vp, vp, vp, vp, vp, vp, vp, vp]),
     "b2y_pack_conv_weights": (i32, [vp, vp, vp, vp, vp, vp, f32, i32, i32, i32, vp, vp, vp, vp]),
     "b2y_upsample_nearest": (i32, [vp, ll, vp, ll, i32, i32, i32, i32, i32, vp]),

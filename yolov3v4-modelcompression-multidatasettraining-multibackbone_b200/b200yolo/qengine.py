@@ -138,6 +138,7 @@ class QPlan:
             elif kind == 'upsample':
                 scale_of[id(st[3])] = scale_of[id(st[2])]
         self.scale_of = scale_of
+        self.stem_w = {}
         self.prepared = True
 
     def forward(self, x):
@@ -156,8 +157,16 @@ class QPlan:
                     lo, hi = -(1 << (bits - 1)), (1 << (bits - 1)) - 1
                     d = ops.make_conv_desc((B, self.H, self.W, self.Cin), self.Cin, conv.out_channels, k, s, p,
                                            ops._pitch(out.view()), act, slope, OUT_I8)
-                    call("b2y_stem_conv_fwd_q", C.byref(d), ptr(x), ptr(wq), ptr(bq), ptr(out.buf), s_a, float(lo),
-                         float(hi), stream_ptr())
+                    if self.Cin * k * k <= 32 and conv.out_channels <= 64 and wq.abs().max() < 6.0e4:
+                        # fused tensor-core stem: the fake-quantised weights are exact in fp16 (int8 code x 2^-n)
+                        ws = self.stem_w.get(i)
+                        if ws is None:
+                            ws = self.stem_w[i] = ops.pack_stem_weights(wq)
+                        call("b2y_stem_conv_fwd_fused_q", C.byref(d), ptr(x), 0, 1.0, ptr(ws), ptr(bq), ptr(out.buf), s_a,
+                             float(lo), float(hi), stream_ptr())
+                    else:
+                        call("b2y_stem_conv_fwd_q", C.byref(d), ptr(x), ptr(wq), ptr(bq), ptr(out.buf), s_a, float(lo),
+                             float(hi), stream_ptr())
                 else:
                     w8, bq, acc_scale, s_a, act, slope, bits = self.packed[i]
                     if head:

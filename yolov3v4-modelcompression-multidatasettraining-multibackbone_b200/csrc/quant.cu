@@ -2,6 +2,8 @@
 // (reference utils/quantized/quantized_ptq_cos.py:14-113, utils/quantized/quantized_google.py:16-219).
 // All HBM-bound: one pass over the data, 16-byte vector accesses, warp-shuffle + one atomic per CTA for reductions.
 #include "b200yolo.h"
+#include <cmath>
+
 #include "common.cuh"
 
 using namespace b2y;
@@ -271,11 +273,64 @@ __global__ void qshortcut_kernel(const int8_t* __restrict__ x, long long xp, con
         reinterpret_cast<uint4*>(out + pix * op)[cv] = ov;
     }
 }
+// v2: a thread owns one 16-channel vector and strides the pixels (no index divisions).  EXACT_MUL: all three scales are
+// powers of two (what the COSPTQ quantiser produces, ptq_cos.py:60-75), so x / s == x * (1/s) bit for bit and the three
+// IEEE divisions per element become multiplications; other scales keep the divisions.
+template <bool EXACT_MUL>
+__global__ void __launch_bounds__(256)
+qshortcut_v2_kernel(const int8_t* __restrict__ x, long long xp, const int8_t* __restrict__ a, long long ap,
+                    int8_t* __restrict__ out, long long op, long long pixels, int CV, float sx_in, float scale_x,
+                    float sa_in, float scale_a, float scale_sum, float lo, float hi) {
+    const int cv = threadIdx.x % CV;
+    const int ppb = 256 / CV;
+    const float rx = 1.f / scale_x, ra = 1.f / scale_a, rs = 1.f / scale_sum;
+    for (long long pix = (long long)blockIdx.x * ppb + threadIdx.x / CV; pix < pixels; pix += (long long)gridDim.x * ppb) {
+        const uint4 xv = __ldg(reinterpret_cast<const uint4*>(x + pix * xp) + cv);
+        const uint4 av = __ldg(reinterpret_cast<const uint4*>(a + pix * ap) + cv);
+        const int8_t* xb = reinterpret_cast<const int8_t*>(&xv);
+        const int8_t* ab = reinterpret_cast<const int8_t*>(&av);
+        uint4 ov;
+        int8_t* ob = reinterpret_cast<int8_t*>(&ov);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const float xs = (float)xb[j] * sx_in, as = (float)ab[j] * sa_in;
+            const float xf = rha(EXACT_MUL ? xs * rx : xs / scale_x) * scale_x;   // rounded, NOT clamped
+            const float af = rha(EXACT_MUL ? as * ra : as / scale_a) * scale_a;
+            const float q = rha(EXACT_MUL ? (xf + af) * rs : (xf + af) / scale_sum);
+            ob[j] = (int8_t)(int)fminf(fmaxf(q, lo), hi);
+        }
+        reinterpret_cast<uint4*>(out + pix * op)[cv] = ov;
+    }
+}
+static inline bool is_pow2f(float v) {
+    int e = 0;
+    return v > 0.f && frexpf(v, &e) == 0.5f;
+}
+
 extern "C" int b2y_qshortcut_i8(const void* x, long long x_pitch, const void* a, long long a_pitch, void* out,
                                 long long out_pitch, long long pixels, int c, float sx_in, float scale_x,
                                 float sa_in, float scale_a, float scale_sum, float lo, float hi, void* stream) {
     if (!x || !a || !out || c % 16 != 0 || x_pitch % 16 != 0 || a_pitch % 16 != 0 || out_pitch % 16 != 0)
         return B2Y_ERR_INVALID;
+    const int CV = c / 16;
+    if (CV <= 256 && 256 % CV == 0) {
+        const int ppb = 256 / CV;
+        long long g = (pixels + ppb - 1) / ppb;
+        if (g > 148 * 8) g = 148 * 8;
+        if (g < 1) g = 1;
+        const bool exact = is_pow2f(scale_x) && is_pow2f(scale_a) && is_pow2f(scale_sum);
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        if (exact)
+            qshortcut_v2_kernel<true><<<(int)g, 256, 0, st>>>(
+                reinterpret_cast<const int8_t*>(x), x_pitch, reinterpret_cast<const int8_t*>(a), a_pitch,
+                reinterpret_cast<int8_t*>(out), out_pitch, pixels, CV, sx_in, scale_x, sa_in, scale_a, scale_sum, lo, hi);
+        else
+            qshortcut_v2_kernel<false><<<(int)g, 256, 0, st>>>(
+                reinterpret_cast<const int8_t*>(x), x_pitch, reinterpret_cast<const int8_t*>(a), a_pitch,
+                reinterpret_cast<int8_t*>(out), out_pitch, pixels, CV, sx_in, scale_x, sa_in, scale_a, scale_sum, lo, hi);
+        B2Y_CUDA_CHECK(cudaGetLastError());
+        return B2Y_OK;
+    }
     qshortcut_kernel<<<grid_for(pixels * (c / 16), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const int8_t*>(x), x_pitch, reinterpret_cast<const int8_t*>(a), a_pitch,
         reinterpret_cast<int8_t*>(out), out_pitch, pixels, c, sx_in, scale_x, sa_in, scale_a, scale_sum, lo, hi);

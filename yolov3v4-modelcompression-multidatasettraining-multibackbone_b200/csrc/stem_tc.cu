@@ -33,7 +33,9 @@ struct StemParams {
     int B, H, W, Ho, Wo, stride, pad;
     const __half* w;      // [BLOCK_N][32] fp16, column (kh*K + kw)*Cin + c  (b2y_pack_stem_weights, full layout)
     const float* bias;    // [Cout] or null
-    __half* out;          // NHWC fp16
+    __half* out;          // NHWC fp16, or int8 codes when out_i8 (first layer of the INT8 graph)
+    int out_i8;
+    float q_scale, q_mul, q_lo, q_hi;   // q = clamp(round_half_away(v / q_scale)); q_mul = 1/q_scale when that is exact
     long long out_pitch;
     int Cout;
     int act;
@@ -222,7 +224,33 @@ __global__ void __launch_bounds__(128 * NG + 64, 1) stem_fused_kernel(const __gr
                                 break;
                         }
                     }
-                    if (prow_ok) {
+                    if (prow_ok && p.out_i8) {
+                        // requantise (ptq_cos.py:14-20 round half away from zero, then clamp) and store 32 codes
+                        int8_t* op8 = reinterpret_cast<int8_t*>(p.out) + (long long)prev_row * p.out_pitch + c0;
+                        const int nvalid = min(32, p.Cout - c0);
+                        uint32_t w[8];
+#pragma unroll
+                        for (int t = 0; t < 8; ++t) {
+                            uint32_t word = 0;
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float vv = v[t * 4 + e];
+                                float q = p.q_mul != 0.f ? vv * p.q_mul : __fdiv_rn(vv, p.q_scale);
+                                q = copysignf(floorf(fabsf(q) + 0.5f), q);
+                                q = fminf(fmaxf(q, p.q_lo), p.q_hi);
+                                word |= ((uint32_t)(uint8_t)(int8_t)(int)q) << (8 * e);
+                            }
+                            w[t] = word;
+                        }
+                        if ((nvalid & 15) == 0 && ((reinterpret_cast<uintptr_t>(op8) & 15) == 0)) {
+                            reinterpret_cast<uint4*>(op8)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                            if (nvalid == 32) reinterpret_cast<uint4*>(op8)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 32; ++q)
+                                if (q < nvalid) op8[q] = (int8_t)((w[q >> 2] >> (8 * (q & 3))) & 0xff);
+                        }
+                    } else if (prow_ok) {
                         __half* op = orow + c0;
                         const int nvalid = min(32, p.Cout - c0);
                         if ((nvalid & 7) == 0 && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
@@ -358,8 +386,8 @@ using namespace b2y;
 
 // x: NCHW image in x_dtype (B2Y_STEM_X_*), value = raw / x_div.  w_stem: the "full" [out_c][32] layout of
 // b2y_pack_stem_weights (in_c*k*k <= 32).  y: NHWC fp16.
-extern "C" int b2y_stem_conv_fwd_fused(const b2y_conv_desc* d, const void* x_nchw, int x_dtype, float x_div,
-                                       const void* w_stem, const float* bias, void* y, void* stream) {
+static int stem_fused_common(const b2y_conv_desc* d, const void* x_nchw, int x_dtype, float x_div, const void* w_stem,
+                             const float* bias, void* y, int out_i8, float q_scale, float q_lo, float q_hi, void* stream) {
     if (!d || !x_nchw || !w_stem || !y) return B2Y_ERR_INVALID;
     if (d->in_c * d->ksize * d->ksize > 32 || d->out_c > 64 || x_div == 0.f) return B2Y_ERR_UNSUPPORTED;
     if (reinterpret_cast<uintptr_t>(w_stem) & 15) return B2Y_ERR_INVALID;
@@ -387,6 +415,15 @@ extern "C" int b2y_stem_conv_fwd_fused(const b2y_conv_desc* d, const void* x_nch
     p.bias = bias;
     p.out = reinterpret_cast<__half*>(y);
     p.out_pitch = d->out_pitch;
+    p.out_i8 = out_i8;
+    if (out_i8) {
+        if (q_scale <= 0.f) return B2Y_ERR_INVALID;
+        int ex = 0;
+        p.q_scale = q_scale;
+        p.q_mul = frexpf(q_scale, &ex) == 0.5f ? 1.f / q_scale : 0.f;
+        p.q_lo = q_lo;
+        p.q_hi = q_hi;
+    }
     p.Cout = d->out_c;
     p.act = d->act;
     p.slope = d->slope;
@@ -402,4 +439,20 @@ extern "C" int b2y_stem_conv_fwd_fused(const b2y_conv_desc* d, const void* x_nch
         case STEM_X_U8: return stem_dispatch<uint8_t>(p, d->in_c, d->ksize, st);
         default: return B2Y_ERR_INVALID;
     }
+}
+
+// x: NCHW image in x_dtype (B2Y_STEM_X_*), value = raw / x_div.  w_stem: the "full" [out_c][32] layout of
+// b2y_pack_stem_weights (in_c*k*k <= 32).  y: NHWC fp16.
+extern "C" int b2y_stem_conv_fwd_fused(const b2y_conv_desc* d, const void* x_nchw, int x_dtype, float x_div,
+                                       const void* w_stem, const float* bias, void* y, void* stream) {
+    return stem_fused_common(d, x_nchw, x_dtype, x_div, w_stem, bias, y, 0, 1.f, 0.f, 0.f, stream);
+}
+
+// First layer of the INT8 graph (ptq_cos.py:288-296 on the float image): the fake-quantised weights (int8 code x
+// power-of-two scale) are exact in fp16 and so are the image values k/256, so every product is exact and only the fp32
+// summation order differs from the reference's fp32 convolution; the output is requantised to int8 codes.
+extern "C" int b2y_stem_conv_fwd_fused_q(const b2y_conv_desc* d, const void* x_nchw, int x_dtype, float x_div,
+                                         const void* w_stem, const float* bias_q, void* y_i8, float out_scale, float lo,
+                                         float hi, void* stream) {
+    return stem_fused_common(d, x_nchw, x_dtype, x_div, w_stem, bias_q, y_i8, 1, out_scale, lo, hi, stream);
 }
