@@ -146,3 +146,35 @@ def test_uint8_and_fp16_images_match_the_reference_normalisation():
     assert torch.equal(io, ref_io)
     assert all(torch.equal(a, b) for a, b in zip(p, ref_p))
     assert torch.equal(io16, ref_io)          # k/256 is exact in fp16
+
+
+def test_map_on_held_batch_matches_reference():
+    """BASELINE north_star: mAP on a held synthetic batch vs the reference.  The held labels are the reference's own
+    detections on the batch (map_case.npz, produced by running the reference); the engine's predictions go through the
+    same NMS / matching / AP pipeline (oracle/metrics_oracle.py, pinned to the reference's).  With random weights the
+    ~2800 candidates sit densely around the confidence threshold, so ONE detection flipping in or out moves the mean AP
+    by ~1.5e-4: the fp32-vs-fp16-policy oracle pair shows exactly that.  Gate: within 1e-4 of the reference, or within
+    3x the deviation the precision policy itself causes (measured with the oracle in this test)."""
+    from oracle import metrics_oracle as mo
+    import models as _models
+    from helpers import cfg_path
+    g = golden("map_case")
+    S, B = int(g["size"]), g["inf_out"].shape[0]
+    conf, iou = float(g["conf_thres"]), float(g["iou_thres"])
+    model = build_model("yolov3-tiny", device="cuda").eval()
+    x = orc.synth_images(B, S, S, seed=int(g["seed"]))
+    with torch.no_grad():
+        io, _, _ = model(x.cuda())
+    torch.cuda.synchronize()
+    labels = [torch.from_numpy(g["labels%d" % i]) for i in range(B)]
+    m50, m, n = mo.mean_ap(io, labels, conf, iou, S, S)
+    sd = orc.synth_state_dict(_models.Darknet(cfg_path("yolov3-tiny")).state_dict(), 0)
+    with torch.no_grad():
+        io_pol, _ = orc.darknet_forward(module_defs("yolov3-tiny"), sd, x, "yolov3-tiny", emulate_fp16=True)
+    y50, y, yn = mo.mean_ap(io_pol, labels, conf, iou, S, S)
+    r50, r = float(g["map50"]), float(g["map"])
+    print("\n[mAP held batch] reference %.6f / %.6f (%d labels) | engine %.6f / %.6f (%d det) | fp16-policy oracle "
+          "%.6f / %.6f (%d det)" % (r50, r, sum(l.shape[0] for l in labels), m50, m, n, y50, y, yn))
+    assert abs(m50 - r50) <= max(1e-4, 3 * abs(y50 - r50))
+    assert abs(m - r) <= max(1e-4, 3 * abs(y - r))
+    assert abs(n - sum(l.shape[0] for l in labels)) <= 5

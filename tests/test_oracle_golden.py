@@ -100,3 +100,26 @@ def test_bn_fold_and_mish_backward_match_reference():
     dx = orc.mish_backward(x, torch.from_numpy(g["mish_g"]))
     np.testing.assert_allclose(dx.numpy(), g["mish_dx_formula"], rtol=1e-6, atol=1e-7)
     np.testing.assert_allclose(dx.numpy(), g["mish_dx_autograd"], rtol=1e-4, atol=1e-5)
+
+
+def test_metrics_oracle_matches_reference():
+    """oracle/metrics_oracle.py (NMS, clip, TP matching, AP) against every intermediate the reference produced for the
+    held batch (oracle/gen_golden_map.py -> map_case.npz): detections bit for bit, TP matrices, AP table, mAP."""
+    from oracle import metrics_oracle as mo
+    g = golden("map_case")
+    pred = torch.from_numpy(g["inf_out"])
+    S = int(g["size"])
+    dets = mo.nms(pred, float(g["conf_thres"]), float(g["iou_thres"]))
+    labels = []
+    for i, d in enumerate(dets):
+        mo.clip_boxes(d, S, S)
+        ref = torch.from_numpy(g["det%d" % i])
+        assert d.shape == ref.shape
+        assert torch.equal(d[:, 5], ref[:, 5])
+        assert torch.allclose(d, ref, rtol=0, atol=1e-4)
+        lab = torch.from_numpy(g["labels%d" % i])
+        labels.append(lab)
+        assert np.array_equal(mo.match_image(d, lab).numpy(), g["correct%d" % i])
+    m50, m, n = mo.mean_ap(pred, labels, float(g["conf_thres"]), float(g["iou_thres"]), S, S)
+    assert n == sum(g["det%d" % i].shape[0] for i in range(len(dets)))
+    assert abs(m50 - float(g["map50"])) < 1e-9 and abs(m - float(g["map"])) < 1e-9
