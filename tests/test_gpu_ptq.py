@@ -53,7 +53,11 @@ def test_ptq_int8_eval_matches_reference():
     x = orc.synth_images(2, 64, 64, seed=0).cuda()
     with torch.no_grad():
         io, p, _ = qm(x)
+        io2, p2, _ = qm(x)          # captures the CUDA graph
+        io3, p3, _ = qm(x)          # replays it
     torch.cuda.synchronize()
+    assert torch.equal(io, io2) and torch.equal(io, io3)
+    assert all(torch.equal(a, b) for a, b in zip(p, p3))
     # head outputs live on the head's power-of-two grid: compare in units of that grid (LSB)
     worst_frac, worst_lsb = 0.0, 0.0
     for k, pi in enumerate(p):

@@ -33,6 +33,9 @@ class QPlan:
         self.B, self.Cin, self.H, self.W = x_shape
         self.steps = []
         self.prepared = False
+        self.runs = 0
+        self.graph = None
+        self._scal = {}
         self._build()
 
     def _build(self):
@@ -142,9 +145,44 @@ class QPlan:
         self.prepared = True
 
     def forward(self, x):
+        """Eval forward of the INT8 graph; after one eager call the static launch sequence replays from a CUDA graph
+        (the quantiser state is frozen in eval; call plan.invalidate() after re-calibrating)."""
+        import os
         if not self.prepared:
             self.prepare()
         x = x.contiguous().float()
+        use_graph = getattr(self.model, 'use_cuda_graph', os.environ.get('B2Y_NO_GRAPH', '0') != '1')
+        if not use_graph or self.runs < 1:
+            self.runs += 1
+            return self._forward_eager(x)
+        if self.graph is None:
+            self.static_x = x.clone()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.static_out = self._forward_eager(self.static_x)
+            self.graph = g
+        self.static_x.copy_(x)
+        self.graph.replay()
+        io, p, feats = self.static_out
+        if getattr(self.model, 'static_outputs', False):
+            return io, p, feats
+        return io.clone(), tuple(t.clone() for t in p), feats
+
+    def _sv(self, t):
+        """python float of a scale buffer, read once (a host sync is illegal while the forward is being captured)"""
+        v = self._scal.get(id(t))
+        if v is None:
+            v = self._scal[id(t)] = _s(t)
+        return v
+
+    def invalidate(self):
+        self.graph = None
+        self._scal = {}
+        self.prepared = False
+        self.runs = 0
+
+    def _forward_eager(self, x):
         B = self.B
         sc = self.scale_of
         for st in self.steps:
@@ -157,11 +195,12 @@ class QPlan:
                     lo, hi = -(1 << (bits - 1)), (1 << (bits - 1)) - 1
                     d = ops.make_conv_desc((B, self.H, self.W, self.Cin), self.Cin, conv.out_channels, k, s, p,
                                            ops._pitch(out.view()), act, slope, OUT_I8)
-                    if self.Cin * k * k <= 32 and conv.out_channels <= 64 and wq.abs().max() < 6.0e4:
-                        # fused tensor-core stem: the fake-quantised weights are exact in fp16 (int8 code x 2^-n)
-                        ws = self.stem_w.get(i)
-                        if ws is None:
-                            ws = self.stem_w[i] = ops.pack_stem_weights(wq)
+                    ws = self.stem_w.get(i)
+                    if ws is None:
+                        # fused tensor-core stem when the fake-quantised weights (int8 code x 2^-n) are exact in fp16
+                        fits = self.Cin * k * k <= 32 and conv.out_channels <= 64 and float(wq.abs().max()) < 6.0e4
+                        ws = self.stem_w[i] = ops.pack_stem_weights(wq) if fits else False
+                    if ws is not False:
                         call("b2y_stem_conv_fwd_fused_q", C.byref(d), ptr(x), 0, 1.0, ptr(ws), ptr(bq), ptr(out.buf), s_a,
                              float(lo), float(hi), stream_ptr())
                     else:
@@ -180,7 +219,7 @@ class QPlan:
                 lo, hi = -(1 << (m.bits - 1)), (1 << (m.bits - 1)) - 1
                 xv, av, ov = xt.view(), at.view(), out.view()
                 call("b2y_qshortcut_i8", ptr(xv), ops._pitch(xv), ptr(av), ops._pitch(av), ptr(ov), ops._pitch(ov),
-                     B * out.H * out.W, out.C, sc[id(xt)], _s(m.scale_x), sc[id(at)], _s(m.scale_a), _s(m.scale_sum),
+                     B * out.H * out.W, out.C, sc[id(xt)], self._sv(m.scale_x), sc[id(at)], self._sv(m.scale_a), self._sv(m.scale_sum),
                      float(lo), float(hi), stream_ptr())
             elif kind == 'concat':
                 _, i, srcs, out, m = st
@@ -190,7 +229,7 @@ class QPlan:
                     tv = t.view()
                     ov = out.buf[..., off:off + t.C]
                     call("b2y_requant_i8", ptr(tv), ops._pitch(tv), ptr(ov), ops._pitch(ov), B * t.H * t.W, t.C,
-                         sc[id(t)], _s(m.scale), float(lo), float(hi), stream_ptr())
+                         sc[id(t)], self._sv(m.scale), float(lo), float(hi), stream_ptr())
                     off += t.C
             elif kind == 'upsample':
                 _, i, src, out, s = st
