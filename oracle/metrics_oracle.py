@@ -103,7 +103,8 @@ def average_precision(recall, precision):
     mpre = np.concatenate(([0.0], precision, [0.0]))
     mpre = np.flip(np.maximum.accumulate(np.flip(mpre)))
     grid = np.linspace(0, 1, 101)
-    return np.trapz(np.interp(grid, mrec, mpre), grid)
+    trapezoid = getattr(np, "trapezoid", None) or np.trapz          # numpy >= 2 renamed trapz
+    return trapezoid(np.interp(grid, mrec, mpre), grid)
 
 
 def ap_per_class(tp, conf, pred_cls, target_cls, pr_score=0.1):
