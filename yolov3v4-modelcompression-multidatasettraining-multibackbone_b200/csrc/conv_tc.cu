@@ -2,6 +2,7 @@
 // C-ABI entry points (include/b200yolo.h).
 #include "conv_tc.cuh"
 
+#include <cmath>
 #include <cstdlib>
 #include <mutex>
 
@@ -291,6 +292,19 @@ int gemm_conv_launch(const GemmConvSpec& g, const EpilogueArgs& e, cudaStream_t 
                      e.stat_sum == nullptr && act_ok && al16(e.out) && e.out_pitch % (out16 ? 8 : 4) == 0 &&
                      (e.bias == nullptr || al16(e.bias)) && (e.res == nullptr || (al16(e.res) && e.res_pitch % 8 == 0)) &&
                      (full || (tma_ok && e.res == nullptr));
+        // int8 graph (B2Y_I8_FAST=0 disables): int8 codes out, no residual, whole N tiles, and a power-of-two accumulator
+        // scale so that fma(acc, s, bias) equals the general path's (acc * s) + bias bit for bit
+        static int i8_fast = -1;
+        if (i8_fast < 0) {
+            const char* ev = getenv("B2Y_I8_FAST");
+            i8_fast = (ev && atoi(ev) == 0) ? 0 : 1;
+        }
+        int ex = 0;
+        const bool pow2 = e.acc_scale > 0.f && frexpf(e.acc_scale, &ex) == 0.5f && e.acc_scale_ptr == nullptr;
+        if (i8_fast && g.kind == CONV_KIND_I8 && e.out_dtype == OUT_I8 && !e.out_fakequant && e.stat_sum == nullptr &&
+            (e.act == B2Y_ACT_LINEAR || (e.act == B2Y_ACT_LEAKY && e.slope >= 0.f && e.slope <= 1.f)) && pow2 && full &&
+            e.res == nullptr && al16(e.out) && e.out_pitch % 16 == 0 && (e.bias == nullptr || al16(e.bias)))
+            p.epi_fast = 1;
     }
 
     CUtensorMap tmA, tmB;
@@ -340,7 +354,7 @@ int gemm_conv_launch(const GemmConvSpec& g, const EpilogueArgs& e, cudaStream_t 
     // output map for the TMA-store epilogue (16-bit outputs on the short path with identity row mapping)
     CUtensorMap tmC = tmB;
     p.epi_tma = 0;
-    if (tma_on && p.epi_fast && p.out_identity) {
+    if (tma_on && p.epi_fast && p.out_identity && e.out_dtype != OUT_I8) {
         const bool o32 = e.out_dtype == OUT_F32;
         rc = make_map_2d(&tmC, e.out, o32 ? 4 : 2, M, g.Nout, e.out_pitch, 32, 32, o32 ? 128 : 64, e.out_dtype == OUT_BF16);
         if (rc != B2Y_OK) return rc;

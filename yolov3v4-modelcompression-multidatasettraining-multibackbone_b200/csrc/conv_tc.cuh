@@ -618,6 +618,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             }
                         }
                     }
+                    if (p.out_dtype == OUT_I8) {
+                        // int8 graph: requantise exactly like the general path (round half away, clamp) and store the
+                        // 32 codes of this lane's row; values are identical because acc_mul is a power of two there
+                        if (row_ok) {
+                            uint32_t w[8];
+#pragma unroll
+                            for (int t = 0; t < 8; ++t) {
+                                uint32_t word = 0;
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    float q = round_half_away(v[t * 4 + e] * p.out_inv_scale);
+                                    q = fminf(fmaxf(q, p.q_lo), p.q_hi);
+                                    word |= ((uint32_t)(uint8_t)(int8_t)(int)q) << (8 * e);
+                                }
+                                w[t] = word;
+                            }
+                            uint4* op8 = reinterpret_cast<uint4*>(reinterpret_cast<int8_t*>(p.out) + row * p.out_pitch + n0 +
+                                                                  c_begin + c);
+                            op8[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                            op8[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                        }
+                        continue;
+                    }
                     if (p.out_dtype == OUT_F32) {
                         // fp32 rows (YOLO head): 32 rows x 128 B, SWIZZLE_128B image, one TMA store; the map clips column 255
                         uint8_t* buf = my_stage;
