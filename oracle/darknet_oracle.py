@@ -148,11 +148,14 @@ def darknet_forward(module_defs, state, x, cfg_name, training=False, emulate_fp1
     for i, d in enumerate(module_defs):
         t = d['type']
         pre = 'module_list.%d.' % i
-        if t == 'convolutional':
+        if t in ('convolutional', 'depthwise'):
+            # depthwise (models.py:115-197): the same block with Conv2d(groups=Cin) registered as 'DepthWise2d'
+            cname = 'Conv2d.' if t == 'convolutional' else 'DepthWise2d.'
+            groups = x.shape[1] if t == 'depthwise' else 1
             k = int(d['size'])
-            pad = (k - 1) // 2 if int(d['pad']) else 0                               # models.py:33
-            w = state[pre + 'Conv2d.weight']
-            b = state.get(pre + 'Conv2d.bias')
+            pad = (k - 1) // 2 if int(d['pad']) else 0                               # models.py:33, 119
+            w = state[pre + cname + 'weight']
+            b = state.get(pre + cname + 'bias')
             slope = 0.25 if maxabsscaler else 0.1
             head = (i + 1 < len(module_defs) and module_defs[i + 1]['type'] == 'yolo')
             if int(d['batch_normalize']) and not training:
@@ -160,10 +163,10 @@ def darknet_forward(module_defs, state, x, cfg_name, training=False, emulate_fp1
                                  state[pre + 'BatchNorm2d.running_mean'], state[pre + 'BatchNorm2d.running_var'], 1e-5)
                 if emulate_fp16 and i > 0:
                     wf = wf.half().float()
-                y = F.conv2d(x, wf, bf, stride=int(d['stride']), padding=pad)
+                y = F.conv2d(x, wf, bf, stride=int(d['stride']), padding=pad, groups=groups)
             elif int(d['batch_normalize']):
                 wq = w.half().float() if (emulate_fp16 and i > 0) else w
-                y = F.conv2d(x, wq, None, stride=int(d['stride']), padding=pad)
+                y = F.conv2d(x, wq, None, stride=int(d['stride']), padding=pad, groups=groups)
                 g_, b_ = state[pre + 'BatchNorm2d.weight'], state[pre + 'BatchNorm2d.bias']
                 rm = state[pre + 'BatchNorm2d.running_mean'].clone()
                 rv = state[pre + 'BatchNorm2d.running_var'].clone()
@@ -184,9 +187,15 @@ def darknet_forward(module_defs, state, x, cfg_name, training=False, emulate_fp1
                 new_stats[pre + 'BatchNorm2d.running_var'] = rv
             else:
                 wq = w.half().float() if (emulate_fp16 and i > 0) else w
-                y = F.conv2d(x, wq, b, stride=int(d['stride']), padding=pad)
+                y = F.conv2d(x, wq, b, stride=int(d['stride']), padding=pad, groups=groups)
             y = activation(y, d['activation'], slope)
             x = y if head else rnd(y)
+        elif t == 'se':
+            # squeeze-excite (utils/layers.py:176-192): x * hsigmoid(W2 relu(W1 avgpool(x))), both Linear without bias
+            w1, w2 = state[pre + 'se.fc.0.weight'], state[pre + 'se.fc.2.weight']
+            sq = x.mean(dim=(2, 3))
+            ex = F.relu6(F.linear(F.relu(F.linear(sq, w1)), w2) + 3.0) / 6.0
+            x = rnd(x * ex.view(x.shape[0], x.shape[1], 1, 1))
         elif t == 'maxpool':
             k, s = d['size'], d['stride']
             if k == 2 and s == 1:                                                   # models.py:211-213

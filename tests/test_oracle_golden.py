@@ -123,3 +123,52 @@ def test_metrics_oracle_matches_reference():
     m50, m, n = mo.mean_ap(pred, labels, float(g["conf_thres"]), float(g["iou_thres"]), S, S)
     assert n == sum(g["det%d" % i].shape[0] for i in range(len(dets)))
     assert abs(m50 - float(g["map50"])) < 1e-9 and abs(m - float(g["map"])) < 1e-9
+
+
+def _mobilenet_case(kind):
+    import json
+    g = golden("yolov3-mobilenet_128_%s" % kind)
+    defs = json.loads(str(g["defs_json"]))
+    for d in defs:
+        if "anchors" in d:
+            d["anchors"] = np.asarray(d["anchors"])
+    shapes = json.loads(str(g["shapes_json"]))
+    state = orc.synth_state_dict({k: torch.zeros(v, dtype=torch.long if k.endswith("num_batches_tracked") else
+                                                 torch.float32) for k, v in shapes.items()}, 0)
+    return g, defs, state
+
+
+def test_mobilenet_depthwise_se_forward_matches_reference():
+    """SURVEY 8a rows a5 (depthwise blocks) and a8 (squeeze-excite): the oracle's branches against the reference's
+    eval forward of yolov3-mobilenet (15 depthwise layers k3/k5 s1/s2, 8 SE blocks, relu6 / h_swish)."""
+    g, defs, state = _mobilenet_case("eval")
+    x = orc.synth_images(2, 128, 128, seed=0)
+    with torch.no_grad():
+        io, p = orc.darknet_forward(defs, state, x, "yolov3-mobilenet")
+    assert io.shape == g["io"].shape
+    assert torch.allclose(io, torch.from_numpy(g["io"]), rtol=1e-4, atol=1e-4)
+    for i, pi in enumerate(p):
+        assert torch.allclose(pi, torch.from_numpy(g["p%d" % i]), rtol=1e-4, atol=2e-4)
+
+
+def test_mobilenet_training_step_matches_reference():
+    g, defs, state = _mobilenet_case("train")
+    for k, v in state.items():
+        if v.dtype.is_floating_point and not k.endswith(("running_mean", "running_var")):
+            v.requires_grad_(True)
+    x = orc.synth_images(4, 128, 128, seed=0)
+    t = orc.synth_targets(4, 6, 80, seed=1)
+    pred, _ = orc.darknet_forward(defs, state, x, "yolov3-mobilenet", training=True)
+    for i, pi in enumerate(pred):
+        assert torch.allclose(pi, torch.from_numpy(g["p%d" % i]), rtol=1e-3, atol=1e-3)
+    anchors = []
+    strides = orc.yolo_strides("yolov3-mobilenet", 3)
+    for d in defs:
+        if d["type"] == "yolo":
+            anchors.append(torch.from_numpy(np.asarray(d["anchors"])[d["mask"]]).float() / strides[len(anchors)])
+    loss, items = orc.compute_loss(pred, t, anchors, dict(orc.DEFAULT_HYP), 80, 1.0)
+    assert np.allclose(items.detach().numpy(), g["items"], rtol=1e-3)
+    loss.backward()
+    ref = dict(zip([str(n) for n in g["grad_names"]], g["grad_norms"]))
+    worst = max(abs(float(state[k].grad.norm()) - v) / (v + 1e-8) for k, v in ref.items())
+    assert worst < 2e-2, worst
