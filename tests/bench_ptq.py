@@ -3,16 +3,18 @@
 with power-of-two scales, tcgen05 kind::i8 convolutions).  The quantiser state is the one calibrated by the reference's
 own PTQ flow (tests/golden/yolov3_64_ptq.npz); timing does not depend on the values.
 
-    python tools/bench_ptq.py [--batch 32] [--size 640] [--steps 10]
+    python tests/bench_ptq.py [--batch 32] [--size 640] [--steps 10]
 
-Prints one JSON line.  Secondary benchmark: bench.py (the driver contract) measures configs[1]."""
+Prints one JSON line.  Secondary benchmark: bench.py (the driver contract) measures configs[1].  Lives under tests/
+because it builds the quantised model with the test helpers (synthetic weights from oracle/, fixture scales); the
+timed region is the engine's INT8 graph only."""
 import argparse
 import json
 import os
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 import torch  # noqa: E402
 
