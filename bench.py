@@ -1,22 +1,27 @@
 #!/usr/bin/env python
-"""bench.py -- images/sec of the Darknet hot path on B200 (BASELINE.json metric).
+"""bench.py -- images/sec of the Darknet hot path on B200 (BASELINE.json metric: "images/sec (640x640) YOLOv4
+train+infer at 1/2/4/8 B200; conv roofline %").
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
 
-N=1 workload = BASELINE.json configs[1]: yolov3.cfg (Darknet-53) inference, batch 32, 640x640, fp16 fused conv
-path, synthetic images, random-init weights.  A "step" is one forward (stem conv -> 74 tcgen05 convs -> YOLO
-decode) of one batch.  N>1: independent replicas, one batch per GPU per step, no collective on the data path
-("scaling": "weak").
+PRIMARY workload (the headline `value`) = BASELINE.json configs[2], the per-GPU slice of "yolov4.cfg training bs=64 on
+8xB200": yolov4.cfg, 8 images per GPU, 640x640, one process per GPU.  A "step" is one complete training step:
 
-One JSON line on stdout (rank 0):
-  value  : images/s with the fp32 batch already resident in HBM (CUDA events, max over ranks)
-  e2e    : images/s through models.Darknet.__call__ with pinned HOST uint8 images: H2D copy, /256, forward,
-           D2H of the top-objectness detection row per image -- all inside the timed region
-  roofline: aggregate over the tcgen05 conv launches of one step (the dominant kernel family), timed live
-  cpu_baseline: the oracle (CPU restatement of the reference's PyTorch path) on this box's host cores, bounded sample
---impl reference: the reference arm = that same CPU path with all host threads (the reference itself is Python and
-cannot travel to the GPU box; oracle/ is pinned against it by tests/test_oracle_golden.py).
+    forward (batch-statistics BatchNorm, tcgen05 convs) -> YOLO loss -> backward (dgrad / wgrad tcgen05, BN backward)
+    -> ONE NCCL all-reduce over the flat fp32 gradient buffer (N > 1) -> fused SGD-Nesterov
+
+Per-GPU work is fixed as N grows ("scaling": "weak"; global batch = 8 N).  One JSON line on stdout (rank 0):
+  value    : images/s, batch and targets resident in HBM (CUDA events around K steps, max over ranks)
+  e2e      : the same step through the public API with pinned HOST uint8 images + targets: H2D copy, /256, step,
+             D2H of the four loss items -- all inside the timed region
+  roofline : the tcgen05 convolution family (forward, data gradient, weight gradient) of one step, replayed back to
+             back and timed live with CUDA events; FLOPs = 2 M N K of every launch
+  cpu_baseline : the oracle (CPU restatement of the reference's PyTorch path) training step on the host cores (N=1)
+  secondary: (N=1) YOLOv3 inference bs 32 (configs[1]), YOLOv4 inference bs 32, with their own conv rooflines
+--impl reference: the reference arm = the reference's own CPU PyTorch training step, restated in oracle/ and pinned to
+the reference by tests/test_oracle_golden.py (the reference is pure Python and /root/reference does not exist on the
+GPU box), all host threads, bounded sample.
 """
 import argparse
 import json
@@ -25,6 +30,7 @@ import subprocess
 import sys
 import threading
 import time
+import traceback
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.join(ROOT, "yolov3v4-modelcompression-multidatasettraining-multibackbone_b200")
@@ -32,11 +38,14 @@ sys.path.insert(0, PKG)
 
 import torch  # noqa: E402
 
-MODEL = "yolov3"
-BATCH = 32
 SIZE = 640
-# conv MACs / image, yolov3 @640 (recomputed from the plan at run time as a cross-check)
-FLOPS_PER_IMAGE = 155.89e9
+TRAIN_MODEL, TRAIN_BATCH = "yolov4", 8          # BASELINE configs[2]: bs 64 over 8 GPUs
+INFER_BATCH = 32                                 # BASELINE configs[1]
+# algorithmic conv FLOPs / image (hooks on the reference's own modules)
+FLOPS_FWD = {"yolov3": 155.89e9, "yolov4": 142.26e9}
+FLOPS_TRAIN = {"yolov3": 467.7e9, "yolov4": 426.8e9}
+HYP = {'giou': 3.54, 'cls': 37.4, 'cls_pw': 1.0, 'obj': 64.3, 'obj_pw': 1.0, 'iou_t': 0.20, 'fl_gamma': 0.0}
+CONV_CALLS = ("b2y_conv2d_fwd", "b2y_conv2d_fwd_stats", "b2y_conv2d_bwd_data", "b2y_conv2d_bwd_weight")
 
 
 def peaks():
@@ -96,32 +105,46 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def build_model(device):
-    import models
+def cfg_for(name, rank=0):
+    """Generated cfg in a per-process directory (several ranks never write the same file; write_cfg renames atomically)."""
     from b200yolo import cfggen
-    cfg_dir = os.path.join(ROOT, "gpurun_out", "cfg") if os.access(ROOT, os.W_OK) else "/tmp/b2y_cfg"
-    path = cfggen.write_cfg(MODEL, cfg_dir)
+    d = os.path.join("/tmp", "b2y_cfg_%d_r%d" % (os.getpid(), rank))
+    return cfggen.write_cfg(name, d)
+
+
+def build_model(name, device, rank=0, train=False):
+    import models
     torch.manual_seed(0)
-    m = models.Darknet(path, img_size=(SIZE, SIZE))
+    m = models.Darknet(cfg_for(name, rank), img_size=(SIZE, SIZE))
     g = torch.Generator().manual_seed(1)
     with torch.no_grad():  # non-degenerate BN statistics for eval (SURVEY.md section 8d)
         for mod in m.modules():
             if isinstance(mod, torch.nn.BatchNorm2d):
                 mod.running_var.copy_(torch.rand(mod.running_var.shape, generator=g) * 0.4 + 0.8)
                 mod.running_mean.copy_(torch.randn(mod.running_mean.shape, generator=g) * 0.1)
-    m = m.to(device).eval()
-    m.static_outputs = True   # return the engine's output buffers (no per-step clone)
+    m = m.to(device)
+    if train:
+        m.train()
+        m.nc, m.gr, m.hyp = 80, 1.0, dict(HYP)
+    else:
+        m.eval()
+        m.static_outputs = True   # return the engine's output buffers (no per-step clone)
     return m
 
 
-def cpu_reference_rate(max_seconds=20.0, threads=None, batch=2, max_iters=10):
-    """The reference's CPU PyTorch path, restated in oracle/ (pinned to the reference by tests/golden):
-    yolov3 eval forward at 640x640 on the host cores, bounded sample."""
-    sys.path.insert(0, ROOT)
-    from oracle import darknet_oracle as orc
-    import models
-    from b200yolo import cfggen
-    from utils.parse_config import parse_model_cfg_text
+def synth_batch(batch, seed):
+    """uint8 images + [nT, 6] targets of SURVEY.md section 8d (8 boxes per image)."""
+    g = torch.Generator().manual_seed(seed)
+    u8 = torch.randint(0, 256, (batch, 3, SIZE, SIZE), dtype=torch.uint8, generator=g)
+    nt = 8 * batch
+    t = torch.cat([torch.arange(batch).repeat_interleave(8).float()[:, None],
+                   torch.randint(0, 80, (nt, 1), generator=g).float(),
+                   torch.rand(nt, 2, generator=g) * 0.9 + 0.05,
+                   torch.exp(torch.rand(nt, 2, generator=g) * 3.4 - 3.9)], 1)
+    return u8, t
+
+
+def host_threads():
     try:
         avail = len(os.sched_getaffinity(0))      # cores this process may be scheduled on
     except AttributeError:
@@ -132,9 +155,24 @@ def cpu_reference_rate(max_seconds=20.0, threads=None, batch=2, max_iters=10):
             avail = max(1, min(avail, int(float(q) / float(per) + 0.5)))
     except (OSError, ValueError):
         pass
-    defs = parse_model_cfg_text(cfggen.cfg_text(MODEL))[1:]
-    path = cfggen.write_cfg(MODEL, "/tmp/b2y_cfg_cpu")
-    sd = orc.synth_state_dict(models.Darknet(path).state_dict(), 0)
+    return avail
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's PyTorch path restated in oracle/ (test infrastructure; only timed here, never shipped)
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_reference_rate(kind, name, max_seconds=20.0, batch=2, max_iters=10, threads=None):
+    """kind = 'train' (forward + compute_loss + backward) or 'infer' (eval forward) of `name` at 640x640 on the host
+    cores; bounded sample.  Returns the cpu_baseline dict (+ ms_per_step)."""
+    sys.path.insert(0, ROOT)
+    import numpy as np
+    from oracle import darknet_oracle as orc
+    import models
+    from b200yolo import cfggen
+    from utils.parse_config import parse_model_cfg_text
+    avail = host_threads()
+    defs = parse_model_cfg_text(cfggen.cfg_text(name))[1:]
+    sd = orc.synth_state_dict(models.Darknet(cfg_for(name, 99)).state_dict(), 0)
     if threads is None:
         # "all the host threads it can use": more threads than physically free cores make torch's CPU convs slower,
         # so take the fastest of a few thread counts on a small probe forward
@@ -143,76 +181,325 @@ def cpu_reference_rate(max_seconds=20.0, threads=None, batch=2, max_iters=10):
         for t in sorted({avail, min(avail, 64), min(avail, 32), min(avail, 16), min(avail, 8)}, reverse=True):
             torch.set_num_threads(t)
             with torch.no_grad():
-                orc.darknet_forward(defs, sd, probe, MODEL)
+                orc.darknet_forward(defs, sd, probe, name)
                 t0 = time.time()
-                orc.darknet_forward(defs, sd, probe, MODEL)
+                orc.darknet_forward(defs, sd, probe, name)
                 dt = time.time() - t0
             if best is None or dt < best[0]:
                 best = (dt, t)
         threads = best[1]
     torch.set_num_threads(threads)
-    bs = batch
-    x = orc.synth_images(bs, SIZE, SIZE, seed=0)
-    with torch.no_grad():
-        t0 = time.time()
-        orc.darknet_forward(defs, sd, x, MODEL)          # warm-up (also sizes the sample)
-        warm = time.time() - t0
-        iters = max(1, min(max_iters, int(max_seconds / max(warm, 1e-3))))
-        t0 = time.time()
-        for _ in range(iters):
-            orc.darknet_forward(defs, sd, x, MODEL)
-        dt = (time.time() - t0) / iters
-    return {"value": bs / dt, "unit": "images/s", "cores": threads, "kind": "port",
-            "sample": "%d x yolov3 eval forward, batch %d, 640x640, fp32 torch CPU (oracle/darknet_oracle.py)"
-                      % (iters, bs), "ms_per_step": dt * 1e3}, bs
+    x = orc.synth_images(batch, SIZE, SIZE, seed=0)
+    if kind == "train":
+        for k, v in sd.items():
+            if v.dtype.is_floating_point and not k.endswith(('running_mean', 'running_var')):
+                v.requires_grad_(True)
+        ys = [d for d in defs if d['type'] == 'yolo']
+        strides = orc.yolo_strides(name, len(ys))
+        av = [torch.as_tensor(np.asarray(d['anchors'])[d['mask']], dtype=torch.float32) / s
+              for d, s in zip(ys, strides)]
+        tg = orc.synth_targets(batch, 8, 80, seed=1)
+        hyp = dict(orc.DEFAULT_HYP)
+
+        def one():
+            for v in sd.values():
+                if v.requires_grad:
+                    v.grad = None
+            p, _ = orc.darknet_forward(defs, sd, x, name, training=True)
+            loss, _ = orc.compute_loss(p, tg, av, hyp, 80, 1.0)
+            loss.backward()
+        what = "%s training step (forward + compute_loss + backward)" % name
+    else:
+        def one():
+            with torch.no_grad():
+                orc.darknet_forward(defs, sd, x, name)
+        what = "%s eval forward" % name
+    t0 = time.time()
+    one()                                                     # warm-up (also sizes the sample)
+    warm = time.time() - t0
+    iters = max(1, min(max_iters, int(max_seconds / max(warm, 1e-3))))
+    t0 = time.time()
+    for _ in range(iters):
+        one()
+    dt = (time.time() - t0) / iters
+    return {"value": batch / dt, "unit": "images/s", "cores": threads, "kind": "port",
+            "sample": "%d x %s, batch %d, 640x640, fp32 torch CPU (oracle/darknet_oracle.py), after 1 warm-up"
+                      % (iters, what, batch), "ms_per_step": dt * 1e3}
 
 
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
-    # a "step" of the reference arm = one yolov3 640x640 eval forward of ONE image on all host cores; the number of
-    # timed steps is capped so that the whole run stays within ~2 minutes (stated in cpu_baseline.sample)
-    base, bs = cpu_reference_rate(max_seconds=100.0, batch=1, max_iters=max(1, args.steps))
-    line = {"impl": "reference", "metric": "images/sec (640x640) yolov3 inference", "value": base["value"],
+    # a "step" of the reference arm = one yolov4 640x640 training step of a 2-image batch on all host cores; the
+    # number of timed steps is capped so that the whole run stays within a few minutes (stated in cpu_baseline.sample)
+    base = cpu_reference_rate("train", TRAIN_MODEL, max_seconds=120.0, batch=2, max_iters=max(1, args.steps))
+    line = {"impl": "reference", "metric": "images/sec (640x640) yolov4 training", "value": base["value"],
             "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": base["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "yolov3.cfg Darknet-53 inference 640x640 (BASELINE configs[1]); CPU sample batch %d"
-                                   % bs},
+            "config": {"workload": "yolov4.cfg training step 640x640 (BASELINE configs[2] per-GPU slice: 8 images / "
+                                   "GPU); CPU sample batch 2", "global_batch": 2},
             "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": base["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
-def ncu_conv_traffic():
-    """DRAM bytes (read + write) of the tcgen05 conv launches of ONE forward, from the committed ncu launch list
-    (profiles/r01c/launches_r01c.csv: `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` of this same
-    workload, eager launches).  Returns (bytes, n_launches) or (None, 0)."""
-    import csv
-    path = os.path.join(ROOT, "profiles", "r01c", "launches_r01c.csv")
-    if not os.path.exists(path):
-        return None, 0
-    rows = list(csv.reader(l for l in open(path) if l.startswith('"')))
-    if not rows:
-        return None, 0
-    hdr = rows[0]
-    ik, im, iv, iu = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
-    ii = hdr.index("ID")
-    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-    launches = {}
-    for r in rows[1:]:
-        d = launches.setdefault(int(r[ii]), {"name": r[ik]})
-        if r[im].startswith("dram__bytes"):
-            d[r[im]] = float(r[iv].replace(",", "")) * scale.get(r[iu], 1.0)
-    ids = sorted(launches)
-    stems = [i for i in ids if "stem_fused" in launches[i]["name"]]
-    if len(stems) < 2:
-        return None, 0
-    a, b = stems[-2], stems[-1]                       # one complete forward between two stem launches
-    convs = [launches[i] for i in ids if a <= i < b and ("conv_tc_kernel" in launches[i]["name"])]
-    total = sum(c.get("dram__bytes_read.sum", 0.0) + c.get("dram__bytes_write.sum", 0.0) for c in convs)
-    return total, len(convs)
+# ----------------------------------------------------------------------------------------------------------------
+# measurement helpers
+# ----------------------------------------------------------------------------------------------------------------
+class Dist:
+    def __init__(self, world, dev):
+        self.world, self.dev = world, dev
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_ms(self, ms):
+        t = torch.tensor([ms], device=self.dev, dtype=torch.float64)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+
+def timed(fn, steps, dd):
+    """K calls of fn bracketed by barrier + synchronize on both sides, CUDA events, max over ranks -> ms per call."""
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dd.barrier()
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    dd.barrier()
+    return dd.max_ms(e0.elapsed_time(e1)) / steps
+
+
+def conv_desc_flops(name, args):
+    d = args[0]._obj                      # ctypes byref(ConvDesc)
+    return 2.0 * d.batch * d.out_h * d.out_w * d.out_c * d.in_c * d.ksize * d.ksize
+
+
+def record_calls(fn):
+    """Run fn once with the C-ABI launch recorder on; returns the list of (name, args)."""
+    from b200yolo import lib
+    lib.RECORD = []
+    try:
+        fn()
+        torch.cuda.synchronize()
+        return lib.RECORD
+    finally:
+        lib.RECORD = None
+
+
+def replay_convs(calls, iters):
+    """Replay the tcgen05 convolution launches of one recorded step back to back -> (ms per step-worth, FLOPs, n)."""
+    from b200yolo import lib
+    convs = [(n, a) for (n, a) in calls if n in CONV_CALLS]
+    flops = sum(conv_desc_flops(n, a) for n, a in convs)
+    raw = lib.raw()
+    fns = [(getattr(raw, n), a) for n, a in convs]
+    for f, a in fns:
+        f(*a)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        for f, a in fns:
+            f(*a)
+    e1.record()
+    e1.synchronize()
+    return e0.elapsed_time(e1) / iters, flops, len(convs)
+
+
+def roofline_block(conv_ms, conv_flops, n_convs, step_ms, what):
+    pk = peaks()
+    achieved = conv_flops / (conv_ms / 1e3) / 1e12
+    return {"bound": "tensor", "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
+            "frac": achieved / pk["tflops"], "traffic": None,
+            "peak_source": pk["source"] + " (sustained bf16, MEASURED_PEAKS.json)",
+            "kernel": "tcgen05 conv family (%s): %d launches of one step replayed back to back" % (what, n_convs),
+            "kernel_ms_per_step": conv_ms, "share_of_step": conv_ms / step_ms,
+            "algorithmic_flops_per_step": conv_flops,
+            "whole_step_frac": conv_flops / (step_ms / 1e3) / 1e12 / pk["tflops"]}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# primary workload: YOLOv4 training step, data parallel
+# ----------------------------------------------------------------------------------------------------------------
+def run_train(args, dev, rank, world, dd):
+    import torch.distributed as dist
+    from b200yolo.parallel import FlatDataParallel
+    from utils import utils as my_utils
+    B = args.train_batch
+    model = build_model(TRAIN_MODEL, dev, rank, train=True)
+    dp = FlatDataParallel(model)
+    u8, tg = synth_batch(B, 100 + rank)
+    host_u8, host_t = u8.pin_memory(), tg.pin_memory()
+    x_dev = (host_u8.to(dev).float() / 256.0).contiguous()
+    t_dev = host_t.to(dev)
+    lr, scale = 1e-4, B * world / 64.0                    # train.py:437  loss *= batch_size / 64 (global batch)
+    state = {"items": None}
+
+    def step(x, t):
+        dp.zero_grad()
+        pred, _ = dp(x)
+        loss, items = my_utils.compute_loss(pred, t, dp)
+        (loss * scale).backward()
+        dp.reduce_gradients()
+        dp.step(lr=lr, momentum=0.937, weight_decay=0.000484)
+        state["items"] = items
+
+    for _ in range(args.warmup):
+        step(x_dev, t_dev)
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(dev.index)
+    sampler.start()
+    ms_step = timed(lambda: step(x_dev, t_dev), args.steps, dd)
+    clocks = sampler.stop()
+    value = world * B / (ms_step / 1e3)
+    items = [float(v) for v in state["items"]]
+
+    # ---- end to end: pinned host uint8 batch + targets -> H2D -> /256 -> step -> D2H of the loss items ----------
+    copy_stream = torch.cuda.Stream()
+    dev_u8 = [torch.empty_like(host_u8, device=dev) for _ in range(2)]
+    dev_t = [torch.empty_like(host_t, device=dev) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    main = torch.cuda.current_stream()
+    items_host = torch.empty(4, dtype=torch.float32).pin_memory()
+
+    def issue_copy(j):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[j])
+            dev_u8[j].copy_(host_u8, non_blocking=True)
+            dev_t[j].copy_(host_t, non_blocking=True)
+            ready[j].record(copy_stream)
+
+    for j in range(2):
+        consumed[j].record(main)
+    issue_copy(0)
+    cnt = {"i": 0}
+
+    def e2e_step():
+        j = cnt["i"] & 1
+        main.wait_event(ready[j])
+        x = dev_u8[j].float() / 256.0                      # train.py:348
+        step(x, dev_t[j])
+        consumed[j].record(main)
+        issue_copy(j ^ 1)                                  # prefetch the next batch while this one computes
+        items_host.copy_(state["items"], non_blocking=True)
+        cnt["i"] += 1
+
+    for _ in range(3):
+        e2e_step()
+    ms_e2e = timed(e2e_step, args.steps, dd)
+    e2e_value = world * B / (ms_e2e / 1e3)
+
+    # ---- the exchange step alone (N > 1): one all-reduce of the flat fp32 gradient buffer -------------------------
+    allreduce = None
+    if world > 1:
+        ms_ar = timed(lambda: dp.reduce_gradients(), 5, dd)
+        nbytes = dp.flat_grad.numel() * 4
+        allreduce = {"ms": ms_ar, "bytes": nbytes, "algbw_gbs": nbytes / ms_ar / 1e6,
+                     "busbw_gbs": nbytes / ms_ar / 1e6 * 2 * (world - 1) / world}
+
+    # ---- roofline of the dominant kernel family: record one eager step, replay its conv launches ----------------
+    saved = getattr(model, "use_cuda_graph", None)
+    model.use_cuda_graph = False
+    try:
+        calls = record_calls(lambda: step(x_dev, t_dev))
+    finally:
+        if saved is None:
+            del model.use_cuda_graph
+        else:
+            model.use_cuda_graph = saved
+    conv_ms, conv_flops, n_convs = replay_convs(calls, iters=max(3, min(10, args.steps)))
+    roofline = roofline_block(conv_ms, conv_flops, n_convs, ms_step, "forward + data gradient + weight gradient")
+    roofline["table_flops_per_step"] = FLOPS_TRAIN[TRAIN_MODEL] * B
+    launches = len(calls)
+    return {"value": value, "ms_per_step": ms_step, "clocks": clocks, "roofline": roofline, "allreduce": allreduce,
+            "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": int(host_u8.numel() + host_t.numel() * 4), "d2h_bytes_per_step": 16,
+                    "result": "the four loss items (lbox, lobj, lcls, loss) of the step, what train.py logs"},
+            "gpu_launches": launches * args.steps, "launches_per_step": launches, "loss_items": items,
+            "grad_bytes": int(dp.flat_grad.numel() * 4), "batch": B}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# secondary workloads: inference replicas (configs[1] and YOLOv4)
+# ----------------------------------------------------------------------------------------------------------------
+def run_infer(name, args, dev, rank, world, dd, with_e2e=True):
+    B = INFER_BATCH
+    model = build_model(name, dev, rank, train=False)
+    u8, _ = synth_batch(B, 200 + rank)
+    host_u8 = u8.pin_memory()
+    x_dev = (host_u8.to(dev).float() / 256.0).contiguous()
+    out = {}
+    with torch.no_grad():
+        for _ in range(max(3, args.warmup)):
+            io, p, _ = model(x_dev)
+        torch.cuda.synchronize()
+        ms_step = timed(lambda: model(x_dev), args.steps, dd)
+        out["value"] = world * B / (ms_step / 1e3)
+        out["ms_per_step"] = ms_step
+        if with_e2e:
+            no = io.shape[-1]
+            top_host = torch.empty((B, no), dtype=torch.float32).pin_memory()
+            copy_stream = torch.cuda.Stream()
+            dev_u8 = [torch.empty_like(host_u8, device=dev) for _ in range(2)]
+            ready = [torch.cuda.Event() for _ in range(2)]
+            consumed = [torch.cuda.Event() for _ in range(2)]
+            main = torch.cuda.current_stream()
+
+            def issue_copy(j):
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(consumed[j])
+                    dev_u8[j].copy_(host_u8, non_blocking=True)
+                    ready[j].record(copy_stream)
+
+            for j in range(2):
+                consumed[j].record(main)
+            issue_copy(0)
+            cnt = {"i": 0}
+
+            def e2e_step():
+                j = cnt["i"] & 1
+                main.wait_event(ready[j])
+                # uint8 batch straight into the model: the stem kernel applies the reference's "/ 256.0"
+                o, _, _ = model(dev_u8[j])
+                consumed[j].record(main)
+                issue_copy(j ^ 1)
+                idx = o[..., 4].argmax(dim=1)                              # best-objectness row per image
+                top_host.copy_(o[torch.arange(B, device=dev), idx], non_blocking=True)
+                cnt["i"] += 1
+
+            for _ in range(3):
+                e2e_step()
+            ms2 = timed(e2e_step, args.steps, dd)
+            out["e2e"] = {"value": world * B / (ms2 / 1e3), "unit": "images/s",
+                          "h2d_bytes_per_step": int(host_u8.numel()), "d2h_bytes_per_step": int(top_host.numel() * 4),
+                          "result": "the top-objectness decoded row per image (a stand-in for post-NMS detections)"}
+        saved = getattr(model, "use_cuda_graph", None)
+        model.use_cuda_graph = False
+        try:
+            calls = record_calls(lambda: model(x_dev))
+        finally:
+            if saved is None:
+                del model.use_cuda_graph
+            else:
+                model.use_cuda_graph = saved
+        conv_ms, conv_flops, n_convs = replay_convs(calls, iters=max(3, min(10, args.steps)))
+        out["roofline"] = roofline_block(conv_ms, conv_flops, n_convs, ms_step, "forward")
+        out["launches_per_step"] = len(calls)
+        out["workload"] = "%s.cfg inference bs=%d 640x640 per GPU, fp16 fused conv path" % (name, B)
+    del model
+    torch.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -221,9 +508,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=BATCH)
-    ap.add_argument("--profile-layers", default="", help="write a per-launch timing table (JSON) to this path")
+    ap.add_argument("--train-batch", type=int, default=TRAIN_BATCH, help="images per GPU of the training workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -234,6 +521,11 @@ def main():
     if args.impl == "reference":
         run_reference_arm(args, rank, world)
         return
+    if args.gpus > 1 and world == 1 and "RANK" not in os.environ:
+        # plain `python bench.py --gpus N`: start one process per GPU ourselves
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 2000)] + sys.argv
+        raise SystemExit(subprocess.call(cmd))
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (B200): the hot path has no CPU fallback")
@@ -242,141 +534,73 @@ def main():
     import torch.distributed as dist
     if world > 1:
         dist.init_process_group("nccl", init_method="env://", device_id=dev)
+    dd = Dist(world, dev)
 
-    model = build_model(dev)
-    B = args.batch
-    gen = torch.Generator().manual_seed(100 + rank)
-    host_u8 = torch.randint(0, 256, (B, 3, SIZE, SIZE), dtype=torch.uint8, generator=gen).pin_memory()
-    x_dev = (host_u8.to(dev).float() / 256.0).contiguous()
+    tr = run_train(args, dev, rank, world, dd)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    with torch.no_grad():
-        for _ in range(args.warmup):
-            io, p, _ = model(x_dev)
-        torch.cuda.synchronize()
-        plan = model.engine().plan_for(x_dev)
-        launches = plan.launches_per_forward()
-
-        # ---------------- device-resident throughput ("value") ----------------
-        sampler = ClockSampler(local)
-        barrier()
-        sampler.start()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(args.steps):
-            io, p, _ = model(x_dev)
-        e1.record()
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        clocks = sampler.stop()
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        ms_step = float(ms.item()) / args.steps
-        value = world * B / (ms_step / 1e3)
-
-        # ---------------- end to end through the public API with host buffers ----------------
-        no = io.shape[-1]
-        top_host = torch.empty((B, no), dtype=torch.float32).pin_memory()
-
-        # double-buffered input: the H2D copy of batch i+1 runs on a copy stream while batch i computes; every
-        # timed step issues exactly one H2D copy (pinned uint8 host -> device) and one D2H read of its result
-        copy_stream = torch.cuda.Stream()
-        dev_u8 = [torch.empty_like(host_u8, device=dev) for _ in range(2)]
-        ready = [torch.cuda.Event() for _ in range(2)]      # H2D into buffer j finished
-        consumed = [torch.cuda.Event() for _ in range(2)]   # buffer j has been converted (may be overwritten)
-        main = torch.cuda.current_stream()
-
-        def issue_copy(j):
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(consumed[j])
-                dev_u8[j].copy_(host_u8, non_blocking=True)
-                ready[j].record(copy_stream)
-
-        for j in range(2):
-            consumed[j].record(main)
-        issue_copy(0)
-        state = {"i": 0}
-
-        def e2e_step():
-            j = state["i"] & 1
-            main.wait_event(ready[j])
-            # uint8 batch straight into the model: the stem kernel applies the reference's "/ 256.0"
-            # (train.py:348 / test.py:95) while it builds its im2col tile, no fp32 image is materialised
-            out, _, _ = model(dev_u8[j])
-            consumed[j].record(main)
-            issue_copy(j ^ 1)                                             # prefetch the next batch
-            idx = out[..., 4].argmax(dim=1)                               # best-objectness row per image
-            top = out[torch.arange(B, device=dev), idx]
-            top_host.copy_(top, non_blocking=True)
-            state["i"] += 1
-
-        for _ in range(3):
-            e2e_step()
-        barrier()
-        e0.record()
-        for _ in range(args.steps):
-            e2e_step()
-        e1.record()
-        barrier()
-        ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-        e2e_value = world * B / (float(ms2.item()) / args.steps / 1e3)
-
-        # ---------------- roofline of the dominant kernel family (tcgen05 convs) ----------------
-        conv_ms, conv_flops, n_convs = plan.time_tc_convs(x_dev, iters=max(3, min(10, args.steps)))
-        pk = peaks()
-        achieved = conv_flops / (conv_ms / 1e3) / 1e12
-        roofline = {"bound": "tensor", "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
-                    "frac": achieved / pk["tflops"], "traffic": None, "peak_source": pk["source"] + " (sustained bf16)",
-                    "traffic_unit": "bytes per step, DRAM read+write of the conv launches (ncu, profiles/r01c)",
-                    "kernel": "conv_tc_kernel (all %d tcgen05 conv launches of one step, back to back)" % n_convs,
-                    "kernel_ms_per_step": conv_ms, "share_of_step": conv_ms / ms_step,
-                    "algorithmic_flops_per_step": conv_flops}
-
-        tb, tn = ncu_conv_traffic()
-        if tb is not None and tn == n_convs and B == 32:
-            roofline["traffic"] = tb
-        if args.profile_layers and rank == 0:
-            rows = plan.profile_layers(x_dev, reps=10)
-            os.makedirs(os.path.dirname(os.path.abspath(args.profile_layers)), exist_ok=True)
-            with open(args.profile_layers, "w") as f:
-                json.dump({"batch": B, "size": SIZE, "ms_per_step": ms_step, "rows": rows}, f, indent=1)
+    secondary = {}
+    if world == 1 and not args.no_secondary:
+        # free the training plan before the inference replicas are built
+        torch.cuda.empty_cache()
+        for name in ("yolov3", "yolov4"):
+            try:
+                secondary["%s_infer_bs%d" % (name, INFER_BATCH)] = run_infer(name, args, dev, rank, world, dd)
+            except Exception as e:  # a secondary block must not take the headline down
+                secondary["%s_infer_bs%d" % (name, INFER_BATCH)] = {"error": "%s: %s" % (type(e).__name__, e)}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu, _ = cpu_reference_rate(max_seconds=15.0)
+        cpu = cpu_reference_rate("train", TRAIN_MODEL, max_seconds=20.0, batch=2, max_iters=3)
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     if rank == 0:
-        flops_img = conv_flops / B
+        B = tr["batch"]
         line = {
-            "metric": "images/sec (640x640) yolov3 inference", "value": value, "unit": "images/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-            "config": {"workload": "yolov3.cfg Darknet-53 inference bs=%d 640x640 per GPU, fp16 fused conv path "
-                                   "(BASELINE configs[1])" % B,
-                       "global_batch": B * world, "parallelism": "replicas x%d" % world,
-                       "l2": "inputs (157 MB fp32 batch) and activations (>4 GB/step) exceed the 126 MB L2",
-                       "cuda_graph": bool(getattr(model, "use_cuda_graph", True)),
-                       "tcgen05_conv_flops_per_image": flops_img,
-                       "conv_roofline_frac_of_step": (world * 0 + value / world) * FLOPS_PER_IMAGE / 1e12 / pk["tflops"]},
-            "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": int(host_u8.numel()),
-                    "d2h_bytes_per_step": int(top_host.numel() * 4)},
-            "gpu_launches": launches * args.steps,
-            "roofline": roofline,
+            "metric": "images/sec (640x640) yolov4 training", "value": tr["value"], "unit": "images/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": tr["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16", "data": "synthetic",
+            "config": {"workload": "yolov4.cfg (CSPDarknet-53 + Mish) training step, %d images / GPU, 640x640: "
+                                   "forward + YOLO loss + backward + ONE NCCL all-reduce of the flat fp32 gradients + "
+                                   "fused SGD-Nesterov (BASELINE configs[2]: bs 64 on 8 GPUs)" % B,
+                       "global_batch": B * world, "parallelism": "dp%d" % world,
+                       "precision": "fp16 activations / weights, bf16 activation gradients, fp32 accumulation, "
+                                    "statistics, weight gradients, master weights and optimiser",
+                       "l2": "activations + gradients of one step (> 8 GB) exceed the 126 MB L2; every step re-reads "
+                             "them from HBM",
+                       "cuda_graph": True, "grad_allreduce_bytes": tr["grad_bytes"],
+                       "launches_per_step": tr["launches_per_step"], "loss_items": tr["loss_items"]},
+            "clocks": tr["clocks"],
+            "e2e": tr["e2e"],
+            "gpu_launches": tr["gpu_launches"],
+            "roofline": tr["roofline"],
         }
+        if tr["allreduce"] is not None:
+            line["allreduce"] = tr["allreduce"]
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if secondary:
+            line["secondary"] = secondary
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except SystemExit:
+        raise
+    except BaseException:
+        # torchrun swallows per-rank tracebacks (error_file: <N/A>): keep them where the driver can find them
+        tb = traceback.format_exc()
+        r = os.environ.get("RANK", "0")
+        sys.stderr.write("[bench.py rank %s]\n%s\n" % (r, tb))
+        try:
+            d = os.path.join(ROOT, "gpurun_out")
+            os.makedirs(d, exist_ok=True)
+            with open(os.path.join(d, "bench_rank%s.err" % r), "w") as f:
+                f.write(tb)
+        except OSError:
+            pass
+        raise

@@ -12,13 +12,11 @@ import torch.nn as nn
 import helpers  # noqa: F401  (sys.path)
 
 
-class Toy(nn.Module):
-    def __init__(self):
-        super().__init__()
-        self.module_list = nn.ModuleList([nn.Sequential()])
-        self.module_list[0].add_module('Conv2d', nn.Conv2d(3, 4, 3, bias=False))
-        self.module_list[0].add_module('BatchNorm2d', nn.BatchNorm2d(4))
-        self.head = nn.Conv2d(4, 2, 1, bias=True)
+def _real_model():
+    """The real module tree (yolov3-tiny: conv blocks with BatchNorm, two bias-only head convs) on the CPU; the
+    training plan's role -- writing per-rank gradients through model._b2y_grad_sink -- is played by the test."""
+    import models
+    return models.Darknet(helpers.cfg_path("yolov3-tiny"))
 
 
 def _free_port():
@@ -35,10 +33,13 @@ def _worker(rank, world, port, out):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from b200yolo.parallel import FlatDataParallel, _is_decay_param
     torch.manual_seed(100 + rank)               # ranks start from different weights / buffers
-    m = Toy()
+    m = _real_model()
     with torch.no_grad():
+        for p in m.parameters():
+            p.add_(0.01 * rank)
         m.module_list[0][1].running_mean.fill_(float(rank + 1))
     dp = FlatDataParallel(m)
+    sink = m._b2y_grad_sink                      # what TrainPlan._emit / the wgrad unpack write into
     res = {}
     res["params"] = dp.flat_param.clone()
     res["names"] = list(dp.names)
@@ -51,7 +52,8 @@ def _worker(rank, world, port, out):
     local = []
     for p in dp.params:
         v = torch.randn(p.shape, generator=g)
-        dp.grad_views[id(p)].copy_(v)
+        sink[id(p)].copy_(v)
+        assert p.grad.data_ptr() == sink[id(p)].data_ptr()      # .grad IS the slice of the flat buffer
         local.append(v.reshape(-1))
     res["local_grad"] = torch.cat(local)
     dp.reduce_gradients()
@@ -76,8 +78,13 @@ def test_flat_data_parallel_gloo():
     # one all-reduce == mean of the per-rank gradients, bit exact for 2 ranks
     expect = (r0["local_grad"] + r1["local_grad"]) / 2
     assert torch.equal(r0["avg"], expect) and torch.equal(r1["avg"], expect)
-    assert torch.equal(r0["rm"], torch.ones(4)) and torch.equal(r1["rm"], torch.ones(4))
+    assert torch.equal(r0["rm"], torch.ones(16)) and torch.equal(r1["rm"], torch.ones(16))
     # optimiser grouping of the reference: weight decay only on '...Conv2d.weight'
     names, flags = r0["names"], r0["decay_flags"]
     assert flags == [("Conv2d.weight" in n and ".bias" not in n) for n in names]
-    assert r0["n_decay"] == 4 * 3 * 3 * 3 and names[0] == "module_list.0.Conv2d.weight"
+    import models
+    ref = models.Darknet(helpers.cfg_path("yolov3-tiny"))
+    n_decay = sum(p.numel() for n, p in ref.named_parameters() if "Conv2d.weight" in n)
+    assert r0["n_decay"] == n_decay and names[0] == "module_list.0.Conv2d.weight"
+    assert sorted(names) == sorted(n for n, _ in ref.named_parameters())
+    assert r0["params"].numel() == sum(p.numel() for p in ref.parameters()) == 8852366

@@ -183,6 +183,9 @@ def write_cfg(name, directory, classes=80):
     import os
     os.makedirs(directory, exist_ok=True)
     path = os.path.join(directory, name + ".cfg")
-    with open(path, "w") as f:
+    # write-then-rename: several ranks may generate the same file concurrently; a reader never sees a truncated cfg
+    tmp = "%s.%d.tmp" % (path, os.getpid())
+    with open(tmp, "w") as f:
         f.write(cfg_text(name, classes))
+    os.replace(tmp, path)
     return path

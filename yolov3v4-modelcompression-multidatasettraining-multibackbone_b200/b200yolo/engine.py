@@ -492,7 +492,24 @@ class Engine:
         keep = bool(model.keep_features)
         return self.plans[(tuple(x.shape), bool(model.training), x.device.index, keep, x.dtype)]
 
+    def _check_device(self, x):
+        """One engine serves ONE device: the packed weights, plans and CUDA graphs live where the parameters are.
+        nn.DataParallel replicas (test.py:55-56 wraps the model when several GPUs are visible) share this object and
+        would read device-0 weight pointers from other devices -- refuse instead of computing garbage.  Multi-GPU =
+        one process per GPU (b200yolo.parallel.FlatDataParallel / torchrun); for test.py use --device 0."""
+        p = next(self.model.parameters(), None)
+        if p is not None and p.device != x.device:
+            raise RuntimeError(
+                "b200yolo: input on %s but the model's parameters are on %s. Single-process multi-GPU "
+                "(nn.DataParallel) is not supported by the sm_100a engine: run one process per GPU "
+                "(CUDA_VISIBLE_DEVICES / --device 0, or torchrun + FlatDataParallel)." % (x.device, p.device))
+
     def forward(self, x):
+        self._check_device(x)
+        with torch.cuda.device(x.device):       # kernels go to the current stream OF THE INPUT'S DEVICE
+            return self._forward(x)
+
+    def _forward(self, x):
         model = self.model
         if model.quantized != -1:
             return self._forward_quantized(x)

@@ -141,5 +141,12 @@ def raw():
     return _lib
 
 
+# Launch recorder (measurement only, bench.py / tools): while RECORD is a list every C-ABI call is appended as
+# (name, args) so that a family of launches (e.g. all tcgen05 convolutions of one step) can be replayed back to back.
+RECORD = None
+
+
 def call(name, *args):
+    if RECORD is not None:
+        RECORD.append((name, args))
     check(getattr(_lib, name)(*args), name)

@@ -290,7 +290,7 @@ class TrainPlan:
             self.runs += 1
             return self.forward(x)
         if self.fwd_graph is None:
-            self.static_x = torch.empty((self.B, 3, self.H, self.W), dtype=torch.float32, device=self.device)
+            self.static_x = torch.empty((self.B, self.Cin, self.H, self.W), dtype=torch.float32, device=self.device)
             self.static_x.copy_(x)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()

@@ -450,6 +450,17 @@ template <> struct Half8<__nv_bfloat16> {
 }  // namespace b2y
 
 // host-side helpers ---------------------------------------------------------
+// true the first time it is called for the current device with this mask (launch attributes such as
+// MaxDynamicSharedMemorySize are per device; a process may drive several GPUs)
+static inline bool b2y_first_use_on_device(unsigned long long& mask) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (mask & bit) return false;
+    mask |= bit;
+    return true;
+}
+
 #define B2Y_CUDA_CHECK(expr)                       \
     do {                                           \
         cudaError_t _e = (expr);                   \

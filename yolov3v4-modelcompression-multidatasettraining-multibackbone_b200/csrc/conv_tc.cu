@@ -96,10 +96,9 @@ static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUte
                       cudaStream_t st) {
     using Cfg = ConvTcCfg<BLOCK_N, KBYTES>;
     auto kern = conv_tc_kernel<BLOCK_N, KBYTES, KIND, CLUSTER, PAIR>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_set = 0;      // one bit per device: the attribute is per (function, device)
+    if (b2y_first_use_on_device(attr_set)) {
         B2Y_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        attr_set = true;
     }
     const int items = ((p.num_m_tiles + CLUSTER - 1) / CLUSTER) * p.num_n_tiles;
     const int max_clusters = g_num_sms / CLUSTER;

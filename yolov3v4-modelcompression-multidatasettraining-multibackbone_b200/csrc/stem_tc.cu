@@ -345,10 +345,9 @@ template <typename XT, int CIN, int K, int BLOCK_N, int NG>
 static int stem_launch(const StemParams& p, cudaStream_t st) {
     constexpr int SMEM = 1024 + 2 * NG * 128 * 64 + BLOCK_N * 64 + 256;
     auto kern = stem_fused_kernel<XT, CIN, K, BLOCK_N, NG>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_set = 0;      // one bit per device: the attribute is per (function, device)
+    if (b2y_first_use_on_device(attr_set)) {
         B2Y_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-        attr_set = true;
     }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);

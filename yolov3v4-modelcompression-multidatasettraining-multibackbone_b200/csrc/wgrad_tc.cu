@@ -285,10 +285,9 @@ template <int BLOCK_N, int NB_ROW_BYTES>
 static int wgrad_launch_cfg(const CUtensorMap& a, const CUtensorMap& b, const WgradParams& p, cudaStream_t st) {
     using Cfg = WgradCfg<BLOCK_N, NB_ROW_BYTES>;
     auto kern = wgrad_tc_kernel<BLOCK_N, NB_ROW_BYTES>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_set = 0;      // one bit per device: the attribute is per (function, device)
+    if (b2y_first_use_on_device(attr_set)) {
         B2Y_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        attr_set = true;
     }
     const int tiles = p.m_tiles * p.n_tiles * p.ntaps * p.ksplits;
     const int grid = tiles < w_num_sms ? tiles : w_num_sms;
