@@ -296,6 +296,45 @@ int b2y_stem_conv_bwd_weight(const b2y_conv_desc* d, const float* x_nchw, const 
 int b2y_sgd_nesterov(float* param, const float* grad, float* momentum_buf, long long n, float lr, float momentum,
                      float weight_decay, float grad_scale, int first_step, void* stream);
 
+/* ---- bandwidth-oriented BatchNorm passes of the training step (csrc/bn_train.cu; models.py:100-113 under autograd) ----
+ * save = fp32 [4][c]: batch mean, invstd, scale = gamma*invstd, shift = beta - mean*scale.
+ * forward: derives them from the conv epilogue's channel sums (biased variance), updates the running statistics
+ * (unbiased variance, `momentum`), writes `save` and y = act(z*scale+shift) [+ residual] in the same launch. */
+int b2y_bn_train_fwd(const void* z, long long z_pitch, const float* stat_sum, const float* stat_sqsum, long long count,
+                     const float* gamma, const float* beta, float eps, float momentum, float* running_mean,
+                     float* running_var, float* save, const void* residual, long long res_pitch, void* y,
+                     long long y_pitch, long long pixels, int c, int act, float slope, void* stream);
+/* sums = fp32 [2][c] (caller zeroes): S1 = sum du, S2 = sum du*xhat with du = dy*act'(z*scale+shift) */
+int b2y_bn_train_bwd_reduce(const void* z, long long z_pitch, const void* dy, long long dy_pitch, const float* save,
+                            float* sums, float* du_absmax /* optional atomicMax of |du|, caller zeroes */,
+                            long long pixels, int c, int act, float slope, int grad_dtype, void* stream);
+/* dz = s * gamma*invstd*(du - S1/N - xhat*S2/N) as fp16 (s = power of two chosen on the device -> scale_out[0..1] =
+ * [s, 1/s]); also emits the parameter gradients dgamma_out = S2*grad_out_scale, dbeta_out = S1*grad_out_scale */
+int b2y_bn_train_bwd_apply(const void* z, long long z_pitch, const void* dy, long long dy_pitch, const float* gamma,
+                           const float* save, const float* sums, void* dz, long long dz_pitch, long long pixels, int c,
+                           int act, float slope, int grad_dtype, const float* du_absmax, float* scale_out,
+                           float* dgamma_out, float* dbeta_out, float grad_out_scale, void* stream);
+
+/* ---- table-driven layout kernels (csrc/multi.cu): one launch for ALL convolutions of a model ----
+ * Tiles: 32 output channels x b2y_layout_tile_i(k) input channels x k*k taps; tile_begin = running sum of
+ * ceil(rows/32) * ceil(in_c / tile_i) over the items (rows = out_c_pad for packing, out_c for unpacking). */
+typedef struct b2y_pack_item {
+    const float* w;     /* master weights, OIHW fp32 [out_c][in_c][k][k] */
+    void* w_fwd;        /* fp16 [out_c_pad][k][k][in_c] (rows >= out_c zero) or NULL */
+    void* w_dgrad;      /* fp16 [phase][in_c][tap][out_c_pad] (see b2y_pack_dgrad_weights) or NULL */
+    int O, Opad, I, k, stride, pad;
+    int tile_begin, reserved;
+} b2y_pack_item;
+typedef struct b2y_unpack_item {
+    const float* src;   /* packed weight gradient fp32 [out_c_pad][k][k][in_c] */
+    float* dst;         /* OIHW fp32 [out_c][in_c][k][k] */
+    int O, I, k, accumulate;
+    int tile_begin, reserved;
+} b2y_unpack_item;
+int b2y_layout_tile_i(int ksize);
+int b2y_pack_conv_weights_multi(const b2y_pack_item* items_dev, int n_items, int total_tiles, void* stream);
+int b2y_unpack_wgrad_multi(const b2y_unpack_item* items_dev, int n_items, int total_tiles, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

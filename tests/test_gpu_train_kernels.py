@@ -160,6 +160,94 @@ def test_bn_act_fwd_bwd(act, gdt):
     assert (dz.permute(0, 3, 1, 2).cpu() - ref_dz).abs().max() < tol * max(1.0, ref_dz.abs().max().item())
 
 
+@pytest.mark.parametrize("gdt", [torch.float16, torch.bfloat16], ids=["f16", "bf16"])
+@pytest.mark.parametrize("act,C", [("leaky", 64), ("mish", 32), ("linear", 24), ("relu6", 40), ("h_swish", 72),
+                                   ("mish", 512), ("leaky", 8)])
+def test_bn_train_fused_passes(act, C, gdt):
+    """csrc/bn_train.cu: finalize fused into the forward pass, unrolled reduce / apply passes with the parameter
+    gradients emitted by the apply kernel -- against torch's training-mode batch_norm + activation under autograd
+    (fp64).  Channel counts cover power-of-two and MobileNet-style (24, 40, 72) vector counts; pixel count is not a
+    multiple of the unroll / block geometry."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(5)
+    B, H, W = 3, 13, 11
+    z = (torch.randn(B, C, H, W, generator=g) * 2 + 0.3).half().float()
+    gamma = torch.rand(C, generator=g) + 0.5
+    beta = torch.randn(C, generator=g) * 0.2
+    res = torch.randn(B, C, H, W, generator=g).half().float()
+    dy = torch.randn(B, C, H, W, generator=g).to(gdt).float()
+    rm, rv = torch.randn(C, generator=g) * 0.1, torch.rand(C, generator=g) + 0.5
+    zr = z.clone().double().requires_grad_(True)
+    gr, br = gamma.clone().double().requires_grad_(True), beta.clone().double().requires_grad_(True)
+    rm_r, rv_r = rm.clone().double(), rv.clone().double()
+    u = F.batch_norm(zr, rm_r, rv_r, gr, br, True, 0.1, 1e-5)
+    y = orc.activation(u, act) + res.double()
+    y.backward(dy.double())
+    zn = _nhwc(z)
+    s1 = z.sum(dim=(0, 2, 3)).cuda()
+    s2 = (z * z).sum(dim=(0, 2, 3)).cuda()
+    rmc, rvc = rm.cuda(), rv.cuda()
+    out, save = ops.bn_train_fwd(zn, s1, s2, gamma.cuda(), beta.cuda(), 1e-5, 0.1, rmc, rvc, act, residual=_nhwc(res))
+    dz, dgamma, dbeta, aux = ops.bn_train_bwd(zn, _nhwc(dy, gdt), gamma.cuda(), save, act, grad_out_scale=0.5)
+    torch.cuda.synchronize()
+    s_dev, inv_dev = float(aux[1]), float(aux[2])
+    assert s_dev > 0 and abs(s_dev * inv_dev - 1.0) < 1e-6 and float(torch.log2(aux[1])) % 1.0 == 0.0
+    assert float(dz.float().abs().max()) <= 8192.0
+    dz = dz.float() * inv_dev
+    assert (_nchw(out) - y.detach().float()).abs().max() < 6e-3
+    np.testing.assert_allclose(rmc.cpu().numpy(), rm_r.float().numpy(), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(rvc.cpu().numpy(), rv_r.float().numpy(), rtol=1e-4, atol=1e-5)
+    mean = z.mean(dim=(0, 2, 3))
+    np.testing.assert_allclose(save[0].cpu().numpy(), mean.numpy(), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(dgamma.cpu().numpy() * 2, gr.grad.float().numpy(), rtol=2e-3, atol=2e-3)
+    np.testing.assert_allclose(dbeta.cpu().numpy() * 2, br.grad.float().numpy(), rtol=2e-3, atol=2e-3)
+    ref_dz = zr.grad.float()
+    tol = 4e-3 if gdt == torch.float16 else 2e-2
+    assert (dz.permute(0, 3, 1, 2).cpu() - ref_dz).abs().max() < tol * max(1.0, ref_dz.abs().max().item())
+
+
+@pytest.mark.parametrize("case", [(64, 32, 3, 1, 1, 64), (128, 64, 3, 2, 1, 128), (255, 256, 1, 1, 0, 256),
+                                  (40, 24, 1, 1, 0, 40), (96, 72, 3, 2, 1, 96), (1024, 512, 3, 1, 1, 1024)],
+                         ids=lambda c: "O%d_I%d_k%d_s%d" % c[:4])
+def test_multi_tensor_pack_and_unpack_bit_exact(case):
+    """csrc/multi.cu: the table-driven pack (fp32 OIHW -> forward + per-phase data-gradient fp16 layouts) and unpack
+    (packed fp32 weight gradients -> OIHW) must reproduce the per-layer kernels bit for bit, with several layers of
+    different geometry in ONE table (tile_begin search), head padding (255 -> 256 rows) and stride-2 phases."""
+    import ctypes as C
+    from b200yolo import lib
+    from b200yolo.lib import PackItem, UnpackItem, call, ptr, stream_ptr
+    ops = _ops()
+    g = torch.Generator().manual_seed(11)
+    layers = [case, (32, 16, 3, 1, 1, 32), (16, 8, 1, 1, 0, 16)]
+    items, uitems, keep, tiles, utiles = [], [], [], 0, 0
+    for (O, I, k, s, pd, Opad) in layers:
+        w = torch.randn(O, I, k, k, generator=g).cuda()
+        wf = torch.full((Opad, k, k, I), 7.0, dtype=torch.float16, device="cuda")
+        wd = torch.full((Opad * I * k * k,), 7.0, dtype=torch.float16, device="cuda")
+        dwp = torch.randn(Opad, k, k, I, generator=g).cuda()
+        dst = torch.zeros(O, I, k, k, device="cuda")
+        ti = lib.raw().b2y_layout_tile_i(k)
+        items.append(PackItem(w.data_ptr(), wf.data_ptr(), wd.data_ptr(), O, Opad, I, k, s, pd, tiles, 0))
+        tiles += ((Opad + 31) // 32) * ((I + ti - 1) // ti)
+        uitems.append(UnpackItem(dwp.data_ptr(), dst.data_ptr(), O, I, k, 0, utiles, 0))
+        utiles += ((O + 31) // 32) * ((I + ti - 1) // ti)
+        keep.append((w, wf, wd, dwp, dst))
+    tab = torch.frombuffer(bytearray(bytes((PackItem * len(items))(*items))), dtype=torch.uint8).cuda()
+    utab = torch.frombuffer(bytearray(bytes((UnpackItem * len(uitems))(*uitems))), dtype=torch.uint8).cuda()
+    call("b2y_pack_conv_weights_multi", ptr(tab), len(items), tiles, stream_ptr())
+    call("b2y_unpack_wgrad_multi", ptr(utab), len(uitems), utiles, stream_ptr())
+    torch.cuda.synchronize()
+    for (O, I, k, s, pd, Opad), (w, wf, wd, dwp, dst) in zip(layers, keep):
+        wpad = torch.cat([w, torch.zeros(Opad - O, I, k, k, device="cuda")], 0)
+        ref_f, _, _ = ops.pack_conv_weights(wpad)
+        H = 16
+        ref_d = ops.pack_dgrad_weights(wpad, s, pd, (H, H))
+        assert torch.equal(wf, ref_f), "forward layout"
+        assert torch.equal(wd, ref_d), "data-gradient layout"
+        ref_u = ops.unpack_wgrad(dwp[:O].contiguous(), torch.empty(O, I, k, k, device="cuda"))
+        assert torch.equal(dst, ref_u), "unpacked weight gradient"
+
+
 def test_sgd_nesterov_matches_torch():
     ops = _ops()
     g = torch.Generator().manual_seed(4)

@@ -57,6 +57,56 @@ def test_train_forward_loss_backward_matches_reference(name):
             np.testing.assert_allclose(stats[k[6:]].numpy(), g[k], rtol=1e-4, atol=1e-5)
 
 
+@pytest.mark.parametrize("name", ["yolov3", "yolov4"])
+def test_eval_forward_640_matches_reference(name):
+    """BASELINE size (640x640, batch 2): every 29th decoded row + float64 sums of the reference's own output
+    (oracle/gen_golden_640.py)."""
+    g = golden("%s_640_eval" % name)
+    x = orc.synth_images(2, 640, 640, seed=0)
+    with torch.no_grad():
+        io, p = orc.darknet_forward(module_defs(name), _state(name), x, name)
+    assert tuple(io.shape) == tuple(g["io_shape"])
+    rows = g["rows"]
+    np.testing.assert_allclose(io[:, rows].numpy(), g["io_rows"], rtol=2e-4, atol=2e-4)
+    np.testing.assert_allclose(io.double().sum(dim=(1, 2)).numpy(), g["io_sum"], rtol=1e-5)
+    np.testing.assert_allclose(io.double().abs().sum(dim=(1, 2)).numpy(), g["io_abs_sum"], rtol=1e-5)
+    off = 0
+    for i, pi in enumerate(p):
+        flat = pi.reshape(2, -1, pi.shape[-1])
+        sel = rows[(rows >= off) & (rows < off + flat.shape[1])] - off
+        np.testing.assert_allclose(flat[:, sel].numpy(), g["p%d_rows" % i], rtol=2e-4, atol=2e-4)
+        off += flat.shape[1]
+
+
+def test_train_step_640_matches_reference():
+    """The per-GPU slice of BASELINE configs[2]: yolov4.cfg, batch 8, 640x640, forward + compute_loss + backward of the
+    reference itself (fixture) vs the oracle: sampled predictions, loss items, every gradient norm, all BatchNorm /
+    bias gradients element-wise, all running statistics."""
+    name = "yolov4"
+    g = golden("yolov4_640_train")
+    sd = _state(name, requires_grad=True)
+    x = orc.synth_images(8, 640, 640, seed=0)
+    t = orc.synth_targets(8, 8, 80, seed=1)
+    p, stats = orc.darknet_forward(module_defs(name), sd, x, name, training=True)
+    for i, pi in enumerate(p):
+        flat = pi.detach().reshape(8, -1, pi.shape[-1])
+        np.testing.assert_allclose(flat[:, ::29].numpy(), g["p%d_rows" % i], rtol=1e-3, atol=1e-3)
+        np.testing.assert_allclose(float(pi.detach().double().abs().sum()), float(g["p%d_abs_sum" % i]), rtol=1e-4)
+    loss, items = orc.compute_loss(p, t, anchor_vecs(name), dict(orc.DEFAULT_HYP), 80, 1.0)
+    np.testing.assert_allclose(items.numpy(), g["items"], rtol=1e-4)
+    loss.backward()
+    names = [str(n) for n in g["grad_names"]]
+    norms = dict(zip(names, g["grad_norms"]))
+    worst = max(abs(float(sd[k].grad.norm()) - norms[k]) / (norms[k] + 1e-6) for k in names if norms[k] > 0)
+    assert worst < 5e-3, worst
+    for k in names:
+        if ("grad::" + k) in g.files:
+            np.testing.assert_allclose(sd[k].grad.numpy(), g["grad::" + k], rtol=5e-3, atol=5e-4 * (1 + norms[k]))
+    for k in g.files:
+        if k.startswith("stat::"):
+            np.testing.assert_allclose(stats[k[6:]].numpy(), g[k], rtol=1e-4, atol=1e-5)
+
+
 def test_loss_and_build_targets_match_reference():
     g = golden("loss_case")
     p = [torch.from_numpy(g["p%d" % i]).requires_grad_(True) for i in range(3)]

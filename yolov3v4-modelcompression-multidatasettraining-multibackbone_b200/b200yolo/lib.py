@@ -29,6 +29,18 @@ class ConvDesc(C.Structure):
     ]
 
 
+class PackItem(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("w_fwd", C.c_void_p), ("w_dgrad", C.c_void_p),
+                ("O", C.c_int), ("Opad", C.c_int), ("I", C.c_int), ("k", C.c_int), ("stride", C.c_int),
+                ("pad", C.c_int), ("tile_begin", C.c_int), ("reserved", C.c_int)]
+
+
+class UnpackItem(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p),
+                ("O", C.c_int), ("I", C.c_int), ("k", C.c_int), ("accumulate", C.c_int),
+                ("tile_begin", C.c_int), ("reserved", C.c_int)]
+
+
 class QConvDesc(C.Structure):
     _fields_ = [
         ("conv", ConvDesc),
@@ -100,6 +112,13 @@ _PROTOS = {
     "b2y_maxpool_bwd": (i32, [vp, ll, vp, ll, vp, ll, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
     "b2y_stem_conv_bwd_weight": (i32, [C.POINTER(ConvDesc), vp, vp, vp, f32, i32, vp]),
     "b2y_sgd_nesterov": (i32, [vp, vp, vp, ll, f32, f32, f32, f32, i32, vp]),
+    "b2y_bn_train_fwd": (i32, [vp, ll, vp, vp, ll, vp, vp, f32, f32, vp, vp, vp, vp, ll, vp, ll, ll, i32, i32, f32, vp]),
+    "b2y_bn_train_bwd_reduce": (i32, [vp, ll, vp, ll, vp, vp, vp, ll, i32, i32, f32, i32, vp]),
+    "b2y_bn_train_bwd_apply": (i32, [vp, ll, vp, ll, vp, vp, vp, vp, ll, ll, i32, i32, f32, i32, vp, vp, vp, vp, f32,
+                                     vp]),
+    "b2y_layout_tile_i": (i32, [i32]),
+    "b2y_pack_conv_weights_multi": (i32, [vp, i32, i32, vp]),
+    "b2y_unpack_wgrad_multi": (i32, [vp, i32, i32, vp]),
 }
 
 EXPORTS = sorted(_PROTOS)

@@ -356,6 +356,41 @@ def bn_act_bwd(x, dy, scale, shift, gamma, mean, invstd, act, slope=0.1, dx=None
     return dx, dgamma, dbeta, aux
 
 
+def bn_train_fwd(z, s1, s2, gamma, beta, eps, momentum, running_mean, running_var, act, slope=0.1, residual=None,
+                 out=None, save=None):
+    """Fused finalize + apply of training-mode BatchNorm (csrc/bn_train.cu). Returns (y, save[4][C])."""
+    B, H, W, Cc = z.shape
+    if out is None:
+        out = torch.empty((B, H, W, Cc), dtype=torch.float16, device=z.device)
+    if save is None:
+        save = torch.empty((4, Cc), dtype=torch.float32, device=z.device)
+    n = B * H * W
+    call("b2y_bn_train_fwd", ptr(z), _pitch(z), ptr(s1), ptr(s2), n, ptr(gamma), ptr(beta), float(eps),
+         float(momentum), ptr(running_mean), ptr(running_var), ptr(save), ptr(residual),
+         _pitch(residual) if residual is not None else 0, ptr(out), _pitch(out), n, Cc,
+         ACT[act] if isinstance(act, str) else int(act), float(slope), stream_ptr())
+    return out, save
+
+
+def bn_train_bwd(z, dy, gamma, save, act, slope=0.1, grad_out_scale=1.0):
+    """Backward of bn_train_fwd. Returns (dz fp16 = s * gradient, dgamma, dbeta, aux=[max|du|, s, 1/s, -])."""
+    B, H, W, Cc = z.shape
+    dev = z.device
+    n = B * H * W
+    a = ACT[act] if isinstance(act, str) else int(act)
+    sums = torch.zeros((2, Cc), dtype=torch.float32, device=dev)
+    aux = torch.zeros(4, dtype=torch.float32, device=dev)
+    dz = torch.empty((B, H, W, Cc), dtype=torch.float16, device=dev)
+    dgamma = torch.empty(Cc, dtype=torch.float32, device=dev)
+    dbeta = torch.empty(Cc, dtype=torch.float32, device=dev)
+    call("b2y_bn_train_bwd_reduce", ptr(z), _pitch(z), ptr(dy), _pitch(dy), ptr(save), ptr(sums), ptr(aux), n, Cc, a,
+         float(slope), _gdt(dy), stream_ptr())
+    call("b2y_bn_train_bwd_apply", ptr(z), _pitch(z), ptr(dy), _pitch(dy), ptr(gamma), ptr(save), ptr(sums), ptr(dz),
+         _pitch(dz), n, Cc, a, float(slope), _gdt(dy), ptr(aux), C.c_void_p(aux.data_ptr() + 4), ptr(dgamma),
+         ptr(dbeta), float(grad_out_scale), stream_ptr())
+    return dz, dgamma, dbeta, aux
+
+
 def bias_act_bwd_reduce(x, dy, scale, shift, act, slope=0.1, dbeta=None):
     """dbias = sum dy*act'(x*scale+shift) for a conv without BN (dgamma not needed)."""
     B, H, W, Cc = x.shape

@@ -24,7 +24,7 @@ import torch.nn as nn
 
 from . import ops
 from .engine import LazyFeatures, _Tensor, _block_parts
-from .lib import ConvDesc, OUT_F16, call, ptr, stream_ptr
+from .lib import ACT, ConvDesc, OUT_F16, call, ptr, stream_ptr
 
 GDT = torch.bfloat16   # gradient tensors: bf16 (range of fp32) -- fp16 over/underflows across ~100 BN layers
 HEAD_PAD = 256  # head convs (255 filters) are run with 256 output channels (zero row) so that K % 16 == 0 in dgrad
@@ -36,7 +36,8 @@ def _round_up(v, m):
 
 class _ConvRec:
     __slots__ = ('i', 'conv', 'bn', 'act', 'slope', 'src', 'z', 'y', 'res', 'head', 'stem', 'k', 's', 'p', 'Cout',
-                 'Cpad', 'w16', 'wT', 'stats', 'mean', 'invstd', 'scale', 'shift', 'ones', 'zeros', 'w32', 'aux_row', 'wstem')
+                 'Cpad', 'w16', 'wT', 'stats', 'mean', 'invstd', 'scale', 'shift', 'ones', 'zeros', 'w32', 'aux_row', 'wstem',
+                 'save', 'sums', 'dw', 'fast_bn')
 
     def __init__(self):
         for k in self.__slots__:
@@ -127,6 +128,10 @@ class TrainPlan:
             pitch = Cc if dtype == torch.float16 else _round_up(Cc, 4)
             return torch.empty((B, H, W, pitch), dtype=dtype, device=dev)
 
+        def zeros_later(shape, dtype):
+            """placeholder (meta tensor) for a buffer that is carved out of the zero-at-start-of-backward arena"""
+            return torch.empty(shape, dtype=dtype, device='meta')
+
         self.grad_of = {}  # id(_Tensor) -> gradient _Tensor (fp16, same placement)
 
         def make_grad(t, gbuf=None, c0=0):
@@ -141,7 +146,7 @@ class TrainPlan:
             srcs = [i + l if l < 0 else l for l in d['layers']]
             dst = tens[i]
             dst.buf = new_buf(dst.C, dst.H, dst.W)
-            gdst = make_grad(dst, torch.zeros(dst.buf.shape, dtype=GDT, device=dev))
+            gdst = make_grad(dst, zeros_later(dst.buf.shape, GDT))
             off = 0
             for s in srcs:
                 st = tens[s]
@@ -160,10 +165,10 @@ class TrainPlan:
                 t.c0 = 0
             if id(t) not in self.grad_of:
                 if t.dtype == torch.float16:
-                    make_grad(t, torch.zeros(t.buf.shape, dtype=GDT, device=dev))
+                    make_grad(t, zeros_later(t.buf.shape, GDT))
                 else:  # head output: its gradient is directly the GEMM operand dZ -> fp16 (times a device-side scale)
                     g = _Tensor(HEAD_PAD, t.H, t.W, torch.float16)
-                    g.buf = torch.zeros((B, t.H, t.W, HEAD_PAD), dtype=torch.float16, device=dev)
+                    g.buf = zeros_later((B, t.H, t.W, HEAD_PAD), torch.float16)
                     self.grad_of[id(t)] = g
             return t
 
@@ -194,7 +199,9 @@ class TrainPlan:
                 if bn is not None:
                     r.z = _Tensor(r.Cout, r.y.H, r.y.W)
                     r.z.buf = new_buf(r.Cout, r.y.H, r.y.W)
-                    r.stats = torch.zeros((2, r.Cout), dtype=torch.float32, device=dev)
+                    r.stats = zeros_later((2, r.Cout), torch.float32)
+                    r.sums = zeros_later((2, r.Cout), torch.float32)
+                    r.fast_bn = r.Cout % 8 == 0 and r.Cout // 8 <= 256
                 else:
                     r.z = r.y   # no BN: the conv epilogue applies bias + activation directly
                     r.ones = torch.ones(r.Cpad, dtype=torch.float32, device=dev)
@@ -236,20 +243,66 @@ class TrainPlan:
                 self.feature_views.append(feat_idx.get(i))
         self.anchors_px = [m.anchors.to(dev).float().contiguous() for (m, _) in self.yolo]
         self.bn_counters = [r.bn.num_batches_tracked for r in self.convs if r.bn is not None]
-        self.grad_bufs = []
-        seen = set()
+        # ---- arenas ------------------------------------------------------------------------------------------------
+        # Everything that has to be zero when a pass starts is carved out of ONE allocation per pass, cleared by ONE
+        # memset (round 1: one fill launch per buffer, ~450 launches per step):
+        #   forward arena : the BatchNorm channel sums (sum z, sum z^2) the conv epilogues accumulate into
+        #   backward arena: activation gradients (bf16; consumers accumulate into them), BN backward sums, the per-layer
+        #                   [max|du|, s, 1/s] scale rows, and the packed fp32 weight gradients (split-K red.add targets)
+        self.dz_aux = torch.empty((len(self.convs) + 1, 4), dtype=torch.float32, device='meta')
+        for r in self.convs:
+            if not r.stem:
+                r.dw = torch.empty((r.Cpad, r.k, r.k, r.conv.in_channels), dtype=torch.float32, device='meta')
+        fwd_req, bwd_req, seen = [], [], {}
+
+        def want(lst, holder, attr):
+            t = getattr(holder, attr)
+            if t is None or t.device.type != 'meta':
+                return
+            key = id(t)
+            if key not in seen:
+                seen[key] = []
+                lst.append(t)
+            seen[key].append((holder, attr))
+
+        for r in self.convs:
+            want(fwd_req, r, 'stats')
         for g in self.grad_of.values():
-            if g.buf is not None and g.buf.data_ptr() not in seen:
-                seen.add(g.buf.data_ptr())
-                self.grad_bufs.append(g.buf)
+            want(bwd_req, g, 'buf')
+        for r in self.convs:
+            want(bwd_req, r, 'sums')
+            want(bwd_req, r, 'dw')
+        want(bwd_req, self, 'dz_aux')
+
+        def carve(reqs):
+            offs, total = [], 0
+            for t in reqs:
+                offs.append(total)
+                total += _round_up(t.numel() * t.element_size(), 256)
+            arena = torch.zeros(max(total, 256), dtype=torch.uint8, device=dev)
+            for t, off in zip(reqs, offs):
+                nbytes = t.numel() * t.element_size()
+                real = arena[off:off + nbytes].view(t.dtype).view(t.shape)
+                for holder, attr in seen[id(t)]:
+                    setattr(holder, attr, real)
+            return arena
+
+        self.fwd_arena = carve(fwd_req)
+        self.bwd_arena = carve(bwd_req)
+        # BatchNorm statistics saved by the forward for the backward: [mean, invstd, scale, shift] per layer
+        for r in self.convs:
+            if r.bn is not None:
+                r.save = torch.empty((4, r.Cout), dtype=torch.float32, device=dev)
         maxz = max(r.Cpad * r.y.H * r.y.W for r in self.convs)
         self.dz_scratch = torch.empty(B * maxz, dtype=torch.float16, device=dev)
-        self.dz_aux = torch.zeros((len(self.convs) + 1, 4), dtype=torch.float32, device=dev)  # [max|du|, s, 1/s, -]
-        maxw = max(r.Cpad * r.conv.in_channels * r.k * r.k for r in self.convs)
-        self.dw_scratch = torch.empty(maxw, dtype=torch.float32, device=dev)
         maxc = max(r.Cpad for r in self.convs)
         self.dgb_scratch = torch.empty((2, maxc), dtype=torch.float32, device=dev)
+        self.stem_dw = torch.empty(maxc * 32, dtype=torch.float32, device=dev)
         self.params = [p for p in model.parameters()]
+        # plan-owned gradient outputs for the plain-autograd path (no flat sink): OIHW fp32 per parameter
+        self.own_grads = None
+        self.pack_table = self.unpack_table = None
+        self.pack_key = self.unpack_key = None
         self.runs = 0
         self.fwd_graph = self.bwd_graph = None
         self.bwd_key = None
@@ -259,19 +312,76 @@ class TrainPlan:
         return sum(p._version for p in self.params)
 
     def _pack(self):
+        """fp32 master weights -> fp16 operand layouts (forward [O][k][k][I], per-phase data-gradient slabs): ONE
+        table-driven launch over all tcgen05 convolutions (csrc/multi.cu) + the stem's own tiny pack."""
+        from .lib import PackItem, raw
+        body = [r for r in self.convs if not r.stem]
+        key = tuple(r.conv.weight.data_ptr() for r in body)
+        if self.pack_table is None or key != self.pack_key:
+            items, tiles = [], 0
+            for r in body:
+                O, I, k = r.conv.weight.shape[0], r.conv.weight.shape[1], r.k
+                if r.w16 is None:
+                    r.w16 = torch.empty((r.Cpad, k, k, I), dtype=torch.float16, device=self.device)
+                    r.wT = torch.empty(r.Cpad * I * k * k, dtype=torch.float16, device=self.device)
+                w = r.conv.weight.detach()
+                assert w.is_contiguous() and w.dtype == torch.float32
+                ti = int(raw().b2y_layout_tile_i(k))
+                if ti <= 0:
+                    raise NotImplementedError("kernel size %d is not supported by the training engine" % k)
+                items.append(PackItem(w.data_ptr(), r.w16.data_ptr(), r.wT.data_ptr(), O, r.Cpad, I, k, r.s, r.p,
+                                      tiles, 0))
+                tiles += ((r.Cpad + 31) // 32) * ((I + ti - 1) // ti)
+            arr = (PackItem * len(items))(*items)
+            host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+            self.pack_table = (host.to(self.device), len(items), tiles)
+            self.pack_key = key
+        tab, n, tiles = self.pack_table
+        call("b2y_pack_conv_weights_multi", ptr(tab), n, tiles, stream_ptr())
         for r in self.convs:
-            w = r.conv.weight.detach()
-            if r.head:
-                pad = torch.zeros((HEAD_PAD - r.Cout,) + tuple(w.shape[1:]), dtype=w.dtype, device=w.device)
-                w = torch.cat([w, pad], 0)
             if r.stem:
+                w = r.conv.weight.detach()
+                if r.head:
+                    pad = torch.zeros((HEAD_PAD - r.Cout,) + tuple(w.shape[1:]), dtype=w.dtype, device=w.device)
+                    w = torch.cat([w, pad], 0)
                 r.w32 = w.float().contiguous()
                 # tensor-core stem: full-im2col weight layout when the receptive field fits one 64-byte GEMM row
                 r.wstem = ops.pack_stem_weights(r.w32) if w.shape[1] * r.k * r.k <= 32 and not r.head else None
-            else:
-                r.w16, _, _ = ops.pack_conv_weights(w)
-                hin, win = r.src.H, r.src.W
-                r.wT = ops.pack_dgrad_weights(w, r.s, r.p, (hin, win), dtype=torch.float16)
+
+    def _grad_dst(self, param):
+        """Where the gradient of `param` is written: its slice of the flat data-parallel buffer (sink), else a
+        plan-owned fp32 tensor (handed to autograd as a copy)."""
+        if self.sink is not None:
+            d = self.sink.get(id(param))
+            if d is not None:
+                return d
+        if self.own_grads is None:
+            self.own_grads = {}
+        d = self.own_grads.get(id(param))
+        if d is None:
+            d = torch.zeros_like(param, dtype=torch.float32, memory_format=torch.contiguous_format)
+            self.own_grads[id(param)] = d
+        return d
+
+    def _unpack_all(self):
+        """packed fp32 weight gradients [O][k][k][I] of all tcgen05 convolutions -> OIHW destinations, ONE launch."""
+        from .lib import UnpackItem, raw
+        body = [r for r in self.convs if not r.stem]
+        dsts = [self._grad_dst(r.conv.weight) for r in body]
+        key = tuple(d.data_ptr() for d in dsts)
+        if self.unpack_table is None or key != self.unpack_key:
+            items, tiles = [], 0
+            for r, d in zip(body, dsts):
+                O, I, k = r.Cout, r.conv.in_channels, r.k
+                ti = int(raw().b2y_layout_tile_i(k))
+                items.append(UnpackItem(r.dw.data_ptr(), d.data_ptr(), O, I, k, 0, tiles, 0))
+                tiles += ((O + 31) // 32) * ((I + ti - 1) // ti)
+            arr = (UnpackItem * len(items))(*items)
+            host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+            self.unpack_table = (host.to(self.device), len(items), tiles)
+            self.unpack_key = key
+        tab, n, tiles = self.unpack_table
+        call("b2y_unpack_wgrad_multi", ptr(tab), n, tiles, stream_ptr())
 
     def _zview(self, r):
         return r.z.buf[..., r.z.c0:r.z.c0 + r.Cpad] if r.head else r.z.view()
@@ -304,7 +414,8 @@ class TrainPlan:
 
     def backward_graphed(self, dps):
         if not self._graphs_enabled() or self.fwd_graph is None:
-            return self.backward(dps)
+            # plan-owned gradient buffers are overwritten by the next step: autograd gets copies
+            return {p: g.clone() for p, g in self.backward(dps).items()}
         sink = getattr(self.model, '_b2y_grad_sink', None)
         key = (id(sink), float(getattr(self.model, 'grad_scale', None) or 1.0))
         if self.bwd_graph is None or key != self.bwd_key:
@@ -334,9 +445,7 @@ class TrainPlan:
             self.param_version = None if force_pack else ver
         x = x.contiguous().float()
         self.x = x
-        for r in self.convs:
-            if r.stats is not None:
-                r.stats.zero_()
+        self.fwd_arena.zero_()                     # all BatchNorm channel sums (one memset)
         for st in self.order:
             kind = st[0]
             if kind == 'conv':
@@ -398,11 +507,20 @@ class TrainPlan:
             ops.conv2d(r.src.view(), r.w16, None, r.k, r.s, r.p, out=z, stats=(r.stats[0], r.stats[1]))
         bn = r.bn
         count = z.shape[0] * z.shape[1] * z.shape[2]
+        res = r.res.view() if r.res is not None else None
+        if r.fast_bn:
+            y = r.y.view()
+            call("b2y_bn_train_fwd", ptr(z), ops._pitch(z), ptr(r.stats[0]), ptr(r.stats[1]), int(count),
+                 ptr(bn.weight.detach()), ptr(bn.bias.detach()), float(bn.eps), float(bn.momentum),
+                 ptr(bn.running_mean), ptr(bn.running_var), ptr(r.save), ptr(res),
+                 ops._pitch(res) if res is not None else 0, ptr(y), ops._pitch(y), int(count), r.Cout,
+                 ACT[r.act], float(r.slope), stream_ptr())
+            r.mean, r.invstd, r.scale, r.shift = r.save[0], r.save[1], r.save[2], r.save[3]
+            return
         r.mean, r.invstd, r.scale, r.shift = ops.bn_finalize(r.stats[0], r.stats[1], count, bn.weight.detach(),
                                                              bn.bias.detach(), bn.eps, bn.momentum, bn.running_mean,
                                                              bn.running_var)
-        ops.bn_act_fwd(z, r.scale, r.shift, r.act, r.slope, residual=r.res.view() if r.res is not None else None,
-                       out=r.y.view())
+        ops.bn_act_fwd(z, r.scale, r.shift, r.act, r.slope, residual=res, out=r.y.view())
 
     # ---------------------------------------------------------------------------------------------------------
     def backward(self, dps):
@@ -412,9 +530,7 @@ class TrainPlan:
         self.last_grad_scale = S
         inv = 1.0 / S
         self.sink = getattr(self.model, '_b2y_grad_sink', None)   # FlatDataParallel: write into the flat buffer
-        for gb in self.grad_bufs:
-            gb.zero_()
-        self.dz_aux.zero_()
+        self.bwd_arena.zero_()      # activation gradients, BN sums, scale rows, packed weight gradients (one memset)
         grads = {}
         # head gradients are GEMM operands (fp16): scale them by a power of two derived on the device from max|dp|
         live = [dp for dp in dps if dp is not None]
@@ -453,6 +569,12 @@ class TrainPlan:
                 gy, gx, xv = G(out).view(), G(src).view(), src.view()
                 call("b2y_maxpool_bwd", ptr(xv), ops._pitch(xv), ptr(gy), ops._pitch(gy), ptr(gx), ops._pitch(gx),
                      self.B, src.H, src.W, src.C, int(k), int(s), 1 if tiny else 0, ops._gdt(gy), stream_ptr())
+        self._unpack_all()
+        if self.own_grads:
+            # plain-autograd path: hand out copies (the plan-owned buffers are overwritten by the next step)
+            by_id = {id(p): p for p in self.params}
+            for pid, g in self.own_grads.items():
+                grads[by_id[pid]] = g
         return grads
 
     def _conv_backward(self, r, grads, S, inv):
@@ -466,14 +588,25 @@ class TrainPlan:
                 gs = self.grad_of[id(r.res)].view()
                 ops.add(gs, dy, out=gs)
             dz = self.dz_scratch[:B * Ho * Wo * r.Cout].view(B, Ho, Wo, r.Cout)
-            dgb = self.dgb_scratch[:, :r.Cout]
-            dgb.zero_()
-            aux = self.dz_aux[self.convs.index(r)] if r.aux_row is None else self.dz_aux[r.aux_row]
-            ops.bn_act_bwd(r.z.view(), dy, r.scale, r.shift, bn.weight.detach(), r.mean, r.invstd, r.act, r.slope,
-                           dx=dz, dgamma=dgb[0], dbeta=dgb[1], aux=aux)
+            aux = self.dz_aux[r.aux_row]
             inv_s = aux[2:3]                                   # device scalar 1/s of this layer's dz
-            self._emit(grads, bn.weight, dgb[0], inv)
-            self._emit(grads, bn.bias, dgb[1], inv)
+            if r.fast_bn:
+                z = r.z.view()
+                pixels = B * Ho * Wo
+                a = ACT[r.act]
+                call("b2y_bn_train_bwd_reduce", ptr(z), ops._pitch(z), ptr(dy), ops._pitch(dy), ptr(r.save),
+                     ptr(r.sums), ptr(aux), pixels, r.Cout, a, float(r.slope), ops._gdt(dy), stream_ptr())
+                call("b2y_bn_train_bwd_apply", ptr(z), ops._pitch(z), ptr(dy), ops._pitch(dy),
+                     ptr(bn.weight.detach()), ptr(r.save), ptr(r.sums), ptr(dz), ops._pitch(dz), pixels, r.Cout, a,
+                     float(r.slope), ops._gdt(dy), ptr(aux), C.c_void_p(aux.data_ptr() + 4),
+                     ptr(self._grad_dst(bn.weight)), ptr(self._grad_dst(bn.bias)), float(inv), stream_ptr())
+            else:
+                dgb = self.dgb_scratch[:, :r.Cout]
+                dgb.zero_()
+                ops.bn_act_bwd(r.z.view(), dy, r.scale, r.shift, bn.weight.detach(), r.mean, r.invstd, r.act, r.slope,
+                               dx=dz, dgamma=dgb[0], dbeta=dgb[1], aux=aux)
+                self._emit(grads, bn.weight, dgb[0], inv)
+                self._emit(grads, bn.bias, dgb[1], inv)
         else:
             dz = gy.buf[..., :r.Cpad] if r.head else gy.view()
             inv_s = self.head_scale[1:2]
@@ -485,38 +618,30 @@ class TrainPlan:
                 ops.bias_act_bwd_reduce(dz, dz, r.ones, r.zeros, 'linear', dbeta=db)
                 self._emit(grads, conv.bias, db[:r.Cout] * inv_s, inv)
         I = conv.in_channels
-        gw = self.sink.get(id(conv.weight)) if self.sink is not None else None
-        if gw is None:
-            gw = torch.empty_like(conv.weight)
-            grads[conv.weight] = gw
         if r.stem and getattr(r, 'wstem', None) is not None and getattr(self, 'stem_ws', None) is not None:
             # dW = dz^T . im2col(x): the pixel-dimension GEMM on the tensor cores over the forward's workspace
+            gw = self._grad_dst(conv.weight)
             kk = I * r.k * r.k
             xcol = self.stem_ws[:B * Ho * Wo * 32].view(B, Ho, Wo, 32)
-            dwp = self.dw_scratch[:r.Cpad * 32].view(r.Cpad, 1, 1, 32)
+            dwp = self.stem_dw[:r.Cpad * 32].view(r.Cpad, 1, 1, 32)
             dwp.zero_()
             ops.conv2d_bwd_weight(xcol, dz, 1, 1, 0, scale=inv, dw=dwp, inv_scale=inv_s)
             gw.copy_(dwp[:r.Cout, 0, 0, :kk].view(r.Cout, r.k, r.k, I).permute(0, 3, 1, 2))
         elif r.stem:
+            gw = self._grad_dst(conv.weight)
             gw.zero_()
             d = ConvDesc(B, self.H, self.W, I, I, r.Cout, r.k, r.s, r.p, Ho, Wo, ops._pitch(dz), 0, 0.0, OUT_F16, 0)
             call("b2y_stem_conv_bwd_weight", C.byref(d), ptr(self.x), ptr(dz), ptr(gw), inv, ops._gdt(dz), stream_ptr())
             gw.mul_(inv_s)
         else:
-            dwp = self.dw_scratch[:r.Cpad * r.k * r.k * I].view(r.Cpad, r.k, r.k, I)
-            dwp.zero_()
-            ops.conv2d_bwd_weight(r.src.view(), dz, r.k, r.s, r.p, scale=inv, dw=dwp, inv_scale=inv_s)
-            ops.unpack_wgrad(dwp[:r.Cout], gw)
+            # packed fp32 gradient slice (zeroed with the backward arena); unpacked for all layers at the end
+            ops.conv2d_bwd_weight(r.src.view(), dz, r.k, r.s, r.p, scale=inv, dw=r.dw, inv_scale=inv_s)
             gx = self.grad_of[id(r.src)]
             ops.conv2d_bwd_data(dz, r.wT, (B, r.src.H, r.src.W, I), r.k, r.s, r.p, out=gx.view(), accumulate=True,
                                 inv_scale=inv_s)
 
     def _emit(self, grads, param, src, alpha):
-        dst = self.sink.get(id(param)) if self.sink is not None else None
-        if dst is None:
-            grads[param] = src * alpha
-        else:
-            ops.axpby(src.contiguous(), dst, alpha, 0.0)
+        ops.axpby(src.contiguous(), self._grad_dst(param), alpha, 0.0)
 
     # ---------------------------------------------------------------------------------------------------------
     def run(self, x):

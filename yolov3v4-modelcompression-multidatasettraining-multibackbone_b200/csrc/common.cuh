@@ -406,6 +406,15 @@ namespace b2y {
 // 16-bit storage helpers so that gradient kernels can be instantiated for fp16 or bf16 tensors
 template <typename T> struct Half8;
 template <> struct Half8<__half> {
+    __device__ static void unpack(const uint4& u, float (&f)[8]) {
+        const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 t = __half22float2(h[j]);
+            f[2 * j] = t.x;
+            f[2 * j + 1] = t.y;
+        }
+    }
     __device__ static void load(const __half* p, float (&f)[8]) {
         const uint4 u = *reinterpret_cast<const uint4*>(p);
         const __half2* h = reinterpret_cast<const __half2*>(&u);
@@ -427,6 +436,15 @@ template <> struct Half8<__half> {
     __device__ static __half from_f(float v) { return __float2half_rn(v); }
 };
 template <> struct Half8<__nv_bfloat16> {
+    __device__ static void unpack(const uint4& u, float (&f)[8]) {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 t = __bfloat1622float2(h[j]);
+            f[2 * j] = t.x;
+            f[2 * j + 1] = t.y;
+        }
+    }
     __device__ static void load(const __nv_bfloat16* p, float (&f)[8]) {
         const uint4 u = *reinterpret_cast<const uint4*>(p);
         const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
