@@ -113,9 +113,11 @@ def cfg_for(name, rank=0):
 
 
 def build_model(name, device, rank=0, train=False):
+    import contextlib
     import models
     torch.manual_seed(0)
-    m = models.Darknet(cfg_for(name, rank), img_size=(SIZE, SIZE))
+    with contextlib.redirect_stdout(sys.stderr):       # "Model Summary: ..." must not pollute the one-JSON-line stdout
+        m = models.Darknet(cfg_for(name, rank), img_size=(SIZE, SIZE))
     g = torch.Generator().manual_seed(1)
     with torch.no_grad():  # non-degenerate BN statistics for eval
         for mod in m.modules():
@@ -172,7 +174,9 @@ def cpu_reference_rate(kind, name, max_seconds=20.0, batch=2, max_iters=10, thre
     from utils.parse_config import parse_model_cfg_text
     avail = host_threads()
     defs = parse_model_cfg_text(cfggen.cfg_text(name))[1:]
-    sd = orc.synth_state_dict(models.Darknet(cfg_for(name, 99)).state_dict(), 0)
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):
+        sd = orc.synth_state_dict(models.Darknet(cfg_for(name, 99)).state_dict(), 0)
     if threads is None:
         # "all the host threads it can use": more threads than physically free cores make torch's CPU convs slower,
         # so take the fastest of a few thread counts on a small probe forward
@@ -301,7 +305,8 @@ def replay_convs(calls, iters):
     convs = [(n, a) for (n, a) in calls if n in CONV_CALLS]
     flops = sum(conv_desc_flops(n, a) for n, a in convs)
     raw = lib.raw()
-    fns = [(getattr(raw, n), a) for n, a in convs]
+    cur = lib.stream_ptr()          # launches may have been recorded on a side stream: replay all on the timed stream
+    fns = [(getattr(raw, n), a[:-1] + (cur,)) for n, a in convs]
     for f, a in fns:
         f(*a)
     torch.cuda.synchronize()

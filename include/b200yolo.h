@@ -335,6 +335,28 @@ int b2y_layout_tile_i(int ksize);
 int b2y_pack_conv_weights_multi(const b2y_pack_item* items_dev, int n_items, int total_tiles, void* stream);
 int b2y_unpack_wgrad_multi(const b2y_unpack_item* items_dev, int n_items, int total_tiles, void* stream);
 
+/* ---- depthwise convolution + squeeze-excite (csrc/depthwise.cu): the `depthwise` / `se` cfg blocks of the MobileNet
+ * backbones, models.py:115-197, utils/layers.py:176-192.  NHWC fp16, channels % 8 == 0, weights are the fp32 module
+ * parameters themselves (Conv2d(groups=C).weight [C][1][k][k]; Linear weights [C/4][C], [C][C/4]). ---- */
+/* y = act(dwconv(x, w) * scale[c] + bias[c])  (scale / bias optional: folded BatchNorm for inference); training passes
+ * act = linear, scale = bias = NULL and the channel sums (sum z, sum z^2; caller zeroes) of the raw output */
+int b2y_dwconv_fwd(const b2y_conv_desc* d, const void* x, const float* w, const float* scale, const float* bias, void* y,
+                   float* stat_sum, float* stat_sqsum, void* stream);
+/* dx (+)= inv_scale * dwconv^T(dz, w)   dz fp16 NHWC [B][out_h][out_w][c], dx fp16 / bf16 [B][in_h][in_w][c] */
+int b2y_dwconv_bwd_data(const b2y_conv_desc* d, const void* dz, const float* w, void* dx, int accumulate,
+                        int out_dtype, const float* inv_scale_ptr, void* stream);
+/* dw[c][k][k] += alpha * inv_scale * sum_pixels dz * x   (fp32, caller zeroes) */
+int b2y_dwconv_bwd_weight(const b2y_conv_desc* d, const void* x, const void* dz, float* dw, float alpha,
+                          const float* inv_scale_ptr, void* stream);
+/* SE forward: y = x * hsigmoid(W2 relu(W1 mean_hw(x))).  ws = fp32 [batch][3c + cr] scratch that the backward reads
+ * (mean, h, pre-activation v, gate s) */
+int b2y_se_fwd(const void* x, long long x_pitch, const float* w1, const float* w2, void* y, long long y_pitch, int batch,
+               int hw, int c, int cr, float* ws, void* stream);
+/* SE backward: dx (+)= dy*s + dmean/hw;  dw1 [cr][c], dw2 [c][cr] = grad_scale * gradients (overwritten) */
+int b2y_se_bwd(const void* x, long long x_pitch, const void* dy, long long dy_pitch, const float* w1, const float* w2,
+               const float* ws, float* ws_bwd /* fp32 [batch][3c + cr] */, void* dx, long long dx_pitch, int accumulate,
+               float* dw1, float* dw2, float grad_scale, int batch, int hw, int c, int cr, int grad_dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -116,6 +116,11 @@ _PROTOS = {
     "b2y_bn_train_bwd_reduce": (i32, [vp, ll, vp, ll, vp, vp, vp, ll, i32, i32, f32, i32, vp]),
     "b2y_bn_train_bwd_apply": (i32, [vp, ll, vp, ll, vp, vp, vp, vp, ll, ll, i32, i32, f32, i32, vp, vp, vp, vp, f32,
                                      vp]),
+    "b2y_dwconv_fwd": (i32, [C.POINTER(ConvDesc), vp, vp, vp, vp, vp, vp, vp, vp]),
+    "b2y_dwconv_bwd_data": (i32, [C.POINTER(ConvDesc), vp, vp, vp, i32, i32, vp, vp]),
+    "b2y_dwconv_bwd_weight": (i32, [C.POINTER(ConvDesc), vp, vp, vp, f32, vp, vp]),
+    "b2y_se_fwd": (i32, [vp, ll, vp, vp, vp, ll, i32, i32, i32, i32, vp, vp]),
+    "b2y_se_bwd": (i32, [vp, ll, vp, ll, vp, vp, vp, vp, vp, ll, i32, vp, vp, f32, i32, i32, i32, i32, i32, vp]),
     "b2y_layout_tile_i": (i32, [i32]),
     "b2y_pack_conv_weights_multi": (i32, [vp, i32, i32, vp]),
     "b2y_unpack_wgrad_multi": (i32, [vp, i32, i32, vp]),
@@ -148,7 +153,11 @@ def check(status, what=""):
 
 def ptr(t):
     """Device pointer of a torch tensor (None -> NULL)."""
-    return None if t is None else C.c_void_p(t.data_ptr())
+    if t is None:
+        return None
+    if RECORD is not None:
+        KEEPALIVE.append(t)
+    return C.c_void_p(t.data_ptr())
 
 
 def stream_ptr():
@@ -163,6 +172,7 @@ def raw():
 # Launch recorder (measurement only, bench.py / tools): while RECORD is a list every C-ABI call is appended as
 # (name, args) so that a family of launches (e.g. all tcgen05 convolutions of one step) can be replayed back to back.
 RECORD = None
+KEEPALIVE = []      # tensors whose pointers were handed out while recording (temporaries must outlive the replay)
 
 
 def call(name, *args):

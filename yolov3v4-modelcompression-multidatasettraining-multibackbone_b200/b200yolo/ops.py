@@ -402,6 +402,76 @@ def bias_act_bwd_reduce(x, dy, scale, shift, act, slope=0.1, dbeta=None):
     return dbeta
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# depthwise convolution + squeeze-excite (MobileNet backbones)
+# ---------------------------------------------------------------------------------------------------------------
+def dwconv2d(x, w, k, stride, pad, scale=None, bias=None, act="linear", slope=0.1, out=None, stats=None):
+    """Depthwise conv: x NHWC fp16 [B,H,W,C], w fp32 [C,1,k,k] (the module parameter).  y = act(conv*scale + bias)."""
+    _require_cuda(x, w)
+    B, H, W, Cc = x.shape
+    Ho, Wo = conv_out_hw(H, W, k, stride, pad)
+    if out is None:
+        out = torch.empty((B, Ho, Wo, Cc), dtype=torch.float16, device=x.device)
+    d = make_conv_desc(x.shape, _pitch(x), Cc, k, stride, pad, _pitch(out), act, slope, OUT_F16)
+    assert w.is_contiguous() and w.dtype == torch.float32 and w.numel() == Cc * k * k
+    call("b2y_dwconv_fwd", C.byref(d), ptr(x), ptr(w), ptr(scale), ptr(bias), ptr(out),
+         ptr(stats[0]) if stats is not None else None, ptr(stats[1]) if stats is not None else None, stream_ptr())
+    return out
+
+
+def dwconv2d_bwd_data(dz, w, in_shape, k, stride, pad, out=None, accumulate=False, inv_scale=None):
+    B, H, W, Cc = in_shape
+    _, Ho, Wo, _ = dz.shape
+    if out is None:
+        out = torch.zeros((B, H, W, Cc), dtype=torch.float16, device=dz.device)
+    d = ConvDesc(B, H, W, Cc, _pitch(out), Cc, k, stride, pad, Ho, Wo, _pitch(dz), 0, 0.0, OUT_F16, 0)
+    call("b2y_dwconv_bwd_data", C.byref(d), ptr(dz), ptr(w), ptr(out), 1 if accumulate else 0, _gdt(out),
+         ptr(inv_scale), stream_ptr())
+    return out
+
+
+def dwconv2d_bwd_weight(x, dz, k, stride, pad, alpha=1.0, dw=None, inv_scale=None):
+    B, H, W, Cc = x.shape
+    _, Ho, Wo, _ = dz.shape
+    if dw is None:
+        dw = torch.zeros((Cc, 1, k, k), dtype=torch.float32, device=x.device)
+    d = ConvDesc(B, H, W, Cc, _pitch(x), Cc, k, stride, pad, Ho, Wo, _pitch(dz), 0, 0.0, OUT_F16, 0)
+    call("b2y_dwconv_bwd_weight", C.byref(d), ptr(x), ptr(dz), ptr(dw), float(alpha), ptr(inv_scale), stream_ptr())
+    return dw
+
+
+def se_workspace(batch, c, cr, device):
+    return torch.empty((batch, 3 * c + cr), dtype=torch.float32, device=device)
+
+
+def se_fwd(x, w1, w2, out=None, ws=None):
+    """Squeeze-excite: x NHWC fp16, w1 [C/r, C], w2 [C, C/r] fp32 (nn.Linear weights). Returns (y, ws)."""
+    B, H, W, Cc = x.shape
+    cr = w1.shape[0]
+    if out is None:
+        out = torch.empty((B, H, W, Cc), dtype=torch.float16, device=x.device)
+    if ws is None:
+        ws = se_workspace(B, Cc, cr, x.device)
+    assert w1.is_contiguous() and w2.is_contiguous() and w1.dtype == torch.float32
+    call("b2y_se_fwd", ptr(x), _pitch(x), ptr(w1), ptr(w2), ptr(out), _pitch(out), B, H * W, Cc, cr, ptr(ws),
+         stream_ptr())
+    return out, ws
+
+
+def se_bwd(x, dy, w1, w2, ws, dx, accumulate=False, dw1=None, dw2=None, grad_scale=1.0, ws_bwd=None):
+    B, H, W, Cc = x.shape
+    cr = w1.shape[0]
+    if ws_bwd is None:
+        ws_bwd = se_workspace(B, Cc, cr, x.device)
+    if dw1 is None:
+        dw1 = torch.empty_like(w1)
+        dw2 = torch.empty_like(w2)
+    call("b2y_se_bwd", ptr(x), _pitch(x), ptr(dy), _pitch(dy), ptr(w1), ptr(w2), ptr(ws), ptr(ws_bwd), ptr(dx),
+         _pitch(dx), 1 if accumulate else 0, ptr(dw1), ptr(dw2), float(grad_scale), B, H * W, Cc, cr, _gdt(dy),
+         stream_ptr())
+    return dx, dw1, dw2
+
+
 def sgd_nesterov(param, grad, buf, lr, momentum, weight_decay, grad_scale=1.0, first_step=False):
     call("b2y_sgd_nesterov", ptr(param), ptr(grad), ptr(buf), param.numel(), float(lr), float(momentum),
          float(weight_decay), float(grad_scale), 1 if first_step else 0, stream_ptr())

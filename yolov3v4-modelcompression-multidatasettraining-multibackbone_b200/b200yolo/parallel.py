@@ -50,7 +50,18 @@ class FlatDataParallel:
                 p.grad = gv
                 self.grad_views[id(p)] = gv
                 off += n
+        # BatchNorm running statistics become views of ONE flat buffer as well, so that "rank 0's buffers win" (DDP
+        # broadcast_buffers, N3) is a single broadcast per forward instead of a cat + 2 copies per BatchNorm layer
         self.buffers = [b for b in model.buffers() if b.dtype.is_floating_point]
+        nb = sum(b.numel() for b in self.buffers)
+        self.flat_buf = torch.empty(nb, dtype=torch.float32, device=dev) if nb else None
+        off = 0
+        with torch.no_grad():
+            for b in self.buffers:
+                n = b.numel()
+                self.flat_buf[off:off + n].copy_(b.detach().reshape(-1).float())
+                b.data = self.flat_buf[off:off + n].view_as(b)
+                off += n
         self.steps = 0
         if self.world > 1:
             dist.broadcast(self.flat_param, src=0, group=self.pg)           # N2: parameters from rank 0
@@ -65,15 +76,9 @@ class FlatDataParallel:
         return getattr(self.__dict__['module'], name)
 
     def _broadcast_buffers(self):
-        if not self.buffers:
+        if self.flat_buf is None:
             return
-        flat = torch.cat([b.reshape(-1) for b in self.buffers])
-        dist.broadcast(flat, src=0, group=self.pg)
-        off = 0
-        for b in self.buffers:
-            n = b.numel()
-            b.copy_(flat[off:off + n].view_as(b))
-            off += n
+        dist.broadcast(self.flat_buf, src=0, group=self.pg)
 
     def __call__(self, x, *a, **k):
         if self.world > 1 and self.broadcast_buffers and self.module.training:

@@ -293,8 +293,15 @@ class TrainPlan:
         for r in self.convs:
             if r.bn is not None:
                 r.save = torch.empty((4, r.Cout), dtype=torch.float32, device=dev)
-        maxz = max(r.Cpad * r.y.H * r.y.W for r in self.convs)
-        self.dz_scratch = torch.empty(B * maxz, dtype=torch.float16, device=dev)
+        # The weight gradients hang off the critical path (dz_i -> dW_i has no consumer until the optimiser), so they run
+        # on a second stream concurrently with the data-gradient / BatchNorm chain.  dz is therefore kept per layer
+        # (no buffer shared between a running wgrad and the next layer's BN backward); B2Y_WGRAD_STREAM=0 serialises.
+        self.side_wgrad = os.environ.get('B2Y_WGRAD_STREAM', '1') != '0'
+        self.dz_bufs = {}
+        if not self.side_wgrad:
+            maxz = max(r.Cpad * r.y.H * r.y.W for r in self.convs)
+            self.dz_scratch = torch.empty(B * maxz, dtype=torch.float16, device=dev)
+        self.side_stream = None
         maxc = max(r.Cpad for r in self.convs)
         self.dgb_scratch = torch.empty((2, maxc), dtype=torch.float32, device=dev)
         self.stem_dw = torch.empty(maxc * 32, dtype=torch.float32, device=dev)
@@ -531,6 +538,8 @@ class TrainPlan:
         inv = 1.0 / S
         self.sink = getattr(self.model, '_b2y_grad_sink', None)   # FlatDataParallel: write into the flat buffer
         self.bwd_arena.zero_()      # activation gradients, BN sums, scale rows, packed weight gradients (one memset)
+        if self.side_wgrad and self.side_stream is None:
+            self.side_stream = torch.cuda.Stream(device=self.device)
         grads = {}
         # head gradients are GEMM operands (fp16): scale them by a power of two derived on the device from max|dp|
         live = [dp for dp in dps if dp is not None]
@@ -569,6 +578,8 @@ class TrainPlan:
                 gy, gx, xv = G(out).view(), G(src).view(), src.view()
                 call("b2y_maxpool_bwd", ptr(xv), ops._pitch(xv), ptr(gy), ops._pitch(gy), ptr(gx), ops._pitch(gx),
                      self.B, src.H, src.W, src.C, int(k), int(s), 1 if tiny else 0, ops._gdt(gy), stream_ptr())
+        if self.side_wgrad:
+            torch.cuda.current_stream().wait_stream(self.side_stream)      # join: every weight gradient is complete
         self._unpack_all()
         if self.own_grads:
             # plain-autograd path: hand out copies (the plan-owned buffers are overwritten by the next step)
@@ -587,7 +598,12 @@ class TrainPlan:
             if r.res is not None:   # fused shortcut: the same gradient also flows to the skip source
                 gs = self.grad_of[id(r.res)].view()
                 ops.add(gs, dy, out=gs)
-            dz = self.dz_scratch[:B * Ho * Wo * r.Cout].view(B, Ho, Wo, r.Cout)
+            if self.side_wgrad:
+                dz = self.dz_bufs.get(r.i)
+                if dz is None:
+                    dz = self.dz_bufs[r.i] = torch.empty((B, Ho, Wo, r.Cout), dtype=torch.float16, device=self.device)
+            else:
+                dz = self.dz_scratch[:B * Ho * Wo * r.Cout].view(B, Ho, Wo, r.Cout)
             aux = self.dz_aux[r.aux_row]
             inv_s = aux[2:3]                                   # device scalar 1/s of this layer's dz
             if r.fast_bn:
@@ -635,7 +651,13 @@ class TrainPlan:
             gw.mul_(inv_s)
         else:
             # packed fp32 gradient slice (zeroed with the backward arena); unpacked for all layers at the end
-            ops.conv2d_bwd_weight(r.src.view(), dz, r.k, r.s, r.p, scale=inv, dw=r.dw, inv_scale=inv_s)
+            if self.side_wgrad:
+                main = torch.cuda.current_stream()
+                self.side_stream.wait_stream(main)              # dz (and 1/s) of this layer are complete
+                with torch.cuda.stream(self.side_stream):
+                    ops.conv2d_bwd_weight(r.src.view(), dz, r.k, r.s, r.p, scale=inv, dw=r.dw, inv_scale=inv_s)
+            else:
+                ops.conv2d_bwd_weight(r.src.view(), dz, r.k, r.s, r.p, scale=inv, dw=r.dw, inv_scale=inv_s)
             gx = self.grad_of[id(r.src)]
             ops.conv2d_bwd_data(dz, r.wT, (B, r.src.H, r.src.W, I), r.k, r.s, r.p, out=gx.view(), accumulate=True,
                                 inv_scale=inv_s)

@@ -107,7 +107,9 @@ struct ConvTcEpi {
 // int8 requantisation.  `v` holds the scaled accumulators on entry.
 template <int KIND>
 __device__ __forceinline__ void epi_chunk_general(float (&v)[32], const ConvTcParams& p, int n0c0, long long row,
-                                               bool row_ok, int lane, uint8_t* stage) {
+                                               bool row_ok, int lane, uint8_t* stage, bool defer_stats, float& ds1,
+                                               float& ds2) {
+    ds1 = ds2 = 0.f;
     if (p.stat_sum != nullptr) {
         // per-channel batch statistics of the raw conv output (training BN): the warp's 32x32 chunk goes through its smem
         // staging tile (rotated columns: conflict-free both ways), then lane j sums column j -- 32 STS + 32 LDS instead of
@@ -124,7 +126,10 @@ __device__ __forceinline__ void epi_chunk_general(float (&v)[32], const ConvTcPa
             s2 = fmaf(t, t, s2);
         }
         __syncwarp();
-        if (n0c0 + lane < p.Cout) {
+        if (defer_stats) {          // single N tile: the warp keeps per-column partial sums across its tiles
+            ds1 = s1;
+            ds2 = s2;
+        } else if (n0c0 + lane < p.Cout) {
             atomicAdd(p.stat_sum + n0c0 + lane, s1);
             atomicAdd(p.stat_sqsum + n0c0 + lane, s2);
         }
@@ -495,6 +500,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint8_t* my_stage = epi_stage + (warp - 4) * 4096;
         int sbuf = 0;
         int it = 0;
+        // training BN statistics: with a single N tile every tile of this warp covers the same columns, so the channel
+        // sums are kept in registers (lane j = column j of chunk q) and flushed with ONE atomic per column per warp at the
+        // end -- instead of one per column per 32-row chunk (millions of same-address L2 atomics on the large early layers)
+        const bool defer_stats = p.stat_sum != nullptr && num_n_tiles == 1;
+        float st1[4] = {0.f, 0.f, 0.f, 0.f}, st2[4] = {0.f, 0.f, 0.f, 0.f};
         for (int item = cluster_id; item < num_items; item += num_clusters, ++it) {
             if (Epi::SPLIT_TILES && (it & 1) != cg) continue;
             const int acc = it % AS;
@@ -592,8 +602,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], v[j] * slope);
                     } else if (act == B2Y_ACT_MISH) {
+                        // inlined closed form (one ex2, one rcp per element): 32 independent dependency chains the
+                        // scheduler can interleave -- as a call per element the epilogue was bound by the serial
+                        // MUFU latency of each chain (yolov4's Mish layers ran 2-6x slower than their leaky twins)
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = mish_noinline(v[j]);
+                        for (int j = 0; j < 32; ++j) v[j] = mish_f(v[j]);
                     }
                     if (row_ok && res_p != nullptr) {
 #pragma unroll
@@ -709,7 +722,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
                         v[j] = ((KIND == CONV_KIND_F16) ? __uint_as_float(raw[j]) : (float)(int)raw[j]) * acc_mul;
-                    epi_chunk_general<KIND>(v, p, n0 + c0, row, row_ok, lane, my_stage);
+                    float ds1, ds2;
+                    epi_chunk_general<KIND>(v, p, n0 + c0, row, row_ok, lane, my_stage, defer_stats, ds1, ds2);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (c == q * 32) {
+                            st1[q] += ds1;
+                            st2[q] += ds2;
+                        }
                 }
             }
             // release this accumulator stage back to the MMA warp
@@ -720,6 +740,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[acc]), 0));   // the leader's MMA warp waits on it
                 else
                     mbar_arrive(&tmem_empty_bar[acc]);
+            }
+        }
+        if (defer_stats) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int col = c_begin + q * 32 + lane;
+                if (q * 32 < COLS_PER_GROUP && col < p.Cout && (st1[q] != 0.f || st2[q] != 0.f)) {
+                    atomicAdd(p.stat_sum + col, st1[q]);
+                    atomicAdd(p.stat_sqsum + col, st2[q]);
+                }
             }
         }
         if (epi_tma && lane == 0) bulk_wait_all();   // outstanding TMA stores complete before the CTA exits

@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(128 * NG + 64, 1) stem_fused_kernel(const __gr
                                 break;
                             case B2Y_ACT_MISH:
 #pragma unroll
-                                for (int q = 0; q < 32; ++q) v[q] = stem_mish(v[q]);
+                                for (int q = 0; q < 32; ++q) v[q] = mish_f(v[q]);   // inlined: 32 independent chains
                                 break;
                             case B2Y_ACT_RELU:
 #pragma unroll

@@ -198,8 +198,45 @@ def compute_loss(p, targets, model):
     dev = p[0].device
     anchors = [_device_anchor_vec(m, dev) for m in _yolo_modules(model)]
     t = targets.to(dev).float()
-    if t.numel() and int(t[:, 1].max()) >= model.nc:
-        raise AssertionError('Model accepts %g classes labeled from 0-%g, however you labelled a class %g. '
-                             'See https://github.com/ultralytics/yolov3/wiki/Train-Custom-Data'
-                             % (model.nc, model.nc - 1, t[:, 1].max()))
+    _check_class_ids(t, int(model.nc))
     return _YoloLoss.apply(t, (anchors, h, float(model.gr), int(model.nc)), *p)
+
+
+# The reference asserts "class id < nc" inside build_targets (utils/utils.py:775) with a blocking .max() on the
+# device tensor.  A blocking read here would stall the launch queue once per training step (the CPU could no longer
+# run ahead of the GPU), so the maximum is copied to pinned host memory asynchronously and verified when it has
+# arrived -- at the latest at the start of the NEXT compute_loss call -- with the reference's message.
+_pending_check = None
+
+
+def _raise_bad_class(nc, cmax):
+    raise AssertionError('Model accepts %g classes labeled from 0-%g, however you labelled a class %g. '
+                         'See https://github.com/ultralytics/yolov3/wiki/Train-Custom-Data' % (nc, nc - 1, cmax))
+
+
+def _check_class_ids(t, nc):
+    global _pending_check
+    if _pending_check is not None:
+        host, ev, pnc = _pending_check
+        ev.synchronize()
+        _pending_check = None
+        if float(host[0]) >= pnc:
+            _raise_bad_class(pnc, float(host[0]))
+    if not t.numel():
+        return
+    if torch.cuda.is_current_stream_capturing():
+        return
+    host = torch.empty(1, dtype=torch.float32).pin_memory()
+    host.copy_(t[:, 1].max().reshape(1), non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record()
+    if ev.query():                      # already there (small queue): behave exactly like the reference
+        if float(host[0]) >= nc:
+            _raise_bad_class(nc, float(host[0]))
+        return
+    _pending_check = (host, ev, nc)
+
+
+def flush_checks():
+    """Force the deferred class-id check of the last compute_loss call (raises like the reference if it failed)."""
+    _check_class_ids(torch.zeros(0, 6), 0)
