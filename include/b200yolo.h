@@ -320,16 +320,16 @@ int b2y_bn_train_bwd_apply(const void* z, long long z_pitch, const void* dy, lon
  * ceil(rows/32) * ceil(in_c / tile_i) over the items (rows = out_c_pad for packing, out_c for unpacking). */
 typedef struct b2y_pack_item {
     const float* w;     /* master weights, OIHW fp32 [out_c][in_c][k][k] */
-    void* w_fwd;        /* fp16 [out_c_pad][k][k][in_c] (rows >= out_c zero) or NULL */
+    void* w_fwd;        /* fp16 [out_c_pad][k][k][in_c_pad] (rows >= out_c zero; columns >= in_c untouched) or NULL */
     void* w_dgrad;      /* fp16 [phase][in_c][tap][out_c_pad] (see b2y_pack_dgrad_weights) or NULL */
     int O, Opad, I, k, stride, pad;
-    int tile_begin, reserved;
+    int tile_begin, Ipad; /* Ipad = row length of w_fwd (in_c rounded up to the MMA K granule of 16) */
 } b2y_pack_item;
 typedef struct b2y_unpack_item {
-    const float* src;   /* packed weight gradient fp32 [out_c_pad][k][k][in_c] */
+    const float* src;   /* packed weight gradient fp32 [out_c_pad][k][k][in_c_pad] */
     float* dst;         /* OIHW fp32 [out_c][in_c][k][k] */
     int O, I, k, accumulate;
-    int tile_begin, reserved;
+    int tile_begin, Ipad;
 } b2y_unpack_item;
 int b2y_layout_tile_i(int ksize);
 int b2y_pack_conv_weights_multi(const b2y_pack_item* items_dev, int n_items, int total_tiles, void* stream);

@@ -227,9 +227,9 @@ def test_multi_tensor_pack_and_unpack_bit_exact(case):
         dwp = torch.randn(Opad, k, k, I, generator=g).cuda()
         dst = torch.zeros(O, I, k, k, device="cuda")
         ti = lib.raw().b2y_layout_tile_i(k)
-        items.append(PackItem(w.data_ptr(), wf.data_ptr(), wd.data_ptr(), O, Opad, I, k, s, pd, tiles, 0))
+        items.append(PackItem(w.data_ptr(), wf.data_ptr(), wd.data_ptr(), O, Opad, I, k, s, pd, tiles, I))
         tiles += ((Opad + 31) // 32) * ((I + ti - 1) // ti)
-        uitems.append(UnpackItem(dwp.data_ptr(), dst.data_ptr(), O, I, k, 0, utiles, 0))
+        uitems.append(UnpackItem(dwp.data_ptr(), dst.data_ptr(), O, I, k, 0, utiles, I))
         utiles += ((O + 31) // 32) * ((I + ti - 1) // ti)
         keep.append((w, wf, wd, dwp, dst))
     tab = torch.frombuffer(bytearray(bytes((PackItem * len(items))(*items))), dtype=torch.uint8).cuda()

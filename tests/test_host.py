@@ -161,7 +161,8 @@ def test_cpu_tensors_fail_loudly():
 
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present (GPU box)")
 @pytest.mark.parametrize("name,rel", [("yolov3", "cfg/yolov3/yolov3.cfg"), ("yolov3-tiny", "cfg/yolov3tiny/yolov3-tiny.cfg"),
-                                      ("yolov4", "cfg/yolov4/yolov4.cfg")])
+                                      ("yolov4", "cfg/yolov4/yolov4.cfg"),
+                                      ("yolov3-mobilenet", "cfg/yolov3-mobilenet/yolov3-mobilenet-coco.cfg")])
 def test_generated_cfg_equals_reference_cfg(name, rel):
     from utils.parse_config import parse_model_cfg
     ours = module_defs(name)

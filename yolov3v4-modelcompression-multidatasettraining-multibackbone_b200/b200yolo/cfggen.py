@@ -29,6 +29,13 @@ class _Cfg:
                                                          ("pad", 1), ("activation", act)]
         return self.block("convolutional", *kv)
 
+    def depthwise(self, filters, size, stride=1, act="relu6"):
+        return self.block("depthwise", ("batch_normalize", 1), ("filters", filters), ("size", size), ("stride", stride),
+                          ("pad", 1), ("activation", act))
+
+    def se(self, filters):
+        return self.block("se", ("filters", filters))
+
     def shortcut(self, frm=-3):
         return self.block("shortcut", ("from", frm), ("activation", "linear"))
 
@@ -171,7 +178,42 @@ def yolov4(classes=80):
     return c.text()
 
 
-ARCHS = {"yolov3": yolov3, "yolov3-tiny": yolov3_tiny, "yolov4": yolov4}
+def yolov3_mobilenet(classes=80):
+    """YOLOv3 head on a MobileNetV3-large backbone (the reference's cfg/yolov3-mobilenet/yolov3-mobilenet-coco.cfg):
+    inverted-residual blocks = 1x1 expand -> depthwise k x k -> [squeeze-excite] -> 1x1 project (linear) [+ shortcut]."""
+    c = _Cfg([("batch", 16), ("subdivisions", 1)] + _net()[2:])
+    nout = 3 * (classes + 5)
+    c.conv(16, 3, 2, act="h_swish")
+    # (expansion, out, kernel, stride, se, activation, residual)
+    blocks = ((16, 16, 3, 1, 0, "relu6", 1), (64, 24, 3, 2, 0, "relu6", 0), (72, 24, 3, 1, 0, "relu6", 1),
+              (72, 40, 5, 2, 1, "relu6", 0), (120, 40, 5, 1, 1, "relu6", 1), (120, 40, 5, 1, 1, "relu6", 1),
+              (240, 80, 3, 2, 0, "h_swish", 0), (200, 80, 3, 1, 0, "h_swish", 1), (184, 80, 3, 1, 0, "h_swish", 1),
+              (184, 80, 3, 1, 0, "h_swish", 1), (480, 112, 3, 1, 1, "h_swish", 0), (672, 112, 3, 1, 1, "h_swish", 1),
+              (672, 160, 5, 2, 1, "h_swish", 0), (960, 160, 5, 1, 1, "h_swish", 1), (960, 160, 5, 1, 1, "h_swish", 1))
+    for exp, out, k, stride, se, act, res in blocks:
+        c.conv(exp, 1, act=act)
+        c.depthwise(exp, k, stride, act=act)
+        if se:
+            c.se(exp)
+        c.conv(out, 1, act="linear")
+        if res:
+            c.shortcut(-5 if se else -4)
+    c.conv(1024, 1, act="h_swish")
+    for scale, (mid, mask, skip) in enumerate(((512, (6, 7, 8), None), (256, (3, 4, 5), 49), (128, (0, 1, 2), 25))):
+        if skip is not None:
+            c.route(-4)
+            c.conv(mid, 1)
+            c.upsample(2)
+            c.route(-1, skip)
+        for _ in range(3):
+            c.conv(mid, 1)
+            c.conv(mid * 2, 3)
+        c.conv(nout, 1, act="linear", bn=0)
+        c.yolo(mask, COCO_ANCHORS_V3, classes, 9, (("random", 1),))
+    return c.text()
+
+
+ARCHS = {"yolov3": yolov3, "yolov3-tiny": yolov3_tiny, "yolov4": yolov4, "yolov3-mobilenet": yolov3_mobilenet}
 
 
 def cfg_text(name, classes=80):

@@ -53,6 +53,19 @@ class _Tensor:
     def view(self):
         return self.buf[..., self.c0:self.c0 + self.C]
 
+    def view_k(self):
+        """View for a tensor-core consumer: the channel count rounded up to 16 (the MMA K granule is 16 fp16 elements).
+        MobileNet widths (24, 40, 72, 120, 184, 200) are not: their buffers are allocated zero-filled with a pitch that
+        is a multiple of 16 and nobody ever writes the pad channels, the packed weights carry zero columns there (a
+        tensor living inside a concat buffer may see its neighbour's channels instead of zeros: finite values times
+        zero weights)."""
+        ck = (self.C + 15) // 16 * 16
+        if ck == self.C:
+            return self.view()
+        if self.c0 + ck > self.buf.shape[3]:
+            raise RuntimeError("activation buffer too narrow for the padded channel view (C=%d)" % self.C)
+        return self.buf[..., self.c0:self.c0 + ck]
+
 
 def _block_parts(block):
     """nn.Sequential conv block -> (conv, bn or None, activation name, slope)."""
@@ -68,6 +81,14 @@ def _block_parts(block):
             if name == 'LeakyReLU':
                 slope = m.negative_slope
     return conv, bn, act, slope
+
+
+def _new_act(shape, device):
+    """fp16 NHWC activation buffer; widths that are not a multiple of 16 get a zero-filled pad (see _Tensor.view_k)."""
+    B, H, W, C = shape
+    if C % 16 == 0:
+        return torch.empty((B, H, W, C), dtype=torch.float16, device=device)
+    return torch.zeros((B, H, W, (C + 15) // 16 * 16), dtype=torch.float16, device=device)
 
 
 class Plan:
@@ -99,11 +120,13 @@ class Plan:
         for i, (d, m) in enumerate(zip(defs, mods)):
             t = d['type']
             C, H, W = prev
-            if t == 'convolutional':
+            if t in ('convolutional', 'depthwise'):
                 conv = _block_parts(m)[0]
                 k, s, p = conv.kernel_size[0], conv.stride[0], conv.padding[0]
                 H, W = ops.conv_out_hw(H, W, k, s, p)
                 C = conv.out_channels
+            elif t == 'se':
+                pass
             elif t == 'maxpool':
                 k, s = d['size'], d['stride']
                 if k == 2 and s == 1:
@@ -171,7 +194,7 @@ class Plan:
                 continue
             srcs = [i + l if l < 0 else l for l in d['layers']]
             dst = tens[i]
-            dst.buf = torch.empty((B, dst.H, dst.W, dst.C), dtype=torch.float16, device=dev)
+            dst.buf = _new_act((B, dst.H, dst.W, dst.C), dev)
             off = 0
             for s in srcs:
                 st = tens[s]
@@ -189,8 +212,10 @@ class Plan:
         # 5) allocate what is left and emit the launch list
         def alloc(t):
             if t.buf is None:
-                pitch = t.C if t.dtype == torch.float16 else ((t.C + 3) // 4) * 4
-                t.buf = torch.empty((B, t.H, t.W, pitch), dtype=t.dtype, device=dev)
+                if t.dtype == torch.float16:
+                    t.buf = _new_act((B, t.H, t.W, t.C), dev)
+                else:
+                    t.buf = torch.empty((B, t.H, t.W, ((t.C + 3) // 4) * 4), dtype=t.dtype, device=dev)
                 t.c0 = 0
             return t
 
@@ -199,7 +224,17 @@ class Plan:
         row_off = 0
         for i, (d, m) in enumerate(zip(defs, mods)):
             t = d['type']
-            if t == 'convolutional':
+            if t == 'depthwise':
+                conv, bn, act, slope = _block_parts(m)
+                if conv.groups != conv.in_channels or conv.out_channels != conv.in_channels:
+                    raise NotImplementedError("only channel-multiplier-1 depthwise convolutions are supported")
+                self.steps.append(('dw', i, tens[i - 1], alloc(tens[i]), conv, bn, act, slope))
+            elif t == 'se':
+                fc = m[0].fc if isinstance(m, nn.Sequential) else m.fc
+                src = tens[i - 1]
+                ws = ops.se_workspace(B, src.C, fc[0].out_features, dev)
+                self.steps.append(('se', i, src, alloc(tens[i]), fc[0], fc[2], ws))
+            elif t == 'convolutional':
                 conv, bn, act, slope = _block_parts(m)
                 if conv.groups != 1:
                     raise NotImplementedError("grouped convolution is not supported by the sm_100a engine yet")
@@ -255,6 +290,20 @@ class Plan:
 
     def _pack_weights(self):
         for st in self.steps:
+            if st[0] == 'dw':
+                _, i, src, out, conv, bn, act, slope = st
+                w = conv.weight.detach().float().contiguous()
+                if bn is not None:           # fold: y = conv * gamma/sqrt(var+eps) + (beta - mean*gamma/sqrt(var+eps))
+                    sc = (bn.weight.detach() / torch.sqrt(bn.running_var + bn.eps)).float()
+                    bi = (bn.bias.detach() - bn.running_mean * sc).float()
+                    if conv.bias is not None:
+                        bi = bi + conv.bias.detach().float() * sc
+                else:
+                    sc = None
+                    bi = conv.bias.detach().float().contiguous() if conv.bias is not None else None
+                self.weights[i] = (w, sc.contiguous() if sc is not None else None,
+                                   bi.contiguous() if bi is not None else None)
+                continue
             if st[0] != 'conv':
                 continue
             _, i, src, out, res, conv, bn, act, slope = st
@@ -264,7 +313,10 @@ class Plan:
                 bnp = (bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var)
                 eps = bn.eps
             stem = conv.in_channels <= 4
-            wp, bias, w32 = ops.pack_conv_weights(conv.weight.detach(), conv.bias.detach() if conv.bias is not None
+            wsrc = conv.weight.detach()
+            if not stem and conv.in_channels % 16 != 0:      # zero columns for the padded K channels (view_k)
+                wsrc = torch.nn.functional.pad(wsrc, (0, 0, 0, 0, 0, (-conv.in_channels) % 16))
+            wp, bias, w32 = ops.pack_conv_weights(wsrc, conv.bias.detach() if conv.bias is not None
                                                   else None, bnp, eps, want_fp32=stem)
             wstem = None
             if stem and (conv.in_channels * conv.kernel_size[0] <= 16 or
@@ -301,8 +353,16 @@ class Plan:
                             x = x.float() / 256.0 if x.dtype == torch.uint8 else x.float()
                         ops.stem_conv(x, w32, bias, k, s, p, act=act, slope=slope, out=out.view())
                 else:
-                    ops.conv2d(src.view(), wp, bias, k, s, p, act=act, slope=slope,
+                    ops.conv2d(src.view_k(), wp, bias, k, s, p, act=act, slope=slope,
                                residual=res.view() if res is not None else None, out=out.view())
+            elif kind == 'dw':
+                _, i, src, out, conv, bn, act, slope = st
+                w, sc, bi = self.weights[i]
+                ops.dwconv2d(src.view(), w, conv.kernel_size[0], conv.stride[0], conv.padding[0], scale=sc, bias=bi,
+                             act=act, slope=slope, out=out.view())
+            elif kind == 'se':
+                _, i, src, out, fc1, fc2, ws = st
+                ops.se_fwd(src.view(), fc1.weight.detach(), fc2.weight.detach(), out=out.view(), ws=ws)
             elif kind == 'add':
                 ops.add(st[1].view(), st[2].view(), out=st[3].view())
             elif kind == 'copy':

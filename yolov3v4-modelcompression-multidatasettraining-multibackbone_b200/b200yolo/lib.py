@@ -32,13 +32,13 @@ class ConvDesc(C.Structure):
 class PackItem(C.Structure):
     _fields_ = [("w", C.c_void_p), ("w_fwd", C.c_void_p), ("w_dgrad", C.c_void_p),
                 ("O", C.c_int), ("Opad", C.c_int), ("I", C.c_int), ("k", C.c_int), ("stride", C.c_int),
-                ("pad", C.c_int), ("tile_begin", C.c_int), ("reserved", C.c_int)]
+                ("pad", C.c_int), ("tile_begin", C.c_int), ("Ipad", C.c_int)]
 
 
 class UnpackItem(C.Structure):
     _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p),
                 ("O", C.c_int), ("I", C.c_int), ("k", C.c_int), ("accumulate", C.c_int),
-                ("tile_begin", C.c_int), ("reserved", C.c_int)]
+                ("tile_begin", C.c_int), ("Ipad", C.c_int)]
 
 
 class QConvDesc(C.Structure):

@@ -34,10 +34,16 @@ def _round_up(v, m):
     return (v + m - 1) // m * m
 
 
+def _widen(view, channels):
+    """The same NHWC view with `channels` channels (its buffer is at least that wide and zero beyond the view)."""
+    B, H, W, C = view.shape
+    return torch.as_strided(view, (B, H, W, channels), view.stride(), view.storage_offset())
+
+
 class _ConvRec:
     __slots__ = ('i', 'conv', 'bn', 'act', 'slope', 'src', 'z', 'y', 'res', 'head', 'stem', 'k', 's', 'p', 'Cout',
                  'Cpad', 'w16', 'wT', 'stats', 'mean', 'invstd', 'scale', 'shift', 'ones', 'zeros', 'w32', 'aux_row', 'wstem',
-                 'save', 'sums', 'dw', 'fast_bn')
+                 'save', 'sums', 'dw', 'fast_bn', 'depthwise', 'Ipad', 'dwg')
 
     def __init__(self):
         for k in self.__slots__:
@@ -64,10 +70,12 @@ class TrainPlan:
         for i, (d, m) in enumerate(zip(defs, mods)):
             t = d['type']
             Cc, H, W = prev
-            if t == 'convolutional':
+            if t in ('convolutional', 'depthwise'):
                 conv = _block_parts(m)[0]
                 H, W = ops.conv_out_hw(H, W, conv.kernel_size[0], conv.stride[0], conv.padding[0])
                 Cc = conv.out_channels
+            elif t == 'se':
+                pass
             elif t == 'maxpool':
                 k, s = d['size'], d['stride']
                 if k == 2 and s == 1:
@@ -125,8 +133,12 @@ class TrainPlan:
         self.bufs = []   # (activation buffer, gradient buffer) pairs to keep alive
 
         def new_buf(Cc, H, W, dtype=torch.float16):
-            pitch = Cc if dtype == torch.float16 else _round_up(Cc, 4)
-            return torch.empty((B, H, W, pitch), dtype=dtype, device=dev)
+            if dtype != torch.float16:
+                return torch.empty((B, H, W, _round_up(Cc, 4)), dtype=dtype, device=dev)
+            if Cc % 16 == 0:
+                return torch.empty((B, H, W, Cc), dtype=dtype, device=dev)
+            # MobileNet widths (24, 40, 72 ...): pitch rounded up to the MMA K granule, pad channels stay zero forever
+            return torch.zeros((B, H, W, _round_up(Cc, 16)), dtype=dtype, device=dev)
 
         def zeros_later(shape, dtype):
             """placeholder (meta tensor) for a buffer that is carved out of the zero-at-start-of-backward arena"""
@@ -177,18 +189,33 @@ class TrainPlan:
         feat_idx = {}
         for i, (d, m) in enumerate(zip(defs, mods)):
             t = d['type']
-            if t == 'convolutional':
+            if t == 'se':
+                fc = m[0].fc if isinstance(m, nn.Sequential) else m.fc
+                src = tens[i - 1]
+                out = alloc(tens[i])
+                cr = fc[0].out_features
+                rec = {'i': i, 'src': src, 'y': out, 'fc1': fc[0], 'fc2': fc[2],
+                       'ws': ops.se_workspace(B, src.C, cr, dev), 'ws_bwd': ops.se_workspace(B, src.C, cr, dev)}
+                self.order.append(('se', rec))
+                feat_idx[i] = out
+            elif t in ('convolutional', 'depthwise'):
                 conv, bn, act, slope = _block_parts(m)
-                if conv.groups != 1:
-                    raise NotImplementedError("grouped convolution is not supported by the sm_100a engine yet")
                 r = _ConvRec()
+                r.depthwise = t == 'depthwise'
+                if r.depthwise:
+                    if conv.groups != conv.in_channels or conv.out_channels != conv.in_channels or bn is None or i == 0:
+                        raise NotImplementedError("depthwise block: channel multiplier 1 with BatchNorm expected")
+                elif conv.groups != 1:
+                    raise NotImplementedError("grouped convolution is not supported by the sm_100a engine yet")
                 r.i, r.conv, r.bn, r.act, r.slope = i, conv, bn, act, slope
                 r.k, r.s, r.p = conv.kernel_size[0], conv.stride[0], conv.padding[0]
                 r.head, r.stem = is_head[i], (i == 0)
                 if r.stem and conv.in_channels > 4:
                     raise NotImplementedError("first layer with more than 4 input channels")
                 r.Cout = conv.out_channels
-                r.Cpad = HEAD_PAD if r.head else r.Cout
+                # GEMM K granule: Cout is the K of the data-gradient GEMM, Cin the K of the forward / weight-gradient one
+                r.Cpad = HEAD_PAD if r.head else _round_up(r.Cout, 16)
+                r.Ipad = _round_up(conv.in_channels, 16)
                 if r.head and (r.Cout > HEAD_PAD or bn is not None or act != 'linear'):
                     raise NotImplementedError("unsupported YOLO head conv")
                 r.src = None if i == 0 else tens[i - 1]
@@ -211,6 +238,8 @@ class TrainPlan:
                 self.order.append(('conv', r))
                 if not is_head[i] and r.res is None:
                     feat_idx[i] = r.y   # (a conv with a fused shortcut never materialises its pre-add output)
+                if r.depthwise:
+                    r.dwg = zeros_later(tuple(conv.weight.shape), torch.float32)
             elif t == 'shortcut':
                 if fused_into[i] is not None:
                     continue
@@ -251,8 +280,8 @@ class TrainPlan:
         #                   [max|du|, s, 1/s] scale rows, and the packed fp32 weight gradients (split-K red.add targets)
         self.dz_aux = torch.empty((len(self.convs) + 1, 4), dtype=torch.float32, device='meta')
         for r in self.convs:
-            if not r.stem:
-                r.dw = torch.empty((r.Cpad, r.k, r.k, r.conv.in_channels), dtype=torch.float32, device='meta')
+            if not r.stem and not r.depthwise:
+                r.dw = torch.empty((r.Cpad, r.k, r.k, r.Ipad), dtype=torch.float32, device='meta')
         fwd_req, bwd_req, seen = [], [], {}
 
         def want(lst, holder, attr):
@@ -272,6 +301,7 @@ class TrainPlan:
         for r in self.convs:
             want(bwd_req, r, 'sums')
             want(bwd_req, r, 'dw')
+            want(bwd_req, r, 'dwg')
         want(bwd_req, self, 'dz_aux')
 
         def carve(reqs):
@@ -322,22 +352,23 @@ class TrainPlan:
         """fp32 master weights -> fp16 operand layouts (forward [O][k][k][I], per-phase data-gradient slabs): ONE
         table-driven launch over all tcgen05 convolutions (csrc/multi.cu) + the stem's own tiny pack."""
         from .lib import PackItem, raw
-        body = [r for r in self.convs if not r.stem]
+        body = [r for r in self.convs if not r.stem and not r.depthwise]
         key = tuple(r.conv.weight.data_ptr() for r in body)
         if self.pack_table is None or key != self.pack_key:
             items, tiles = [], 0
             for r in body:
                 O, I, k = r.conv.weight.shape[0], r.conv.weight.shape[1], r.k
                 if r.w16 is None:
-                    r.w16 = torch.empty((r.Cpad, k, k, I), dtype=torch.float16, device=self.device)
-                    r.wT = torch.empty(r.Cpad * I * k * k, dtype=torch.float16, device=self.device)
+                    # zero-filled once: the K-pad columns (>= I) and pad rows (>= O) are never written again
+                    r.w16 = torch.zeros((r.Cpad, k, k, r.Ipad), dtype=torch.float16, device=self.device)
+                    r.wT = torch.zeros(r.Cpad * I * k * k, dtype=torch.float16, device=self.device)
                 w = r.conv.weight.detach()
                 assert w.is_contiguous() and w.dtype == torch.float32
                 ti = int(raw().b2y_layout_tile_i(k))
                 if ti <= 0:
                     raise NotImplementedError("kernel size %d is not supported by the training engine" % k)
                 items.append(PackItem(w.data_ptr(), r.w16.data_ptr(), r.wT.data_ptr(), O, r.Cpad, I, k, r.s, r.p,
-                                      tiles, 0))
+                                      tiles, r.Ipad))
                 tiles += ((r.Cpad + 31) // 32) * ((I + ti - 1) // ti)
             arr = (PackItem * len(items))(*items)
             host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
@@ -373,7 +404,7 @@ class TrainPlan:
     def _unpack_all(self):
         """packed fp32 weight gradients [O][k][k][I] of all tcgen05 convolutions -> OIHW destinations, ONE launch."""
         from .lib import UnpackItem, raw
-        body = [r for r in self.convs if not r.stem]
+        body = [r for r in self.convs if not r.stem and not r.depthwise]
         dsts = [self._grad_dst(r.conv.weight) for r in body]
         key = tuple(d.data_ptr() for d in dsts)
         if self.unpack_table is None or key != self.unpack_key:
@@ -381,7 +412,7 @@ class TrainPlan:
             for r, d in zip(body, dsts):
                 O, I, k = r.Cout, r.conv.in_channels, r.k
                 ti = int(raw().b2y_layout_tile_i(k))
-                items.append(UnpackItem(r.dw.data_ptr(), d.data_ptr(), O, I, k, 0, tiles, 0))
+                items.append(UnpackItem(r.dw.data_ptr(), d.data_ptr(), O, I, k, 0, tiles, r.Ipad))
                 tiles += ((O + 31) // 32) * ((I + ti - 1) // ti)
             arr = (UnpackItem * len(items))(*items)
             host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
@@ -458,6 +489,10 @@ class TrainPlan:
             if kind == 'conv':
                 r = st[1]
                 self._conv_forward(r, x)
+            elif kind == 'se':
+                e = st[1]
+                ops.se_fwd(e['src'].view(), e['fc1'].weight.detach(), e['fc2'].weight.detach(), out=e['y'].view(),
+                           ws=e['ws'])
             elif kind == 'add':
                 cur = st[1]
                 for s in st[2]:
@@ -488,7 +523,7 @@ class TrainPlan:
             if r.stem:
                 ops.stem_conv(x, r.w32, bias, r.k, r.s, r.p, act=r.act, slope=r.slope, out=out)
             else:
-                ops.conv2d(r.src.view(), r.w16, bias, r.k, r.s, r.p, act=r.act, slope=r.slope, out=out)
+                ops.conv2d(r.src.view_k(), r.w16, bias, r.k, r.s, r.p, act=r.act, slope=r.slope, out=out)
             return
         z = r.z.view()
         if r.stem and getattr(r, 'wstem', None) is not None:
@@ -510,8 +545,10 @@ class TrainPlan:
             call("b2y_bn_act_bwd_reduce", ptr(z), ops._pitch(z), ptr(z), ops._pitch(z), ptr(r.ones), ptr(r.zeros),
                  ptr(r.zeros), ptr(r.ones), ptr(r.stats[1]), ptr(r.stats[0]), None, B_ * H_ * W_, C_, 0, 0.0, 0,
                  stream_ptr())
+        elif r.depthwise:
+            ops.dwconv2d(r.src.view(), r.conv.weight.detach(), r.k, r.s, r.p, out=z, stats=(r.stats[0], r.stats[1]))
         else:
-            ops.conv2d(r.src.view(), r.w16, None, r.k, r.s, r.p, out=z, stats=(r.stats[0], r.stats[1]))
+            ops.conv2d(r.src.view_k(), r.w16[:r.Cout], None, r.k, r.s, r.p, out=z, stats=(r.stats[0], r.stats[1]))
         bn = r.bn
         count = z.shape[0] * z.shape[1] * z.shape[2]
         res = r.res.view() if r.res is not None else None
@@ -557,6 +594,11 @@ class TrainPlan:
             kind = st[0]
             if kind == 'conv':
                 self._conv_backward(st[1], grads, S, inv)
+            elif kind == 'se':
+                e = st[1]
+                ops.se_bwd(e['src'].view(), G(e['y']).view(), e['fc1'].weight.detach(), e['fc2'].weight.detach(),
+                           e['ws'], G(e['src']).view(), accumulate=True, dw1=self._grad_dst(e['fc1'].weight),
+                           dw2=self._grad_dst(e['fc2'].weight), grad_scale=inv, ws_bwd=e['ws_bwd'])
             elif kind == 'add':
                 _, first, others, out = st
                 go = G(out).view()
@@ -601,8 +643,12 @@ class TrainPlan:
             if self.side_wgrad:
                 dz = self.dz_bufs.get(r.i)
                 if dz is None:
-                    dz = self.dz_bufs[r.i] = torch.empty((B, Ho, Wo, r.Cout), dtype=torch.float16, device=self.device)
+                    # pitch = Cout rounded up to the K granule of the data-gradient GEMM; the pad channels stay zero
+                    full = torch.zeros((B, Ho, Wo, r.Cpad), dtype=torch.float16, device=self.device)
+                    dz = self.dz_bufs[r.i] = full[..., :r.Cout]
             else:
+                if r.Cpad != r.Cout:
+                    raise NotImplementedError("B2Y_WGRAD_STREAM=0 needs channel counts that are multiples of 16")
                 dz = self.dz_scratch[:B * Ho * Wo * r.Cout].view(B, Ho, Wo, r.Cout)
             aux = self.dz_aux[r.aux_row]
             inv_s = aux[2:3]                                   # device scalar 1/s of this layer's dz
@@ -649,17 +695,27 @@ class TrainPlan:
             d = ConvDesc(B, self.H, self.W, I, I, r.Cout, r.k, r.s, r.p, Ho, Wo, ops._pitch(dz), 0, 0.0, OUT_F16, 0)
             call("b2y_stem_conv_bwd_weight", C.byref(d), ptr(self.x), ptr(dz), ptr(gw), inv, ops._gdt(dz), stream_ptr())
             gw.mul_(inv_s)
+        elif r.depthwise:
+            xs = r.src.view()
+            ops.dwconv2d_bwd_weight(xs, dz, r.k, r.s, r.p, alpha=inv, dw=r.dwg, inv_scale=inv_s)
+            ops.axpby(r.dwg.reshape(-1), self._grad_dst(conv.weight).reshape(-1), 1.0, 0.0)
+            gx = self.grad_of[id(r.src)]
+            ops.dwconv2d_bwd_data(dz, conv.weight.detach(), (B, r.src.H, r.src.W, I), r.k, r.s, r.p, out=gx.view(),
+                                  accumulate=True, inv_scale=inv_s)
         else:
-            # packed fp32 gradient slice (zeroed with the backward arena); unpacked for all layers at the end
+            # packed fp32 gradient slice (zeroed with the backward arena); unpacked for all layers at the end.
+            # K operands are taken with their zero pad: x with Ipad channels, dz with Cpad channels.
+            xk = r.src.view_k()
+            dzk = dz if dz.shape[3] == r.Cpad else _widen(dz, r.Cpad)
             if self.side_wgrad:
                 main = torch.cuda.current_stream()
                 self.side_stream.wait_stream(main)              # dz (and 1/s) of this layer are complete
                 with torch.cuda.stream(self.side_stream):
-                    ops.conv2d_bwd_weight(r.src.view(), dz, r.k, r.s, r.p, scale=inv, dw=r.dw, inv_scale=inv_s)
+                    ops.conv2d_bwd_weight(xk, dzk, r.k, r.s, r.p, scale=inv, dw=r.dw, inv_scale=inv_s)
             else:
-                ops.conv2d_bwd_weight(r.src.view(), dz, r.k, r.s, r.p, scale=inv, dw=r.dw, inv_scale=inv_s)
+                ops.conv2d_bwd_weight(xk, dzk, r.k, r.s, r.p, scale=inv, dw=r.dw, inv_scale=inv_s)
             gx = self.grad_of[id(r.src)]
-            ops.conv2d_bwd_data(dz, r.wT, (B, r.src.H, r.src.W, I), r.k, r.s, r.p, out=gx.view(), accumulate=True,
+            ops.conv2d_bwd_data(dzk, r.wT, (B, r.src.H, r.src.W, I), r.k, r.s, r.p, out=gx.view(), accumulate=True,
                                 inv_scale=inv_s)
 
     def _emit(self, grads, param, src, alpha):

@@ -4,9 +4,10 @@
 // (pack_weights / pack_dgrad / unpack_wgrad / axpby: ~10 % of the step, launch bound).
 //
 //   master   W  fp32 [O][I][k][k]                       (nn.Conv2d.weight, checkpoint layout, models.py:92-99)
-//   forward  Wf fp16 [Opad][k][k][I]                    (K-major B operand of the implicit GEMM, conv_tc.cuh)
+//   forward  Wf fp16 [Opad][k][k][Ipad]                 (K-major B operand of the implicit GEMM, conv_tc.cuh; columns
+//                                                        >= I are never written: the caller zero-fills them once)
 //   dgrad    Wd fp16 [phase][I][tap][Opad]              (per output-phase slabs, conv_tc.cu enumerate_dgrad_phases)
-//   wgrad    dW fp32 [Opad][k][k][I]  ->  OIHW fp32     (wgrad_tc.cu writes the packed form with red.global.add)
+//   wgrad    dW fp32 [Opad][k][k][Ipad] -> OIHW fp32    (wgrad_tc.cu writes the packed form with red.global.add)
 //
 // Work unit = a tile of 32 output channels x TI input channels x all taps, staged through shared memory so that both
 // the global reads and the global writes are contiguous runs (>= 64 bytes).  b2y_layout_tile_i(k) gives TI.
@@ -89,7 +90,7 @@ pack_multi_kernel(const b2y_pack_item* __restrict__ items, int n_items) {
             const int tap = tmp % k2, ol = tmp / k2;
             const int o = o0 + ol;
             if (o < it.Opad)
-                wf[((long long)o * k2 + tap) * it.I + i0 + il] = __float2half_rn(tile[ol][il * k2 + tap]);
+                wf[((long long)o * k2 + tap) * it.Ipad + i0 + il] = __float2half_rn(tile[ol][il * k2 + tap]);
         }
     }
     // ---- data-gradient layout [phase][i][tap][o]: runs of 32 output channels ----
@@ -123,7 +124,7 @@ unpack_multi_kernel(const b2y_unpack_item* __restrict__ items, int n_items) {
         const int il = idx % ni;
         const int tmp = idx / ni;
         const int tap = tmp % k2, ol = tmp / k2;
-        tile[ol][il * k2 + tap] = __ldg(it.src + ((long long)(o0 + ol) * k2 + tap) * it.I + i0 + il);
+        tile[ol][il * k2 + tap] = __ldg(it.src + ((long long)(o0 + ol) * k2 + tap) * it.Ipad + i0 + il);
     }
     __syncthreads();
     const int run = ni * k2;
