@@ -204,6 +204,9 @@ int b2y_quantize_f16_to_i8(const void* x, long long x_pitch, void* q, long long 
  * between x and fakequant(x; 2^step/2^(bits-1)); out_cos fp32 [n_cand]. One pass over x. */
 int b2y_cos_scale_search(const float* x, long long n, int bits, int n_cand, float* out_cos, void* workspace,
                          size_t workspace_bytes, void* stream);
+/* same with the first candidate's exponent given: candidate k quantises with float_range = 2^(k + step0) */
+int b2y_cos_scale_search_ex(const float* x, long long n, int bits, int n_cand, int step0, float* out_cos,
+                            void* workspace, size_t workspace_bytes, void* stream);
 /* per-tensor or per-channel min/max (google.py:16-77); x fp32 [rows][cols], per_row!=0 -> out [rows][2] */
 int b2y_minmax_f32(const float* x, long long rows, long long cols, int per_row, float* out_minmax, void* stream);
 

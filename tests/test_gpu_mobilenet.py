@@ -138,13 +138,16 @@ def test_mobilenet_training_step_matches_reference():
     p_abs = max(float((pi - torch.from_numpy(g["p%d" % i])).abs().max()) for i, pi in enumerate(preds))
     items_rel = float((np.abs(first_items - g["items"]) / np.abs(g["items"])).max())
     ref = dict(zip([str(n) for n in g["grad_names"]], g["grad_norms"]))
-    rel = np.array([abs(float(grads[k].norm()) - v) / (v + 1e-8) for k, v in ref.items()])
-    order = np.argsort(-rel)[:6]
-    keys = list(ref)
-    print("worst:", [(keys[j], float(rel[j]), float(grads[keys[j]].norm()), float(ref[keys[j]])) for j in order])
+    # The BatchNorm bias of a linear projection conv that feeds only conv -> batch-stat BatchNorm has a mathematically
+    # ZERO gradient (a per-channel shift is removed by the next normalisation); the reference shows ~1e-6 there and the
+    # fp16-stored dz leaves ~1e-2 -- compared with gradient norms of 1..100 elsewhere.  Norm errors are therefore taken
+    # relative to max(reference norm, 1e-3 x the median reference norm).
+    floor = 1e-3 * float(np.median(list(ref.values())))
+    rel = np.array([abs(float(grads[k].norm()) - v) / max(v, floor) for k, v in ref.items()])
     print("\n[%s 4x128x128 train] vs fp32 reference: max|dp| %.3g | loss items rel %.3g | grad-norm rel median %.3g worst "
           "%.3g | losses %s" % (NAME, p_abs, items_rel, np.median(rel), rel.max(), losses))
     assert all(np.isfinite(losses)) and max(abs(a - losses[0]) / abs(losses[0]) for a in losses) < 5e-3
     assert all(torch.isfinite(v).all() for v in grads.values())
-    assert items_rel < 2e-2
-    assert np.median(rel) < 5e-2
+    assert items_rel < 1.2e-2            # measured 5.2e-3
+    assert np.median(rel) < 4.1e-2       # measured 2.0e-2
+    assert p_abs < 0.5                   # measured 0.24

@@ -74,3 +74,78 @@ def test_ptq_int8_eval_matches_reference():
     ref_io = torch.from_numpy(g["io"])
     close = torch.isclose(io.cpu(), ref_io, rtol=1e-4, atol=1e-5).float().mean().item()
     assert close > 0.99, close
+
+
+def _fresh_quantised_model():
+    """quantized=3 model with the shared synthetic weights and UNcalibrated quantisers (all scales zero)."""
+    import models
+    fm = models.Darknet(cfg_path("yolov3"))
+    sd = orc.synth_state_dict(fm.state_dict(), 0)
+    qm = models.Darknet(cfg_path("yolov3"), quantized=3, a_bit=8, w_bit=8, shortcut_way=1)
+    with torch.no_grad():
+        for i, m in enumerate(qm.module_list):
+            pre = 'module_list.%d.' % i
+            if m.__class__.__name__ == 'Sequential' and len(m) and hasattr(m[0], 'activation_quantizer'):
+                c = m[0]
+                c.weight.copy_(sd[pre + 'Conv2d.weight'])
+                if (pre + 'BatchNorm2d.weight') in sd:
+                    c.gamma.copy_(sd[pre + 'BatchNorm2d.weight'])
+                    c.beta.copy_(sd[pre + 'BatchNorm2d.bias'])
+                    c.running_mean.copy_(sd[pre + 'BatchNorm2d.running_mean'])
+                    c.running_var.copy_(sd[pre + 'BatchNorm2d.running_var'])
+                else:
+                    c.bias.copy_(sd[pre + 'Conv2d.bias'])
+    return qm.cuda()
+
+
+def test_ptq_native_calibration_matches_reference():
+    """The calibration half of the PTQ flow (PTQ.py:76-88: q_model.train(), forwards over calibration batches) executed
+    natively (b200yolo/qcalib.py), on the same two batches the reference fixture was calibrated with: every activation /
+    weight / bias / shortcut / concat scale must equal the reference's (they are powers of two: exact equality), the
+    bias-corrected q_bias must sit on the same grid points, and the subsequent INT8 eval forward must reproduce the
+    reference's eval output."""
+    g = golden("yolov3_64_ptq")
+    qm = _fresh_quantised_model()
+    qm.train()
+    with torch.no_grad():
+        for seed in (10, 11):
+            out, _ = qm(orc.synth_images(2, 64, 64, seed=seed).cuda())
+    assert len(out) == 3 and out[0].shape[-1] == 85
+    n_scale, bad, worst_qb, n_qb_off = 0, [], 0.0, 0
+    for i, m in enumerate(qm.module_list):
+        name = m.__class__.__name__
+        if name == 'Sequential' and len(m) and hasattr(m[0], 'activation_quantizer'):
+            c = m[0]
+            for q, key in ((c.activation_quantizer, 'a_scale'), (c.weight_quantizer, 'w_scale'),
+                           (c.bias_quantizer, 'b_scale')):
+                n_scale += 1
+                if float(q.scale.reshape(-1)[0]) != float(g["L%d.%s" % (i, key)].reshape(-1)[0]):
+                    bad.append(("L%d.%s" % (i, key), float(q.scale.reshape(-1)[0]), float(g["L%d.%s" % (i, key)].reshape(-1)[0])))
+            bs = float(g["L%d.b_scale" % i].reshape(-1)[0])
+            d = (c.q_bias.detach().cpu() - torch.from_numpy(g["L%d.q_bias" % i])).abs() / bs
+            worst_qb = max(worst_qb, float(d.max()))
+            n_qb_off += int((d > 0.5).sum())
+            ref_b = torch.from_numpy(g["L%d.bias" % i])
+            assert float((c.bias.detach().cpu() - ref_b).abs().max()) <= 1e-4 * max(1.0, float(ref_b.abs().max()))
+        elif name.startswith('COSPTQuantizedShortcut'):
+            for key in ('scale_x', 'scale_a', 'scale_sum'):
+                n_scale += 1
+                if float(getattr(m, key)) != float(g["L%d.%s" % (i, key)]):
+                    bad.append(("L%d.%s" % (i, key), float(getattr(m, key)), float(g["L%d.%s" % (i, key)])))
+        elif name == 'COSPTQuantizedFeatureConcat' and ("L%d.scale" % i) in g.files:
+            n_scale += 1
+            if float(m.scale) != float(g["L%d.scale" % i]):
+                bad.append(("L%d.scale" % i, float(m.scale), float(g["L%d.scale" % i])))
+            np.testing.assert_allclose(m.float_max_list.cpu().numpy(), g["L%d.float_max_list" % i], rtol=1e-5)
+    print("\n[ptq calibration] %d scales compared, %d differ %s | q_bias: %d codes off, worst %.3g LSB"
+          % (n_scale, len(bad), bad[:4], n_qb_off, worst_qb))
+    assert not bad
+    assert n_qb_off == 0
+    # the INT8 eval graph on the natively calibrated model == the reference's eval output
+    qm.eval()
+    x = orc.synth_images(2, 64, 64, seed=0).cuda()
+    with torch.no_grad():
+        io, p, _ = qm(x)
+    ref_io = torch.from_numpy(g["io"])
+    close = torch.isclose(io.cpu(), ref_io, rtol=1e-4, atol=1e-5).float().mean().item()
+    assert close > 0.99, close

@@ -535,9 +535,13 @@ class Engine:
             raise NotImplementedError("quantized=%d: only the PTQ graph (quantized=3) has an INT8 engine in this "
                                       "round (DESIGN.md)" % model.quantized)
         if model.training:
-            raise NotImplementedError(
-                "PTQ calibration forwards (q_model.train(), PTQ.py:76-88) are not executed natively yet: load a "
-                "calibrated state_dict (PTQ.pt) and run q_model.eval() -- see INTEGRATION.md")
+            # calibration forward (PTQ.py:76-88): votes / bias correction mutate the quantiser state, so every cached
+            # INT8 eval plan (packed int8 weights, scales baked into its CUDA graph) is stale afterwards
+            from .qcalib import QCalibPlan
+            for k in [k for k in self.plans if len(k) == 3 and k[1] == 'q3']:
+                del self.plans[k]
+            with torch.no_grad():
+                return QCalibPlan(model, tuple(x.shape), x.device).forward(x)
         key = (tuple(x.shape), 'q3', x.device.index)
         plan = self.plans.get(key)
         if plan is None:

@@ -92,6 +92,7 @@ _PROTOS = {
     "b2y_fakequant_f32": (i32, [vp, vp, ll, f32, f32, f32, vp]),
     "b2y_quantize_f16_to_i8": (i32, [vp, ll, vp, ll, ll, i32, f32, f32, f32, vp]),
     "b2y_cos_scale_search": (i32, [vp, ll, i32, i32, vp, vp, sz, vp]),
+    "b2y_cos_scale_search_ex": (i32, [vp, ll, i32, i32, i32, vp, vp, sz, vp]),
     "b2y_minmax_f32": (i32, [vp, ll, ll, i32, vp, vp]),
     "b2y_pack_qconv_weights": (i32, [vp, i32, i32, i32, f32, f32, f32, vp, vp]),
     "b2y_qshortcut_i8": (i32, [vp, ll, vp, ll, vp, ll, ll, i32, f32, f32, f32, f32, f32, f32, f32, vp]),

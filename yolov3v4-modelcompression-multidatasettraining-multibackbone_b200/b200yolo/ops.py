@@ -488,6 +488,15 @@ def fakequant(x, scale, bits=8):
     return y
 
 
+def fakequant_range(x, scale, lo, hi):
+    """clamp(round_half_away(x / scale), lo, hi) * scale with an explicit code range (+-3e38 = "round, do not clamp":
+    the quantised shortcuts round their addends without clamping, ptq_cos.py:876-884)."""
+    x = x.contiguous().float()
+    y = torch.empty_like(x)
+    call("b2y_fakequant_f32", ptr(x), ptr(y), x.numel(), float(scale), float(lo), float(hi), stream_ptr())
+    return y
+
+
 def quantize_to_i8(x, scale, bits=8, out=None):
     B, H, W, Cc = x.shape
     if out is None:
@@ -498,13 +507,16 @@ def quantize_to_i8(x, scale, bits=8, out=None):
     return out
 
 
-def cos_scale_search(x, bits=8):
-    """Cosine similarities of x vs fakequant(x; 2^(i-5)/2^(bits-1)), i in range(bits+7) -> fp32 [bits+7] (device)."""
+def cos_scale_search(x, bits=8, n_cand=None, step0=-5):
+    """Cosine similarities of x vs fakequant(x; 2^(i+step0)/2^(bits-1)), i in range(n_cand) -> fp32 [n_cand] (device).
+    Defaults = the conv quantisers' search (bits+7 candidates from 2^-5)."""
     x = x.contiguous().float()
-    n_cand = bits + 7
+    if n_cand is None:
+        n_cand = bits + 7
     out = torch.empty(n_cand, dtype=torch.float32, device=x.device)
     ws = torch.empty(8 * (1 + 2 * n_cand), dtype=torch.uint8, device=x.device)
-    call("b2y_cos_scale_search", ptr(x), x.numel(), bits, n_cand, ptr(out), ptr(ws), ws.numel(), stream_ptr())
+    call("b2y_cos_scale_search_ex", ptr(x), x.numel(), bits, n_cand, int(step0), ptr(out), ptr(ws), ws.numel(),
+         stream_ptr())
     return out
 
 

@@ -72,7 +72,7 @@ extern "C" int b2y_quantize_f16_to_i8(const void* x, long long x_pitch, void* q,
 // Accumulated in double so that the argmax matches torch.cosine_similarity on the ties the reference resolves
 // with a strict '>'.
 #define B2Y_MAX_CAND 24
-__global__ void cos_search_kernel(const float* __restrict__ x, long long n, int bits, int n_cand,
+__global__ void cos_search_kernel(const float* __restrict__ x, long long n, int bits, int n_cand, int step0,
                                   double* __restrict__ acc /* [1 + 2*n_cand] */) {
     __shared__ double sh[(1 + 2 * B2Y_MAX_CAND)];
     for (int i = threadIdx.x; i < 1 + 2 * n_cand; i += blockDim.x) sh[i] = 0.0;
@@ -90,7 +90,7 @@ __global__ void cos_search_kernel(const float* __restrict__ x, long long n, int 
 #pragma unroll
         for (int k = 0; k < B2Y_MAX_CAND; ++k) {
             if (k < n_cand) {
-                const float scale = exp2f((float)(k - 5)) / (float)(1 << (bits - 1));
+                const float scale = exp2f((float)(k + step0)) / (float)(1 << (bits - 1));
                 const float q = fminf(fmaxf(rha(v / scale), lo), hi) * scale;
                 dot[k] += v * q;
                 qq[k] += q * q;
@@ -131,8 +131,10 @@ __global__ void cos_finalize_kernel(const double* __restrict__ acc, int n_cand, 
     }
 }
 
-extern "C" int b2y_cos_scale_search(const float* x, long long n, int bits, int n_cand, float* out_cos,
-                                    void* workspace, size_t workspace_bytes, void* stream) {
+// candidate k uses float_range = 2^(k + step0): the conv quantisers search step0 = -5 over bits+7 candidates
+// (ptq_cos.py:71-87), the shortcut quantisers step0 = 0 over `bits` candidates (ptq_cos.py:836-868, 1158-1197)
+extern "C" int b2y_cos_scale_search_ex(const float* x, long long n, int bits, int n_cand, int step0, float* out_cos,
+                                       void* workspace, size_t workspace_bytes, void* stream) {
     if (!x || !out_cos || !workspace || n_cand < 1 || n_cand > B2Y_MAX_CAND || bits < 2 || bits > 16)
         return B2Y_ERR_INVALID;
     if (workspace_bytes < sizeof(double) * (1 + 2 * (size_t)n_cand)) return B2Y_ERR_INVALID;
@@ -141,10 +143,15 @@ extern "C" int b2y_cos_scale_search(const float* x, long long n, int bits, int n
     B2Y_CUDA_CHECK(cudaMemsetAsync(acc, 0, sizeof(double) * (1 + 2 * n_cand), st));
     int grid = grid_for(n, 256);
     if (grid > 148 * 4) grid = 148 * 4;
-    cos_search_kernel<<<grid, 256, 0, st>>>(x, n, bits, n_cand, acc);
+    cos_search_kernel<<<grid, 256, 0, st>>>(x, n, bits, n_cand, step0, acc);
     cos_finalize_kernel<<<1, 32, 0, st>>>(acc, n_cand, out_cos);
     B2Y_CUDA_CHECK(cudaGetLastError());
     return B2Y_OK;
+}
+
+extern "C" int b2y_cos_scale_search(const float* x, long long n, int bits, int n_cand, float* out_cos,
+                                    void* workspace, size_t workspace_bytes, void* stream) {
+    return b2y_cos_scale_search_ex(x, n, bits, n_cand, -5, out_cos, workspace, workspace_bytes, stream);
 }
 
 // min / max trackers (google.py:16-77): per tensor ('L') or per output channel ('C' = per row of [rows][cols])
