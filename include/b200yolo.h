@@ -360,6 +360,16 @@ int b2y_se_bwd(const void* x, long long x_pitch, const void* dy, long long dy_pi
                const float* ws, float* ws_bwd /* fp32 [batch][3c + cr] */, void* dx, long long dx_pitch, int accumulate,
                float* dw1, float* dw2, float grad_scale, int batch, int hw, int c, int cr, int grad_dtype, void* stream);
 
+/* ---- quantisation-aware training pieces (csrc/quant.cu) ----
+ * straight-through backward of b2y_fakequant_f32 (google.py:81-92, 124-143): dx = g * [lo <= round(x/s) <= hi] * gain */
+int b2y_fakequant_bwd_f32(const float* x, const float* g, float* dx, long long n, float scale, float lo, float hi,
+                          float gain, void* stream);
+/* TPSQ quantiser (quantized_TPSQ.py:66-130) with the power-of-two range P = Search_Pow2(scale):
+ * y = round(softclamp(x, P) * (2^(b-1) - 1) / P) * P / 2^(b-1); backward gives dx and sum(g * dy/dP) (double) */
+int b2y_tpsq_fwd_f32(const float* x, float* y, long long n, float range_pow2, int bits, void* stream);
+int b2y_tpsq_bwd_f32(const float* x, const float* g, float* dx /* may be NULL */, double* dp_sum, long long n,
+                     float range_pow2, int bits, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -531,9 +531,15 @@ class Engine:
 
     def _forward_quantized(self, x):
         model = self.model
+        if model.quantized in (1, 2):
+            # QAT graphs (google / TPSQ): the module forwards themselves, over NHWC fp32 tensors (b200yolo/qat.py)
+            from .qat import QatRunner
+            if model.training:
+                return QatRunner(model).forward(x)
+            with torch.no_grad():
+                return QatRunner(model).forward(x)
         if model.quantized != 3:
-            raise NotImplementedError("quantized=%d: only the PTQ graph (quantized=3) has an INT8 engine in this "
-                                      "round (DESIGN.md)" % model.quantized)
+            raise NotImplementedError("quantized=%d is not a mode of the reference" % model.quantized)
         if model.training:
             # calibration forward (PTQ.py:76-88): votes / bias correction mutate the quantiser state, so every cached
             # INT8 eval plan (packed int8 weights, scales baked into its CUDA graph) is stale afterwards

@@ -122,6 +122,9 @@ _PROTOS = {
     "b2y_dwconv_bwd_weight": (i32, [C.POINTER(ConvDesc), vp, vp, vp, f32, vp, vp]),
     "b2y_se_fwd": (i32, [vp, ll, vp, vp, vp, ll, i32, i32, i32, i32, vp, vp]),
     "b2y_se_bwd": (i32, [vp, ll, vp, ll, vp, vp, vp, vp, vp, ll, i32, vp, vp, f32, i32, i32, i32, i32, i32, vp]),
+    "b2y_fakequant_bwd_f32": (i32, [vp, vp, vp, ll, f32, f32, f32, f32, vp]),
+    "b2y_tpsq_fwd_f32": (i32, [vp, vp, ll, f32, i32, vp]),
+    "b2y_tpsq_bwd_f32": (i32, [vp, vp, vp, vp, ll, f32, i32, vp]),
     "b2y_layout_tile_i": (i32, [i32]),
     "b2y_pack_conv_weights_multi": (i32, [vp, i32, i32, vp]),
     "b2y_unpack_wgrad_multi": (i32, [vp, i32, i32, vp]),

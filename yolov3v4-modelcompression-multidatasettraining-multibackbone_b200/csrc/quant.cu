@@ -36,6 +36,80 @@ extern "C" int b2y_fakequant_f32(const float* x, float* y, long long n, float sc
     return B2Y_OK;
 }
 
+// Straight-through backward of the fake-quantiser (google.py:81-92 Round STE + torch.clamp's gradient mask):
+//   dx = g * [lo <= round(x / s) <= hi] * gain       (gain = 1 for the symmetric power-of-two quantisers)
+__global__ void fakequant_bwd_kernel(const float* __restrict__ x, const float* __restrict__ g, float* __restrict__ dx,
+                                     long long n, float scale, float lo, float hi, float gain) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const float q = rha(x[i] / scale);
+        dx[i] = (q >= lo && q <= hi) ? g[i] * gain : 0.f;
+    }
+}
+
+extern "C" int b2y_fakequant_bwd_f32(const float* x, const float* g, float* dx, long long n, float scale, float lo,
+                                     float hi, float gain, void* stream) {
+    if (!x || !g || !dx || n < 0 || !(scale > 0.f)) return B2Y_ERR_INVALID;
+    fakequant_bwd_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, g, dx, n, scale, lo, hi,
+                                                                                         gain);
+    B2Y_CUDA_CHECK(cudaGetLastError());
+    return B2Y_OK;
+}
+
+// TPSQ quantiser (quantized_TPSQ.py:66-130): soft clamp to [-P, P], q = round(c * qmax / P), y = q * P / 2^(bits-1)
+//   forward:  y;   backward pieces for the learned range P:  dy/dx = [|x| < P] * qmax / 2^(bits-1),
+//   dy/dP = q / 2^(bits-1) + (qmax / 2^(bits-1)) * (sign(x) [|x| >= P] - c / P)       -> sum(g * dy/dP) in *dp_sum (double)
+__global__ void tpsq_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, float P, float qmax,
+                                float qden) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const float v = x[i];
+        const float c = 0.5f * (fabsf(v + P) - fabsf(v - P));
+        y[i] = rha(c * qmax / P) * P / qden;
+    }
+}
+__global__ void tpsq_bwd_kernel(const float* __restrict__ x, const float* __restrict__ g, float* __restrict__ dx,
+                                double* __restrict__ dp_sum, long long n, float P, float qmax, float qden) {
+    double acc = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const float v = x[i], gi = g[i];
+        const float c = 0.5f * (fabsf(v + P) - fabsf(v - P));
+        const float q = rha(c * qmax / P);
+        // d c / d x = 0.5 (sign(x+P) - sign(x-P)),  d c / d P = 0.5 (sign(x+P) + sign(x-P))   (torch.abs' subgradient)
+        const float sp = (v + P > 0.f) - (v + P < 0.f), sm = (v - P > 0.f) - (v - P < 0.f);
+        const float dcdx = 0.5f * (sp - sm), dcdp = 0.5f * (sp + sm);
+        if (dx != nullptr) dx[i] = gi * dcdx * qmax / qden;
+        acc += (double)gi * ((double)q / qden + (double)(qmax / qden) * ((double)dcdp - (double)c / P));
+    }
+    __shared__ double sh[256];
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) atomicAdd(dp_sum, sh[0]);
+}
+
+extern "C" int b2y_tpsq_fwd_f32(const float* x, float* y, long long n, float range_pow2, int bits, void* stream) {
+    if (!x || !y || n < 0 || !(range_pow2 > 0.f) || bits < 2 || bits > 16) return B2Y_ERR_INVALID;
+    tpsq_fwd_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, y, n, range_pow2, (float)((1 << (bits - 1)) - 1), (float)(1 << (bits - 1)));
+    B2Y_CUDA_CHECK(cudaGetLastError());
+    return B2Y_OK;
+}
+extern "C" int b2y_tpsq_bwd_f32(const float* x, const float* g, float* dx, double* dp_sum, long long n, float range_pow2,
+                                int bits, void* stream) {
+    if (!x || !g || !dp_sum || n < 0 || !(range_pow2 > 0.f) || bits < 2 || bits > 16) return B2Y_ERR_INVALID;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    B2Y_CUDA_CHECK(cudaMemsetAsync(dp_sum, 0, sizeof(double), st));
+    tpsq_bwd_kernel<<<grid_for(n, 256), 256, 0, st>>>(x, g, dx, dp_sum, n, range_pow2, (float)((1 << (bits - 1)) - 1),
+                                                      (float)(1 << (bits - 1)));
+    B2Y_CUDA_CHECK(cudaGetLastError());
+    return B2Y_OK;
+}
+
 // fp16 NHWC -> int8 NHWC integer codes
 __global__ void quantize_f16_i8_kernel(const __half* __restrict__ x, long long xp, int8_t* __restrict__ q,
                                        long long qp, long long pixels, int C, float scale, float lo, float hi) {
