@@ -52,9 +52,44 @@ def run(mode, tag):
     qm.train()
     x = orc.synth_images(B, S, S, seed=0)
     t = orc.synth_targets(B, 6, 80, seed=1)
+    # module-boundary tensors of a few QAT conv layers (teacher forcing in tests/test_gpu_qat.py): input, output,
+    # gradient w.r.t. the output and w.r.t. the input
+    lay = {}
+    LAYERS = (5, 13, 39, 63, 81)
+
+    def fwd_hook(i):
+        def f(m, inp, out):
+            lay["L%d.x" % i] = inp[0].detach().numpy().copy()
+            lay["L%d.y" % i] = out.detach().numpy().copy()
+        return f
+
+    def bwd_hook(i):
+        def f(m, gin, gout):
+            if gin[0] is not None:
+                lay["L%d.gx" % i] = gin[0].detach().numpy().copy()
+            lay["L%d.gy" % i] = gout[0].detach().numpy().copy()
+        return f
+
+    for i in LAYERS:
+        qm.module_list[i][0].register_forward_hook(fwd_hook(i))
+        qm.module_list[i][0].register_full_backward_hook(bwd_hook(i))
     pred, _ = qm(x)
     loss, items = ru.compute_loss(pred, t, qm)
     loss.backward()
+    for i in LAYERS:
+        c = qm.module_list[i][0]
+        for n, p_ in c.named_parameters():
+            if p_.grad is not None:
+                g_ = p_.grad
+                lay["L%d.gnorm.%s" % (i, n)] = np.float64(float(g_.norm()))
+                lay["L%d.grad.%s" % (i, n)] = (g_ if g_.numel() <= 300000 else g_[:8]).numpy().copy()
+        for n, b_ in c.named_buffers():
+            if n.endswith(("scale", "running_mean", "running_var", "min_val", "max_val")) and b_.numel() <= 4096:
+                lay["L%d.buf.%s" % (i, n)] = b_.detach().numpy().copy()
+        for n, p_ in c.named_parameters():
+            if n.endswith("scale"):
+                lay["L%d.par.%s" % (i, n)] = p_.detach().numpy().copy()
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "yolov3_64_%s_layers.npz" % tag), **lay)
     out = {"items": items.numpy(), "loss": loss.detach().numpy()}
     for i, pi in enumerate(pred):
         out["p%d" % i] = pi.detach().numpy()

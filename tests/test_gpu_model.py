@@ -183,3 +183,117 @@ def test_map_on_held_batch_matches_reference():
     assert abs(m50 - r50) <= tol50, (m50, r50, y50)
     assert abs(m - r) <= tol, (m, r, y)
     assert abs(n - sum(l.shape[0] for l in labels)) <= 0.01 * n
+
+
+SLICED_CFG = """
+[net]
+width=64
+height=64
+channels=3
+
+[convolutional]
+batch_normalize=1
+filters=32
+size=3
+stride=1
+pad=1
+activation=leaky
+
+[convolutional]
+batch_normalize=1
+filters=64
+size=3
+stride=1
+pad=1
+activation=leaky
+
+[convolutional]
+batch_normalize=1
+filters=64
+size=1
+stride=1
+pad=1
+activation=leaky
+
+[shortcut]
+from=-3
+activation=linear
+
+[convolutional]
+batch_normalize=1
+filters=32
+size=1
+stride=1
+pad=1
+activation=leaky
+
+[shortcut]
+from=-3
+activation=linear
+
+[convolutional]
+batch_normalize=1
+filters=64
+size=3
+stride=2
+pad=1
+activation=leaky
+
+[convolutional]
+filters=255
+size=1
+stride=1
+pad=1
+activation=linear
+
+[yolo]
+mask = 0,1,2
+anchors = 10,13, 16,30, 33,23, 30,61, 62,45, 59,119, 116,90, 156,198, 373,326
+classes=80
+num=9
+"""
+
+
+def test_channel_sliced_shortcuts():
+    """utils/layers.py:57-72: a shortcut whose addend is narrower (the sum covers its channels, the rest of x passes
+    through) or wider (only its first channels are added) than x -- inference and training plans against the oracle."""
+    import os
+    import tempfile
+    import models
+    from utils.parse_config import parse_model_cfg
+    from utils import utils as my_utils
+    d = tempfile.mkdtemp(prefix="b2y_sliced_")
+    path = os.path.join(d, "sliced-yolov3.cfg")
+    with open(path, "w") as f:
+        f.write(SLICED_CFG)
+    defs = parse_model_cfg(path)[1:]
+    m = models.Darknet(path)
+    sd = orc.synth_state_dict(m.state_dict(), 0)
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    x = orc.synth_images(2, 64, 64, seed=4)
+    with torch.no_grad():
+        io, p, _ = m(x.cuda())
+        ref, _ = orc.darknet_forward(defs, sd, x, "yolov3", emulate_fp16=True)
+    b, pr = _errs(io.cpu(), ref)
+    print("\n[sliced shortcuts eval] box_rel=%.3g prob_abs=%.3g" % (b, pr))
+    assert b < 5e-3 and pr < 2e-3
+    # training step: loss and gradient norms against the fp32 oracle
+    m = attach_hyp(m).train()
+    t = orc.synth_targets(2, 6, 80, seed=1)
+    pred, _ = m(x.cuda())
+    loss, items = my_utils.compute_loss(pred, t.cuda(), m)
+    loss.backward()
+    sdr = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and not k.endswith(("running_mean", "running_var")) else v.clone())
+           for k, v in orc.synth_state_dict(models.Darknet(path).state_dict(), 0).items()}
+    pe, _ = orc.darknet_forward(defs, sdr, x, "yolov3", training=True)
+    ys = [dd for dd in defs if dd['type'] == 'yolo']
+    av = [m.module_list[j].anchor_vec.detach().float().cpu() for j in m.yolo_layers]   # the model's own anchors / stride
+    le, ie = orc.compute_loss(pe, t, av, dict(m.hyp), 80, 1.0)
+    le.backward()
+    rel = [abs(float(pp.grad.norm()) - float(sdr[k].grad.norm())) / (float(sdr[k].grad.norm()) + 1e-6)
+           for k, pp in m.named_parameters()]
+    print("[sliced shortcuts train] loss %.5f vs %.5f, grad-norm rel median %.3g worst %.3g"
+          % (float(loss), float(le), float(np.median(rel)), max(rel)))
+    assert abs(float(loss) - float(le)) / abs(float(le)) < 1e-2
+    assert float(np.median(rel)) < 2e-2

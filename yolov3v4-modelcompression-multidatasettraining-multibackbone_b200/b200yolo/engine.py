@@ -254,8 +254,8 @@ class Plan:
                 out = alloc(tens[i])
                 cur = tens[i - 1]
                 for s in frm:
-                    if tens[s].C != cur.C:
-                        raise NotImplementedError("channel-sliced shortcut is not supported by the sm_100a engine yet")
+                    # widths may differ (layers.py:57-72): the sum covers the first min(nx, na) channels, the rest of x
+                    # passes through
                     self.steps.append(('add', cur, tens[s], out))
                     cur = out
             elif t == 'route':
@@ -364,7 +364,11 @@ class Plan:
                 _, i, src, out, fc1, fc2, ws = st
                 ops.se_fwd(src.view(), fc1.weight.detach(), fc2.weight.detach(), out=out.view(), ws=ws)
             elif kind == 'add':
-                ops.add(st[1].view(), st[2].view(), out=st[3].view())
+                xv, av, ov = st[1].view(), st[2].view(), st[3].view()
+                n = min(xv.shape[3], av.shape[3])
+                ops.add(xv[..., :n], av[..., :n], out=ov[..., :n])
+                if xv.shape[3] > n and st[1] is not st[3]:
+                    ops.copy_channels(xv[..., n:], ov[..., n:])
             elif kind == 'copy':
                 _, srct, dst, off = st
                 ops.copy_channels(srct.view(), dst.buf[..., off:off + srct.C])

@@ -44,11 +44,21 @@ class ConvFn(torch.autograd.Function):
         wk = w.detach().float()
         if Ik != I:
             wk = torch.nn.functional.pad(wk, (0, 0, 0, 0, 0, Ik - I))
-        wp, _, _ = ops.pack_conv_weights(wk.contiguous())
         stats = None
         if want_stats:
+            # The statistics pass multiplies the (exactly fp16-representable) activations with the FLOAT weights
+            # (google.py:326-338).  fp16-rounded weights would move the batch statistics by ~1e-3, enough to flip
+            # quantised weight codes after the fold, so the weights go in as a two-term split in ONE tensor-core conv
+            # over a doubled K:  [x | x * 2^-12] * [hi | lo * 2^12]  =  x * (hi + lo), every product exact, fp32 sums.
+            hi = wk.half().float()
+            lo = ((wk - hi) * 4096.0).half().float()
+            xa = torch.cat([x16, (x16.float() * (1.0 / 4096.0)).half()], 3).contiguous()
+            wp, _, _ = ops.pack_conv_weights(torch.cat([hi, lo], 1).contiguous())
             stats = torch.zeros((2, O), dtype=torch.float32, device=x.device)
-        y = ops.conv2d(x16, wp, None, k, s, p, out_dtype=torch.float32, stats=(stats[0], stats[1]) if want_stats else None)
+            y = ops.conv2d(xa, wp, None, k, s, p, out_dtype=torch.float32, stats=(stats[0], stats[1]))
+        else:
+            wp, _, _ = ops.pack_conv_weights(wk.contiguous())
+            y = ops.conv2d(x16, wp, None, k, s, p, out_dtype=torch.float32)
         ctx.geom = (k, s, p, C, I, Ik, O, (B, H, W))
         ctx.want_stats = want_stats
         ctx.save_for_backward(x16, wk, y if want_stats else None)

@@ -244,8 +244,8 @@ class TrainPlan:
                 if fused_into[i] is not None:
                     continue
                 frm = [i + l if l < 0 else l for l in d['from']]
-                if getattr(m, 'weight', False) or any(tens[s].C != tens[i - 1].C for s in frm):
-                    raise NotImplementedError("weighted / channel-sliced shortcut is not supported yet")
+                if getattr(m, 'weight', False):
+                    raise NotImplementedError("weighted shortcut is not supported yet")
                 out = alloc(tens[i])
                 self.order.append(('add', tens[i - 1], [tens[s] for s in frm], out))
             elif t == 'route':
@@ -495,8 +495,12 @@ class TrainPlan:
                            ws=e['ws'])
             elif kind == 'add':
                 cur = st[1]
-                for s in st[2]:
-                    ops.add(cur.view(), s.view(), out=st[3].view())
+                for s in st[2]:                     # channel-sliced when the widths differ (layers.py:57-72)
+                    xv, av, ov = cur.view(), s.view(), st[3].view()
+                    n = min(xv.shape[3], av.shape[3])
+                    ops.add(xv[..., :n], av[..., :n], out=ov[..., :n])
+                    if xv.shape[3] > n and cur is not st[3]:
+                        ops.copy_channels(xv[..., n:], ov[..., n:])
                     cur = st[3]
             elif kind == 'copy':
                 _, srct, dst, off = st
@@ -604,7 +608,8 @@ class TrainPlan:
                 go = G(out).view()
                 for s in [first] + list(others):
                     gs = G(s).view()
-                    ops.add(gs, go, out=gs)
+                    n = min(gs.shape[3], go.shape[3])      # sliced addends receive the matching gradient channels
+                    ops.add(gs[..., :n], go[..., :n], out=gs[..., :n])
             elif kind == 'copy':
                 _, srct, dst, off = st
                 gd = G(dst)

@@ -43,9 +43,6 @@ class Quantizer(nn.Module):
         from b200yolo import qat
         return qat.search_pow2(float(self.scale.detach().reshape(-1)[0]))
 
-    def _apply(self_, input):          # noqa: N805  (kept distinct from nn.Module._apply's signature on purpose)
-        raise NotImplementedError
-
     def quantise_with(self, input, P):
         from b200yolo import qat
         out = qat.TpsqFn.apply(input, self.scale, P, self.bits)
