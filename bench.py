@@ -231,6 +231,61 @@ def cpu_reference_rate(kind, name, max_seconds=20.0, batch=2, max_iters=10, thre
                       % (iters, what, batch), "ms_per_step": dt * 1e3}
 
 
+def torch_gpu_baseline(dev, batch, iters=5):
+    """INFORMATIONAL ("the kernel to beat"): the reference's own op sequence -- the oracle port --
+    executed by stock PyTorch on the same B200 (eager ATen + cuDNN, autocast fp16, channels_last), yolov4 forward +
+    compute_loss + backward of `batch` images at 640x640 (no optimiser step, no all-reduce).  Part of the baseline leg:
+    never on the product path, never used to compute `value`."""
+    sys.path.insert(0, ROOT)
+    import contextlib
+    import numpy as np
+    from oracle import darknet_oracle as orc
+    import models
+    from b200yolo import cfggen
+    from utils.parse_config import parse_model_cfg_text
+    name = TRAIN_MODEL
+    defs = parse_model_cfg_text(cfggen.cfg_text(name))[1:]
+    with contextlib.redirect_stdout(sys.stderr):
+        sd = orc.synth_state_dict(models.Darknet(cfg_for(name, 98)).state_dict(), 0)
+    for k in list(sd):
+        v = sd[k].to(dev)
+        if v.dim() == 4:
+            v = v.contiguous(memory_format=torch.channels_last)
+        if v.dtype.is_floating_point and not k.endswith(('running_mean', 'running_var')):
+            v.requires_grad_(True)
+        sd[k] = v
+    ys = [d for d in defs if d['type'] == 'yolo']
+    strides = orc.yolo_strides(name, len(ys))
+    av = [(torch.as_tensor(np.asarray(d['anchors'])[d['mask']], dtype=torch.float32) / s).to(dev) for d, s in zip(ys, strides)]
+    x = orc.synth_images(batch, SIZE, SIZE, seed=0).to(dev).contiguous(memory_format=torch.channels_last)
+    tg = orc.synth_targets(batch, 8, 80, seed=1).to(dev)
+    hyp = dict(orc.DEFAULT_HYP)
+
+    def one():
+        for v in sd.values():
+            if v.requires_grad:
+                v.grad = None
+        with torch.autocast("cuda", dtype=torch.float16):
+            p, _ = orc.darknet_forward(defs, sd, x, name, training=True)
+        loss, _ = orc.compute_loss([pi.float() for pi in p], tg, av, hyp, 80, 1.0)
+        loss.backward()
+
+    for _ in range(2):
+        one()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        one()
+    e1.record()
+    e1.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    return {"value": batch / (ms / 1e3), "unit": "images/s", "ms_per_step": ms,
+            "what": "oracle port (the reference's op sequence) on stock PyTorch %s eager + cuDNN on this B200, autocast "
+                    "fp16, channels_last: yolov4 forward + compute_loss + backward, %d images 640x640, no optimiser step"
+                    % (torch.__version__, batch)}
+
+
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
@@ -553,10 +608,15 @@ def main():
             except Exception as e:  # a secondary block must not take the headline down
                 secondary["%s_infer_bs%d" % (name, INFER_BATCH)] = {"error": "%s: %s" % (type(e).__name__, e)}
 
-    cpu = None
+    cpu, tgpu = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_reference_rate("train", TRAIN_MODEL, max_seconds=20.0, batch=2, max_iters=3)
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        try:
+            torch.cuda.empty_cache()
+            tgpu = torch_gpu_baseline(dev, tr["batch"])
+        except Exception as e:      # informational only
+            tgpu = {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}
 
     if rank == 0:
         B = tr["batch"]
@@ -584,6 +644,8 @@ def main():
             line["allreduce"] = tr["allreduce"]
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if tgpu is not None:
+            line["torch_gpu_baseline"] = tgpu
         if secondary:
             line["secondary"] = secondary
         print(json.dumps(line), flush=True)

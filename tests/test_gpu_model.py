@@ -297,3 +297,40 @@ def test_channel_sliced_shortcuts():
           % (float(loss), float(le), float(np.median(rel)), max(rel)))
     assert abs(float(loss) - float(le)) / abs(float(le)) < 1e-2
     assert float(np.median(rel)) < 2e-2
+
+
+@pytest.mark.parametrize("name,B,S,seed", [("yolov3-tiny", 1, 416, 0), ("yolov3", 2, 64, 0), ("yolov4", 2, 64, 0)])
+def test_accurate_mode_matches_fp32_reference(name, B, S, seed):
+    """model.accurate = True: split-fp16 tensor-core convolutions with fp32 activations (b200yolo/accurate.py).
+    north_star: "fp32 loss and box coords within 1e-4 rel" against the reference's own fp32 output."""
+    g = golden("%s_%d_eval" % (name, S))
+    model = build_model(name, device="cuda").eval()
+    model.accurate = True
+    x = orc.synth_images(B, S, S, seed=seed)
+    with torch.no_grad():
+        io, p, _ = model(x.cuda())
+    torch.cuda.synchronize()
+    b, pr = _errs(io.cpu(), torch.from_numpy(g["io"]))
+    print("\n[%s %dx%d accurate mode] vs fp32 reference: box_rel=%.3g prob_abs=%.3g" % (name, S, S, b, pr))
+    assert b <= 1e-4 and pr <= 1e-4
+
+
+def test_map_on_held_batch_accurate_mode():
+    """BASELINE north_star: mAP on a held synthetic batch within 1e-4 of the reference -- in the fp32-accurate mode."""
+    from oracle import metrics_oracle as mo
+    g = golden("map_case")
+    S, B = int(g["size"]), g["inf_out"].shape[0]
+    conf, iou = float(g["conf_thres"]), float(g["iou_thres"])
+    model = build_model("yolov3-tiny", device="cuda").eval()
+    model.accurate = True
+    x = orc.synth_images(B, S, S, seed=int(g["seed"]))
+    with torch.no_grad():
+        io, _, _ = model(x.cuda())
+    torch.cuda.synchronize()
+    labels = [torch.from_numpy(g["labels%d" % i]) for i in range(B)]
+    m50, m, n = mo.mean_ap(io, labels, conf, iou, S, S)
+    r50, r = float(g["map50"]), float(g["map"])
+    dmax = float((io.cpu() - torch.from_numpy(g["inf_out"])).abs().max())
+    print("\n[mAP held batch, accurate mode] reference %.6f / %.6f | engine %.6f / %.6f (%d det) | max |io - ref| %.3g"
+          % (r50, r, m50, m, n, dmax))
+    assert abs(m50 - r50) <= 1e-4 and abs(m - r) <= 1e-4

@@ -139,3 +139,40 @@ def test_graph_replay_matches_eager_training(name):
     print("      eager-vs-eager   ", noise, "\n      eager-vs-replay  ", replay, "\n      model-vs-model   ", cross)
     assert replay[0][0] < max(5e-2, 3 * noise[0][0])
     assert cross[0][0] < max(5e-2, 3 * noise[0][0])
+
+
+@pytest.mark.parametrize("name,B,S", [("yolov3-tiny", 8, 416), ("yolov3", 8, 256)])
+def test_flat_sink_matches_plain_autograd(name, B, S):
+    """FlatDataParallel (world size 1): the training plan writes every gradient straight into the flat buffer (BatchNorm
+    backward kernels, the table-driven weight-gradient unpack) -- the result must equal the plain autograd path (plan-owned
+    buffers handed to .grad) up to the fp32 reordering of the split-K / BN-sum atomics."""
+    from utils import utils as my_utils
+    from b200yolo.parallel import FlatDataParallel
+    x = orc.synth_images(B, S, S, seed=10).cuda()
+    t = orc.synth_targets(B, 6, 80, seed=20).cuda()
+    plain = attach_hyp(build_model(name, device="cuda")).train()
+    plain.use_cuda_graph = False
+    runs = []
+    for _ in range(2):                       # twice: the run-to-run noise of the atomics is the yardstick
+        plain.zero_grad(set_to_none=True)
+        pred, _ = plain(x)
+        loss, _ = my_utils.compute_loss(pred, t, plain)
+        loss.backward()
+        runs.append({k: p.grad.detach().clone() for k, p in plain.named_parameters()})
+    wrapped = attach_hyp(build_model(name, device="cuda")).train()
+    dp = FlatDataParallel(wrapped)
+    dp.zero_grad()
+    pred, _ = dp(x)
+    loss2, _ = my_utils.compute_loss(pred, t, dp)
+    loss2.backward()
+    torch.cuda.synchronize()
+    noise = max(float((runs[0][k] - runs[1][k]).norm() / (runs[0][k].norm() + 1e-12)) for k in runs[0])
+    errs = sorted(((float((dp.grad_views[id(p)] - runs[0][n]).norm() / (runs[0][n].norm() + 1e-12)), n)
+                   for n, p in zip(dp.names, dp.params)), reverse=True)
+    print("\n[%s sink vs plain] loss %.6f vs %.6f | run-to-run noise %.3g | worst sink-vs-plain %s"
+          % (name, float(loss2), float(loss), noise, errs[:3]))
+    # (a randomly initialised batch-statistics network is chaotic in the backward direction: at 4x128x128 two runs of the
+    #  SAME model differ by 9 % / 39 % element-wise in the early layers from the fp32 reordering of the atomics alone --
+    #  measured -- so the comparison is made at sizes where every BatchNorm sees >= 512 samples, relative to that noise)
+    assert abs(float(loss2) - float(loss)) / abs(float(loss)) < 1e-3
+    assert errs[0][0] < max(1e-3, 3 * noise)

@@ -286,7 +286,14 @@ class Plan:
 
     # ---------------------------------------------------------------------------------------------------------
     def _params_version(self):
-        return sum(p._version for p in self.model.parameters()) + sum(b._version for b in self.model.buffers())
+        # tensor versions catch optimiser steps and copy_(); the data pointers catch re-assigned `.data` (nn.Module.to /
+        # half, FlatDataParallel); the model-level epoch is bumped by the training plan, whose kernels update the
+        # BatchNorm running statistics through raw pointers (no version bump, invisible under CUDA-graph replay).
+        # Edits through `.data` that keep the storage (w.data.mul_()) are invisible: call model.engine().invalidate().
+        v = getattr(self.model, '_b2y_epoch', 0)
+        for t in list(self.model.parameters()) + list(self.model.buffers()):
+            v += t._version + (t.data_ptr() & 0xffff)
+        return v
 
     def _pack_weights(self):
         for st in self.steps:
@@ -323,13 +330,47 @@ class Plan:
                          conv.in_channels * conv.kernel_size[0] ** 2 <= 32):
                 wstem = ops.pack_stem_weights(w32)
             self.weights[i] = (wp, bias, w32, wstem)
+            if self._pair_packable(st):
+                self.weights[i] = self.weights[i] + (self._pair_pack(conv, bnp, eps),)
+
+    # ---- pixel-pair packing of the Cin = 32 3x3 layers --------------------------------------------------------------
+    # With 32 input channels a tap of the im2col gather is a 64-byte row: one TMA request per pixel per tap, and the
+    # layer is bound by the TMA request rate (0.16 of the tensor peak, 31-46 % of HBM in round 1), not by HBM.  The NHWC
+    # tensor [B,H,W,32] is the same memory as [B,H,W/2,64]: viewed as pixel PAIRS the same convolution is a 3x3 conv
+    # with 64 input and 2*Cout output channels whose weights are the original taps placed at
+    # s = 2(kwp-1) + i_sub - o_sub + 1 (zero elsewhere).  Half of the MACs multiply zeros, but the rows are 128 bytes,
+    # the tile count halves and N = 128 brings the CTA-pair path in -- no new kernel, only a weight layout.
+    def _pair_packable(self, st):
+        if os.environ.get('B2Y_PAIRPACK', '1') == '0':
+            return False
+        _, i, src, out, res, conv, bn, act, slope = st
+        if src is None or conv.kernel_size[0] != 3 or conv.stride[0] != 1 or conv.padding[0] != 1:
+            return False
+        if conv.in_channels != 32 or conv.out_channels > 128 or conv.out_channels % 8 or src.W % 2:
+            return False
+        full = lambda t: t.c0 == 0 and t.buf.shape[3] == t.C and t.dtype == torch.float16
+        return full(src) and full(out) and (res is None or full(res))
+
+    def _pair_pack(self, conv, bnp, eps):
+        O, I = conv.out_channels, conv.in_channels
+        _, bias, w32 = ops.pack_conv_weights(conv.weight.detach(), conv.bias.detach() if conv.bias is not None else None,
+                                             bnp, eps, want_fp32=True)
+        w2 = torch.zeros((2 * O, 2 * I, 3, 3), dtype=torch.float32, device=w32.device)
+        for o_sub in range(2):
+            for i_sub in range(2):
+                for kwp in range(3):
+                    s_ = 2 * (kwp - 1) + i_sub - o_sub + 1
+                    if 0 <= s_ <= 2:
+                        w2[o_sub * O:(o_sub + 1) * O, i_sub * I:(i_sub + 1) * I, :, kwp] = w32[:, :, :, s_]
+        wp2, _, _ = ops.pack_conv_weights(w2)
+        return wp2, torch.cat([bias, bias]).contiguous()
 
     def _launch_all(self, x):
         for st in self.steps:
             kind = st[0]
             if kind == 'conv':
                 _, i, src, out, res, conv, bn, act, slope = st
-                wp, bias, w32, wstem = self.weights[i]
+                wp, bias, w32, wstem = self.weights[i][:4]
                 k, s, p = conv.kernel_size[0], conv.stride[0], conv.padding[0]
                 if src is None:
                     if conv.in_channels > 4:
@@ -352,6 +393,11 @@ class Plan:
                         if x.dtype != torch.float32:
                             x = x.float() / 256.0 if x.dtype == torch.uint8 else x.float()
                         ops.stem_conv(x, w32, bias, k, s, p, act=act, slope=slope, out=out.view())
+                elif len(self.weights[i]) == 5:
+                    wp2, bias2 = self.weights[i][4]
+                    pairs = lambda t: t.buf.view(t.buf.shape[0], t.H, t.W // 2, 2 * t.C)
+                    ops.conv2d(pairs(src), wp2, bias2, 3, 1, 1, act=act, slope=slope,
+                               residual=pairs(res) if res is not None else None, out=pairs(out))
                 else:
                     ops.conv2d(src.view_k(), wp, bias, k, s, p, act=act, slope=slope,
                                residual=res.view() if res is not None else None, out=out.view())
@@ -587,16 +633,29 @@ class Engine:
         model = self.model
         if model.quantized != -1:
             return self._forward_quantized(x)
+        if getattr(model, 'accurate', False) and not model.training:
+            # fp32-accurate verification mode (split-fp16 tensor-core convs, fp32 activations): accurate.py
+            if getattr(self, '_accurate', None) is None:
+                from .accurate import AccurateRunner
+                self._accurate = AccurateRunner(model)
+            return self._accurate.forward(x)
         keep = bool(model.keep_features)
         key = (tuple(x.shape), bool(model.training), x.device.index, keep, x.dtype)
         plan = self.plans.get(key)
         if plan is None:
+            # bounded plan cache (multi-scale training visits ~11 image sizes, each plan owns all its activation /
+            # gradient buffers and CUDA graphs): least recently used plans are dropped beyond B2Y_MAX_PLANS (default 6)
+            limit = int(os.environ.get('B2Y_MAX_PLANS', '6'))
+            while len(self.plans) >= limit > 0:
+                self.plans.pop(next(iter(self.plans)))
             if model.training:
                 from .train_engine import TrainPlan
                 plan = TrainPlan(model, tuple(x.shape), x.device, keep)
             else:
                 plan = Plan(model, tuple(x.shape), x.device, False, keep)
             self.plans[key] = plan
+        else:
+            self.plans[key] = self.plans.pop(key)      # move to the most-recently-used end
         self.last_plan = plan
         if model.training:
             return plan.run(x)

@@ -88,8 +88,21 @@ class FlatDataParallel:
     def zero_grad(self):
         self.flat_grad.zero_()
 
+    def accumulate(self):
+        """Gradient accumulation over micro-batches (train.py:437-447, `accumulate = 64 / batch_size`): the training plan
+        OVERWRITES the flat gradient buffer on every backward (its kernels write, they do not add), so call this after
+        each micro-batch's backward; reduce_gradients() / step() then use the sum.  Without it, two backward calls
+        before a step keep only the last one."""
+        if getattr(self, '_acc', None) is None:
+            self._acc = self.flat_grad.clone()
+        else:
+            self._acc.add_(self.flat_grad)
+
     def reduce_gradients(self, async_op=False):
         """The single exchange step of the data-parallel path (N4): SUM over ranks; the mean is taken in step()."""
+        if getattr(self, '_acc', None) is not None:
+            self.flat_grad.copy_(self._acc)
+            self._acc = None
         if self.world > 1:
             return dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.pg, async_op=async_op)
         return None

@@ -511,6 +511,7 @@ class TrainPlan:
                 ops.maxpool(st[1].view(), st[3], st[4], tiny_pad=st[5], out=st[2].view())
         if self.bn_counters:
             torch._foreach_add_(self.bn_counters, 1)
+
         outs = []
         for (m, raw), anc in zip(self.yolo, self.anchors_px):
             _, p = ops.yolo_decode(raw.buf, m.na, m.no, anc, m.stride, io=None)
@@ -730,6 +731,8 @@ class TrainPlan:
     def run(self, x):
         """autograd entry: returns (yolo_out list, feature_out)."""
         outs = _DarknetTrain.apply(self, x, *self.params)
+        # the running statistics were just updated through raw pointers (also under graph replay): eval plans re-fold
+        object.__setattr__(self.model, '_b2y_epoch', getattr(self.model, '_b2y_epoch', 0) + 1)
         feats = LazyFeatures([None if t is None else t.view() for t in self.feature_views])
         return list(outs), feats
 
