@@ -298,6 +298,10 @@ int b2y_stem_conv_bwd_weight(const b2y_conv_desc* d, const float* x_nchw, const 
  * grad_scale (1/world_size after the NCCL sum) */
 int b2y_sgd_nesterov(float* param, const float* grad, float* momentum_buf, long long n, float lr, float momentum,
                      float weight_decay, float grad_scale, int first_step, void* stream);
+/* the same step with the model EMA (utils/torch_utils.py:171-183: ema = d*ema + (1-d)*w) updated in the same pass */
+int b2y_sgd_nesterov_ema(float* param, const float* grad, float* momentum_buf, float* ema, long long n, float lr,
+                         float momentum, float weight_decay, float grad_scale, int first_step, float ema_decay,
+                         void* stream);
 
 /* ---- bandwidth-oriented BatchNorm passes of the training step (csrc/bn_train.cu; models.py:100-113 under autograd) ----
  * save = fp32 [4][c]: batch mean, invstd, scale = gamma*invstd, shift = beta - mean*scale.

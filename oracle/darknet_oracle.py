@@ -278,15 +278,15 @@ def build_targets(p, targets, anchor_vecs, iou_t):
     """utils.py:725-779 with use_all_anchors=True, reject=True -> (tcls, tbox, indices, av) per yolo layer."""
     nt = targets.shape[0]
     tcls, tbox, indices, av = [], [], [], []
-    gain = torch.ones(6)
+    gain = torch.ones(6, device=targets.device)
     for i, anchors in enumerate(anchor_vecs):
-        gain[2:] = torch.tensor(p[i].shape)[[3, 2, 3, 2]].float()                  # utils.py:742
+        gain[2:] = torch.tensor(p[i].shape)[[3, 2, 3, 2]].float().to(targets.device)   # utils.py:742
         t, a = targets * gain, []
         gwh = t[:, 4:6]
         if nt:
             iou = wh_iou(anchors, gwh)
             na = anchors.shape[0]
-            a = torch.arange(na).view(-1, 1).repeat(1, nt).view(-1)                # utils.py:750 (anchor-major)
+            a = torch.arange(na, device=targets.device).view(-1, 1).repeat(1, nt).view(-1)   # utils.py:750 (anchor-major)
             t = t.repeat(na, 1)
             j = iou.view(-1) > iou_t                                               # utils.py:757
             t, a = t[j], a[j]
@@ -304,10 +304,11 @@ def build_targets(p, targets, anchor_vecs, iou_t):
 
 def compute_loss(p, targets, anchor_vecs, hyp, nc, gr=1.0):
     """utils.py:368-432 with red='mean', smooth_BCE(eps=0) -> (loss[1], items[4] = lbox, lobj, lcls, loss)."""
-    lcls, lbox, lobj = torch.zeros(1), torch.zeros(1), torch.zeros(1)
+    dev = p[0].device
+    lcls, lbox, lobj = torch.zeros(1, device=dev), torch.zeros(1, device=dev), torch.zeros(1, device=dev)
     tcls, tbox, indices, av = build_targets(p, targets, anchor_vecs, hyp['iou_t'])
-    BCEcls = torch.nn.BCEWithLogitsLoss(pos_weight=torch.tensor([hyp['cls_pw']]), reduction='mean')
-    BCEobj = torch.nn.BCEWithLogitsLoss(pos_weight=torch.tensor([hyp['obj_pw']]), reduction='mean')
+    BCEcls = torch.nn.BCEWithLogitsLoss(pos_weight=torch.tensor([hyp['cls_pw']], device=dev), reduction='mean')
+    BCEobj = torch.nn.BCEWithLogitsLoss(pos_weight=torch.tensor([hyp['obj_pw']], device=dev), reduction='mean')
     for i, pi in enumerate(p):
         b, a, gj, gi = indices[i]
         tobj = torch.zeros_like(pi[..., 0])

@@ -353,3 +353,25 @@ def test_data_movement_backward_kernels(gdt):
          stream_ptr())
     want = (dp.permute(0, 2, 3, 1, 4).reshape(B, 4, 5, 255) * 8.0).to(gdt)
     assert torch.equal(raw[..., :255].cpu(), want) and float(raw[..., 255].abs().max()) == 0.0
+
+
+def test_fused_sgd_ema_matches_torch_and_model_ema():
+    """SGD-Nesterov + ModelEMA (utils/torch_utils.py:171-183) in one pass over the flat buffer."""
+    import math
+    ops = _ops()
+    g = torch.Generator().manual_seed(8)
+    n = 20011
+    p0 = torch.randn(n, generator=g)
+    pt = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.SGD([pt], lr=0.01, momentum=0.937, nesterov=True, weight_decay=5e-4)
+    ema_ref = p0.clone()
+    pc, buf, ema = p0.clone().cuda(), torch.zeros(n, device="cuda"), p0.clone().cuda()
+    for step in range(1, 4):
+        gr = torch.randn(n, generator=g)
+        pt.grad = gr.clone()
+        opt.step()
+        d = 0.9999 * (1 - math.exp(-step / 2000))
+        ema_ref.mul_(d).add_(pt.detach(), alpha=1 - d)
+        ops.sgd_nesterov(pc, gr.cuda(), buf, 0.01, 0.937, 5e-4, first_step=(step == 1), ema=ema, ema_decay=d)
+    np.testing.assert_allclose(pc.cpu().numpy(), pt.detach().numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(ema.cpu().numpy(), ema_ref.numpy(), rtol=1e-5, atol=1e-6)

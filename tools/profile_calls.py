@@ -32,7 +32,7 @@ def describe(name, args):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--mode", default="train", choices=["train", "infer"])
+    ap.add_argument("--mode", default="train", choices=["train", "infer", "ptq"])
     ap.add_argument("--model", default="yolov4")
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--reps", type=int, default=8)
@@ -44,7 +44,13 @@ def main():
     from b200yolo import lib
     from utils import utils as my_utils
     B = args.batch or (8 if args.mode == "train" else 32)
-    model = bench.build_model(args.model, dev, 0, train=args.mode == "train")
+    if args.mode == "ptq":
+        # INT8 graph of the PTQ-calibrated yolov3 (fixture scales; timing does not depend on the values)
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from test_gpu_ptq import _load_quantised_model
+        model, _ = _load_quantised_model()
+    else:
+        model = bench.build_model(args.model, dev, 0, train=args.mode == "train")
     model.use_cuda_graph = False
     u8, tg = bench.synth_batch(B, 100)
     x = (u8.to(dev).float() / 256.0).contiguous()

@@ -113,6 +113,7 @@ _PROTOS = {
     "b2y_maxpool_bwd": (i32, [vp, ll, vp, ll, vp, ll, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
     "b2y_stem_conv_bwd_weight": (i32, [C.POINTER(ConvDesc), vp, vp, vp, f32, i32, vp]),
     "b2y_sgd_nesterov": (i32, [vp, vp, vp, ll, f32, f32, f32, f32, i32, vp]),
+    "b2y_sgd_nesterov_ema": (i32, [vp, vp, vp, vp, ll, f32, f32, f32, f32, i32, f32, vp]),
     "b2y_bn_train_fwd": (i32, [vp, ll, vp, vp, ll, vp, vp, f32, f32, vp, vp, vp, vp, ll, vp, ll, ll, i32, i32, f32, vp]),
     "b2y_bn_train_bwd_reduce": (i32, [vp, ll, vp, ll, vp, vp, vp, ll, i32, i32, f32, i32, vp]),
     "b2y_bn_train_bwd_apply": (i32, [vp, ll, vp, ll, vp, vp, vp, vp, ll, ll, i32, i32, f32, i32, vp, vp, vp, vp, f32,

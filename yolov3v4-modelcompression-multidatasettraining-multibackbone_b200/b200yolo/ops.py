@@ -472,7 +472,13 @@ def se_bwd(x, dy, w1, w2, ws, dx, accumulate=False, dw1=None, dw2=None, grad_sca
     return dx, dw1, dw2
 
 
-def sgd_nesterov(param, grad, buf, lr, momentum, weight_decay, grad_scale=1.0, first_step=False):
+def sgd_nesterov(param, grad, buf, lr, momentum, weight_decay, grad_scale=1.0, first_step=False, ema=None,
+                 ema_decay=0.0):
+    if ema is not None:
+        call("b2y_sgd_nesterov_ema", ptr(param), ptr(grad), ptr(buf), ptr(ema), param.numel(), float(lr),
+             float(momentum), float(weight_decay), float(grad_scale), 1 if first_step else 0, float(ema_decay),
+             stream_ptr())
+        return
     call("b2y_sgd_nesterov", ptr(param), ptr(grad), ptr(buf), param.numel(), float(lr), float(momentum),
          float(weight_decay), float(grad_scale), 1 if first_step else 0, stream_ptr())
 

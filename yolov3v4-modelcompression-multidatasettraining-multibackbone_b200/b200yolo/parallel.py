@@ -111,19 +111,48 @@ class FlatDataParallel:
         """flat gradient divided by world (what DDP leaves in .grad) -- used by the tests."""
         return self.flat_grad / float(self.world)
 
+    def enable_ema(self, decay=0.9999):
+        """Model EMA (utils/torch_utils.py:141-183, train.py --ema) fused into the optimiser pass: flat copies of the
+        parameters and of the BatchNorm running buffers, decay ramp d(t) = decay * (1 - exp(-t / 2000))."""
+        import math
+        self.ema_param = self.flat_param.clone()
+        self.ema_buf = self.flat_buf.clone() if self.flat_buf is not None else None
+        self.ema_updates = 0
+        self._ema_decay = lambda t: decay * (1 - math.exp(-t / 2000))
+
+    def ema_state_dict(self):
+        """name -> EMA tensor for every parameter and floating-point buffer (views of the flat EMA buffers)."""
+        out, off = {}, 0
+        for n, p in zip(self.names, self.params):
+            out[n] = self.ema_param[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        off = 0
+        names = [n for n, b in self.module.named_buffers() if b.dtype.is_floating_point]
+        for n, b in zip(names, self.buffers):
+            out[n] = self.ema_buf[off:off + b.numel()].view_as(b)
+            off += b.numel()
+        return out
+
     def step(self, lr, momentum=0.937, weight_decay=0.000484, nesterov=True):
-        """Fused SGD-Nesterov over the flat buffers (two launches: decayed conv weights, everything else)."""
+        """Fused SGD-Nesterov (+ EMA when enabled) over the flat buffers (two launches: decayed conv weights, the rest)."""
         from . import ops
         assert nesterov, "the fused kernel implements the reference's nesterov=True configuration"
         first = self.steps == 0
         gs = 1.0 / float(self.world)
         nd = self.n_decay
+        ema = getattr(self, 'ema_param', None)
+        d = 0.0
+        if ema is not None:
+            self.ema_updates += 1
+            d = self._ema_decay(self.ema_updates)
         if nd:
             ops.sgd_nesterov(self.flat_param[:nd], self.flat_grad[:nd], self.flat_mom[:nd], lr, momentum, weight_decay,
-                             grad_scale=gs, first_step=first)
+                             grad_scale=gs, first_step=first, ema=ema[:nd] if ema is not None else None, ema_decay=d)
         if nd < self.flat_param.numel():
             ops.sgd_nesterov(self.flat_param[nd:], self.flat_grad[nd:], self.flat_mom[nd:], lr, momentum, 0.0,
-                             grad_scale=gs, first_step=first)
+                             grad_scale=gs, first_step=first, ema=ema[nd:] if ema is not None else None, ema_decay=d)
+        if ema is not None and self.ema_buf is not None:
+            ops.axpby(self.flat_buf, self.ema_buf, 1.0 - d, d)         # running statistics: ema = d*ema + (1-d)*buf
         self.steps += 1
         eng = self.module.__dict__.get('_engine')
         if eng is not None:

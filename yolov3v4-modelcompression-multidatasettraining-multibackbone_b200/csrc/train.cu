@@ -536,14 +536,18 @@ extern "C" int b2y_bn_act_bwd_apply(const void* x, long long x_pitch, const void
 //   g = grad*grad_scale + wd*p ; buf = first ? g : mu*buf + g ; p -= lr * (g + mu*buf)
 // ------------------------------------------------------------------------------------------------
 __global__ void sgd_nesterov_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf,
-                                    long long n, float lr, float mu, float wd, float gs, int first) {
+                                    long long n, float lr, float mu, float wd, float gs, int first,
+                                    float* __restrict__ ema, float ema_decay) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (long long)gridDim.x * blockDim.x) {
         const float w = p[i];
         const float grad = fmaf(wd, w, g[i] * gs);
         const float b = first ? grad : fmaf(mu, buf[i], grad);
         buf[i] = b;
-        p[i] = w - lr * fmaf(mu, b, grad);
+        const float wn = w - lr * fmaf(mu, b, grad);
+        p[i] = wn;
+        // ModelEMA.update (utils/torch_utils.py:171-183) fused into the optimiser pass: ema = d*ema + (1-d)*w_new
+        if (ema != nullptr) ema[i] = fmaf(ema_decay, ema[i], (1.f - ema_decay) * wn);
     }
 }
 
@@ -551,7 +555,17 @@ extern "C" int b2y_sgd_nesterov(float* param, const float* grad, float* momentum
                                 float momentum, float weight_decay, float grad_scale, int first_step, void* stream) {
     if (!param || !grad || !momentum_buf || n < 0) return B2Y_ERR_INVALID;
     sgd_nesterov_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        param, grad, momentum_buf, n, lr, momentum, weight_decay, grad_scale, first_step);
+        param, grad, momentum_buf, n, lr, momentum, weight_decay, grad_scale, first_step, nullptr, 0.f);
+    B2Y_CUDA_CHECK(cudaGetLastError());
+    return B2Y_OK;
+}
+
+extern "C" int b2y_sgd_nesterov_ema(float* param, const float* grad, float* momentum_buf, float* ema, long long n,
+                                    float lr, float momentum, float weight_decay, float grad_scale, int first_step,
+                                    float ema_decay, void* stream) {
+    if (!param || !grad || !momentum_buf || !ema || n < 0) return B2Y_ERR_INVALID;
+    sgd_nesterov_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        param, grad, momentum_buf, n, lr, momentum, weight_decay, grad_scale, first_step, ema, ema_decay);
     B2Y_CUDA_CHECK(cudaGetLastError());
     return B2Y_OK;
 }
