@@ -221,6 +221,14 @@ typedef struct b2y_qconv_desc {
 /* INT8 conv on tcgen05 kind::i8 with int32 accumulation (exact whenever the fp32 reference is). */
 int b2y_qconv2d_fwd(const b2y_qconv_desc* d, const void* x_i8, const void* w_i8, const float* bias, void* y,
                     void* stream);
+/* The same conv with the FOLLOWING quantised shortcut layer (ptq_cos.py:876-884 _min / 931-933 _max, eval) folded into its
+ * epilogue: y = clamp(round((round(q*out_scale/scale_x)*scale_x + round(a*sa_in/scale_a)*scale_a) / scale_sum)), q being
+ * this conv's int8 code and a the other addend's codes (NHWC int8, pitch a_pitch).  Bit-identical to b2y_qconv2d_fwd
+ * followed by b2y_qshortcut_i8.  Returns B2Y_ERR_UNSUPPORTED (nothing launched) unless every scale is a power of two and
+ * the layer qualifies for the short epilogue (whole channel tiles, 16-byte aligned tensors): run the two calls then. */
+int b2y_qconv2d_shortcut_fwd(const b2y_qconv_desc* d, const void* x_i8, const void* w_i8, const float* bias,
+                             const void* a_i8, long long a_pitch, float sa_in, float scale_x, float scale_a,
+                             float scale_sum, float sum_lo, float sum_hi, void* y, void* stream);
 /* BN-fold + weight quantisation + pack: OIHW fp32 -> int8 [O][kh][kw][I] with scale w_scale (ptq_cos.py:193-212) */
 int b2y_pack_qconv_weights(const float* w_oihw_folded, int out_c, int in_c, int ksize, float w_scale, float lo,
                            float hi, void* w_i8, void* stream);

@@ -339,6 +339,20 @@ def test_data_movement_backward_kernels(gdt):
         call("b2y_maxpool_bwd", ptr(xn), ops._pitch(xn), ptr(dyn), ops._pitch(dyn), ptr(gxm), ops._pitch(gxm), B, 8, 8,
              Cc, k, s, 0, ops._gdt(dyn), stream_ptr())
         assert (_nchw(gxm) - x.grad).abs().max() <= 4 * tol * max(1.0, x.grad.abs().max().item())
+    # SPP windows over a 20 x 19 map with many tied maxima (first maximum in row-major window order wins, as in torch),
+    # accumulated into a buffer that already holds another branch's gradient: the plane-in-shared-memory kernel
+    for k in (5, 9, 13):
+        x = (torch.randn(B, Cc, 20, 19, generator=g) * 2).round().div(2).requires_grad_(True)
+        y = F.max_pool2d(x, k, 1, (k - 1) // 2)
+        dy = torch.randn(y.shape, generator=g).to(gdt).float()
+        y.backward(dy)
+        base = torch.randn(B, Cc, 20, 19, generator=g).to(gdt).float()
+        gxm = _nhwc(base, gdt)
+        xn, dyn = _nhwc(x.detach()), _nhwc(dy, gdt)
+        call("b2y_maxpool_bwd", ptr(xn), ops._pitch(xn), ptr(dyn), ops._pitch(dyn), ptr(gxm), ops._pitch(gxm), B, 20,
+             19, Cc, k, 1, 0, ops._gdt(dyn), stream_ptr())
+        want = (base + x.grad).to(gdt).float()          # one rounding of the exact fp32 sum
+        assert (_nchw(gxm) - want).abs().max() <= 2.0 ** (-10 if gdt == torch.float16 else -7) * want.abs().max()
     # add (gradient accumulation into a slice)
     a = torch.randn(B, Cc, H, W, generator=g).to(gdt)
     b = torch.randn(B, Cc, H, W, generator=g).to(gdt)

@@ -89,6 +89,7 @@ _PROTOS = {
                             vp, vp]),
     "b2y_build_targets": (i32, [vp, i32, vp, i32, i32, i32, f32, vp, vp, vp, vp, vp]),
     "b2y_qconv2d_fwd": (i32, [C.POINTER(QConvDesc), vp, vp, vp, vp, vp]),
+    "b2y_qconv2d_shortcut_fwd": (i32, [C.POINTER(QConvDesc), vp, vp, vp, vp, ll, f32, f32, f32, f32, f32, f32, vp, vp]),
     "b2y_fakequant_f32": (i32, [vp, vp, ll, f32, f32, f32, vp]),
     "b2y_quantize_f16_to_i8": (i32, [vp, ll, vp, ll, ll, i32, f32, f32, f32, vp]),
     "b2y_cos_scale_search": (i32, [vp, ll, i32, i32, vp, vp, sz, vp]),

@@ -5,19 +5,21 @@ floats (utils/quantized/quantized_ptq_cos.py:288-296).  Because all scales are p
 integers times a power of two, so the same arithmetic runs here on the real int8 codes:
 
    conv      int8 x int8 -> int32 on tcgen05 kind::i8, epilogue  acc*(s_in*s_w) + q_bias -> act -> requant(s_act)
-   shortcut  b2y_qshortcut_i8 (both addends rounded onto scale_x / scale_a, sum requantised to scale_sum)
+   shortcut  folded into the epilogue of the conv that feeds it (b2y_qconv2d_shortcut_fwd) when nothing else reads that
+             conv's output; otherwise b2y_qshortcut_i8 (both addends rounded onto scale_x / scale_a, sum requantised)
    concat    b2y_requant_i8 of every source onto the concat scale, written into its channel slot
    upsample  nearest copy of codes
    layer 0   fp32 direct conv of the float image on the fake-quantised weights (as the reference), int8 out
    heads     fp32 fake-quant values for the (fp32) YOLO decode kernel
 """
 import ctypes as C
+import os
 
 import torch
 
 from . import ops
 from .engine import _Tensor
-from .lib import OUT_F32, OUT_I8, call, ptr, stream_ptr
+from .lib import OUT_F32, OUT_I8, B2YError, call, ptr, stream_ptr
 
 _ACT_NAME = {'leaky': 'leaky', 'relu6': 'relu6', 'h_swish': 'h_swish', 'relu': 'relu', 'mish': 'mish',
              'linear': 'linear'}
@@ -36,6 +38,7 @@ class QPlan:
         self.runs = 0
         self.graph = None
         self._scal = {}
+        self._fusable = {}
         self._build()
 
     def _build(self):
@@ -46,6 +49,13 @@ class QPlan:
         tens = [None] * n
         self.yolo = []
         row_off = 0
+        # layers whose output is read by somebody other than the next layer (route sources, shortcut 'from' addends)
+        readers = set()
+        for j, dj in enumerate(defs):
+            if dj['type'] == 'route':
+                readers.update(j + l if l < 0 else l for l in dj['layers'])
+            elif dj['type'] == 'shortcut':
+                readers.update(j + l if l < 0 else l for l in dj['from'])
         for i, (d, m) in enumerate(zip(defs, mods)):
             t = d['type']
             Cc, H, W = prev
@@ -72,7 +82,16 @@ class QPlan:
                 src = tens[i + l if l < 0 else l]
                 out = _Tensor(Cc, H, W, torch.int8)
                 out.buf = torch.empty((B, H, W, Cc), dtype=torch.int8, device=dev)
-                self.steps.append(('shortcut', i, tens[i - 1], src, out, m))
+                prev_step = self.steps[-1] if self.steps else None
+                fuse = (os.environ.get('B2Y_Q_FUSE_SHORTCUT', '1') != '0' and prev_step is not None
+                        and prev_step[0] == 'conv' and prev_step[1] == i - 1 and prev_step[2] is not None
+                        and not prev_step[5] and (i - 1) not in readers and src is not tens[i - 1])
+                if fuse:
+                    # the conv writes the shortcut's result; its own output tensor is never materialised
+                    self.steps[-1] = ('conv_sc', i - 1, prev_step[2], out, prev_step[4], (i, src, m, tens[i - 1]))
+                    tens[i - 1].buf = None
+                else:
+                    self.steps.append(('shortcut', i, tens[i - 1], src, out, m))
                 tens[i] = out
             elif t == 'route':
                 srcs = [i + l if l < 0 else l for l in d['layers']]
@@ -133,6 +152,19 @@ class QPlan:
                     self.packed[i] = (w8, conv.q_bias.detach().float().contiguous(), scale_of[id(src)] * s_w, s_a, act,
                                       slope, bits_a)
                 scale_of[id(out)] = s_a
+            elif kind == 'conv_sc':
+                _, i, src, out, conv, (isc, a, m, own) = st
+                conv.fold_and_quantize()
+                s_w, s_a = _s(conv.weight_quantizer.scale), _s(conv.activation_quantizer.scale)
+                if s_w <= 0 or s_a <= 0:
+                    raise RuntimeError("layer %d is not calibrated (scale == 0): load a calibrated state_dict" % i)
+                if conv.w_bits > 8 or conv.a_bits > 8:
+                    raise NotImplementedError("the tcgen05 kind::i8 path covers <= 8 bit weights and activations")
+                w8 = ops.pack_qconv_weights(conv.q_weight.detach(), s_w, conv.w_bits)
+                self.packed[i] = (w8, conv.q_bias.detach().float().contiguous(), scale_of[id(src)] * s_w, s_a,
+                                  _ACT_NAME[conv.activate], 0.25 if conv.maxabsscaler else 0.1, conv.a_bits)
+                scale_of[id(own)] = s_a
+                scale_of[id(out)] = _s(m.scale_sum)
             elif kind == 'shortcut':
                 _, i, x, a, out, m = st
                 scale_of[id(out)] = _s(m.scale_sum)
@@ -214,6 +246,35 @@ class QPlan:
                     else:
                         ops.qconv2d(src.view(), w8, bq, k, s, p, acc_scale, s_a, act=act, slope=slope, bits=bits,
                                     out=out.view(), out_kind=OUT_I8)
+            elif kind == 'conv_sc':
+                _, i, src, out, conv, (isc, at, m, own) = st
+                k, s, p = conv.kernel_size[0], conv.stride[0], conv.padding[0]
+                w8, bq, acc_scale, s_a, act, slope, bits = self.packed[i]
+                slo, shi = -(1 << (m.bits - 1)), (1 << (m.bits - 1)) - 1
+                xv, av, ov = src.view(), at.view(), out.view()
+                fused = self._fusable.get(i, True)
+                if fused:
+                    cd = ops.make_conv_desc(xv.shape, ops._pitch(xv), conv.out_channels, k, s, p, ops._pitch(ov), act,
+                                            slope, OUT_I8)
+                    qd = ops.QConvDesc(cd, float(acc_scale), float(s_a), float(-(1 << (bits - 1))),
+                                       float((1 << (bits - 1)) - 1), OUT_I8, 1)
+                    try:
+                        call("b2y_qconv2d_shortcut_fwd", C.byref(qd), ptr(xv), ptr(w8), ptr(bq), ptr(av), ops._pitch(av),
+                             sc[id(at)], self._sv(m.scale_x), self._sv(m.scale_a), self._sv(m.scale_sum), float(slo),
+                             float(shi), ptr(ov), stream_ptr())
+                    except B2YError as e:
+                        if 'unsupported' not in str(e).lower():
+                            raise
+                        fused = self._fusable[i] = False       # e.g. a scale that is not a power of two
+                if not fused:
+                    if own.buf is None:
+                        own.buf = torch.empty((B, own.H, own.W, own.C), dtype=torch.int8, device=self.device)
+                    ops.qconv2d(xv, w8, bq, k, s, p, acc_scale, s_a, act=act, slope=slope, bits=bits, out=own.view(),
+                                out_kind=OUT_I8)
+                    wv = own.view()
+                    call("b2y_qshortcut_i8", ptr(wv), ops._pitch(wv), ptr(av), ops._pitch(av), ptr(ov), ops._pitch(ov),
+                         B * out.H * out.W, out.C, s_a, self._sv(m.scale_x), sc[id(at)], self._sv(m.scale_a),
+                         self._sv(m.scale_sum), float(slo), float(shi), stream_ptr())
             elif kind == 'shortcut':
                 _, i, xt, at, out, m = st
                 lo, hi = -(1 << (m.bits - 1)), (1 << (m.bits - 1)) - 1

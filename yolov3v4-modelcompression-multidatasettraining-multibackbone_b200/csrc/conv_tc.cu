@@ -191,6 +191,10 @@ struct EpilogueArgs {
     float* stat_sqsum = nullptr;
     int res_bf16 = 0;
     const float* acc_scale_ptr = nullptr;
+    // int8 graph: quantised shortcut folded into the epilogue (see ConvTcParams::qres)
+    const void* qres = nullptr;
+    long long qres_pitch = 0;
+    float qs_a_in = 1.f, qs_x = 1.f, qs_a = 1.f, qs_sum = 1.f, qs_lo = -128.f, qs_hi = 127.f;
 };
 
 // Generic implicit-GEMM launch description: A = NHWC activation-like tensor gathered tap by tap, B = [Nout][ntaps*C].
@@ -304,6 +308,26 @@ int gemm_conv_launch(const GemmConvSpec& g, const EpilogueArgs& e, cudaStream_t 
             (e.act == B2Y_ACT_LINEAR || (e.act == B2Y_ACT_LEAKY && e.slope >= 0.f && e.slope <= 1.f)) && pow2 && full &&
             e.res == nullptr && al16(e.out) && e.out_pitch % 16 == 0 && (e.bias == nullptr || al16(e.bias)))
             p.epi_fast = 1;
+        // fake-quantised / linear fp32 rows of the int8 graph (the YOLO heads): through the TMA store, which clips Cout = 255
+        if (i8_fast && g.kind == CONV_KIND_I8 && out32 && tma_ok && e.stat_sum == nullptr && e.act == B2Y_ACT_LINEAR &&
+            pow2 && e.res == nullptr && al16(e.out) && e.out_pitch % 4 == 0 && (e.bias == nullptr || al16(e.bias)))
+            p.epi_fast = 1;
+        if (e.qres != nullptr) {
+            auto p2 = [](float v) { int x = 0; return v > 0.f && frexpf(v, &x) == 0.5f; };
+            if (!p.epi_fast || e.out_dtype != OUT_I8 || !al16(e.qres) || e.qres_pitch % 16 != 0 || !p2(e.out_scale) ||
+                !p2(e.qs_a_in) || !p2(e.qs_x) || !p2(e.qs_a) || !p2(e.qs_sum))
+                return B2Y_ERR_UNSUPPORTED;     // the caller runs the stand-alone shortcut kernel instead
+            p.qres = reinterpret_cast<const int8_t*>(e.qres);
+            p.qres_pitch = e.qres_pitch;
+            p.qs_rx = 1.f / e.qs_x;
+            p.qs_x = e.qs_x;
+            p.qs_a_in = e.qs_a_in;
+            p.qs_ra = 1.f / e.qs_a;
+            p.qs_a = e.qs_a;
+            p.qs_rsum = 1.f / e.qs_sum;
+            p.qs_lo = e.qs_lo;
+            p.qs_hi = e.qs_hi;
+        }
     }
 
     CUtensorMap tmA, tmB;
@@ -353,9 +377,10 @@ int gemm_conv_launch(const GemmConvSpec& g, const EpilogueArgs& e, cudaStream_t 
     // output map for the TMA-store epilogue (16-bit outputs on the short path with identity row mapping)
     CUtensorMap tmC = tmB;
     p.epi_tma = 0;
-    if (tma_on && p.epi_fast && p.out_identity && e.out_dtype != OUT_I8) {
-        const bool o32 = e.out_dtype == OUT_F32;
-        rc = make_map_2d(&tmC, e.out, o32 ? 4 : 2, M, g.Nout, e.out_pitch, 32, 32, o32 ? 128 : 64, e.out_dtype == OUT_BF16);
+    if (tma_on && p.epi_fast && p.out_identity) {
+        const bool o32 = e.out_dtype == OUT_F32, o8 = e.out_dtype == OUT_I8;
+        rc = make_map_2d(&tmC, e.out, o32 ? 4 : (o8 ? 1 : 2), M, g.Nout, e.out_pitch, 32, 32, o32 ? 128 : (o8 ? 32 : 64),
+                         e.out_dtype == OUT_BF16);
         if (rc != B2Y_OK) return rc;
         p.epi_tma = 1;
     }
@@ -843,5 +868,31 @@ extern "C" int b2y_qconv2d_fwd(const b2y_qconv_desc* d, const void* x_i8, const 
         e.out_dtype = d->out_kind == B2Y_OUT_F32 ? OUT_F32 : OUT_F16;
         e.out_fakequant = d->requant ? 1 : 0;
     }
+    return conv_tc_launch(CONV_KIND_I8, &d->conv, x_i8, w_i8, e, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int b2y_qconv2d_shortcut_fwd(const b2y_qconv_desc* d, const void* x_i8, const void* w_i8, const float* bias,
+                                        const void* a_i8, long long a_pitch, float sa_in, float scale_x, float scale_a,
+                                        float scale_sum, float sum_lo, float sum_hi, void* y, void* stream) {
+    if (!d || !a_i8 || d->out_kind != B2Y_OUT_I8) return B2Y_ERR_INVALID;
+    EpilogueArgs e;
+    e.bias = bias;
+    e.act = d->conv.act;
+    e.slope = d->conv.slope;
+    e.acc_scale = d->acc_scale;
+    e.out = y;
+    e.out_pitch = d->conv.out_pitch;
+    e.out_scale = d->out_scale;
+    e.q_lo = d->q_lo;
+    e.q_hi = d->q_hi;
+    e.out_dtype = OUT_I8;
+    e.qres = a_i8;
+    e.qres_pitch = a_pitch;
+    e.qs_a_in = sa_in;
+    e.qs_x = scale_x;
+    e.qs_a = scale_a;
+    e.qs_sum = scale_sum;
+    e.qs_lo = sum_lo;
+    e.qs_hi = sum_hi;
     return conv_tc_launch(CONV_KIND_I8, &d->conv, x_i8, w_i8, e, static_cast<cudaStream_t>(stream));
 }

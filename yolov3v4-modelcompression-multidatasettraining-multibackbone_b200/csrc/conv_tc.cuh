@@ -62,6 +62,12 @@ struct ConvTcParams {
     int pair;               // host: launch the cta_group::2 variant (cluster of two)
     int epi_tma;            // the short epilogue stores through smem + TMA (tmC valid); rows / columns clipped by the map
     int epi_fast;           // host-checked: 16-bit out, whole channel tiles, 16-byte aligned bias/residual/output
+    // int8 graph: quantised shortcut folded into the epilogue (COSPTQuantizedShortcut eval, ptq_cos.py:876-884 / 931-933):
+    //   code = clamp(rha((rha(q*out_scale*qs_rx)*qs_x + rha(a*qs_a_in*qs_ra)*qs_a) * qs_rsum)),  q = this conv's int8 code,
+    // all scales powers of two (host-checked), so every product is exact and equals the stand-alone kernel bit for bit
+    const int8_t* qres;     // the other addend's int8 codes (NHWC) or null
+    long long qres_pitch;
+    float qs_rx, qs_x, qs_a_in, qs_ra, qs_a, qs_rsum, qs_lo, qs_hi;
 };
 
 template <int BLOCK_N, int KBYTES>
@@ -578,6 +584,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                         for (int q = 0; q < 8; ++q) bv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
                     }
+                    uint4 qa[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+                    if (KIND == CONV_KIND_I8 && p.qres != nullptr && row_ok) {
+                        const uint4* ap = reinterpret_cast<const uint4*>(p.qres + row * p.qres_pitch + n0 + c_begin + c);
+                        qa[0] = __ldg(ap);
+                        qa[1] = __ldg(ap + 1);
+                    }
                     uint4 rcur[4];
 #pragma unroll
                     for (int q = 0; q < 4; ++q) rcur[q] = rnext[q];
@@ -631,22 +643,54 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             }
                         }
                     }
-                    if (p.out_dtype == OUT_I8) {
-                        // int8 graph: requantise exactly like the general path (round half away, clamp) and store the
-                        // 32 codes of this lane's row; values are identical because acc_mul is a power of two there
-                        if (row_ok) {
-                            uint32_t w[8];
+                    if (KIND == CONV_KIND_I8 && (p.out_dtype == OUT_I8 || p.out_fakequant)) {
+                        // int8 graph: requantise exactly like the general path (round half away, clamp); values are
+                        // identical because acc_mul is a power of two there
 #pragma unroll
-                            for (int t = 0; t < 8; ++t) {
-                                uint32_t word = 0;
+                        for (int j = 0; j < 32; ++j) {
+                            const float q = round_half_away(v[j] * p.out_inv_scale);
+                            v[j] = fminf(fmaxf(q, p.q_lo), p.q_hi);
+                        }
+                        if (p.qres != nullptr) {
+                            const int8_t* ab = reinterpret_cast<const int8_t*>(qa);
 #pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    float q = round_half_away(v[t * 4 + e] * p.out_inv_scale);
-                                    q = fminf(fmaxf(q, p.q_lo), p.q_hi);
-                                    word |= ((uint32_t)(uint8_t)(int8_t)(int)q) << (8 * e);
-                                }
-                                w[t] = word;
+                            for (int j = 0; j < 32; ++j) {
+                                const float xf = round_half_away(v[j] * p.out_scale * p.qs_rx) * p.qs_x;   // rounded, NOT clamped
+                                const float af = round_half_away((float)ab[j] * p.qs_a_in * p.qs_ra) * p.qs_a;
+                                const float q = round_half_away((xf + af) * p.qs_rsum);
+                                v[j] = fminf(fmaxf(q, p.qs_lo), p.qs_hi);
                             }
+                        } else if (p.out_fakequant) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] *= p.out_scale;
+                        }
+                    }
+                    if (p.out_dtype == OUT_I8) {
+                        uint32_t w[8];
+#pragma unroll
+                        for (int t = 0; t < 8; ++t) {
+                            uint32_t word = 0;
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) word |= ((uint32_t)(uint8_t)(int8_t)(int)v[t * 4 + e]) << (8 * e);
+                            w[t] = word;
+                        }
+                        if (epi_tma) {
+                            // 32 rows x 32 B through smem (SWIZZLE_32B image) and one TMA store: whole 32-byte sectors per
+                            // row reach L2 in one request instead of 2 x 32 scattered 16-byte pieces
+                            uint8_t* buf = my_stage + sbuf * 2048;
+                            if (lane == 0) bulk_wait_read<1>();
+                            __syncwarp();
+                            const int sw = (lane >> 2) & 1;
+                            *reinterpret_cast<uint4*>(buf + lane * 32 + ((0 ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+                            *reinterpret_cast<uint4*>(buf + lane * 32 + ((1 ^ sw) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
+                            fence_proxy_async_cta();
+                            __syncwarp();
+                            if (lane == 0) {
+                                tma_store_2d(&tmC, smem_u32(buf), n0 + c_begin + c, m_tile * 128 + ew * 32);
+                                bulk_commit();
+                            }
+                            sbuf ^= 1;
+                        } else if (row_ok) {
                             uint4* op8 = reinterpret_cast<uint4*>(reinterpret_cast<int8_t*>(p.out) + row * p.out_pitch + n0 +
                                                                   c_begin + c);
                             op8[0] = make_uint4(w[0], w[1], w[2], w[3]);

@@ -236,6 +236,42 @@ __global__ void maxpool_kernel(const __half* __restrict__ x, long long xp, __hal
     }
 }
 
+// Stride-1 "same" pooling over a small map (the SPP block: 5/9/13 windows over the 20x20 map): one CTA owns the whole
+// plane of one image x 8 channels in shared memory and does the window as two 1-D passes (k + k loads instead of k*k).
+constexpr int POOL_PLANE_MAX = 576;   // <= 24 x 24 pixels
+__global__ void __launch_bounds__(256) maxpool_plane_kernel(const __half* __restrict__ x, long long xp,
+                                                            __half* __restrict__ y, long long yp, int H, int W, int C,
+                                                            int k) {
+    __shared__ __align__(16) __half sx[POOL_PLANE_MAX * 8];
+    __shared__ __align__(16) __half sr[POOL_PLANE_MAX * 8];
+    const int CV = C / 8;
+    const int n = blockIdx.x / CV, cv = blockIdx.x - n * CV;
+    const int HW = H * W, pad = (k - 1) / 2;
+    for (int i = threadIdx.x; i < HW; i += blockDim.x)
+        reinterpret_cast<uint4*>(sx)[i] = __ldg(reinterpret_cast<const uint4*>(x + ((long long)n * HW + i) * xp) + cv);
+    __syncthreads();
+    for (int i = threadIdx.x; i < HW * 8; i += blockDim.x) {
+        const int c = i & 7, pix = i >> 3;
+        const int yi = pix / W, xo = pix - yi * W;
+        const int x0 = max(xo - pad, 0), x1 = min(xo - pad + k, W);
+        __half m = sx[(yi * W + x0) * 8 + c];
+        for (int xi = x0 + 1; xi < x1; ++xi) m = __hmax(m, sx[(yi * W + xi) * 8 + c]);
+        sr[i] = m;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < HW * 8; i += blockDim.x) {
+        const int c = i & 7, pix = i >> 3;
+        const int yo = pix / W, xo = pix - yo * W;
+        const int y0 = max(yo - pad, 0), y1 = min(yo - pad + k, H);
+        __half m = sr[(y0 * W + xo) * 8 + c];
+        for (int yi = y0 + 1; yi < y1; ++yi) m = __hmax(m, sr[(yi * W + xo) * 8 + c]);
+        sx[i] = m;      // every thread reads sr only in this pass: sx is free to take the result
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < HW; i += blockDim.x)
+        reinterpret_cast<uint4*>(y + ((long long)n * HW + i) * yp)[cv] = reinterpret_cast<const uint4*>(sx)[i];
+}
+
 extern "C" int b2y_maxpool(const void* x, long long x_pitch, void* y, long long y_pitch, int batch, int in_h, int in_w,
                            int c, int ksize, int stride, int pad_mode, void* stream) {
     if (!x || !y || c % 8 != 0 || x_pitch % 8 != 0 || y_pitch % 8 != 0 || ksize < 1 || stride < 1)
@@ -252,6 +288,13 @@ extern "C" int b2y_maxpool(const void* x, long long x_pitch, void* y, long long 
         Wo = (in_w + 2 * pad - ksize) / stride + 1;
     }
     const long long total = (long long)batch * Ho * Wo * (c / 8);
+    if (pad_mode != 1 && stride == 1 && (ksize & 1) && in_h * in_w <= POOL_PLANE_MAX &&
+        (long long)batch * (c / 8) <= 0x7fffffffLL) {
+        maxpool_plane_kernel<<<batch * (c / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+            reinterpret_cast<const __half*>(x), x_pitch, reinterpret_cast<__half*>(y), y_pitch, in_h, in_w, c, ksize);
+        B2Y_CUDA_CHECK(cudaGetLastError());
+        return B2Y_OK;
+    }
     maxpool_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const __half*>(x), x_pitch, reinterpret_cast<__half*>(y), y_pitch, batch, in_h, in_w, c,
         ksize, stride, pad, Ho, Wo, pad_mode == 1 ? 1 : 0);

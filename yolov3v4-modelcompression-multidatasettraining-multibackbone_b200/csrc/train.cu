@@ -708,6 +708,65 @@ __global__ void maxpool_bwd_kernel(const __half* __restrict__ x, long long xp, c
         }
     }
 }
+// Stride-1 "same" pooling over a small map (SPP: 5/9/13 over 20x20): one CTA owns the plane of one image x 8 channels.
+// Pass 1 finds, per input row and window position, the row-window maximum and its FIRST column; pass 2 walks the window
+// rows with a strict '>' -- together the first maximum in row-major window order, as the k*k scan of the general kernel
+// (and torch's max_pool2d) finds it, with k + k loads.  Gradients are summed in shared memory (fp32) and added to dx by
+// the owner, so there are no global atomics and the result does not depend on scheduling.
+constexpr int POOL_PLANE_MAX = 576;
+template <typename GT>
+__global__ void __launch_bounds__(256) maxpool_plane_bwd_kernel(const __half* __restrict__ x, long long xp,
+                                                                const GT* __restrict__ dy, long long dyp,
+                                                                GT* __restrict__ dx, long long dxp, int H, int W,
+                                                                int C, int k) {
+    __shared__ __align__(16) __half sx[POOL_PLANE_MAX * 8];
+    __shared__ __align__(16) __half sr[POOL_PLANE_MAX * 8];
+    __shared__ unsigned char sa[POOL_PLANE_MAX * 8];
+    __shared__ float acc[POOL_PLANE_MAX * 8];
+    const int CV = C / 8;
+    const int n = blockIdx.x / CV, cv = blockIdx.x - n * CV;
+    const int HW = H * W, pad = (k - 1) / 2;
+    for (int i = threadIdx.x; i < HW; i += blockDim.x)
+        reinterpret_cast<uint4*>(sx)[i] = __ldg(reinterpret_cast<const uint4*>(x + ((long long)n * HW + i) * xp) + cv);
+    for (int i = threadIdx.x; i < HW * 8; i += blockDim.x) acc[i] = 0.f;
+    __syncthreads();
+    for (int i = threadIdx.x; i < HW * 8; i += blockDim.x) {
+        const int c = i & 7, pix = i >> 3;
+        const int yi = pix / W, xo = pix - yi * W;
+        const int x0 = max(xo - pad, 0), x1 = min(xo - pad + k, W);
+        float m = __half2float(sx[(yi * W + x0) * 8 + c]);
+        int a = x0;
+        for (int xi = x0 + 1; xi < x1; ++xi) {
+            const float v = __half2float(sx[(yi * W + xi) * 8 + c]);
+            if (v > m) { m = v; a = xi; }
+        }
+        sr[i] = __float2half(m);        // exact: m is one of the fp16 inputs
+        sa[i] = (unsigned char)a;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < HW * 8; i += blockDim.x) {
+        const int c = i & 7, pix = i >> 3;
+        const int yo = pix / W, xo = pix - yo * W;
+        const int y0 = max(yo - pad, 0), y1 = min(yo - pad + k, H);
+        float m = __half2float(sr[(y0 * W + xo) * 8 + c]);
+        int ay = y0;
+        for (int yi = y0 + 1; yi < y1; ++yi) {
+            const float v = __half2float(sr[(yi * W + xo) * 8 + c]);
+            if (v > m) { m = v; ay = yi; }
+        }
+        // NaN rows never win a strict '>' (same as the general kernel, whose -inf start is replaced by the first value)
+        const int ax = sa[(ay * W + xo) * 8 + c];
+        const float g = Half8<GT>::to_f(dy[((long long)n * HW + pix) * dyp + cv * 8 + c]);
+        atomicAdd(&acc[(ay * W + ax) * 8 + c], g);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < HW * 8; i += blockDim.x) {
+        const int c = i & 7, pix = i >> 3;
+        GT* d = dx + ((long long)n * HW + pix) * dxp + cv * 8 + c;
+        *d = Half8<GT>::from_f(Half8<GT>::to_f(*d) + acc[i]);
+    }
+}
+
 extern "C" int b2y_maxpool_bwd(const void* x, long long x_pitch, const void* dy, long long dy_pitch, void* dx,
                                long long dx_pitch, int batch, int in_h, int in_w, int c, int ksize, int stride,
                                int pad_mode, int grad_dtype, void* stream) {
@@ -724,6 +783,20 @@ extern "C" int b2y_maxpool_bwd(const void* x, long long x_pitch, const void* dy,
         Wo = (in_w + 2 * pad - ksize) / stride + 1;
     }
     const long long total = (long long)batch * Ho * Wo * (c / 2);
+    if (pad_mode != 1 && stride == 1 && (ksize & 1) && c % 8 == 0 && x_pitch % 8 == 0 && in_w <= 255 &&
+        in_h * in_w <= POOL_PLANE_MAX && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+        const int grid = batch * (c / 8);
+        if (grad_dtype == B2Y_DT_BF16)
+            maxpool_plane_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+                reinterpret_cast<const __half*>(x), x_pitch, reinterpret_cast<const __nv_bfloat16*>(dy), dy_pitch,
+                reinterpret_cast<__nv_bfloat16*>(dx), dx_pitch, in_h, in_w, c, ksize);
+        else
+            maxpool_plane_bwd_kernel<__half><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+                reinterpret_cast<const __half*>(x), x_pitch, reinterpret_cast<const __half*>(dy), dy_pitch,
+                reinterpret_cast<__half*>(dx), dx_pitch, in_h, in_w, c, ksize);
+        B2Y_CUDA_CHECK(cudaGetLastError());
+        return B2Y_OK;
+    }
     if (grad_dtype == B2Y_DT_BF16)
         maxpool_bwd_kernel<__nv_bfloat16, __nv_bfloat162><<<grid_for(total, 256), 256, 0,
                                                             static_cast<cudaStream_t>(stream)>>>(
