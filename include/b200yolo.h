@@ -74,7 +74,16 @@ typedef struct b2y_conv_desc {
     float slope;         /* leaky slope (0.1; 0.25 with maxabsscaler, models.py:103) */
     int out_dtype;       /* B2Y_OUT_F16 or B2Y_OUT_F32 */
     long long res_pitch; /* pitch of the residual tensor (ignored when residual == NULL) */
+    int w_layout;        /* B2Y_WLAYOUT_*: how w_packed is laid out (0 = [out_c][k][k][in_c]) */
 } b2y_conv_desc;
+
+/* Weight layouts of the forward convolutions (b2y_conv2d_fwd / _fwd_stats / b2y_qconv2d_fwd).
+ * B2Y_WLAYOUT_S2_PAIRS: 3x3 / stride 2 / pad 1 layers with a narrow, dense input (in_c = 32, in_pitch == in_c, even
+ * in_w): the NHWC input is read as pixel PAIRS [B][H][W/2][2*in_c], which turns the layer into a 3(h) x 2(w) window with
+ * stride 2 x 1 over 128-byte rows -- 6 im2col boxes per tile instead of 9 half-width ones.  w_packed is
+ * [out_c][3][2][2*in_c]: (r, 0, in_c + c) = W[r][0][c], (r, 1, c) = W[r][1][c], (r, 1, in_c + c) = W[r][2][c], rest 0. */
+#define B2Y_WLAYOUT_DENSE 0
+#define B2Y_WLAYOUT_S2_PAIRS 1
 
 /* y = act(conv(x, w) + bias) [+ residual]
  *   x        fp16 NHWC

@@ -121,6 +121,44 @@ def test_conv_stats():
     assert torch.allclose(st[1].cpu(), s2, rtol=1e-4, atol=1e-2)
 
 
+@pytest.mark.parametrize("shape", [(2, 40, 36, 64), (3, 22, 50, 128), (1, 96, 64, 64)], ids=str)
+def test_conv_s2_pixel_pair_layout(shape):
+    """B2Y_WLAYOUT_S2_PAIRS (include/b200yolo.h): the 3x3 / stride-2 / Cin = 32 layer through the pixel-pair view (3 x 2
+    window, stride 2 x 1) against fp64 and against the dense-layout launch of the same kernel; with statistics and with
+    a residual; rejected for odd widths / non-dense inputs."""
+    from b200yolo.lib import B2YError, WLAYOUT_S2_PAIRS
+    ops = _ops()
+    B, H, W, Cout = shape
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(B, 32, H, W, generator=g).half().float()
+    w = (torch.randn(Cout, 32, 3, 3, generator=g) / 17).half().float()
+    b = torch.randn(Cout, generator=g)
+    ref = F.leaky_relu(F.conv2d(x.double(), w.double(), b.double(), stride=2, padding=1), 0.1).float()
+    xv = x.permute(0, 2, 3, 1).contiguous().half().cuda()
+    wd = w.permute(0, 2, 3, 1).contiguous().half().cuda()
+    wp = ops.s2_pair_weights(w.cuda()).half()
+    res = torch.randn(ref.shape, generator=g).half()
+    resv = res.permute(0, 2, 3, 1).contiguous().cuda()
+    y_pair = ops.conv2d(xv, wp, b.cuda(), 3, 2, 1, act="leaky", residual=resv, w_layout=WLAYOUT_S2_PAIRS)
+    y_dense = ops.conv2d(xv, wd, b.cuda(), 3, 2, 1, act="leaky", residual=resv)
+    torch.cuda.synchronize()
+    got = y_pair.float().permute(0, 3, 1, 2).cpu()
+    want = ref + res.float()
+    assert (got - want).abs().max() <= 4e-3 * max(1.0, want.abs().max().item())
+    # same products, different summation order inside the tensor core: at most an fp16 ulp apart
+    assert (y_pair.float() - y_dense.float()).abs().max() <= 2.0 ** -9 * max(1.0, want.abs().max().item())
+    st = (torch.zeros(Cout, device="cuda"), torch.zeros(Cout, device="cuda"))
+    ops.conv2d(xv, wp, None, 3, 2, 1, stats=st, w_layout=WLAYOUT_S2_PAIRS)
+    raw = F.conv2d(x.double(), w.double(), None, stride=2, padding=1)
+    assert torch.allclose(st[0].cpu(), raw.sum(dim=(0, 2, 3)).float(), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(st[1].cpu(), (raw * raw).sum(dim=(0, 2, 3)).float(), rtol=1e-4, atol=1e-2)
+    with pytest.raises(B2YError):
+        ops.conv2d(xv[:, :, :W - 1].contiguous(), wp, None, 3, 2, 1, w_layout=WLAYOUT_S2_PAIRS)      # odd width
+    wide = torch.zeros(B, H, W, 64, dtype=torch.float16, device="cuda")
+    with pytest.raises(B2YError):
+        ops.conv2d(wide[..., :32], wp, None, 3, 2, 1, w_layout=WLAYOUT_S2_PAIRS)                     # pitch != in_c
+
+
 def test_stem_conv():
     ops = _ops()
     g = torch.Generator().manual_seed(1)

@@ -74,8 +74,9 @@ def test_ptq_int8_eval_matches_reference():
 
 
 def test_ptq_fused_shortcut_epilogue_is_bit_identical(monkeypatch):
-    """b2y_qconv2d_shortcut_fwd (shortcut folded into the producing conv's epilogue, TMA int8 store) against the two-kernel
-    form b2y_qconv2d_fwd + b2y_qshortcut_i8: same codes everywhere, at a size with partial M tiles."""
+    """b2y_qconv2d_shortcut_fwd (shortcut folded into the producing conv's epilogue, TMA int8 store) and the pixel-pair
+    forms of the two Cin = 32 layers against the plain graph (b2y_qconv2d_fwd + b2y_qshortcut_i8, dense weights): same
+    codes everywhere, at a size with partial M tiles."""
     from b200yolo import qengine
     qm, g = _load_quantised_model()
     x = orc.synth_images(3, 96, 64, seed=5).cuda()
@@ -84,7 +85,10 @@ def test_ptq_fused_shortcut_epilogue_is_bit_identical(monkeypatch):
     plans = [pl for pl in qm._engine.plans.values() if isinstance(pl, qengine.QPlan)]
     assert plans and any(st[0] == 'conv_sc' for st in plans[0].steps)
     assert all(plans[0]._fusable.get(st[1], True) for st in plans[0].steps if st[0] == 'conv_sc')
+    assert [plans[0].packed[st[1]][7] for st in plans[0].steps if st[0] in ('conv', 'conv_sc') and st[2] is not None][:3] \
+        == ['s2', None, 's1']       # the two narrow 3x3 layers run in their pixel-pair forms
     monkeypatch.setenv('B2Y_Q_FUSE_SHORTCUT', '0')
+    monkeypatch.setenv('B2Y_PAIRPACK', '0')
     qm2, _ = _load_quantised_model()
     with torch.no_grad():
         io_u, p_u, _ = qm2(x)

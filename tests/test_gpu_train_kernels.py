@@ -70,6 +70,13 @@ GRAD_CASES = [
     (2, 10, 10, 512, 256, 1, 1),    # yolo head sized (Cout padded to 256 by the caller)
     (2, 12, 12, 256, 512, 3, 1),    # 4 co tiles, N=256
     (4, 40, 40, 128, 128, 3, 1),    # many k-steps -> split-K > 1
+    # narrow-input 3x3 layers: the tap-transposed weight-gradient kernel (wgrad_taps_kernel)
+    (2, 24, 24, 32, 128, 3, 1),     # Cin 32, N = 128 tile
+    (3, 20, 22, 32, 64, 3, 2),      # Cin 32, stride 2
+    (4, 40, 40, 64, 64, 3, 1),      # Cin 64, 100 k-steps over many split-K slices
+    (1, 16, 16, 32, 32, 3, 1),      # Cout 32 < tile: clipped dY columns
+    (2, 16, 16, 64, 192, 3, 1),     # Cin 64, three N tiles
+    (1, 9, 7, 32, 64, 3, 1),        # fewer pixels than one k-step
 ]
 
 

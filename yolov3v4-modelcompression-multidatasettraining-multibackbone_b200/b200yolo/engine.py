@@ -16,6 +16,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
+from .lib import WLAYOUT_S2_PAIRS
 
 _ACT_OF_CLASS = {'LeakyReLU': 'leaky', 'Mish': 'mish', 'ReLU6': 'relu6', 'HardSwish': 'h_swish', 'ReLU': 'relu',
                  'Swish': 'swish'}
@@ -332,6 +333,10 @@ class Plan:
             self.weights[i] = (wp, bias, w32, wstem)
             if self._pair_packable(st):
                 self.weights[i] = self.weights[i] + (self._pair_pack(conv, bnp, eps),)
+            elif self._s2_pair_packable(st):
+                _, bias_f, w32f = ops.pack_conv_weights(conv.weight.detach(), conv.bias.detach() if conv.bias is not None
+                                                        else None, bnp, eps, want_fp32=True)
+                self.weights[i] = self.weights[i] + (('s2', ops.s2_pair_weights(w32f).half(), bias_f),)
 
     # ---- pixel-pair packing of the Cin = 32 3x3 layers --------------------------------------------------------------
     # With 32 input channels a tap of the im2col gather is a 64-byte row: one TMA request per pixel per tap, and the
@@ -350,6 +355,18 @@ class Plan:
             return False
         full = lambda t: t.c0 == 0 and t.buf.shape[3] == t.C and t.dtype == torch.float16
         return full(src) and full(out) and (res is None or full(res))
+
+    def _s2_pair_packable(self, st):
+        """3x3 / stride-2 layers with 32 input channels (the first downsampling conv): B2Y_WLAYOUT_S2_PAIRS -- the input
+        read as pixel pairs makes it a 3 x 2 window with stride 2 x 1 over 128-byte rows (6 im2col boxes, not 9 halves)."""
+        if os.environ.get('B2Y_PAIRPACK', '1') == '0':
+            return False
+        _, i, src, out, res, conv, bn, act, slope = st
+        if src is None or conv.kernel_size[0] != 3 or conv.stride[0] != 2 or conv.padding[0] != 1:
+            return False
+        if conv.in_channels != 32 or src.W % 2:
+            return False
+        return src.c0 == 0 and src.buf.shape[3] == src.C and src.dtype == torch.float16
 
     def _pair_pack(self, conv, bnp, eps):
         O, I = conv.out_channels, conv.in_channels
@@ -393,6 +410,11 @@ class Plan:
                         if x.dtype != torch.float32:
                             x = x.float() / 256.0 if x.dtype == torch.uint8 else x.float()
                         ops.stem_conv(x, w32, bias, k, s, p, act=act, slope=slope, out=out.view())
+                elif len(self.weights[i]) == 5 and isinstance(self.weights[i][4][0], str):
+                    _, wps2, bias_s2 = self.weights[i][4]
+                    ops.conv2d(src.view(), wps2, bias_s2, k, s, p, act=act, slope=slope,
+                               residual=res.view() if res is not None else None, out=out.view(),
+                               w_layout=WLAYOUT_S2_PAIRS)
                 elif len(self.weights[i]) == 5:
                     wp2, bias2 = self.weights[i][4]
                     pairs = lambda t: t.buf.view(t.buf.shape[0], t.H, t.W // 2, 2 * t.C)

@@ -26,7 +26,11 @@ class ConvDesc(C.Structure):
         ("act", C.c_int), ("slope", C.c_float),
         ("out_dtype", C.c_int),
         ("res_pitch", C.c_longlong),
+        ("w_layout", C.c_int),
     ]
+
+
+WLAYOUT_DENSE, WLAYOUT_S2_PAIRS = 0, 1
 
 
 class PackItem(C.Structure):

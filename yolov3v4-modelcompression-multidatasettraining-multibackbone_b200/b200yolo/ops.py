@@ -39,11 +39,11 @@ def conv_out_hw(h, w, k, stride, pad):
 
 
 def make_conv_desc(x_shape, in_pitch, out_c, k, stride, pad, out_pitch, act="linear", slope=0.1,
-                   out_dtype=OUT_F16, res_pitch=0):
+                   out_dtype=OUT_F16, res_pitch=0, w_layout=0):
     B, H, W, Cin = x_shape
     Ho, Wo = conv_out_hw(H, W, k, stride, pad)
     return ConvDesc(B, H, W, Cin, in_pitch, out_c, k, stride, pad, Ho, Wo, out_pitch, ACT[act] if isinstance(act, str)
-                    else int(act), float(slope), out_dtype, res_pitch)
+                    else int(act), float(slope), out_dtype, res_pitch, int(w_layout))
 
 
 def pack_conv_weights(w, conv_bias=None, bn=None, eps=1e-5, want_fp32=False):
@@ -63,8 +63,21 @@ def pack_conv_weights(w, conv_bias=None, bn=None, eps=1e-5, want_fp32=False):
     return wp, bias, w32
 
 
+def s2_pair_weights(w_oihw):
+    """[O][I][3][3] -> [O][3][2][2I]: the B2Y_WLAYOUT_S2_PAIRS form of a 3x3 / stride-2 / pad-1 filter
+    (include/b200yolo.h): window column 0 = the pixel pair left of the output, whose second pixel meets tap kw = 0;
+    column 1 = the output's own pair = taps kw = 1, 2."""
+    O, I = w_oihw.shape[:2]
+    w = w_oihw.permute(0, 2, 3, 1)                       # [O][kh][kw][I]
+    out = torch.zeros((O, 3, 2, 2 * I), dtype=w_oihw.dtype, device=w_oihw.device)
+    out[:, :, 0, I:] = w[:, :, 0]
+    out[:, :, 1, :I] = w[:, :, 1]
+    out[:, :, 1, I:] = w[:, :, 2]
+    return out.contiguous()
+
+
 def conv2d(x, w_packed, bias, k, stride, pad, act="linear", slope=0.1, residual=None, out=None,
-           out_dtype=torch.float16, stats=None):
+           out_dtype=torch.float16, stats=None, w_layout=0):
     """y = act(conv(x, w) + bias) [+ residual]; x NHWC fp16 view, w_packed [O][k][k][I] fp16."""
     _require_cuda(x, w_packed)
     B, H, W, Cin = x.shape
@@ -75,7 +88,7 @@ def conv2d(x, w_packed, bias, k, stride, pad, act="linear", slope=0.1, residual=
     assert out.shape == (B, Ho, Wo, O)
     od = OUT_F32 if out.dtype == torch.float32 else OUT_F16
     d = make_conv_desc(x.shape, _pitch(x), O, k, stride, pad, _pitch(out), act, slope, od,
-                       _pitch(residual) if residual is not None else 0)
+                       _pitch(residual) if residual is not None else 0, w_layout)
     if stats is not None:
         assert residual is None
         call("b2y_conv2d_fwd_stats", C.byref(d), ptr(x), ptr(w_packed), ptr(bias), ptr(out), ptr(stats[0]),
@@ -544,7 +557,7 @@ def pack_qconv_weights(w_folded_oihw, w_scale, bits=8):
 
 
 def qconv2d(x_i8, w_i8, bias, k, stride, pad, acc_scale, out_scale, act="linear", slope=0.1, bits=8, out=None,
-            out_kind=OUT_I8, requant=True):
+            out_kind=OUT_I8, requant=True, w_layout=0):
     """INT8 conv: y = requant(act(acc*acc_scale + bias)); x int8 NHWC, w int8 [O][k][k][I]."""
     B, H, W, Cin = x_i8.shape
     O = w_i8.shape[0]
@@ -553,7 +566,7 @@ def qconv2d(x_i8, w_i8, bias, k, stride, pad, acc_scale, out_scale, act="linear"
         dt = {OUT_I8: torch.int8, OUT_F16: torch.float16, OUT_F32: torch.float32}[out_kind]
         out = torch.empty((B, Ho, Wo, O), dtype=dt, device=x_i8.device)
     lo, hi = -(1 << (bits - 1)), (1 << (bits - 1)) - 1
-    cd = make_conv_desc(x_i8.shape, _pitch(x_i8), O, k, stride, pad, _pitch(out), act, slope, out_kind)
+    cd = make_conv_desc(x_i8.shape, _pitch(x_i8), O, k, stride, pad, _pitch(out), act, slope, out_kind, 0, w_layout)
     qd = QConvDesc(cd, float(acc_scale), float(out_scale), float(lo), float(hi), out_kind, 1 if requant else 0)
     call("b2y_qconv2d_fwd", C.byref(qd), ptr(x_i8), ptr(w_i8), ptr(bias), ptr(out), stream_ptr())
     return out

@@ -19,10 +19,15 @@ import torch
 
 from . import ops
 from .engine import _Tensor
-from .lib import OUT_F32, OUT_I8, B2YError, call, ptr, stream_ptr
+from .lib import OUT_F32, OUT_I8, WLAYOUT_S2_PAIRS, B2YError, call, ptr, stream_ptr
 
 _ACT_NAME = {'leaky': 'leaky', 'relu6': 'relu6', 'h_swish': 'h_swish', 'relu': 'relu', 'mish': 'mish',
              'linear': 'linear'}
+
+
+def _pairs(t):
+    """[B,H,W,C] int8 tensor seen as pixel pairs [B,H,W/2,2C] (same memory)"""
+    return t.buf.view(t.buf.shape[0], t.H, t.W // 2, 2 * t.C)
 
 
 def _s(t):
@@ -127,6 +132,30 @@ class QPlan:
         self.total_rows = row_off
         self.anchors_px = [m.anchors.to(dev).float().contiguous() for (m, _, _, _) in self.yolo]
 
+    def _pack_qconv(self, src, conv, s_w):
+        """int8 weight codes [O][kh][kw][I] + bias, in the pixel-pair forms for the two narrow (Cin = 32) 3x3 layers:
+        's1' = engine.py _pair_pack (the tensors viewed as [B,H,W/2,2C], doubled output channels), 's2' =
+        B2Y_WLAYOUT_S2_PAIRS.  q_weight holds code * s_w exactly, so the codes are recovered without rounding."""
+        k, s, p = conv.kernel_size[0], conv.stride[0], conv.padding[0]
+        bias = conv.q_bias.detach().float().contiguous()
+        qw = conv.q_weight.detach().float()
+        O, I = conv.out_channels, conv.in_channels
+        lo, hi = -(1 << (conv.w_bits - 1)), (1 << (conv.w_bits - 1)) - 1
+        pair_ok = os.environ.get('B2Y_PAIRPACK', '1') != '0' and k == 3 and p == 1 and I == 32 and src.W % 2 == 0
+        if pair_ok and s == 1 and O <= 128 and O % 8 == 0:
+            w2 = torch.zeros((2 * O, 2 * I, 3, 3), dtype=torch.float32, device=qw.device)
+            for o_sub in range(2):
+                for i_sub in range(2):
+                    for kwp in range(3):
+                        s_ = 2 * (kwp - 1) + i_sub - o_sub + 1
+                        if 0 <= s_ <= 2:
+                            w2[o_sub * O:(o_sub + 1) * O, i_sub * I:(i_sub + 1) * I, :, kwp] = qw[:, :, :, s_]
+            return ops.pack_qconv_weights(w2, s_w, conv.w_bits), torch.cat([bias, bias]).contiguous(), 's1'
+        if pair_ok and s == 2:
+            codes = (ops.s2_pair_weights(qw) / s_w).round().clamp(lo, hi).to(torch.int8).contiguous()
+            return codes, bias, 's2'
+        return ops.pack_qconv_weights(qw, s_w, conv.w_bits), bias, None
+
     def prepare(self):
         """fold BN + quantise weights (reference first-call behaviour), pack int8 weights, resolve tensor scales."""
         scale_of = {}
@@ -148,9 +177,8 @@ class QPlan:
                     self.packed[i] = (conv.q_weight.detach().float().contiguous(), conv.q_bias.detach().float(), s_a,
                                       act, slope, bits_a)
                 else:
-                    w8 = ops.pack_qconv_weights(conv.q_weight.detach(), s_w, bits_w)
-                    self.packed[i] = (w8, conv.q_bias.detach().float().contiguous(), scale_of[id(src)] * s_w, s_a, act,
-                                      slope, bits_a)
+                    w8, bq, mode = self._pack_qconv(src, conv, s_w)
+                    self.packed[i] = (w8, bq, scale_of[id(src)] * s_w, s_a, act, slope, bits_a, mode)
                 scale_of[id(out)] = s_a
             elif kind == 'conv_sc':
                 _, i, src, out, conv, (isc, a, m, own) = st
@@ -160,9 +188,9 @@ class QPlan:
                     raise RuntimeError("layer %d is not calibrated (scale == 0): load a calibrated state_dict" % i)
                 if conv.w_bits > 8 or conv.a_bits > 8:
                     raise NotImplementedError("the tcgen05 kind::i8 path covers <= 8 bit weights and activations")
-                w8 = ops.pack_qconv_weights(conv.q_weight.detach(), s_w, conv.w_bits)
-                self.packed[i] = (w8, conv.q_bias.detach().float().contiguous(), scale_of[id(src)] * s_w, s_a,
-                                  _ACT_NAME[conv.activate], 0.25 if conv.maxabsscaler else 0.1, conv.a_bits)
+                w8, bq, mode = self._pack_qconv(src, conv, s_w)
+                self.packed[i] = (w8, bq, scale_of[id(src)] * s_w, s_a, _ACT_NAME[conv.activate],
+                                  0.25 if conv.maxabsscaler else 0.1, conv.a_bits, mode)
                 scale_of[id(own)] = s_a
                 scale_of[id(out)] = _s(m.scale_sum)
             elif kind == 'shortcut':
@@ -239,23 +267,29 @@ class QPlan:
                         call("b2y_stem_conv_fwd_q", C.byref(d), ptr(x), ptr(wq), ptr(bq), ptr(out.buf), s_a, float(lo),
                              float(hi), stream_ptr())
                 else:
-                    w8, bq, acc_scale, s_a, act, slope, bits = self.packed[i]
+                    w8, bq, acc_scale, s_a, act, slope, bits, mode = self.packed[i]
                     if head:
                         ops.qconv2d(src.view(), w8, bq, k, s, p, acc_scale, s_a, act=act, slope=slope, bits=bits,
                                     out=out.buf[..., :conv.out_channels], out_kind=OUT_F32, requant=True)
+                    elif mode == 's1':
+                        ops.qconv2d(_pairs(src), w8, bq, k, s, p, acc_scale, s_a, act=act, slope=slope, bits=bits,
+                                    out=_pairs(out), out_kind=OUT_I8)
                     else:
                         ops.qconv2d(src.view(), w8, bq, k, s, p, acc_scale, s_a, act=act, slope=slope, bits=bits,
-                                    out=out.view(), out_kind=OUT_I8)
+                                    out=out.view(), out_kind=OUT_I8, w_layout=WLAYOUT_S2_PAIRS if mode == 's2' else 0)
             elif kind == 'conv_sc':
                 _, i, src, out, conv, (isc, at, m, own) = st
                 k, s, p = conv.kernel_size[0], conv.stride[0], conv.padding[0]
-                w8, bq, acc_scale, s_a, act, slope, bits = self.packed[i]
+                w8, bq, acc_scale, s_a, act, slope, bits, mode = self.packed[i]
                 slo, shi = -(1 << (m.bits - 1)), (1 << (m.bits - 1)) - 1
-                xv, av, ov = src.view(), at.view(), out.view()
+                if mode == 's1':
+                    xv, av, ov = _pairs(src), _pairs(at), _pairs(out)
+                else:
+                    xv, av, ov = src.view(), at.view(), out.view()
                 fused = self._fusable.get(i, True)
                 if fused:
-                    cd = ops.make_conv_desc(xv.shape, ops._pitch(xv), conv.out_channels, k, s, p, ops._pitch(ov), act,
-                                            slope, OUT_I8)
+                    cd = ops.make_conv_desc(xv.shape, ops._pitch(xv), w8.shape[0], k, s, p, ops._pitch(ov), act,
+                                            slope, OUT_I8, 0, WLAYOUT_S2_PAIRS if mode == 's2' else 0)
                     qd = ops.QConvDesc(cd, float(acc_scale), float(s_a), float(-(1 << (bits - 1))),
                                        float((1 << (bits - 1)) - 1), OUT_I8, 1)
                     try:
@@ -269,11 +303,13 @@ class QPlan:
                 if not fused:
                     if own.buf is None:
                         own.buf = torch.empty((B, own.H, own.W, own.C), dtype=torch.int8, device=self.device)
-                    ops.qconv2d(xv, w8, bq, k, s, p, acc_scale, s_a, act=act, slope=slope, bits=bits, out=own.view(),
-                                out_kind=OUT_I8)
-                    wv = own.view()
+                    ops.qconv2d(xv, w8, bq, k, s, p, acc_scale, s_a, act=act, slope=slope, bits=bits,
+                                out=_pairs(own) if mode == 's1' else own.view(), out_kind=OUT_I8,
+                                w_layout=WLAYOUT_S2_PAIRS if mode == 's2' else 0)
+                    wv = _pairs(own) if mode == 's1' else own.view()
                     call("b2y_qshortcut_i8", ptr(wv), ops._pitch(wv), ptr(av), ops._pitch(av), ptr(ov), ops._pitch(ov),
-                         B * out.H * out.W, out.C, s_a, self._sv(m.scale_x), sc[id(at)], self._sv(m.scale_a),
+                         wv.shape[0] * wv.shape[1] * wv.shape[2], wv.shape[3], s_a, self._sv(m.scale_x), sc[id(at)],
+                         self._sv(m.scale_a),
                          self._sv(m.scale_sum), float(slo), float(shi), stream_ptr())
             elif kind == 'shortcut':
                 _, i, xt, at, out, m = st

@@ -63,6 +63,8 @@ bn_train_fwd_kernel(const __half* __restrict__ z, long long zp, const float* __r
                     float count, float eps, float momentum, float* __restrict__ rmean, float* __restrict__ rvar,
                     float* __restrict__ save, const __half* __restrict__ res, long long rp, __half* __restrict__ y,
                     long long yp, long long pixels, int CV, int PPB, int act_rt, float slope) {
+    pdl_wait();                     // launched as a programmatic dependent (launch_pdl): the statistics / z come from
+    pdl_launch_dependents();        // the previous kernel
     const int tid = threadIdx.x;
     if (tid >= CV * PPB) return;
     const int cv = tid % CV, prow = tid / CV;
@@ -133,6 +135,8 @@ bn_train_bwd_reduce_kernel(const __half* __restrict__ z, long long zp, const GT*
                            const float* __restrict__ save, float* __restrict__ sums, float* __restrict__ du_absmax,
                            long long pixels, int CV, int PPB, int act_rt, float slope) {
     __shared__ float red[256][17];
+    pdl_wait();
+    pdl_launch_dependents();
     const int tid = threadIdx.x;
     const int C = CV * 8;
     const bool active = tid < CV * PPB;
@@ -213,6 +217,8 @@ bn_train_bwd_apply_kernel(const __half* __restrict__ z, long long zp, const GT* 
                           int CV, int PPB, int act_rt, float slope, const float* __restrict__ du_absmax,
                           float* __restrict__ scale_out, float* __restrict__ dgamma_out,
                           float* __restrict__ dbeta_out, float grad_out_scale) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int C = CV * 8;
     const int tid = threadIdx.x;
     const float inv_n = 1.f / (float)pixels;
@@ -318,7 +324,7 @@ extern "C" int b2y_bn_train_fwd(const void* z, long long z_pitch, const float* s
     const int grid = wave_grid(pixels, g.PPB, 2);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     dispatch_act(act, [&](auto A) {
-        bn_train_fwd_kernel<decltype(A)::value, 4><<<grid, 256, 0, st>>>(
+        launch_pdl(bn_train_fwd_kernel<decltype(A)::value, 4>, dim3(grid), dim3(256), 0, st, 
             reinterpret_cast<const __half*>(z), z_pitch, stat_sum, stat_sqsum, gamma, beta, (float)count, eps, momentum,
             running_mean, running_var, save, reinterpret_cast<const __half*>(residual), res_pitch,
             reinterpret_cast<__half*>(y), y_pitch, pixels, g.CV, g.PPB, act, slope);
@@ -338,11 +344,11 @@ extern "C" int b2y_bn_train_bwd_reduce(const void* z, long long z_pitch, const v
     dispatch_act(act, [&](auto A) {
         constexpr int ACT = decltype(A)::value;
         if (grad_dtype == B2Y_DT_BF16)
-            bn_train_bwd_reduce_kernel<__nv_bfloat16, ACT, 4><<<grid, 256, 0, st>>>(
+            launch_pdl(bn_train_bwd_reduce_kernel<__nv_bfloat16, ACT, 4>, dim3(grid), dim3(256), 0, st, 
                 reinterpret_cast<const __half*>(z), z_pitch, reinterpret_cast<const __nv_bfloat16*>(dy), dy_pitch, save,
                 sums, du_absmax, pixels, g.CV, g.PPB, act, slope);
         else
-            bn_train_bwd_reduce_kernel<__half, ACT, 4><<<grid, 256, 0, st>>>(
+            launch_pdl(bn_train_bwd_reduce_kernel<__half, ACT, 4>, dim3(grid), dim3(256), 0, st, 
                 reinterpret_cast<const __half*>(z), z_pitch, reinterpret_cast<const __half*>(dy), dy_pitch, save, sums,
                 du_absmax, pixels, g.CV, g.PPB, act, slope);
     });
@@ -363,12 +369,12 @@ extern "C" int b2y_bn_train_bwd_apply(const void* z, long long z_pitch, const vo
     dispatch_act(act, [&](auto A) {
         constexpr int ACT = decltype(A)::value;
         if (grad_dtype == B2Y_DT_BF16)
-            bn_train_bwd_apply_kernel<__nv_bfloat16, ACT, 4><<<grid, 256, 0, st>>>(
+            launch_pdl(bn_train_bwd_apply_kernel<__nv_bfloat16, ACT, 4>, dim3(grid), dim3(256), 0, st, 
                 reinterpret_cast<const __half*>(z), z_pitch, reinterpret_cast<const __nv_bfloat16*>(dy), dy_pitch, gamma,
                 save, sums, reinterpret_cast<__half*>(dz), dz_pitch, pixels, g.CV, g.PPB, act, slope, du_absmax,
                 scale_out, dgamma_out, dbeta_out, grad_out_scale);
         else
-            bn_train_bwd_apply_kernel<__half, ACT, 4><<<grid, 256, 0, st>>>(
+            launch_pdl(bn_train_bwd_apply_kernel<__half, ACT, 4>, dim3(grid), dim3(256), 0, st, 
                 reinterpret_cast<const __half*>(z), z_pitch, reinterpret_cast<const __half*>(dy), dy_pitch, gamma, save,
                 sums, reinterpret_cast<__half*>(dz), dz_pitch, pixels, g.CV, g.PPB, act, slope, du_absmax, scale_out,
                 dgamma_out, dbeta_out, grad_out_scale);

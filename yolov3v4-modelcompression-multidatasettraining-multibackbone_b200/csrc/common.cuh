@@ -81,6 +81,38 @@ __device__ __forceinline__ void mbar_expect_tx_s(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// Host side: launch `kern` as a programmatic dependent of the previous kernel in the stream (B2Y_PDL=0: plain stream
+// order).  The grid may become resident while its predecessor drains, so the kernel MUST execute pdl_wait() before it
+// touches anything the predecessor wrote (and should call pdl_launch_dependents() right after, so that at most one
+// grid is ever parked behind a running one).  In a captured graph the edge becomes a programmatic dependency.
+inline bool b2y_pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("B2Y_PDL");
+        v = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    return v != 0;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    int na = 0;
+    if (b2y_pdl_enabled()) {
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        na = 1;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // one lane of a converged warp
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
@@ -380,9 +412,13 @@ __device__ __forceinline__ float act_grad(float v, int act, float slope) {
         case B2Y_ACT_LEAKY: return v > 0.f ? 1.f : slope;
         case B2Y_ACT_MISH: {
             // reference utils/layers.py:123-128: fx + x * sigmoid(x) * (1 - fx^2), fx = tanh(softplus(x))
-            float e;
-            const float fx = mish_tanh_softplus(v, e);
-            const float sx = __fdividef(e, 1.f + e);        // sigmoid(x) = e / (1 + e)  (-> 1 for the clamped large x)
+            // fx = n / (n + 2) and sigmoid(x) = e / (1 + e) share ONE reciprocal, 1 / ((n + 2)(1 + e)) (<= e^60, no
+            // overflow): the backward BN passes are bound by the MUFU pipe (exp + reciprocals), this drops a third of it
+            const float e = __expf(fminf(v, 20.f));
+            const float n = e * (e + 2.f), d1 = n + 2.f, d2 = 1.f + e;
+            const float r = __fdividef(1.f, d1 * d2);
+            const float fx = n * d2 * r;
+            const float sx = e * d1 * r;
             return fx + v * sx * (1.f - fx * fx);
         }
         case B2Y_ACT_RELU: return v > 0.f ? 1.f : 0.f;

@@ -69,7 +69,8 @@ static int make_map_2d(CUtensorMap* m, const void* base, int esize, long long ro
 // im2col map over an NHWC activation tensor (dims C,W,H,N) for an RxS / stride / pad convolution.
 static int make_map_im2col(CUtensorMap* m, const void* base, int esize, int N, int H, int W, int C,
                            long long pitch_elems, int lower_w, int lower_h, int upper_w, int upper_h, int stride,
-                           int block_k, int kbytes, int pixels_per_column = 128, bool bf16 = false) {
+                           int block_k, int kbytes, int pixels_per_column = 128, bool bf16 = false,
+                           int stride_h = 0) {
     if (!g_encodeIm2col) return B2Y_ERR_DRIVER;
     cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     cuuint64_t gstride[3] = {(cuuint64_t)(pitch_elems * esize), (cuuint64_t)(pitch_elems * esize * W),
@@ -77,7 +78,7 @@ static int make_map_im2col(CUtensorMap* m, const void* base, int esize, int N, i
     // bounding box of the *base pixel* (the tap with offset 0): for fprop lower = -pad, upper = pad - (filter-1)
     int lower[2] = {lower_w, lower_h};
     int upper[2] = {upper_w, upper_h};
-    cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+    cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)(stride_h > 0 ? stride_h : stride), 1};
     CUresult r = g_encodeIm2col(m, tm_dtype(esize, bf16), 4,
                                 const_cast<void*>(base), gdim, gstride, lower, upper, (cuuint32_t)block_k,
                                 (cuuint32_t)pixels_per_column, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_enum(kbytes),
@@ -204,7 +205,8 @@ struct GemmConvSpec {
     int N = 0, H = 0, W = 0, C = 0;
     long long a_pitch = 0;
     int MH = 0, MW = 0;          // base-pixel grid per image (GEMM rows = N*MH*MW)
-    int stride = 1;              // TMA traversal stride
+    int stride = 1;              // TMA traversal stride (along W; along H too unless stride_h is set)
+    int stride_h = 0;            // 0: same as stride
     int lower_w = 0, lower_h = 0, upper_w = 0, upper_h = 0;
     int ntaps = 1;
     unsigned char tap_ow[16] = {0}, tap_oh[16] = {0};
@@ -241,6 +243,7 @@ int gemm_conv_launch(const GemmConvSpec& g, const EpilogueArgs& e, cudaStream_t 
     p.MH = g.MH;
     p.MW = g.MW;
     p.stride = g.stride;
+    p.stride_h = g.stride_h > 0 ? g.stride_h : g.stride;
     p.lower_w = g.lower_w;
     p.lower_h = g.lower_h;
     for (int t = 0; t < 16; ++t) {
@@ -306,11 +309,14 @@ int gemm_conv_launch(const GemmConvSpec& g, const EpilogueArgs& e, cudaStream_t 
         const bool pow2 = e.acc_scale > 0.f && frexpf(e.acc_scale, &ex) == 0.5f && e.acc_scale_ptr == nullptr;
         if (i8_fast && g.kind == CONV_KIND_I8 && e.out_dtype == OUT_I8 && !e.out_fakequant && e.stat_sum == nullptr &&
             (e.act == B2Y_ACT_LINEAR || (e.act == B2Y_ACT_LEAKY && e.slope >= 0.f && e.slope <= 1.f)) && pow2 && full &&
-            e.res == nullptr && al16(e.out) && e.out_pitch % 16 == 0 && (e.bias == nullptr || al16(e.bias)))
+            e.res == nullptr && al16(e.out) && e.out_pitch % 16 == 0 && (e.bias == nullptr || al16(e.bias)) &&
+            e.q_lo >= -128.f && e.q_hi <= 127.f && e.q_lo == floorf(e.q_lo) && e.q_hi == floorf(e.q_hi))
             p.epi_fast = 1;
         // fake-quantised / linear fp32 rows of the int8 graph (the YOLO heads): through the TMA store, which clips Cout = 255
         if (i8_fast && g.kind == CONV_KIND_I8 && out32 && tma_ok && e.stat_sum == nullptr && e.act == B2Y_ACT_LINEAR &&
-            pow2 && e.res == nullptr && al16(e.out) && e.out_pitch % 4 == 0 && (e.bias == nullptr || al16(e.bias)))
+            pow2 && e.res == nullptr && al16(e.out) && e.out_pitch % 4 == 0 && (e.bias == nullptr || al16(e.bias)) &&
+            (!e.out_fakequant || (e.q_lo >= -4194304.f && e.q_hi <= 4194303.f && e.q_lo == floorf(e.q_lo) &&
+                                  e.q_hi == floorf(e.q_hi))))
             p.epi_fast = 1;
         if (e.qres != nullptr) {
             auto p2 = [](float v) { int x = 0; return v > 0.f && frexpf(v, &x) == 0.5f; };
@@ -327,6 +333,10 @@ int gemm_conv_launch(const GemmConvSpec& g, const EpilogueArgs& e, cudaStream_t 
             p.qs_rsum = 1.f / e.qs_sum;
             p.qs_lo = e.qs_lo;
             p.qs_hi = e.qs_hi;
+            p.qs_cx = e.out_scale / e.qs_sum;
+            p.qs_ca = e.qs_a_in / e.qs_sum;
+            p.qs_simple = e.out_scale >= e.qs_x && e.qs_a_in >= e.qs_a && p.qs_cx <= 4096.f && p.qs_ca <= 4096.f &&
+                          p.qs_cx >= 1.f / 4096.f && p.qs_ca >= 1.f / 4096.f && e.qs_lo >= -128.f && e.qs_hi <= 127.f;
         }
     }
 
@@ -338,7 +348,7 @@ int gemm_conv_launch(const GemmConvSpec& g, const EpilogueArgs& e, cudaStream_t 
     } else {
         p.a_mode = A_MODE_IM2COL;
         rc = make_map_im2col(&tmA, g.a, esize, g.N, g.H, g.W, g.C, g.a_pitch, g.lower_w, g.lower_h, g.upper_w,
-                             g.upper_h, g.stride, block_k, kbytes, 128, g.a_bf16);
+                             g.upper_h, g.stride, block_k, kbytes, 128, g.a_bf16, p.stride_h);
     }
     if (rc != B2Y_OK) return rc;
     const long long Ktot = (long long)g.ntaps * g.C;
@@ -400,6 +410,34 @@ int conv_tc_launch(int kind, const b2y_conv_desc* d, const void* x, const void* 
     GemmConvSpec g;
     g.kind = kind;
     g.a = x;
+    g.w = w;
+    g.Nout = d->out_c;
+    if (d->w_layout == B2Y_WLAYOUT_S2_PAIRS) {
+        // pixel-pair view of a narrow stride-2 3x3 layer (include/b200yolo.h): 3 x 2 window, stride 2 x 1, pad top/left 1
+        if (d->ksize != 3 || d->stride != 2 || d->pad != 1 || (d->in_w & 1) || d->in_pitch != d->in_c ||
+            (d->in_c * (kind == CONV_KIND_F16 ? 2 : 1)) % 32 != 0)
+            return B2Y_ERR_UNSUPPORTED;
+        g.N = d->batch;
+        g.H = d->in_h;
+        g.W = d->in_w / 2;
+        g.C = 2 * d->in_c;
+        g.a_pitch = 2 * d->in_pitch;
+        g.MH = Ho;
+        g.MW = Wo;
+        g.stride = 1;
+        g.stride_h = 2;
+        g.lower_w = g.lower_h = -1;
+        g.upper_w = -1;              // pad_right 0 - (kw - 1)
+        g.upper_h = -1;              // pad_bottom 1 - (kh - 1)
+        g.ntaps = 6;
+        for (int r = 0; r < 3; ++r)
+            for (int s = 0; s < 2; ++s) {
+                g.tap_oh[r * 2 + s] = (unsigned char)r;
+                g.tap_ow[r * 2 + s] = (unsigned char)s;
+            }
+        return gemm_conv_launch(g, e, st);
+    }
+    if (d->w_layout != B2Y_WLAYOUT_DENSE) return B2Y_ERR_INVALID;
     g.N = d->batch;
     g.H = d->in_h;
     g.W = d->in_w;

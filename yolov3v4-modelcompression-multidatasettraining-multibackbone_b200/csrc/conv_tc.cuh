@@ -28,7 +28,8 @@ struct ConvTcParams {
     int Cin;          // elements per tap (GEMM K per tap)
     int ntaps;        // filter taps visited (9 for 3x3; a subset for the stride-2 data-gradient phases)
     int MH, MW;       // GEMM row space = batch x MH x MW "base pixels"
-    int stride;       // TMA traversal stride (conv stride for fprop, 1 for dgrad)
+    int stride;       // TMA traversal stride along W (conv stride for fprop, 1 for dgrad)
+    int stride_h;     // ... along H (differs from `stride` only for the pixel-pair view of narrow stride-2 layers)
     int lower_w, lower_h;     // coordinate of base pixel (0,0): base = q*stride + lower
     unsigned char tap_ow[16]; // per-tap im2col offsets (>= 0)
     unsigned char tap_oh[16];
@@ -68,6 +69,8 @@ struct ConvTcParams {
     const int8_t* qres;     // the other addend's int8 codes (NHWC) or null
     long long qres_pitch;
     float qs_rx, qs_x, qs_a_in, qs_ra, qs_a, qs_rsum, qs_lo, qs_hi;
+    int qs_simple;          // both addend roundings are identities: code = clamp(rha(q*qs_cx + a*qs_ca))
+    float qs_cx, qs_ca;     // out_scale / scale_sum, a_in / scale_sum
 };
 
 template <int BLOCK_N, int KBYTES>
@@ -96,6 +99,19 @@ __device__ __noinline__ float swish_noinline(float x) { return x * sigmoid_f(x);
 __device__ __forceinline__ float round_half_away(float x) {
     // reference utils/quantized/quantized_ptq_cos.py:14-20  sign(x)*floor(|x|+0.5)
     return copysignf(floorf(fabsf(x) + 0.5f), x);
+}
+
+// The same rounding for |x| < 2^22 without the conversion pipe (FRND / F2I issue at a quarter of the FP32 rate and bound
+// the int8 epilogues): floor(t) = (t + 2^23 rounded DOWN) - 2^23 for 0 <= t < 2^23.
+__device__ __forceinline__ float round_half_away_small(float x) {
+    const float t = fabsf(x) + 0.5f;
+    return copysignf(__fadd_rd(t, 8388608.f) - 8388608.f, x);
+}
+// four integer-valued floats in [-128, 127] -> packed int8: the low byte of (v + 1.5 * 2^23) is v's two's complement
+__device__ __forceinline__ uint32_t pack_i8x4(float a, float b, float c, float d) {
+    const uint32_t ua = __float_as_uint(a + 12582912.f), ub = __float_as_uint(b + 12582912.f);
+    const uint32_t uc = __float_as_uint(c + 12582912.f), ud = __float_as_uint(d + 12582912.f);
+    return __byte_perm(__byte_perm(ua, ub, 0x0040), __byte_perm(uc, ud, 0x0040), 0x5410);
 }
 
 template <int BLOCK_N>
@@ -380,7 +396,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int rem = m0 - img * HoWo;
                 const int po = rem / MW;
                 base_w = (rem - po * MW) * cstride + lower_w;
-                base_h = po * cstride + lower_h;
+                base_h = po * p.stride_h + lower_h;
             }
             const int b_row = n_tile * BLOCK_N + (CLUSTER > 1 ? cta_rank * (BLOCK_N / CLUSTER) : 0);
             int b_k = 0;
@@ -646,12 +662,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (KIND == CONV_KIND_I8 && (p.out_dtype == OUT_I8 || p.out_fakequant)) {
                         // int8 graph: requantise exactly like the general path (round half away, clamp); values are
                         // identical because acc_mul is a power of two there
+                        // clamp first: the bounds are integers and the rounding is monotone, so the result is the same
+                        // and the rounding operand is small
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float q = round_half_away(v[j] * p.out_inv_scale);
-                            v[j] = fminf(fmaxf(q, p.q_lo), p.q_hi);
-                        }
-                        if (p.qres != nullptr) {
+                        for (int j = 0; j < 32; ++j)
+                            v[j] = round_half_away_small(fminf(fmaxf(v[j] * p.out_inv_scale, p.q_lo), p.q_hi));
+                        if (p.qres != nullptr && p.qs_simple) {
+                            // both addends already sit on the common grid (scale_x <= out_scale, scale_a <= sa_in: what the
+                            // _min / _max shortcuts vote): their roundings are identities, the sum is exact in fp32
+                            const uint32_t* aw = reinterpret_cast<const uint32_t*>(qa);
+#pragma unroll
+                            for (int t = 0; t < 8; ++t) {
+                                const uint32_t ax = aw[t] ^ 0x80808080u;
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float af = __uint_as_float(__byte_perm(ax, 0x4B400000u, 0x7650u | e)) - 12583040.f;
+                                    const float tt = fmaf(af, p.qs_ca, v[t * 4 + e] * p.qs_cx);
+                                    v[t * 4 + e] = round_half_away_small(fminf(fmaxf(tt, p.qs_lo), p.qs_hi));
+                                }
+                            }
+                        } else if (p.qres != nullptr) {
                             const int8_t* ab = reinterpret_cast<const int8_t*>(qa);
 #pragma unroll
                             for (int j = 0; j < 32; ++j) {
@@ -668,12 +698,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (p.out_dtype == OUT_I8) {
                         uint32_t w[8];
 #pragma unroll
-                        for (int t = 0; t < 8; ++t) {
-                            uint32_t word = 0;
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) word |= ((uint32_t)(uint8_t)(int8_t)(int)v[t * 4 + e]) << (8 * e);
-                            w[t] = word;
-                        }
+                        for (int t = 0; t < 8; ++t) w[t] = pack_i8x4(v[t * 4], v[t * 4 + 1], v[t * 4 + 2], v[t * 4 + 3]);
                         if (epi_tma) {
                             // 32 rows x 32 B through smem (SWIZZLE_32B image) and one TMA store: whole 32-byte sectors per
                             // row reach L2 in one request instead of 2 x 32 scattered 16-byte pieces

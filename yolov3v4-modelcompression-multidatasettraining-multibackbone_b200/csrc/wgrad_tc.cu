@@ -250,6 +250,209 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant_
     }
 }
 
+// ---- narrow-input 3x3 layers (Cin = 32 / 64) -----------------------------------------------------------------
+// The kernel above re-reads dY once per filter tap and feeds the tensor core N = Cin <= 64 columns: on the first
+// (largest) layers of the net -- 3x3, 32->64 at 320x320 -- it moved 108 KB through L2 per 64 pixels and ran at 106 TF/s
+// (0.28 ms, 12x its HBM time).  Here the GEMM is transposed:
+//
+//   dW^T[(tap, ci)][co] = sum_{pixel m} X[m @ tap][ci] * dY[m][co]
+//
+// A = X: the nine im2col boxes [64 pixels][Cin] of one k-step sit back to back in smem; 128 / Cin consecutive boxes
+//        are one MN-major M = 128 operand (LBO = box size), so the 9 taps are GROUPS = 3 (Cin 32) or 5 (Cin 64) MMAs;
+// B = dY: one [64 pixels][BLOCK_N] tile per k-step, loaded ONCE and shared by all taps.
+// Per 64 pixels 44 KB (Cin 32) / 80 KB (Cin 64) instead of 108 / 144 KB.  The last group's missing taps read whatever
+// follows in smem (the allocation is padded): garbage rows of D that the epilogue never stores.  Work = n_tiles x
+// split-K slices (~ one per SM); D rows are (tap, ci), columns co -> red.global.add into dW[co][tap][ci], 128 B per warp.
+template <int ROW_BYTES, int BLOCK_N>
+struct WgradTCfg {
+    static constexpr int BK = 64;
+    static constexpr int CIN = ROW_BYTES / 2;
+    static constexpr int NTAPS = 9;
+    static constexpr int TPG = 128 / CIN;
+    static constexpr int GROUPS = (NTAPS + TPG - 1) / TPG;
+    static constexpr int X_ATOM_BYTES = BK * ROW_BYTES;
+    static constexpr int DY_ATOMS = BLOCK_N / 64;
+    static constexpr int DY_BYTES = DY_ATOMS * BK * 128;
+    static constexpr int STAGE_BYTES = DY_BYTES + NTAPS * X_ATOM_BYTES;
+    static constexpr int NUM_STAGES = (190 * 1024) / STAGE_BYTES;
+    static constexpr int PAD_BYTES = (GROUPS * TPG - NTAPS) * X_ATOM_BYTES;
+    static constexpr int TMEM_COLS = 512;
+    static constexpr int SMEM_BYTES = 1024 + NUM_STAGES * STAGE_BYTES + PAD_BYTES + 1024;
+    static_assert(GROUPS * BLOCK_N <= 512, "accumulators exceed TMEM");
+    static_assert(STAGE_BYTES % 1024 == 0, "stage alignment");
+};
+
+template <int ROW_BYTES, int BLOCK_N>
+__global__ void __launch_bounds__(256, 1)
+wgrad_taps_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUtensorMap tmX,
+                  const WgradParams p) {
+    using Cfg = WgradTCfg<ROW_BYTES, BLOCK_N>;
+    constexpr int NS = Cfg::NUM_STAGES;
+    constexpr int BK = Cfg::BK;
+    constexpr uint32_t IDESC = make_idesc(/*c=F32*/ 1, /*a=F16*/ 0, /*b=F16*/ 0, /*a MN-major*/ 1, /*b MN-major*/ 1,
+                                          128, BLOCK_N);
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* aux = smem + NS * Cfg::STAGE_BYTES + Cfg::PAD_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);
+    uint64_t* empty_bar = full_bar + NS;
+    uint64_t* tmem_full_bar = empty_bar + NS;
+    uint64_t* tmem_empty_bar = tmem_full_bar + 1;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmDy);
+        prefetch_tmap(&tmX);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < NS; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        mbar_init(tmem_full_bar, 1);
+        mbar_init(tmem_empty_bar, 4);
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    const int num_items = p.n_tiles * p.ksplits;      // item -> (n_tile, split), split fastest
+
+    if (warp == 0) {
+        uint32_t stage = 0, phase = 0;
+        const int HoWo = p.MH * p.MW;
+        const uint32_t smem_base = smem_u32(smem), full_base = smem_u32(full_bar), empty_base = smem_u32(empty_bar);
+        for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+            const int split = item % p.ksplits, n_tile = item / p.ksplits;
+            const int ks0 = split * p.ksteps_per_split;
+            const int ks1 = min(ks0 + p.ksteps_per_split, p.ksteps_total);
+            int k0 = ks0 * BK;
+            int img = k0 / HoWo;
+            int rem = k0 - img * HoWo;
+            for (int ks = ks0; ks < ks1; ++ks) {
+                const int po = rem / p.MW, qo = rem - po * p.MW;
+                mbar_wait_s(empty_base + stage * 8, phase ^ 1);
+                if (elect_one()) {
+                    const uint32_t dy_dst = smem_base + stage * Cfg::STAGE_BYTES;
+                    const uint32_t x_dst = dy_dst + Cfg::DY_BYTES;
+                    const uint32_t fb = full_base + stage * 8;
+                    mbar_expect_tx_s(fb, Cfg::STAGE_BYTES);
+#pragma unroll
+                    for (int at = 0; at < Cfg::DY_ATOMS; ++at)
+                        tma_load_2d_s(dy_dst + at * (BK * 128), &tmDy, fb, n_tile * BLOCK_N + at * 64, k0);
+#pragma unroll
+                    for (int tap = 0; tap < Cfg::NTAPS; ++tap)
+                        tma_load_im2col_4d_s(x_dst + tap * Cfg::X_ATOM_BYTES, &tmX, fb, 0, qo * p.stride - p.pad,
+                                             po * p.stride - p.pad, img, (uint16_t)(tap % 3), (uint16_t)(tap / 3));
+                }
+                k0 += BK;
+                rem += BK;
+                if (rem >= HoWo) {
+                    img += rem / HoWo;
+                    rem = rem % HoWo;
+                }
+                if (++stage == NS) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        int stage = 0;
+        uint32_t phase = 0, acc_phase = 0;
+        const uint64_t adesc_base =
+            smem_desc_base(Cfg::X_ATOM_BYTES, 8 * ROW_BYTES, swizzle_layout_type(ROW_BYTES));
+        const uint64_t bdesc_base = smem_desc_base(BK * 128, 8 * 128, swizzle_layout_type(128));
+        const uint32_t idesc = IDESC | p.idesc_ab;
+        for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+            const int split = item % p.ksplits;
+            const int ks0 = split * p.ksteps_per_split;
+            const int ks1 = min(ks0 + p.ksteps_per_split, p.ksteps_total);
+            mbar_wait(tmem_empty_bar, acc_phase ^ 1);
+            tc_fence_after();
+            uint32_t accum = 0;
+            for (int ks = ks0; ks < ks1; ++ks) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t dy_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                    const uint32_t x_addr = dy_addr + Cfg::DY_BYTES;
+#pragma unroll
+                    for (int g = 0; g < Cfg::GROUPS; ++g) {
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k) {
+                            const uint64_t adesc = smem_desc_at(
+                                adesc_base, x_addr + g * Cfg::TPG * Cfg::X_ATOM_BYTES + k * 16 * ROW_BYTES);
+                            const uint64_t bdesc = smem_desc_at(bdesc_base, dy_addr + k * 16 * 128);
+                            mma_f16_ss(tmem_base + (uint32_t)(g * BLOCK_N), adesc, bdesc, idesc, k > 0 ? 1u : accum);
+                        }
+                    }
+                    tc_commit(&empty_bar[stage]);
+                }
+                accum = 1;
+                if (++stage == NS) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+            if (elect_one()) tc_commit(tmem_full_bar);
+            acc_phase ^= 1;
+        }
+    } else if (warp >= 4) {
+        const int ew = warp - 4;
+        uint32_t acc_phase = 0;
+        const float wscale = p.scale * (p.scale_ptr != nullptr ? __ldg(p.scale_ptr) : 1.f);
+        const int m = ew * 32 + lane;
+        const int tap_local = m / Cfg::CIN, ci = m % Cfg::CIN;
+        for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+            const int split = item % p.ksplits, n_tile = item / p.ksplits;
+            const bool has_work = split * p.ksteps_per_split < p.ksteps_total;
+            mbar_wait(tmem_full_bar, acc_phase);
+            tc_fence_after();
+            const uint32_t taddr_row = tmem_base + ((uint32_t)(ew * 32) << 16);
+#pragma unroll 1
+            for (int g = 0; g < Cfg::GROUPS; ++g) {
+                const int tap = g * Cfg::TPG + tap_local;       // warp-uniform (a warp covers 32 channels of one tap)
+#pragma unroll 1
+                for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+                    uint32_t raw[32];
+                    tmem_ld_32x32(taddr_row + (uint32_t)(g * BLOCK_N + c0), raw);
+                    tc_wait_ld();
+                    if (has_work && tap < Cfg::NTAPS) {
+                        const int co0 = n_tile * BLOCK_N + c0;
+                        float* dst = p.dw + ((long long)co0 * Cfg::NTAPS + tap) * p.Cin + ci;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (co0 + j < p.Cout)
+                                atomicAdd(dst + (long long)j * Cfg::NTAPS * p.Cin, __uint_as_float(raw[j]) * wscale);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty_bar);
+            acc_phase ^= 1;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
 // ---- host ------------------------------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -291,6 +494,21 @@ static int wgrad_launch_cfg(const CUtensorMap& a, const CUtensorMap& b, const Wg
     }
     const int tiles = p.m_tiles * p.n_tiles * p.ntaps * p.ksplits;
     const int grid = tiles < w_num_sms ? tiles : w_num_sms;
+    kern<<<grid, 256, Cfg::SMEM_BYTES, st>>>(a, b, p);
+    B2Y_CUDA_CHECK(cudaGetLastError());
+    return B2Y_OK;
+}
+
+template <int ROW_BYTES, int BLOCK_N>
+static int wgrad_taps_launch(const CUtensorMap& a, const CUtensorMap& b, const WgradParams& p, cudaStream_t st) {
+    using Cfg = WgradTCfg<ROW_BYTES, BLOCK_N>;
+    auto kern = wgrad_taps_kernel<ROW_BYTES, BLOCK_N>;
+    static unsigned long long attr_set = 0;
+    if (b2y_first_use_on_device(attr_set)) {
+        B2Y_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    }
+    const int items = p.n_tiles * p.ksplits;
+    const int grid = items < w_num_sms ? items : w_num_sms;
     kern<<<grid, 256, Cfg::SMEM_BYTES, st>>>(a, b, p);
     B2Y_CUDA_CHECK(cudaGetLastError());
     return B2Y_OK;
@@ -386,6 +604,23 @@ extern "C" int b2y_conv2d_bwd_weight(const b2y_conv_desc* d, const void* x, cons
         }
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    static int taps_on = -1;        // B2Y_WGRAD_TAPS=0: narrow 3x3 layers use the general kernel as well
+    if (taps_on < 0) {
+        const char* ev = getenv("B2Y_WGRAD_TAPS");
+        taps_on = (ev && atoi(ev) == 0) ? 0 : 1;
+    }
+    if (taps_on && d->ksize == 3 && (d->in_c == 32 || d->in_c == 64)) {
+        const int bn = (d->in_c == 32 && d->out_c > 64) ? 128 : 64;
+        p.n_tiles = (d->out_c + bn - 1) / bn;
+        int sp = w_num_sms / p.n_tiles;
+        if (sp < 1) sp = 1;
+        if (sp > p.ksteps_total) sp = p.ksteps_total;
+        p.ksteps_per_split = (p.ksteps_total + sp - 1) / sp;
+        p.ksplits = (p.ksteps_total + p.ksteps_per_split - 1) / p.ksteps_per_split;
+        if (d->in_c == 32) return bn == 128 ? wgrad_taps_launch<64, 128>(tmDy, tmX, p, st)
+                                            : wgrad_taps_launch<64, 64>(tmDy, tmX, p, st);
+        return wgrad_taps_launch<128, 64>(tmDy, tmX, p, st);
+    }
     if (row_bytes == 128) {
         if (block_n == 256) return wgrad_launch_cfg<256, 128>(tmDy, tmX, p, st);
         if (block_n == 128) return wgrad_launch_cfg<128, 128>(tmDy, tmX, p, st);

@@ -56,6 +56,60 @@ __global__ void __launch_bounds__(256) yolo_decode_kernel(const float* __restric
     }
 }
 
+// Same decode, one warp per PIXEL: the na*no <= 256 raw floats of a pixel are one contiguous run, so a lane issues all of
+// its (<= 8) loads before the first use -- 1 KB in flight per warp instead of 340 B -- and the (anchor, output) split of
+// every element is computed once per thread instead of once per run.  Values are computed by the same expressions.
+__global__ void __launch_bounds__(256) yolo_decode_pixel_kernel(const float* __restrict__ raw, long long raw_pitch,
+                                                                float* __restrict__ p, float* __restrict__ io,
+                                                                long long total_rows, long long row_offset, int B,
+                                                                int na, int no, int ny, int nx,
+                                                                const float* __restrict__ anchors_px, float stride) {
+    const int lane = threadIdx.x & 31;
+    const unsigned plane = (unsigned)(ny * nx);
+    const unsigned pixels = (unsigned)B * plane;
+    const unsigned warps = (gridDim.x * blockDim.x) >> 5;
+    const int nel = na * no;
+    int ea[8], eo[8];
+    float ew[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int e = lane + 32 * i;
+        ea[i] = e < nel ? e / no : 0;
+        eo[i] = e < nel ? e - ea[i] * no : -1;
+        ew[i] = 0.f;
+        if (eo[i] == 2) ew[i] = __ldg(anchors_px + ea[i] * 2) / stride;          // anchor_vec
+        if (eo[i] == 3) ew[i] = __ldg(anchors_px + ea[i] * 2 + 1) / stride;
+    }
+    for (unsigned pix = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; pix < pixels; pix += warps) {
+        const unsigned b = pix / plane;
+        const unsigned yx = pix - b * plane;
+        const unsigned y = yx / (unsigned)nx, x = yx - y * (unsigned)nx;
+        const float* src = raw + (long long)pix * raw_pitch;
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = eo[i] >= 0 ? __ldg(src + lane + 32 * i) : 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int o = eo[i];
+            if (o < 0) continue;
+            const long long prow = ((long long)b * na + ea[i]) * plane + yx;
+            if (p != nullptr) p[prow * no + o] = v[i];
+            if (io != nullptr) {
+                float r;
+                if (o < 2) {
+                    const float g = (o == 0) ? (float)x : (float)y;
+                    r = (sigmoid_f(v[i]) + g) * stride;
+                } else if (o < 4) {
+                    r = (expf(v[i]) * ew[i]) * stride;
+                } else {
+                    r = sigmoid_f(v[i]);
+                }
+                io[((long long)b * total_rows + row_offset + (long long)ea[i] * plane + yx) * no + o] = r;
+            }
+        }
+    }
+}
+
 extern "C" int b2y_yolo_decode(const float* raw, long long raw_pitch, float* p, float* io, long long total_rows,
                                long long row_offset, int batch, int na, int no, int ny, int nx,
                                const float* anchors_px, float stride, void* stream) {
@@ -63,6 +117,20 @@ extern "C" int b2y_yolo_decode(const float* raw, long long raw_pitch, float* p, 
     if (raw_pitch < (long long)na * no) return B2Y_ERR_INVALID;
     const long long runs = (long long)batch * na * ny * nx;
     if (runs > 0x7fffffffLL) return B2Y_ERR_UNSUPPORTED;
+    static int per_pixel = -1;     // B2Y_DECODE_PIXEL=0: the one-warp-per-run kernel for every shape
+    if (per_pixel < 0) {
+        const char* ev = getenv("B2Y_DECODE_PIXEL");
+        per_pixel = (ev && atoi(ev) == 0) ? 0 : 1;
+    }
+    if (per_pixel && na * no <= 256) {
+        const long long pixels = (long long)batch * ny * nx;
+        long long pb = (pixels + 7) / 8;
+        if (pb > 148 * 8) pb = 148 * 8;
+        yolo_decode_pixel_kernel<<<(int)pb, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+            raw, raw_pitch, p, io, total_rows, row_offset, batch, na, no, ny, nx, anchors_px, stride);
+        B2Y_CUDA_CHECK(cudaGetLastError());
+        return B2Y_OK;
+    }
     long long blocks = (runs + 7) / 8;                 // 8 warps per block
     if (blocks > 148 * 16) blocks = 148 * 16;
     yolo_decode_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
