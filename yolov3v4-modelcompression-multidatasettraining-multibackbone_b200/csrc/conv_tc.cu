@@ -294,8 +294,16 @@ int gemm_conv_launch(const GemmConvSpec& g, const EpilogueArgs& e, cudaStream_t 
         const bool out32 = e.out_dtype == OUT_F32;
         const bool tma_ok = tma_on && g.out_identity;
         const bool full = g.Nout % block_n == 0;
+        static int stats_fast = -1;   // B2Y_STATS_FAST=0: training forward convs (BN statistics) use the general epilogue
+        if (stats_fast < 0) {
+            const char* ev = getenv("B2Y_STATS_FAST");
+            stats_fast = (ev && atoi(ev) == 0) ? 0 : 1;
+        }
+        // batch statistics ride on the short path when it stores through TMA and nothing is added to the accumulators
+        const bool stats_ok = e.stat_sum == nullptr ||
+                              (stats_fast && out16 && tma_ok && e.bias == nullptr && e.res == nullptr);
         p.epi_fast = g.kind == CONV_KIND_F16 && (out16 || (out32 && tma_ok)) && !e.out_fakequant &&
-                     e.stat_sum == nullptr && act_ok && al16(e.out) && e.out_pitch % (out16 ? 8 : 4) == 0 &&
+                     stats_ok && act_ok && al16(e.out) && e.out_pitch % (out16 ? 8 : 4) == 0 &&
                      (e.bias == nullptr || al16(e.bias)) && (e.res == nullptr || (al16(e.res) && e.res_pitch % 8 == 0)) &&
                      (full || (tma_ok && e.res == nullptr));
         // int8 graph (B2Y_I8_FAST=0 disables): int8 codes out, no residual, whole N tiles, and a power-of-two accumulator

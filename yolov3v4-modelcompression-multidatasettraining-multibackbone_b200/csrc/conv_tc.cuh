@@ -626,6 +626,47 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         v[4 * q + 2] = fmaf(a2, acc_mul, bv[q].z);
                         v[4 * q + 3] = fmaf(a3, acc_mul, bv[q].w);
                     }
+                    if (KIND == CONV_KIND_F16 && p.stat_sum != nullptr) {
+                        // training BN statistics on the short path (host: TMA store, no bias, no residual): column sums of
+                        // the warp's 32 x 32 chunk through the 2 KB staging buffer the NEXT TMA store will use, 16 columns
+                        // at a time (rotated columns; lane L sums column L & 15 over rows 16 (L >> 4) .. + 15)
+                        float* tile = reinterpret_cast<float*>(my_stage + sbuf * 2048);
+                        if (lane == 0) bulk_wait_read<1>();      // the store that last read this buffer is done with it
+                        __syncwarp();
+                        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) tile[lane * 16 + ((j + lane) & 15)] = row_ok ? v[h * 16 + j] : 0.f;
+                            __syncwarp();
+                            const int col = lane & 15, r0 = (lane >> 4) * 16;
+                            float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                const float t = tile[(r0 + i) * 16 + ((col + r0 + i) & 15)];
+                                t1 += t;
+                                t2 = fmaf(t, t, t2);
+                            }
+                            t1 += __shfl_xor_sync(0xffffffffu, t1, 16);
+                            t2 += __shfl_xor_sync(0xffffffffu, t2, 16);
+                            if ((lane >> 4) == h) {
+                                s1 = t1;
+                                s2 = t2;
+                            }
+                            __syncwarp();
+                        }
+                        if (defer_stats) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                if (c == q * 32) {
+                                    st1[q] += s1;
+                                    st2[q] += s2;
+                                }
+                        } else if (n0 + c_begin + c + lane < p.Cout) {
+                            atomicAdd(p.stat_sum + n0 + c_begin + c + lane, s1);
+                            atomicAdd(p.stat_sqsum + n0 + c_begin + c + lane, s2);
+                        }
+                    }
                     if (act == B2Y_ACT_LEAKY) {       // 0 <= slope <= 1 on this path: max(v, slope*v)
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], v[j] * slope);
