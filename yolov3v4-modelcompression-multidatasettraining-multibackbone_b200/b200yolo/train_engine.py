@@ -272,6 +272,7 @@ class TrainPlan:
                 self.feature_views.append(feat_idx.get(i))
         self.anchors_px = [m.anchors.to(dev).float().contiguous() for (m, _) in self.yolo]
         self.bn_counters = [r.bn.num_batches_tracked for r in self.convs if r.bn is not None]
+        self._plan_grad_writes()
         # ---- arenas ------------------------------------------------------------------------------------------------
         # Everything that has to be zero when a pass starts is carved out of ONE allocation per pass, cleared by ONE
         # memset (round 1: one fill launch per buffer, ~450 launches per step):
@@ -303,6 +304,12 @@ class TrainPlan:
             want(bwd_req, r, 'dw')
             want(bwd_req, r, 'dwg')
         want(bwd_req, self, 'dz_aux')
+
+        # gradient buffers whose first writer overwrites (see _plan_grad_writes) go behind the part that is memset
+        grad_ids = {id(g.buf) for g in self.grad_of.values()}
+        is_clean = lambda t: id(t) in grad_ids and id(t) not in self.dirty_grad_bufs
+        bwd_req = [t for t in bwd_req if not is_clean(t)] + [t for t in bwd_req if is_clean(t)]
+        self.bwd_zero_bytes = sum(_round_up(t.numel() * t.element_size(), 256) for t in bwd_req if not is_clean(t))
 
         def carve(reqs):
             offs, total = [], 0
@@ -385,6 +392,77 @@ class TrainPlan:
                 r.w32 = w.float().contiguous()
                 # tensor-core stem: full-im2col weight layout when the receptive field fits one 64-byte GEMM row
                 r.wstem = ops.pack_stem_weights(r.w32) if w.shape[1] * r.k * r.k <= 32 and not r.head else None
+
+    def _plan_grad_writes(self):
+        """Which backward write into an activation-gradient buffer is the FIRST one of its channel range.
+
+        Consumers used to accumulate into gradient buffers that the start-of-backward memset had cleared: for yolov4 at
+        8 x 640^2 that is ~2.4 GB of memset per step plus a read of zeros by every data-gradient GEMM (another ~2 GB).
+        The launch order of the backward pass is static, so the first writer of every (buffer, channel range) is known
+        when the plan is built: it OVERWRITES (dgrad accumulate=False, copy instead of add) and the buffer leaves the
+        zeroed arena.  A buffer stays 'dirty' (zeroed, accumulate-only) when a first writer cannot overwrite (up-sample /
+        max-pool / depthwise / SE backward, stride > kernel dgrad), when ranges overlap partially, or when something would
+        read channels nobody has written.  B2Y_GRAD_FIRSTWRITE=0 keeps every buffer dirty."""
+        self.first_write, cov, dirty = {}, {}, set()
+        G = lambda t: self.grad_of[id(t)]
+        enabled = os.environ.get('B2Y_GRAD_FIRSTWRITE', '1') != '0'
+
+        def write(g, n, key, can_overwrite):
+            b, R = id(g.buf), set(range(g.c0, g.c0 + n))
+            c = cov.setdefault(b, set())
+            inter = R & c
+            if not inter and can_overwrite and enabled:
+                self.first_write[key] = True
+            else:
+                self.first_write[key] = False
+                if inter != R:              # partial overlap, or a first writer that can only accumulate
+                    dirty.add(b)
+            c |= R
+
+        def read(g, n, c0=None):
+            b = id(g.buf)
+            c0 = g.c0 if c0 is None else c0
+            if not set(range(c0, c0 + n)) <= cov.get(b, set()):
+                dirty.add(b)
+
+        for (m, raw) in self.yolo:              # head gradients: written by yolo_grad_to_raw only where a loss exists
+            g = G(raw)
+            dirty.add(id(g.buf))
+            cov[id(g.buf)] = set(range(0, HEAD_PAD))
+        for idx in range(len(self.order) - 1, -1, -1):
+            st = self.order[idx]
+            kind = st[0]
+            if kind == 'conv':
+                r = st[1]
+                read(G(r.y), G(r.y).C)
+                if r.bn is not None and r.res is not None:
+                    write(G(r.res), G(r.res).C, ('res', r.i), True)
+                if r.stem:
+                    continue
+                if r.depthwise:
+                    write(G(r.src), r.conv.in_channels, ('dwd', r.i), False)
+                else:
+                    write(G(r.src), r.conv.in_channels, ('dgrad', r.i), r.k >= r.s)
+            elif kind == 'se':
+                e = st[1]
+                read(G(e['y']), G(e['y']).C)
+                write(G(e['src']), G(e['src']).C, ('se', idx), False)
+            elif kind == 'add':
+                _, first, others, out = st
+                go = G(out)
+                read(go, go.C)
+                for j, t in enumerate([first] + list(others)):
+                    write(G(t), min(G(t).C, go.C), ('add', idx, j), True)
+            elif kind == 'copy':
+                _, srct, dst, off = st
+                gd = G(dst)
+                read(gd, srct.C, gd.c0 + off)
+                write(G(srct), srct.C, ('copy', idx), True)
+            elif kind in ('upsample', 'maxpool'):
+                src, out = st[1], st[2]
+                read(G(out), G(out).C)
+                write(G(src), G(src).C, (kind, idx), False)
+        self.dirty_grad_bufs = dirty
 
     def _grad_dst(self, param):
         """Where the gradient of `param` is written: its slice of the flat data-parallel buffer (sink), else a
@@ -579,7 +657,8 @@ class TrainPlan:
         self.last_grad_scale = S
         inv = 1.0 / S
         self.sink = getattr(self.model, '_b2y_grad_sink', None)   # FlatDataParallel: write into the flat buffer
-        self.bwd_arena.zero_()      # activation gradients, BN sums, scale rows, packed weight gradients (one memset)
+        # one memset: BN sums, scale rows, packed weight gradients and the activation gradients that are accumulate-only
+        self.bwd_arena[:max(self.bwd_zero_bytes, 1)].zero_()
         if self.side_wgrad and self.side_stream is None:
             self.side_stream = torch.cuda.Stream(device=self.device)
         grads = {}
@@ -595,7 +674,8 @@ class TrainPlan:
             call("b2y_yolo_grad_to_raw", ptr(dp.contiguous().float()), ptr(g.buf), HEAD_PAD, self.B, m.na, m.no, raw.H,
                  raw.W, S, ptr(self.head_scale), ops._gdt(g.buf), stream_ptr())
         G = lambda t: self.grad_of[id(t)]
-        for st in reversed(self.order):
+        for idx in range(len(self.order) - 1, -1, -1):
+            st = self.order[idx]
             kind = st[0]
             if kind == 'conv':
                 self._conv_backward(st[1], grads, S, inv)
@@ -607,15 +687,21 @@ class TrainPlan:
             elif kind == 'add':
                 _, first, others, out = st
                 go = G(out).view()
-                for s in [first] + list(others):
+                for j, s in enumerate([first] + list(others)):
                     gs = G(s).view()
                     n = min(gs.shape[3], go.shape[3])      # sliced addends receive the matching gradient channels
-                    ops.add(gs[..., :n], go[..., :n], out=gs[..., :n])
+                    if self.first_write.get(('add', idx, j)):
+                        ops.copy_channels(go[..., :n], gs[..., :n])
+                    else:
+                        ops.add(gs[..., :n], go[..., :n], out=gs[..., :n])
             elif kind == 'copy':
                 _, srct, dst, off = st
                 gd = G(dst)
                 gs = G(srct).view()
-                ops.add(gs, gd.buf[..., gd.c0 + off:gd.c0 + off + srct.C], out=gs)
+                if self.first_write.get(('copy', idx)):
+                    ops.copy_channels(gd.buf[..., gd.c0 + off:gd.c0 + off + srct.C], gs)
+                else:
+                    ops.add(gs, gd.buf[..., gd.c0 + off:gd.c0 + off + srct.C], out=gs)
             elif kind == 'upsample':
                 _, src, out, s = st
                 gy, gx = G(out).view(), G(src).view()
@@ -645,7 +731,10 @@ class TrainPlan:
             dy = gy.view()
             if r.res is not None:   # fused shortcut: the same gradient also flows to the skip source
                 gs = self.grad_of[id(r.res)].view()
-                ops.add(gs, dy, out=gs)
+                if self.first_write.get(('res', r.i)):
+                    ops.copy_channels(dy, gs)
+                else:
+                    ops.add(gs, dy, out=gs)
             if self.side_wgrad:
                 dz = self.dz_bufs.get(r.i)
                 if dz is None:
@@ -721,8 +810,8 @@ class TrainPlan:
             else:
                 ops.conv2d_bwd_weight(xk, dzk, r.k, r.s, r.p, scale=inv, dw=r.dw, inv_scale=inv_s)
             gx = self.grad_of[id(r.src)]
-            ops.conv2d_bwd_data(dzk, r.wT, (B, r.src.H, r.src.W, I), r.k, r.s, r.p, out=gx.view(), accumulate=True,
-                                inv_scale=inv_s)
+            ops.conv2d_bwd_data(dzk, r.wT, (B, r.src.H, r.src.W, I), r.k, r.s, r.p, out=gx.view(),
+                                accumulate=not self.first_write.get(('dgrad', r.i), False), inv_scale=inv_s)
 
     def _emit(self, grads, param, src, alpha):
         ops.axpby(src.contiguous(), self._grad_dst(param), alpha, 0.0)
