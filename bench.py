@@ -375,11 +375,19 @@ def replay_convs(calls, iters):
     return e0.elapsed_time(e1) / iters, flops, len(convs)
 
 
-def roofline_block(conv_ms, conv_flops, n_convs, step_ms, what):
+# DRAM bytes (read + write) of the conv-family launches of ONE yolov4 training step, 8 x 640 x 640, from the ncu launch list
+# profiles/r02/final/launches_train_r02_final.csv (240 conv_tc_kernel + 110 weight-gradient launches of the second step,
+# eager, cold cache): 11.65 GB, i.e. 33.3 MB per launch -- against 13.4 GB of algorithmic bytes (every operand and result
+# of the 328 GEMM launches once: activations / gradients 16-bit, packed weight gradients fp32): no wasted re-reads, the
+# 3x3 tap re-reads and part of the producer -> consumer traffic are served by the 126 MB L2
+NCU_TRAIN_CONV_DRAM_BYTES_PER_STEP = 11651468800
+
+
+def roofline_block(conv_ms, conv_flops, n_convs, step_ms, what, traffic=None):
     pk = peaks()
     achieved = conv_flops / (conv_ms / 1e3) / 1e12
     return {"bound": "tensor", "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
-            "frac": achieved / pk["tflops"], "traffic": None,
+            "frac": achieved / pk["tflops"], "traffic": traffic,
             "peak_source": pk["source"] + " (sustained bf16, MEASURED_PEAKS.json)",
             "kernel": "tcgen05 conv family (%s): %d launches of one step replayed back to back" % (what, n_convs),
             "kernel_ms_per_step": conv_ms, "share_of_step": conv_ms / step_ms,
@@ -479,7 +487,11 @@ def run_train(args, dev, rank, world, dd):
         else:
             model.use_cuda_graph = saved
     conv_ms, conv_flops, n_convs = replay_convs(calls, iters=max(3, min(10, args.steps)))
-    roofline = roofline_block(conv_ms, conv_flops, n_convs, ms_step, "forward + data gradient + weight gradient")
+    roofline = roofline_block(conv_ms, conv_flops, n_convs, ms_step, "forward + data gradient + weight gradient",
+                              traffic=NCU_TRAIN_CONV_DRAM_BYTES_PER_STEP if (TRAIN_MODEL == "yolov4" and B == 8) else None)
+    if roofline["traffic"] is not None:
+        roofline["traffic_unit"] = "bytes per step (all conv-family launches; ncu dram__bytes_read.sum + dram__bytes_write.sum)"
+        roofline["algorithmic_bytes_per_step"] = 13389727744
     roofline["table_flops_per_step"] = FLOPS_TRAIN[TRAIN_MODEL] * B
     launches = len(calls)
     return {"value": value, "ms_per_step": ms_step, "clocks": clocks, "roofline": roofline, "allreduce": allreduce,

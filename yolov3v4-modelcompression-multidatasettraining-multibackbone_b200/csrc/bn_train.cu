@@ -33,6 +33,10 @@ __device__ __forceinline__ float actg(float v, int act_rt, float slope) {
     return act_grad(v, ACT == ACT_RT ? act_rt : ACT, slope);
 }
 
+// L2 prefetch of the 16-byte vector a thread will load one iteration ahead: the register file caps the loads in flight at
+// U per operand (2 CTAs x 256 threads x ~120 registers), prefetches cost no registers and double the bytes in flight.
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 struct Geo {
     int CV, PPB, T;     // channel vectors, pixel rows per block, active threads
 };
@@ -62,7 +66,7 @@ bn_train_fwd_kernel(const __half* __restrict__ z, long long zp, const float* __r
                     const float* __restrict__ s2, const float* __restrict__ gamma, const float* __restrict__ beta,
                     float count, float eps, float momentum, float* __restrict__ rmean, float* __restrict__ rvar,
                     float* __restrict__ save, const __half* __restrict__ res, long long rp, __half* __restrict__ y,
-                    long long yp, long long pixels, int CV, int PPB, int act_rt, float slope) {
+                    long long yp, long long pixels, int CV, int PPB, int act_rt, float slope, int pf) {
     pdl_wait();                     // launched as a programmatic dependent (launch_pdl): the statistics / z come from
     pdl_launch_dependents();        // the previous kernel
     const int tid = threadIdx.x;
@@ -101,6 +105,11 @@ bn_train_fwd_kernel(const __half* __restrict__ z, long long zp, const float* __r
                 v[u] = __ldg(reinterpret_cast<const uint4*>(z + pix * zp) + cv);
                 if (res != nullptr) r[u] = __ldg(reinterpret_cast<const uint4*>(res + pix * rp) + cv);
             }
+            const long long nxt = pix + stride * U;
+            if (pf && nxt < pixels) {
+                prefetch_l2(reinterpret_cast<const uint4*>(z + nxt * zp) + cv);
+                if (res != nullptr) prefetch_l2(reinterpret_cast<const uint4*>(res + nxt * rp) + cv);
+            }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -133,7 +142,7 @@ template <typename GT, int ACT, int U>
 __global__ void __launch_bounds__(256, 2)
 bn_train_bwd_reduce_kernel(const __half* __restrict__ z, long long zp, const GT* __restrict__ dy, long long dp,
                            const float* __restrict__ save, float* __restrict__ sums, float* __restrict__ du_absmax,
-                           long long pixels, int CV, int PPB, int act_rt, float slope) {
+                           long long pixels, int CV, int PPB, int act_rt, float slope, int pf) {
     __shared__ float red[256][17];
     pdl_wait();
     pdl_launch_dependents();
@@ -161,6 +170,11 @@ bn_train_bwd_reduce_kernel(const __half* __restrict__ z, long long zp, const GT*
                 if (pix < pixels) {
                     v[u] = __ldg(reinterpret_cast<const uint4*>(z + pix * zp) + cv);
                     g[u] = __ldg(reinterpret_cast<const uint4*>(dy + pix * dp) + cv);
+                }
+                const long long nxt = pix + stride * U;
+                if (pf && nxt < pixels) {
+                    prefetch_l2(reinterpret_cast<const uint4*>(z + nxt * zp) + cv);
+                    prefetch_l2(reinterpret_cast<const uint4*>(dy + nxt * dp) + cv);
                 }
             }
 #pragma unroll
@@ -216,7 +230,7 @@ bn_train_bwd_apply_kernel(const __half* __restrict__ z, long long zp, const GT* 
                           const float* __restrict__ sums, __half* __restrict__ dz, long long dzp, long long pixels,
                           int CV, int PPB, int act_rt, float slope, const float* __restrict__ du_absmax,
                           float* __restrict__ scale_out, float* __restrict__ dgamma_out,
-                          float* __restrict__ dbeta_out, float grad_out_scale) {
+                          float* __restrict__ dbeta_out, float grad_out_scale, int pf) {
     pdl_wait();
     pdl_launch_dependents();
     const int C = CV * 8;
@@ -279,6 +293,11 @@ bn_train_bwd_apply_kernel(const __half* __restrict__ z, long long zp, const GT* 
                 v[u] = __ldg(reinterpret_cast<const uint4*>(z + pix * zp) + cv);
                 g[u] = __ldg(reinterpret_cast<const uint4*>(dy + pix * dp) + cv);
             }
+            const long long nxt = pix + stride * U;
+            if (pf && nxt < pixels) {
+                prefetch_l2(reinterpret_cast<const uint4*>(z + nxt * zp) + cv);
+                prefetch_l2(reinterpret_cast<const uint4*>(dy + nxt * dp) + cv);
+            }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -307,6 +326,15 @@ inline void dispatch_act(int act, F&& f) {
     else f(std::integral_constant<int, ACT_RT>{});
 }
 
+inline int bn_prefetch() {       // B2Y_BN_PREFETCH=0: no L2 prefetch one iteration ahead
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("B2Y_BN_PREFETCH");
+        v = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    return v;
+}
+
 inline bool shape_ok(int c, long long p0, long long p1, long long p2 = 8) {
     return c > 0 && c % 8 == 0 && c / 8 <= 256 && p0 % 8 == 0 && p1 % 8 == 0 && p2 % 8 == 0;
 }
@@ -327,7 +355,7 @@ extern "C" int b2y_bn_train_fwd(const void* z, long long z_pitch, const float* s
         launch_pdl(bn_train_fwd_kernel<decltype(A)::value, 4>, dim3(grid), dim3(256), 0, st, 
             reinterpret_cast<const __half*>(z), z_pitch, stat_sum, stat_sqsum, gamma, beta, (float)count, eps, momentum,
             running_mean, running_var, save, reinterpret_cast<const __half*>(residual), res_pitch,
-            reinterpret_cast<__half*>(y), y_pitch, pixels, g.CV, g.PPB, act, slope);
+            reinterpret_cast<__half*>(y), y_pitch, pixels, g.CV, g.PPB, act, slope, bn_prefetch());
     });
     B2Y_CUDA_CHECK(cudaGetLastError());
     return B2Y_OK;
@@ -346,11 +374,11 @@ extern "C" int b2y_bn_train_bwd_reduce(const void* z, long long z_pitch, const v
         if (grad_dtype == B2Y_DT_BF16)
             launch_pdl(bn_train_bwd_reduce_kernel<__nv_bfloat16, ACT, 4>, dim3(grid), dim3(256), 0, st, 
                 reinterpret_cast<const __half*>(z), z_pitch, reinterpret_cast<const __nv_bfloat16*>(dy), dy_pitch, save,
-                sums, du_absmax, pixels, g.CV, g.PPB, act, slope);
+                sums, du_absmax, pixels, g.CV, g.PPB, act, slope, bn_prefetch());
         else
             launch_pdl(bn_train_bwd_reduce_kernel<__half, ACT, 4>, dim3(grid), dim3(256), 0, st, 
                 reinterpret_cast<const __half*>(z), z_pitch, reinterpret_cast<const __half*>(dy), dy_pitch, save, sums,
-                du_absmax, pixels, g.CV, g.PPB, act, slope);
+                du_absmax, pixels, g.CV, g.PPB, act, slope, bn_prefetch());
     });
     B2Y_CUDA_CHECK(cudaGetLastError());
     return B2Y_OK;
@@ -372,12 +400,12 @@ extern "C" int b2y_bn_train_bwd_apply(const void* z, long long z_pitch, const vo
             launch_pdl(bn_train_bwd_apply_kernel<__nv_bfloat16, ACT, 4>, dim3(grid), dim3(256), 0, st, 
                 reinterpret_cast<const __half*>(z), z_pitch, reinterpret_cast<const __nv_bfloat16*>(dy), dy_pitch, gamma,
                 save, sums, reinterpret_cast<__half*>(dz), dz_pitch, pixels, g.CV, g.PPB, act, slope, du_absmax,
-                scale_out, dgamma_out, dbeta_out, grad_out_scale);
+                scale_out, dgamma_out, dbeta_out, grad_out_scale, bn_prefetch());
         else
             launch_pdl(bn_train_bwd_apply_kernel<__half, ACT, 4>, dim3(grid), dim3(256), 0, st, 
                 reinterpret_cast<const __half*>(z), z_pitch, reinterpret_cast<const __half*>(dy), dy_pitch, gamma, save,
                 sums, reinterpret_cast<__half*>(dz), dz_pitch, pixels, g.CV, g.PPB, act, slope, du_absmax, scale_out,
-                dgamma_out, dbeta_out, grad_out_scale);
+                dgamma_out, dbeta_out, grad_out_scale, bn_prefetch());
     });
     B2Y_CUDA_CHECK(cudaGetLastError());
     return B2Y_OK;
