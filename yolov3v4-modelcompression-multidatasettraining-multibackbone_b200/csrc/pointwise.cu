@@ -309,11 +309,25 @@ __global__ void copy_channels_kernel(const __half* __restrict__ x, long long xp,
                                      long long pixels, int C) {
     const int CV = C / 8;
     const long long total = pixels * CV;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        const int cv = (int)(idx % CV);
-        const long long pix = idx / CV;
-        reinterpret_cast<uint4*>(y + pix * yp)[cv] = __ldg(reinterpret_cast<const uint4*>(x + pix * xp) + cv);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    // four independent 16-byte loads per thread before the first store (one per iteration left the copy latency bound)
+    for (long long idx0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx0 < total; idx0 += 4 * stride) {
+        uint4 v[4];
+        uint4* dst[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long long idx = idx0 + u * stride;
+            dst[u] = nullptr;
+            if (idx < total) {
+                const int cv = (int)(idx % CV);
+                const long long pix = idx / CV;
+                v[u] = __ldg(reinterpret_cast<const uint4*>(x + pix * xp) + cv);
+                dst[u] = reinterpret_cast<uint4*>(y + pix * yp) + cv;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (dst[u] != nullptr) *dst[u] = v[u];
     }
 }
 
@@ -321,7 +335,7 @@ extern "C" int b2y_copy_channels(const void* x, long long x_pitch, void* y, long
                                  void* stream) {
     if (!x || !y || c % 8 != 0 || x_pitch % 8 != 0 || y_pitch % 8 != 0) return B2Y_ERR_INVALID;
     if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15)) return B2Y_ERR_INVALID;
-    copy_channels_kernel<<<grid_for(pixels * (c / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    copy_channels_kernel<<<grid_for((pixels * (c / 8) + 3) / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const __half*>(x), x_pitch, reinterpret_cast<__half*>(y), y_pitch, pixels, c);
     B2Y_CUDA_CHECK(cudaGetLastError());
     return B2Y_OK;
@@ -332,17 +346,33 @@ __global__ void add_kernel(const T* __restrict__ a, long long ap, const T* __res
                            T* __restrict__ y, long long yp, long long pixels, int C) {
     const int CV = C / 8;
     const long long total = pixels * CV;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        const int cv = (int)(idx % CV);
-        const long long pix = idx / CV;
-        // fp32 add then a single rounding (the reference adds fp32 tensors)
-        float fa[8], fb[8];
-        Half8<T>::load(a + pix * ap + cv * 8, fa);
-        Half8<T>::load(b + pix * bp + cv * 8, fb);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long idx0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx0 < total; idx0 += 2 * stride) {
+        uint4 va[2], vb[2];
+        T* dst[2];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) fa[j] += fb[j];
-        Half8<T>::store(y + pix * yp + cv * 8, fa);
+        for (int u = 0; u < 2; ++u) {
+            const long long idx = idx0 + u * stride;
+            dst[u] = nullptr;
+            if (idx < total) {
+                const int cv = (int)(idx % CV);
+                const long long pix = idx / CV;
+                va[u] = *reinterpret_cast<const uint4*>(a + pix * ap + cv * 8);
+                vb[u] = *reinterpret_cast<const uint4*>(b + pix * bp + cv * 8);
+                dst[u] = y + pix * yp + cv * 8;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (dst[u] == nullptr) continue;
+            // fp32 add then a single rounding (the reference adds fp32 tensors)
+            float fa[8], fb[8];
+            Half8<T>::unpack(va[u], fa);
+            Half8<T>::unpack(vb[u], fb);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) fa[j] += fb[j];
+            Half8<T>::store(dst[u], fa);
+        }
     }
 }
 
@@ -351,11 +381,11 @@ extern "C" int b2y_add(const void* a, long long a_pitch, const void* b, long lon
     if (!a || !b || !y || c % 8 != 0 || a_pitch % 8 != 0 || b_pitch % 8 != 0 || y_pitch % 8 != 0)
         return B2Y_ERR_INVALID;
     if (dtype == B2Y_DT_BF16)
-        add_kernel<__nv_bfloat16><<<grid_for(pixels * (c / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        add_kernel<__nv_bfloat16><<<grid_for((pixels * (c / 8) + 1) / 2, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
             reinterpret_cast<const __nv_bfloat16*>(a), a_pitch, reinterpret_cast<const __nv_bfloat16*>(b), b_pitch,
             reinterpret_cast<__nv_bfloat16*>(y), y_pitch, pixels, c);
     else
-        add_kernel<__half><<<grid_for(pixels * (c / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        add_kernel<__half><<<grid_for((pixels * (c / 8) + 1) / 2, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
             reinterpret_cast<const __half*>(a), a_pitch, reinterpret_cast<const __half*>(b), b_pitch,
             reinterpret_cast<__half*>(y), y_pitch, pixels, c);
     B2Y_CUDA_CHECK(cudaGetLastError());

@@ -744,6 +744,12 @@ __global__ void __launch_bounds__(256) maxpool_plane_bwd_kernel(const __half* __
         sa[i] = (unsigned char)a;
     }
     __syncthreads();
+    // sx is dead now: stage the plane of dy in it with 16-byte loads (the scalar 2-byte global loads of the first version
+    // put one DRAM round trip into every iteration of the pass below)
+    GT* sdy = reinterpret_cast<GT*>(sx);
+    for (int i = threadIdx.x; i < HW; i += blockDim.x)
+        reinterpret_cast<uint4*>(sdy)[i] = __ldg(reinterpret_cast<const uint4*>(dy + ((long long)n * HW + i) * dyp) + cv);
+    __syncthreads();
     for (int i = threadIdx.x; i < HW * 8; i += blockDim.x) {
         const int c = i & 7, pix = i >> 3;
         const int yo = pix / W, xo = pix - yo * W;
@@ -756,14 +762,17 @@ __global__ void __launch_bounds__(256) maxpool_plane_bwd_kernel(const __half* __
         }
         // NaN rows never win a strict '>' (same as the general kernel, whose -inf start is replaced by the first value)
         const int ax = sa[(ay * W + xo) * 8 + c];
-        const float g = Half8<GT>::to_f(dy[((long long)n * HW + pix) * dyp + cv * 8 + c]);
+        const float g = Half8<GT>::to_f(sdy[i]);
         atomicAdd(&acc[(ay * W + ax) * 8 + c], g);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < HW * 8; i += blockDim.x) {
-        const int c = i & 7, pix = i >> 3;
-        GT* d = dx + ((long long)n * HW + pix) * dxp + cv * 8 + c;
-        *d = Half8<GT>::from_f(Half8<GT>::to_f(*d) + acc[i]);
+    for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+        GT* d = dx + ((long long)n * HW + i) * dxp + cv * 8;
+        float f[8];
+        Half8<GT>::load(d, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] += acc[i * 8 + j];
+        Half8<GT>::store(d, f);
     }
 }
 
@@ -784,7 +793,8 @@ extern "C" int b2y_maxpool_bwd(const void* x, long long x_pitch, const void* dy,
     }
     const long long total = (long long)batch * Ho * Wo * (c / 2);
     if (pad_mode != 1 && stride == 1 && (ksize & 1) && c % 8 == 0 && x_pitch % 8 == 0 && in_w <= 255 &&
-        in_h * in_w <= POOL_PLANE_MAX && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+        in_h * in_w <= POOL_PLANE_MAX && dy_pitch % 8 == 0 && dx_pitch % 8 == 0 &&
+        ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0) {
         const int grid = batch * (c / 8);
         if (grad_dtype == B2Y_DT_BF16)
             maxpool_plane_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
