@@ -160,27 +160,15 @@ unpack_multi_kernel(const b2y_unpack_item* __restrict__ items, int n_items) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int sh = (ni & (ni - 1)) == 0 ? 31 - __clz(ni) : -1;
     // packed [o][tap][i]: runs of ni floats (a warp per output channel, lanes along i)
-    {
-        float v[TO / 8][9];
-#pragma unroll
-        for (int r = 0; r < TO / 8; ++r) {
-            const int ol = warp + 8 * r;
-            const float* src = it.src + (long long)(o0 + ol) * k2 * it.Ipad + i0;
-#pragma unroll
-            for (int t = 0; t < 9; ++t) {
-                const int j = lane + 32 * t;
-                const int tap = sh >= 0 ? (j >> sh) : (j / ni);
-                v[r][t] = (ol < no && j < k2 * ni) ? __ldg(src + (long long)tap * it.Ipad + (j - tap * ni)) : 0.f;
-            }
+    for (int ol = warp; ol < no; ol += 8) {
+        const float* src = it.src + (long long)(o0 + ol) * k2 * it.Ipad + i0;
+        float* row = tile[ol];
+#pragma unroll 4
+        for (int j = lane; j < k2 * ni; j += 32) {
+            const int tap = sh >= 0 ? (j >> sh) : (j / ni);
+            const int il = j - tap * ni;
+            row[il * k2 + tap] = __ldg(src + (long long)tap * it.Ipad + il);
         }
-#pragma unroll
-        for (int r = 0; r < TO / 8; ++r)
-#pragma unroll
-            for (int t = 0; t < 9; ++t) {
-                const int j = lane + 32 * t;
-                const int tap = sh >= 0 ? (j >> sh) : (j / ni);
-                if (warp + 8 * r < no && j < k2 * ni) tile[warp + 8 * r][(j - tap * ni) * k2 + tap] = v[r][t];
-            }
     }
     __syncthreads();
     const int run = ni * k2;
