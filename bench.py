@@ -398,13 +398,21 @@ def roofline_block(conv_ms, conv_flops, n_convs, step_ms, what, traffic=None):
 # ----------------------------------------------------------------------------------------------------------------
 # primary workload: YOLOv4 training step, data parallel
 # ----------------------------------------------------------------------------------------------------------------
+def note(rank, msg):
+    """progress marker on stderr (per rank): the driver's log shows how far a failing multi-GPU run got"""
+    sys.stderr.write("[bench.py rank %d] %s\n" % (rank, msg))
+    sys.stderr.flush()
+
+
 def run_train(args, dev, rank, world, dd):
     import torch.distributed as dist
     from b200yolo.parallel import FlatDataParallel
     from utils import utils as my_utils
     B = args.train_batch
     model = build_model(TRAIN_MODEL, dev, rank, train=True)
+    note(rank, "model built")
     dp = FlatDataParallel(model)
+    note(rank, "flat data-parallel buffers ready (world %d)" % world)
     u8, tg = synth_batch(B, 100 + rank)
     host_u8, host_t = u8.pin_memory(), tg.pin_memory()
     x_dev = (host_u8.to(dev).float() / 256.0).contiguous()
@@ -424,6 +432,7 @@ def run_train(args, dev, rank, world, dd):
     for _ in range(args.warmup):
         step(x_dev, t_dev)
     torch.cuda.synchronize()
+    note(rank, "warm-up done")
 
     sampler = ClockSampler(dev.index)
     sampler.start()
@@ -431,6 +440,7 @@ def run_train(args, dev, rank, world, dd):
     clocks = sampler.stop()
     value = world * B / (ms_step / 1e3)
     items = [float(v) for v in state["items"]]
+    note(rank, "timed region done: %.3f ms/step" % ms_step)
 
     # ---- end to end: pinned host uint8 batch + targets -> H2D -> /256 -> step -> D2H of the loss items ----------
     copy_stream = torch.cuda.Stream()
@@ -597,7 +607,10 @@ def main():
         # plain `python bench.py --gpus N`: start one process per GPU ourselves
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
                "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 2000)] + sys.argv
-        raise SystemExit(subprocess.call(cmd))
+        rc = subprocess.call(cmd)
+        if rc != 0:
+            sys.stderr.write("[bench.py] torchrun exited with status %d\n" % rc)
+        raise SystemExit(rc)
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (B200): the hot path has no CPU fallback")
@@ -661,6 +674,7 @@ def main():
         if secondary:
             line["secondary"] = secondary
         print(json.dumps(line), flush=True)
+    note(rank, "done")
     if world > 1:
         dist.destroy_process_group()
 

@@ -596,11 +596,57 @@ __global__ void yolo_grad_to_raw_kernel(const float* __restrict__ dp, GT* __rest
         draw[idx] = Half8<GT>::from_f(v);
     }
 }
+// The same permutation, one warp per PIXEL (pitch <= 256): the (anchor, output) split of every element is computed once
+// per thread, a lane issues its 8 loads (three contiguous runs of `no` floats in dp) back to back and the warp writes one
+// contiguous 512-byte row -- no per-element index divisions.
+template <typename GT>
+__global__ void __launch_bounds__(256) yolo_grad_to_raw_pixel_kernel(const float* __restrict__ dp, GT* __restrict__ draw,
+                                                                     long long pitch, int B, int na, int no, int ny,
+                                                                     int nx, float scale,
+                                                                     const float* __restrict__ scale_ptr) {
+    if (scale_ptr != nullptr) scale *= __ldg(scale_ptr);
+    const int lane = threadIdx.x & 31;
+    const unsigned plane = (unsigned)(ny * nx);
+    const unsigned pixels = (unsigned)B * plane;
+    const unsigned warps = (gridDim.x * blockDim.x) >> 5;
+    const int nel = na * no;
+    long long eoff[8];       // offset of element e inside dp relative to the pixel's (b, a = 0, y, x, o = 0) entry, or -1
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int e = lane + 32 * i;
+        const int a = e / no;
+        eoff[i] = e < nel ? (long long)a * plane * no + (e - a * no) : -1;
+    }
+    for (unsigned pix = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; pix < pixels; pix += warps) {
+        const unsigned b = pix / plane, yx = pix - b * plane;
+        const float* src = dp + ((long long)b * na * plane + yx) * no;
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = eoff[i] >= 0 ? __ldg(src + eoff[i]) * scale : 0.f;
+        GT* dst = draw + (long long)pix * pitch;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (lane + 32 * i < pitch) dst[lane + 32 * i] = Half8<GT>::from_f(v[i]);
+    }
+}
+
 extern "C" int b2y_yolo_grad_to_raw(const float* dp, void* draw, long long raw_pitch, int batch, int na, int no,
                                     int ny, int nx, float scale, const float* scale_ptr, int grad_dtype,
                                     void* stream) {
     if (!dp || !draw || raw_pitch < (long long)na * no) return B2Y_ERR_INVALID;
     const long long total = (long long)batch * ny * nx * raw_pitch;
+    if (raw_pitch <= 256 && (long long)batch * ny * nx < 0x7fffffffLL) {
+        long long pb = ((long long)batch * ny * nx + 7) / 8;
+        if (pb > 148 * 8) pb = 148 * 8;
+        if (grad_dtype == B2Y_DT_BF16)
+            yolo_grad_to_raw_pixel_kernel<__nv_bfloat16><<<(int)pb, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+                dp, reinterpret_cast<__nv_bfloat16*>(draw), raw_pitch, batch, na, no, ny, nx, scale, scale_ptr);
+        else
+            yolo_grad_to_raw_pixel_kernel<__half><<<(int)pb, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+                dp, reinterpret_cast<__half*>(draw), raw_pitch, batch, na, no, ny, nx, scale, scale_ptr);
+        B2Y_CUDA_CHECK(cudaGetLastError());
+        return B2Y_OK;
+    }
     if (grad_dtype == B2Y_DT_BF16)
         yolo_grad_to_raw_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
             dp, reinterpret_cast<__nv_bfloat16*>(draw), raw_pitch, batch, na, no, ny, nx, scale, scale_ptr);
