@@ -21,7 +21,7 @@ from .lib import call, ptr, stream_ptr
 def _pow2_scale(g):
     """device-side power-of-two factor that brings max|g| to ~2^12 (fp16 operand of the gradient GEMMs)"""
     amax = g.abs().max().clamp(min=1e-30)
-    s = torch.exp2(torch.floor(torch.log2(4096.0 / amax))).clamp(1e-30, 1e30).float()
+    s = ((4096.0 / amax).float().view(torch.int32) & 0x7F800000).view(torch.float32).clamp(1e-30, 1e30)
     return torch.stack([s, 1.0 / s]).contiguous()
 
 

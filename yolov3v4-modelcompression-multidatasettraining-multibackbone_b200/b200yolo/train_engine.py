@@ -665,7 +665,9 @@ class TrainPlan:
         # head gradients are GEMM operands (fp16): scale them by a power of two derived on the device from max|dp|
         live = [dp for dp in dps if dp is not None]
         amax = torch.stack([dp.detach().abs().max() for dp in live]).max().clamp(min=1e-30)
-        hs = torch.exp2(torch.floor(torch.log2(4096.0 / amax))).clamp(1e-30, 1e30).float()
+        # 2^floor(log2(4096 / amax)) = the value with its mantissa bits cleared (no exp2 / log2: torch compiles those
+        # through NVRTC on first use, which every rank of a multi-GPU job would do at the same moment)
+        hs = ((4096.0 / amax).float().view(torch.int32) & 0x7F800000).view(torch.float32).clamp(1e-30, 1e30)
         self.head_scale = torch.stack([hs, 1.0 / hs]).contiguous()           # device [s, 1/s]
         for (m, raw), dp in zip(self.yolo, dps):
             g = self.grad_of[id(raw)]
