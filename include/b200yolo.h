@@ -391,6 +391,33 @@ int b2y_tpsq_fwd_f32(const float* x, float* y, long long n, float range_pow2, in
 int b2y_tpsq_bwd_f32(const float* x, const float* g, float* dx /* may be NULL */, double* dp_sum, long long n,
                      float range_pow2, int bits, void* stream);
 
+/* ---- detection post-processing (csrc/nms.cu): replaces utils.utils.non_max_suppression (utils/utils.py:782-860) and the
+ * true-positive matching loop of test.py:137, 150-170.  Two calls because the number of candidates is data dependent:
+ *   1. b2y_nms_count: per-row candidate counts -> exclusive scan row_off [batch*rows + 1] and img_off [batch + 1]
+ *      (device; the caller reads img_off[batch] = total to size the buffers of step 2)
+ *   2. b2y_nms_run: candidates in nonzero() order, stable descending score sort per image, greedy suppression with
+ *      torchvision's arithmetic (fp32 IoU, threshold compared in double), merge-NMS for 1 < n < 3000.
+ * pred fp32 [batch][rows][5 + nc] (xywh px, obj, class probabilities).  det fp32 [total][6]: image b owns rows
+ * img_off[b] .. img_off[b] + det_count[b] (x1, y1, x2, y2, conf, cls), in descending score order.
+ * class_allow: NULL or uint8 [nc] (the `classes=` filter).  multi_label is forced off for nc == 1 like the reference. */
+size_t b2y_nms_count_workspace_bytes(int batch, int rows);
+int b2y_nms_count(const float* pred, int batch, int rows, int nc, float conf_thres, int multi_label,
+                  const unsigned char* class_allow, int* row_off, int* img_off, void* workspace, size_t workspace_bytes,
+                  void* stream);
+size_t b2y_nms_run_workspace_bytes(long long total);
+int b2y_nms_run(const float* pred, int batch, int rows, int nc, float conf_thres, double iou_thres, int multi_label,
+                int agnostic, const unsigned char* class_allow, const int* row_off, const int* img_off, long long total,
+                void* workspace, size_t workspace_bytes, float* det, int* det_count, void* stream);
+/* test.py:137 + 150-170 for a whole batch: boxes clipped in place to [0, clip_w] x [0, clip_h] (skipped if clip_w <= 0),
+ * then per image and class the predictions (in their given = score order) claim their best-IoU target once;
+ * correct uint8 [n_det][niou] = (best IoU > iouv[q]) for the winners, 0 elsewhere.  det_off / det_count int32 [batch],
+ * lab_off int32 [batch + 1] into tcls fp32 [n_lab] / tbox fp32 [n_lab][4] (xyxy px, 16-byte aligned). */
+size_t b2y_tp_match_workspace_bytes(long long n_det, long long n_lab);
+int b2y_tp_match(float* det, const int* det_off, const int* det_count, long long n_det, const float* tcls,
+                 const float* tbox, const int* lab_off, long long n_lab, const float* iouv, int niou, int batch,
+                 float clip_w, float clip_h, void* workspace, size_t workspace_bytes, unsigned char* correct,
+                 void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -39,7 +39,7 @@ def pairwise_iou(a, b):
     return inter / (area_a[:, None] + area_b[None, :] - inter)
 
 
-def nms(prediction, conf_thres=0.1, iou_thres=0.6, multi_label=True):
+def nms(prediction, conf_thres=0.1, iou_thres=0.6, multi_label=True, classes=None, agnostic=False):
     """prediction [B, rows, 5+nc] (xywh px, obj, cls probs) -> list of [n, 6] (xyxy, conf, cls) or None per image."""
     nc = prediction.shape[2] - 5
     multi = multi_label and nc > 1
@@ -60,11 +60,14 @@ def nms(prediction, conf_thres=0.1, iou_thres=0.6, multi_label=True):
         else:
             conf, cls = x[:, 5:].max(1)
             det = torch.cat((box, conf.unsqueeze(1), cls.float().unsqueeze(1)), 1)
+        if classes:                                        # utils.py:823-824
+            det = det[(det[:, 5:6] == torch.tensor(classes, dtype=det.dtype)).any(1)]
         det = det[torch.isfinite(det).all(1)]
         n = det.shape[0]
         if n == 0:
             continue
-        shifted = det[:, :4] + det[:, 5:6] * MAX_WH       # per-class offset so one NMS call handles all classes
+        offs = det[:, 5:6] * 0 if agnostic else det[:, 5:6]
+        shifted = det[:, :4] + offs * MAX_WH              # per-class offset so one NMS call handles all classes
         scores = det[:, 4]
         keep = torchvision.ops.nms(shifted, scores, iou_thres)
         if 1 < n < 3000:                                  # 'merge': score-weighted mean of the overlapping boxes

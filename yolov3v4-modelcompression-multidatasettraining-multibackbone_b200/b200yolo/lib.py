@@ -134,6 +134,12 @@ _PROTOS = {
     "b2y_layout_tile_i": (i32, [i32]),
     "b2y_pack_conv_weights_multi": (i32, [vp, i32, i32, vp]),
     "b2y_unpack_wgrad_multi": (i32, [vp, i32, i32, vp]),
+    "b2y_nms_count_workspace_bytes": (sz, [i32, i32]),
+    "b2y_nms_count": (i32, [vp, i32, i32, i32, f32, i32, vp, vp, vp, vp, sz, vp]),
+    "b2y_nms_run_workspace_bytes": (sz, [ll]),
+    "b2y_nms_run": (i32, [vp, i32, i32, i32, f32, C.c_double, i32, i32, vp, vp, vp, ll, vp, sz, vp, vp, vp]),
+    "b2y_tp_match_workspace_bytes": (sz, [ll, ll]),
+    "b2y_tp_match": (i32, [vp, vp, vp, ll, vp, vp, vp, ll, vp, i32, i32, f32, f32, vp, sz, vp, vp]),
 }
 
 EXPORTS = sorted(_PROTOS)

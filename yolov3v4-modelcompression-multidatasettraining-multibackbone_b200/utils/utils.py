@@ -4,8 +4,10 @@
     build_targets(p, targets, model)  reference utils/utils.py:725-779
     bbox_iou / wh_iou                 reference utils/utils.py:254-297, 325-330
     FocalLoss / smooth_BCE            reference utils/utils.py:333-365
+    non_max_suppression(...)          reference utils/utils.py:782-860   (csrc/nms.cu, whole batch on the device)
+    xywh2xyxy / xyxy2xywh / box_iou / clip_coords   reference utils/utils.py:118-159, 300-322 (tensor helpers)
 
-Everything else of the reference's utils/utils.py (NMS, AP, plotting, KD losses, dataset helpers) is outside the
+Everything else of the reference's utils/utils.py (AP, plotting, KD losses, dataset helpers) is outside the
 accelerated hot path; with B2Y_REFERENCE_ROOT set those names are re-exported from the reference's own file so
 train.py / test.py keep working unchanged.
 """
@@ -240,3 +242,45 @@ def _check_class_ids(t, nc):
 def flush_checks():
     """Force the deferred class-id check of the last compute_loss call (raises like the reference if it failed)."""
     _check_class_ids(torch.zeros(0, 6), 0)
+
+
+# ---- detection post-processing (SURVEY section 8 f1) -------------------------------------------------------------------
+def xyxy2xywh(x):
+    """[n, 4] corner boxes -> (centre x, centre y, width, height)."""
+    y = torch.zeros_like(x) if isinstance(x, torch.Tensor) else np.zeros_like(x)
+    y[:, 0] = (x[:, 0] + x[:, 2]) / 2
+    y[:, 1] = (x[:, 1] + x[:, 3]) / 2
+    y[:, 2] = x[:, 2] - x[:, 0]
+    y[:, 3] = x[:, 3] - x[:, 1]
+    return y
+
+
+def xywh2xyxy(x):
+    """[n, 4] (centre x, centre y, width, height) -> corner boxes."""
+    y = torch.zeros_like(x) if isinstance(x, torch.Tensor) else np.zeros_like(x)
+    y[:, 0] = x[:, 0] - x[:, 2] / 2
+    y[:, 1] = x[:, 1] - x[:, 3] / 2
+    y[:, 2] = x[:, 0] + x[:, 2] / 2
+    y[:, 3] = x[:, 1] + x[:, 3] / 2
+    return y
+
+
+def clip_coords(boxes, img_shape):
+    """Clamp corner boxes in place to an image of shape (height, width)."""
+    for col, hi in ((0, img_shape[1]), (1, img_shape[0]), (2, img_shape[1]), (3, img_shape[0])):
+        boxes[:, col].clamp_(0, hi)
+
+
+def box_iou(box1, box2):
+    """[N, 4] x [M, 4] corner boxes -> [N, M] IoU."""
+    a1 = (box1[:, 2] - box1[:, 0]) * (box1[:, 3] - box1[:, 1])
+    a2 = (box2[:, 2] - box2[:, 0]) * (box2[:, 3] - box2[:, 1])
+    inter = (torch.min(box1[:, None, 2:], box2[:, 2:]) - torch.max(box1[:, None, :2], box2[:, :2])).clamp(0).prod(2)
+    return inter / (a1[:, None] + a2 - inter)
+
+
+def non_max_suppression(prediction, conf_thres=0.1, iou_thres=0.6, multi_label=True, classes=None, agnostic=False):
+    """Batched NMS on the device with the reference's candidate order, tie-breaking and merge refinement
+    (b200yolo/detect.py -> csrc/nms.cu).  Returns a list of [n, 6] (x1, y1, x2, y2, conf, cls) tensors or None."""
+    from b200yolo import detect
+    return detect.non_max_suppression(prediction, conf_thres, iou_thres, multi_label, classes, agnostic)
