@@ -584,6 +584,56 @@ def run_infer(name, args, dev, rank, world, dd, with_e2e=True):
     return out
 
 
+def run_nms(args, dev, dd):
+    """Secondary block: non_max_suppression + TP matching of a batch of 32 x 25 200 x 85 predictions with
+    the statistics of a trained detector at test.py's conf_thres 0.001 (synthetic: ~60 objects per image, each a cluster
+    of jittered boxes, a few per cent of background rows above the threshold; random-weight predictions would make
+    every one of the 2 M (row, class) pairs a candidate, which the reference cannot process either)."""
+    from b200yolo import detect
+    B, R, nc = INFER_BATCH, 25200, 80
+    g = torch.Generator(device=dev).manual_seed(11)
+    p = torch.zeros((B, R, 5 + nc), device=dev)
+    p[..., 0:2] = torch.rand((B, R, 2), device=dev, generator=g) * SIZE
+    p[..., 2:4] = torch.exp(torch.rand((B, R, 2), device=dev, generator=g) * 4.0 + 1.0)
+    p[..., 4] = torch.rand((B, R), device=dev, generator=g) * 0.0009               # background: below conf_thres
+    p[..., 5:] = torch.rand((B, R, nc), device=dev, generator=g) * 0.001           # obj * cls stays below it
+    n_obj, per = 60, 40
+    rows = torch.stack([torch.randperm(R, device=dev, generator=g)[:n_obj * per] for _ in range(B)])
+    ctr = (torch.rand((B, n_obj, 1, 2), device=dev, generator=g) * (SIZE - 140) + 70)
+    wh = torch.exp(torch.rand((B, n_obj, 1, 2), device=dev, generator=g) * 2.5 + 2.5)
+    box = torch.cat((ctr + torch.randn((B, n_obj, per, 2), device=dev, generator=g) * 0.06 * wh,
+                     wh * torch.exp(torch.randn((B, n_obj, per, 2), device=dev, generator=g) * 0.08)), 3)
+    obj = torch.rand((B, n_obj, per), device=dev, generator=g) * 0.9 + 0.05
+    cls = torch.randint(0, nc, (B, n_obj, 1), device=dev, generator=g).expand(B, n_obj, per)
+    bi = torch.arange(B, device=dev)[:, None].expand(B, n_obj * per)
+    p[bi, rows, 0:4] = box.reshape(B, -1, 4)
+    p[bi, rows, 4] = obj.reshape(B, -1)
+    p[bi, rows, 5 + cls.reshape(B, -1)] = torch.rand((B, n_obj * per), device=dev, generator=g) * 0.7 + 0.3
+    extra = torch.rand((B, R), device=dev, generator=g) < 0.02                     # weak background detections
+    extra &= p[..., 4] < 0.001
+    p[..., 4] = torch.where(extra, torch.rand((B, R), device=dev, generator=g) * 0.05, p[..., 4])
+    ecls = torch.randint(0, nc, (B, R), device=dev, generator=g)
+    p[..., 5:].scatter_(2, ecls[..., None], torch.where(extra, 0.9, 0.0005)[..., None].to(p.dtype))
+    targets = torch.cat([torch.cat((torch.full((n_obj, 1), float(b), device=dev), cls[b, :, :1].float(),
+                                    (ctr[b, :, 0] / SIZE), (wh[b, :, 0] / SIZE)), 1) for b in range(B)])
+    iouv = torch.linspace(0.5, 0.95, 10)
+
+    def step():
+        packed = detect.nms_packed(p, conf_thres=0.001, iou_thres=0.6)
+        detect.match_batch(packed, targets, SIZE, SIZE, iouv)
+        return packed
+
+    for _ in range(3):
+        packed = step()
+    ms = timed(step, max(3, min(args.steps, 10)), dd)
+    return {"value": B / (ms / 1e3), "unit": "images/s", "ms_per_step": ms,
+            "candidates_per_image": sum(torch.diff(packed.offsets_dev).tolist()) / B,
+            "detections_per_image": sum(packed.counts) / B, "launches_per_step": 10,
+            "workload": "non_max_suppression (conf 0.001, iou 0.6, multi-label, merge) + TP matching, batch %d x %d rows x "
+                        "%d classes resident in HBM, synthetic trained-detector statistics; includes the two host reads "
+                        "of the candidate / detection counts" % (B, R, nc)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -632,6 +682,10 @@ def main():
                 secondary["%s_infer_bs%d" % (name, INFER_BATCH)] = run_infer(name, args, dev, rank, world, dd)
             except Exception as e:  # a secondary block must not take the headline down
                 secondary["%s_infer_bs%d" % (name, INFER_BATCH)] = {"error": "%s: %s" % (type(e).__name__, e)}
+        try:
+            secondary["nms_bs%d" % INFER_BATCH] = run_nms(args, dev, dd)
+        except Exception as e:
+            secondary["nms_bs%d" % INFER_BATCH] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
 
     cpu, tgpu = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

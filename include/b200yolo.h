@@ -319,6 +319,10 @@ int b2y_sgd_nesterov(float* param, const float* grad, float* momentum_buf, long 
 int b2y_sgd_nesterov_ema(float* param, const float* grad, float* momentum_buf, float* ema, long long n, float lr,
                          float momentum, float weight_decay, float grad_scale, int first_step, float ema_decay,
                          void* stream);
+/* BatchNorm-scale L1 sparsity of network slimming (prune_utils.py:133-138 BNOptimizer.updateBN, train.py:444-445):
+ * grad[off + i] += coeff * sign(param[off + i]) for every (off, len) pair of ranges_dev (int64 [n_ranges][2]) */
+int b2y_l1_subgrad_ranges(float* grad, const float* param, const long long* ranges_dev, int n_ranges, float coeff,
+                          void* stream);
 
 /* ---- bandwidth-oriented BatchNorm passes of the training step (csrc/bn_train.cu; models.py:100-113 under autograd) ----
  * save = fp32 [4][c]: batch mean, invstd, scale = gamma*invstd, shift = beta - mean*scale.

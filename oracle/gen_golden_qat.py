@@ -1,6 +1,7 @@
 """Golden fixtures for the QAT graphs: run the REFERENCE's own quantized=1 (google, shortcut_way=1) and quantized=2
 (TPSQ) models on CPU for ONE training step (forward, compute_loss, backward) and an eval forward afterwards.
-Output: tests/golden/yolov3_64_qat1.npz, tests/golden/yolov3_64_qat2.npz.   Run here only."""
+Output: tests/golden/yolov3_64_qat{1,2}.npz (+ _layers), tests/golden/yolov3-tiny_64_qat{1,2}.npz (the max-pool /
+zero-pad layers of the tiny backbone inside the QAT graphs).   Run here only."""
 import os
 import sys
 
@@ -42,9 +43,12 @@ def load_synth(qm, cfg):
     qm.load_state_dict(new)
 
 
-def run(mode, tag):
+CFGS = {"yolov3": "cfg/yolov3/yolov3.cfg", "yolov3-tiny": "cfg/yolov3tiny/yolov3-tiny.cfg"}
+
+
+def run(mode, tag, name="yolov3"):
     torch.manual_seed(0)
-    cfg = "cfg/yolov3/yolov3.cfg"
+    cfg = CFGS[name]
     qm = ref_models.Darknet(cfg, quantized=mode, a_bit=8, w_bit=8, shortcut_way=1, steps=STEPS)
     load_synth(qm, cfg)
     qm.nc, qm.gr, qm.hyp = 80, 1.0, dict(orc.DEFAULT_HYP)
@@ -55,7 +59,7 @@ def run(mode, tag):
     # module-boundary tensors of a few QAT conv layers (teacher forcing in tests/test_gpu_qat.py): input, output,
     # gradient w.r.t. the output and w.r.t. the input
     lay = {}
-    LAYERS = (5, 13, 39, 63, 81)
+    LAYERS = (5, 13, 39, 63, 81) if name == "yolov3" else ()
 
     def fwd_hook(i):
         def f(m, inp, out):
@@ -89,7 +93,8 @@ def run(mode, tag):
         for n, p_ in c.named_parameters():
             if n.endswith("scale"):
                 lay["L%d.par.%s" % (i, n)] = p_.detach().numpy().copy()
-    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "yolov3_64_%s_layers.npz" % tag), **lay)
+    if LAYERS:
+        np.savez_compressed(os.path.join(ROOT, "tests", "golden", "%s_64_%s_layers.npz" % (name, tag)), **lay)
     out = {"items": items.numpy(), "loss": loss.detach().numpy()}
     for i, pi in enumerate(pred):
         out["p%d" % i] = pi.detach().numpy()
@@ -97,6 +102,8 @@ def run(mode, tag):
     out["grad_names"] = np.array(list(named))
     out["grad_norms"] = np.array([float(p.grad.norm()) for p in named.values()], dtype=np.float64)
     keep = [k for k in named if named[k].numel() <= 1024 and k.split('.')[1] in ('0', '1', '2', '79', '80', '81')]
+    if name != "yolov3":
+        keep = [k for k in named if named[k].numel() <= 4096]
     for k in keep:
         out["grad::" + k] = named[k].grad.numpy()
     sd = qm.state_dict()
@@ -111,12 +118,15 @@ def run(mode, tag):
     with torch.no_grad():
         io, p, _ = qm(orc.synth_images(B, S, S, seed=5))
     out["eval_io"] = io.numpy()
-    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "yolov3_64_%s.npz" % tag), **out)
-    print(tag, "loss", float(loss), items.tolist(), "n scales", len(all_scales), "eval io mean", float(io.abs().mean()))
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "%s_64_%s.npz" % (name, tag)), **out)
+    print(name, tag, "loss", float(loss), items.tolist(), "n scales", len(all_scales), "eval io mean", float(io.abs().mean()))
 
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    for mode, tag in ((1, "qat1"), (2, "qat2")):
-        if len(sys.argv) < 2 or tag in sys.argv[1:]:
-            run(mode, tag)
+    names = [a for a in sys.argv[1:] if a in CFGS] or list(CFGS)
+    tags = [a for a in sys.argv[1:] if a.startswith("qat")] or ["qat1", "qat2"]
+    for name in names:
+        for mode, tag in ((1, "qat1"), (2, "qat2")):
+            if tag in tags:
+                run(mode, tag, name)

@@ -13,11 +13,11 @@ pytestmark = pytest.mark.gpu
 STEPS = 100
 
 
-def _model(mode):
+def _model(mode, name="yolov3"):
     import models
-    fm = models.Darknet(cfg_path("yolov3"))
+    fm = models.Darknet(cfg_path(name))
     sd = orc.synth_state_dict(fm.state_dict(), 0)
-    qm = models.Darknet(cfg_path("yolov3"), quantized=mode, a_bit=8, w_bit=8, shortcut_way=1, steps=STEPS)
+    qm = models.Darknet(cfg_path(name), quantized=mode, a_bit=8, w_bit=8, shortcut_way=1, steps=STEPS)
     with torch.no_grad():
         for i, m in enumerate(qm.module_list):
             pre = 'module_list.%d.' % i
@@ -32,11 +32,14 @@ def _model(mode):
     return attach_hyp(qm.cuda())
 
 
-@pytest.mark.parametrize("mode,tag", [(1, "qat1"), (2, "qat2")])
-def test_qat_training_step_and_eval_match_reference(mode, tag):
+@pytest.mark.parametrize("name,mode,tag", [("yolov3", 1, "qat1"), ("yolov3", 2, "qat2"),
+                                           ("yolov3-tiny", 1, "qat1"), ("yolov3-tiny", 2, "qat2")])
+def test_qat_training_step_and_eval_match_reference(name, mode, tag):
+    """yolov3: 75 QAT conv layers with quantised shortcuts / concats; yolov3-tiny: the max-pool (and zero-pad + max-pool)
+    layers inside the QAT graphs (models.py:207-215)."""
     from utils import utils as my_utils
-    g = golden("yolov3_64_%s" % tag)
-    qm = _model(mode).train()
+    g = golden("%s_64_%s" % (name, tag))
+    qm = _model(mode, name).train()
     x = orc.synth_images(2, 64, 64, seed=0).cuda()
     t = orc.synth_targets(2, 6, 80, seed=1).cuda()
     pred, _ = qm(x)
@@ -63,6 +66,7 @@ def test_qat_training_step_and_eval_match_reference(mode, tag):
         if k.startswith("state::") and k.endswith(("running_mean", "running_var")):
             r = torch.from_numpy(g[k])
             stat = max(stat, float((sd[k[7:]].cpu() - r).abs().max() / r.abs().max().clamp(min=1e-6)))
+    tag = "%s %s" % (name, tag)
     print("\n[%s train step vs reference] loss items rel %.3g | p abs %.3g rms %.3g | grad-norm rel median %.3g worst %.3g "
           "(%d params without grad) | scales differing %d of %d %s | running stats rel %.3g"
           % (tag, items_rel, p_abs, p_rms, np.median(rel), rel.max(), len(missing), len(diff), len(sn), diff[:3], stat))

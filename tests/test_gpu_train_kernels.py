@@ -396,3 +396,44 @@ def test_fused_sgd_ema_matches_torch_and_model_ema():
         ops.sgd_nesterov(pc, gr.cuda(), buf, 0.01, 0.937, 5e-4, first_step=(step == 1), ema=ema, ema_decay=d)
     np.testing.assert_allclose(pc.cpu().numpy(), pt.detach().numpy(), rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(ema.cpu().numpy(), ema_ref.numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_bn_l1_sparsity_matches_update_bn():
+    """BNOptimizer.updateBN (prune_utils.py:133-138, train.py:444-445) as one launch over a range table of
+    the flat buffers, and through FlatDataParallel.set_bn_sparsity + step() on the real yolov3-tiny module tree."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(3)
+    n = 5000
+    p = torch.randn(n, generator=g)
+    p[::17] = 0.0                                           # torch.sign(0) == 0
+    gr = torch.randn(n, generator=g)
+    ranges = torch.tensor([[0, 32], [100, 1000], [4093, 907], [2000, 1]], dtype=torch.int64)
+    want = gr.clone()
+    for off, ln in ranges.tolist():
+        want[off:off + ln] += 0.01 * torch.sign(p[off:off + ln])
+    gc = gr.clone().cuda()
+    ops.l1_subgrad_ranges(gc, p.cuda(), ranges.cuda(), 0.01)
+    assert torch.equal(gc.cpu(), want)
+
+    from b200yolo.parallel import FlatDataParallel
+    from helpers import build_model
+    model = build_model("yolov3-tiny", device="cuda").train()
+    ref = {n_: q.detach().clone().cpu() for n_, q in model.named_parameters()}
+    dp = FlatDataParallel(model)
+    prune_idx = [0, 2, 4, 6]
+    s = 0.001
+    dp.set_bn_sparsity(prune_idx, s)
+    grads = {}
+    for n_, q in model.named_parameters():
+        grads[n_] = torch.randn(q.shape, generator=g) * 0.01
+        q.grad.copy_(grads[n_].cuda())                      # views of the flat gradient buffer
+    dp.step(lr=0.01, momentum=0.937, weight_decay=0.000484)
+    bn_names = {"module_list.%d.BatchNorm2d.weight" % i for i in prune_idx}
+    for n_, q in model.named_parameters():
+        gref = grads[n_].clone()
+        if n_ in bn_names:
+            gref += s * torch.sign(ref[n_])
+        wd = 0.000484 if ("Conv2d.weight" in n_ and ".bias" not in n_) else 0.0
+        gref = gref + wd * ref[n_]
+        want_p = ref[n_] - 0.01 * (gref + 0.937 * gref)     # first Nesterov step: buf = g
+        np.testing.assert_allclose(q.detach().cpu().numpy(), want_p.numpy(), rtol=1e-5, atol=1e-7, err_msg=n_)

@@ -496,6 +496,14 @@ def sgd_nesterov(param, grad, buf, lr, momentum, weight_decay, grad_scale=1.0, f
          float(weight_decay), float(grad_scale), 1 if first_step else 0, stream_ptr())
 
 
+def l1_subgrad_ranges(grad, param, ranges, coeff):
+    """grad[off:off+len] += coeff * sign(param[off:off+len]) for each row (off, len) of the int64 device table `ranges`
+    (BNOptimizer.updateBN, prune_utils.py:133-138)."""
+    _require_cuda(grad, param, ranges)
+    assert ranges.dtype == torch.int64 and ranges.dim() == 2 and ranges.shape[1] == 2 and ranges.is_contiguous()
+    call("b2y_l1_subgrad_ranges", ptr(grad), ptr(param), ptr(ranges), int(ranges.shape[0]), float(coeff), stream_ptr())
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # quantisation kernels
 # ---------------------------------------------------------------------------------------------------------------

@@ -133,6 +133,22 @@ class FlatDataParallel:
             off += b.numel()
         return out
 
+    def set_bn_sparsity(self, prune_idx, s):
+        """Network-slimming sparsity training (train.py -sr --s, :444-445; prune_utils.py:133-138 BNOptimizer.updateBN):
+        from now on step() adds s * sign(gamma) to the (averaged) gradient of the BatchNorm scale of every
+        module_list[idx] in prune_idx -- one launch over a range table of the flat buffers, before the fused optimiser.
+        s = 0 or an empty list switches it off."""
+        offsets, off = {}, 0
+        for p in self.params:
+            offsets[id(p)] = off
+            off += p.numel()
+        rows = []
+        for idx in (prune_idx if s else []):
+            bn = self.module.module_list[idx][1]
+            rows.append((offsets[id(bn.weight)], bn.weight.numel()))
+        self._l1 = (torch.tensor(rows, dtype=torch.int64, device=self.flat_param.device).reshape(-1, 2).contiguous(),
+                    float(s)) if rows else None
+
     def step(self, lr, momentum=0.937, weight_decay=0.000484, nesterov=True):
         """Fused SGD-Nesterov (+ EMA when enabled) over the flat buffers (two launches: decayed conv weights, the rest)."""
         from . import ops
@@ -145,6 +161,10 @@ class FlatDataParallel:
         if ema is not None:
             self.ema_updates += 1
             d = self._ema_decay(self.ema_updates)
+        l1 = getattr(self, '_l1', None)
+        if l1 is not None:
+            # updateBN runs after DDP has averaged the gradients: s * sign(w) is NOT divided by world -> pre-multiply
+            ops.l1_subgrad_ranges(self.flat_grad, self.flat_param, l1[0], l1[1] / gs)
         if nd:
             ops.sgd_nesterov(self.flat_param[:nd], self.flat_grad[:nd], self.flat_mom[:nd], lr, momentum, weight_decay,
                              grad_scale=gs, first_step=first, ema=ema[:nd] if ema is not None else None, ema_decay=d)

@@ -244,6 +244,10 @@ class QatRunner:
             elif t == 'upsample':
                 s = int(d['stride'])
                 h = h.repeat_interleave(s, dim=1).repeat_interleave(s, dim=2)
+            elif t == 'maxpool':
+                # plain nn.MaxPool2d (+ ZeroPad2d for the tiny k=2 s=1 variant) in the reference's QAT graphs as well
+                # (models.py:207-215): values already sit on the producer's grid and pass through unchanged
+                h = m(h.permute(0, 3, 1, 2)).permute(0, 2, 3, 1).contiguous()
             elif t == 'yolo':
                 B, ny, nx, _ = h.shape
                 m.nx, m.ny = nx, ny

@@ -570,6 +570,28 @@ extern "C" int b2y_sgd_nesterov_ema(float* param, const float* grad, float* mome
     return B2Y_OK;
 }
 
+// Network-slimming sparsity term of the BatchNorm scales (prune_utils.py:133-138, BNOptimizer.updateBN, called between
+// backward and optimizer.step at train.py:444-445): grad += coeff * sign(w) on a table of [offset, length] ranges of
+// the flat buffers.  One CTA per range (a BatchNorm layer: 32 .. 1024 scales).
+__global__ void l1_subgrad_ranges_kernel(float* __restrict__ g, const float* __restrict__ p,
+                                         const long long* __restrict__ ranges, float coeff) {
+    const long long off = ranges[2 * blockIdx.x], len = ranges[2 * blockIdx.x + 1];
+    for (long long i = threadIdx.x; i < len; i += blockDim.x) {
+        const float w = p[off + i];
+        const float sgn = (float)((w > 0.f) - (w < 0.f));           // torch.sign: 0 at 0
+        g[off + i] = fmaf(coeff, sgn, g[off + i]);
+    }
+}
+
+extern "C" int b2y_l1_subgrad_ranges(float* grad, const float* param, const long long* ranges_dev, int n_ranges,
+                                     float coeff, void* stream) {
+    if (!grad || !param || n_ranges < 0 || (n_ranges > 0 && !ranges_dev)) return B2Y_ERR_INVALID;
+    if (n_ranges == 0) return B2Y_OK;
+    l1_subgrad_ranges_kernel<<<n_ranges, 128, 0, static_cast<cudaStream_t>(stream)>>>(grad, param, ranges_dev, coeff);
+    B2Y_CUDA_CHECK(cudaGetLastError());
+    return B2Y_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // backward of the data-movement layers (gradients are NHWC fp16, accumulated in place)
 // ------------------------------------------------------------------------------------------------
