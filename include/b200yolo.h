@@ -422,6 +422,20 @@ int b2y_tp_match(float* det, const int* det_off, const int* det_count, long long
                  float clip_w, float clip_h, void* workspace, size_t workspace_bytes, unsigned char* correct,
                  void* stream);
 
+/* ---- knowledge-distillation losses of the YOLO head (csrc/kd.cu; utils/utils.py:435-520 compute_lost_KD / KD2 / KD3) ----
+ * soft targets: loss_acc[0] += sum over rows of KL(softmax(teacher / T) || softmax(student / T)) over `width` columns
+ * starting at col0 of rows of row_len floats; dstudent (NULL or same shape as student) receives
+ * (softmax(student / T) - softmax(teacher / T)) * grad_scale / T in those columns (other columns untouched). */
+int b2y_kd_soft_rows(const float* student, const float* teacher, long long rows, int row_len, int col0, int width,
+                     float temperature, float grad_scale, double* loss_acc, float* dstudent, void* stream);
+/* box term on the n matched cells of b2y_build_targets (idx int64 [4][n] = image, anchor, gy, gx; tbox fp32 [n][4];
+ * anchor_vec fp32 [na][2]; student / teacher fp32 [batch][na][ny][nx][no]).  mode 2 (KD2): squared distance to the
+ * target box where it exceeds the teacher's (+ reg_m), reg_num counts those cells; mode 3 (KD3..5): squared distance to
+ * the teacher's box.  loss_acc[0] += the sum; dstudent[cell][0..3] += gradient * grad_scale (atomic: duplicate cells add). */
+int b2y_kd_box(const float* student, const float* teacher, const long long* idx, const float* tbox,
+               const float* anchor_vec, int n, int na, int ny, int nx, int no, int mode, float reg_m, float grad_scale,
+               double* loss_acc, int* reg_num, float* dstudent, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -200,3 +200,34 @@ def test_reference_entry_point_and_cpu_tensor():
     assert _compare(out, want, "entry") <= MERGE_RTOL
     with pytest.raises(lib.B2YError):
         my_utils.non_max_suppression(pred)
+
+
+def test_map_through_the_device_pipeline_matches_reference():
+    """BASELINE north_star (mAP on a held batch within 1e-4 of the reference) with EVERYTHING on the device: engine forward
+    in the fp32-accurate mode -> csrc/nms.cu NMS -> clip + TP matching kernel; only the AP bookkeeping (ap_per_class,
+    numpy in the reference too, utils.py:162-251) runs on the host."""
+    from b200yolo import detect
+    from helpers import build_model, orc
+    g = golden("map_case")
+    S, B = int(g["size"]), g["inf_out"].shape[0]
+    model = build_model("yolov3-tiny", device="cuda").eval()
+    model.accurate = True
+    x = orc.synth_images(B, S, S, seed=int(g["seed"]))
+    with torch.no_grad():
+        io, _, _ = model(x.cuda())
+    packed = detect.nms_packed(io, conf_thres=0.3, iou_thres=0.6)
+    labels = [torch.from_numpy(g["labels%d" % i]) for i in range(B)]
+    tcls = torch.cat([lab[:, 0] for lab in labels])
+    tbox = torch.cat([lab[:, 1:5] for lab in labels])
+    lab_off = torch.tensor([0] + list(np.cumsum([lab.shape[0] for lab in labels])), dtype=torch.int32)
+    correct = detect.match_labels(packed, tcls, tbox, lab_off, mo.IOU_THRESHOLDS, S, S)
+    dets = packed.to_list()
+    stats = [(correct[b].cpu().numpy(), dets[b][:, 4].cpu().numpy(), dets[b][:, 5].cpu().numpy(),
+              labels[b][:, 0].numpy()) for b in range(B) if dets[b] is not None]
+    cols = [np.concatenate(c, 0) for c in zip(*stats)]
+    _, _, ap, _ = mo.ap_per_class(*cols)
+    m50, m = float(ap[:, 0].mean()), float(ap.mean(1).mean())
+    r50, r = float(g["map50"]), float(g["map"])
+    print("\n[mAP, device pipeline] reference %.6f / %.6f | device %.6f / %.6f (%d detections)"
+          % (r50, r, m50, m, cols[0].shape[0]))
+    assert abs(m50 - r50) <= 1e-4 and abs(m - r) <= 1e-4

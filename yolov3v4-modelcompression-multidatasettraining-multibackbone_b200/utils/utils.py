@@ -6,6 +6,7 @@
     FocalLoss / smooth_BCE            reference utils/utils.py:333-365
     non_max_suppression(...)          reference utils/utils.py:782-860   (csrc/nms.cu, whole batch on the device)
     xywh2xyxy / xyxy2xywh / box_iou / clip_coords   reference utils/utils.py:118-159, 300-322 (tensor helpers)
+    compute_lost_KD / KD2 / KD3       reference utils/utils.py:435-520   (csrc/kd.cu)
 
 Everything else of the reference's utils/utils.py (AP, plotting, KD losses, dataset helpers) is outside the
 accelerated hot path; with B2Y_REFERENCE_ROOT set those names are re-exported from the reference's own file so
@@ -284,3 +285,19 @@ def non_max_suppression(prediction, conf_thres=0.1, iou_thres=0.6, multi_label=T
     (b200yolo/detect.py -> csrc/nms.cu).  Returns a list of [n, 6] (x1, y1, x2, y2, conf, cls) tensors or None."""
     from b200yolo import detect
     return detect.non_max_suppression(prediction, conf_thres, iou_thres, multi_label, classes, agnostic)
+
+
+# ---- knowledge distillation (SURVEY section 8 f4) ------------------------------------------------------------------------
+def compute_lost_KD(output_s, output_t, num_classes, batch_size):
+    from b200yolo import kd
+    return kd.compute_lost_KD(output_s, output_t, num_classes, batch_size)
+
+
+def compute_lost_KD2(model, targets, output_s, output_t):
+    from b200yolo import kd
+    return kd.compute_lost_KD2(model, targets, output_s, output_t)
+
+
+def compute_lost_KD3(model, targets, output_s, output_t):
+    from b200yolo import kd
+    return kd.compute_lost_KD3(model, targets, output_s, output_t)
