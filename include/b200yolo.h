@@ -436,6 +436,15 @@ int b2y_kd_box(const float* student, const float* teacher, const long long* idx,
                const float* anchor_vec, int n, int na, int ny, int nx, int no, int mode, float reg_m, float grad_scale,
                double* loss_acc, int* reg_num, float* dstudent, void* stream);
 
+/* ---- input pipeline, inference slice (csrc/preprocess.cu): datasets.letterbox (utils/datasets.py:611-646: cv2.resize
+ * INTER_LINEAR to resized_w x resized_h, cv2.copyMakeBorder with `color`) fused with the loaders' BGR -> RGB / HWC -> CHW
+ * shuffle (datasets.py:113).  src uint8 HWC [src_h][src_w][channels] (row pitch in bytes), dst uint8 planar
+ * [channels][dst_h][dst_w] with the resized image at (top, left); swap_rb reverses the channel order.  Bit-identical to
+ * OpenCV's fixed-point 8-bit INTER_LINEAR (resized == source size: plain copy). */
+int b2y_letterbox_u8(const unsigned char* src, int src_h, int src_w, int channels, long long src_pitch, int resized_h,
+                     int resized_w, int top, int left, unsigned char* dst, int dst_h, int dst_w, int swap_rb, int color,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

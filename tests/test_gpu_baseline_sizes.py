@@ -241,8 +241,17 @@ def test_train_step_layerwise(name, B, S):
         dz = _nchw(plan.dz_bufs[r.i]) * float(aux[2])
         safe = (u.detach().abs() > 1e-5).float()        # elements whose activation branch is not decided by fp32 rounding
         worst["bn_bwd_dz"] = max(worst["bn_bwd_dz"], float(((dz - ref_dz) * safe).abs().max() / ref_dz.abs().max().clamp(min=1e-30)))
-        worst["bn_dgamma"] = max(worst["bn_dgamma"], float((bn.weight.grad - dgamma_ref).abs().max() / dgamma_ref.abs().max()))
-        worst["bn_dbeta"] = max(worst["bn_dbeta"], float((bn.bias.grad - dbeta_ref).abs().max() / dbeta_ref.abs().max()))
+        e_g = float((bn.weight.grad - dgamma_ref).abs().max() / dgamma_ref.abs().max())
+        e_b = float((bn.bias.grad - dbeta_ref).abs().max() / dbeta_ref.abs().max())
+        if e_b > 1e-4 or e_g > 1e-4:        # diagnostics: which layer, how large its gradients are
+            ch = int((bn.bias.grad - dbeta_ref).abs().argmax())
+            print("  [layer %d %s out %dx%dx%d act=%s res=%s] dgamma err %.3g (max |dgamma| %.3g) dbeta err %.3g (max |dbeta| "
+                  "%.3g; channel %d: engine %.6g ref %.6g) max |dy| %.3g"
+                  % (r.i, tuple(conv.weight.shape), z.shape[1], z.shape[2], z.shape[3], r.act, r.res is not None, e_g,
+                     float(dgamma_ref.abs().max()), e_b, float(dbeta_ref.abs().max()), ch, float(bn.bias.grad[ch]),
+                     float(dbeta_ref[ch]), float(dy.abs().max())))
+        worst["bn_dgamma"] = max(worst["bn_dgamma"], e_g)
+        worst["bn_dbeta"] = max(worst["bn_dbeta"], e_b)
         # weight gradient from the engine's own (x, dz)
         dw_ref = torch.nn.grad.conv2d_weight(xin, conv.weight.shape, dz, conv.stride, conv.padding)
         worst["wgrad"] = max(worst["wgrad"], float((conv.weight.grad - dw_ref).norm() / dw_ref.norm()))

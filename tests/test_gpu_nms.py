@@ -187,7 +187,7 @@ def test_tp_matching_matches_oracle():
         want = mo.match_image(dets[b].cpu(), labels[b])                            # same boxes in: bit-exact out
         assert torch.equal(correct[b].cpu(), want), "TP matrix of image %d differs" % b
         n_tp += int(want[:, 0].sum())
-    assert n_tp > 50, "degenerate case"
+    assert n_tp > 20, "degenerate case"           # measured: 41 true positives at IoU 0.5
 
 
 def test_reference_entry_point_and_cpu_tensor():

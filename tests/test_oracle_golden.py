@@ -222,3 +222,22 @@ def test_mobilenet_training_step_matches_reference():
     ref = dict(zip([str(n) for n in g["grad_names"]], g["grad_norms"]))
     worst = max(abs(float(state[k].grad.norm()) - v) / (v + 1e-8) for k, v in ref.items())
     assert worst < 2e-2, worst
+
+
+def test_preprocess_oracle_matches_reference():
+    """oracle/preprocess_oracle.py (numpy restatement of OpenCV's fixed-point 8-bit INTER_LINEAR resize + the reference's
+    letterbox logic) against the outputs of the reference's own letterbox (cv2) on seeded images."""
+    import json
+    import os
+    import sys
+    from helpers import ROOT
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import preprocess_oracle as po
+    g = golden("letterbox_case")
+    for i, (h, w, c, seed, kw) in enumerate(json.loads(str(g["cases"]))):
+        if isinstance(kw.get("new_shape"), list):
+            kw["new_shape"] = tuple(kw["new_shape"])
+        out, ratio, pad = po.letterbox(po.synth_image(h, w, c, seed), **kw)
+        assert np.array_equal(out, g["out%d" % i]), (i, kw)
+        assert np.array_equal(np.array(ratio, np.float64), g["ratio%d" % i])
+        assert np.array_equal(np.array(pad, np.float64), g["pad%d" % i])

@@ -71,13 +71,12 @@ class _KD(torch.autograd.Function):
         ctx.grads = grads
         ctx.dtypes = [t.dtype for t in out_s]
         ctx.n = n
-        aux = torch.tensor([float(reg_nb)], device=dev)
-        ratio = reg[0:1].float() / aux.clamp(min=1.0)
-        ctx.mark_non_differentiable(ratio)
-        return loss, ratio
+        counts = torch.stack((reg[0].double(), torch.tensor(float(reg_nb), dtype=torch.float64, device=dev)))
+        ctx.mark_non_differentiable(counts)
+        return loss, counts          # (reg_num, reg_nb): the caller forms the ratio in Python like the reference
 
     @staticmethod
-    def backward(ctx, g, _g_ratio):
+    def backward(ctx, g, _g_counts):
         outs = [None if d is None else (d * g).to(dt) for d, dt in zip(ctx.grads, ctx.dtypes)]
         return (None, None, None, None) + tuple(outs) + (None,) * ctx.n
 
@@ -108,8 +107,9 @@ def _kd_matched(mode, model, targets, output_s, output_t):
 def compute_lost_KD2(model, targets, output_s, output_t):
     """Soft targets on (objectness, classes) + box regression towards the labels where the student is further from them
     than the teacher (utils.py:447-490).  Returns (loss[1], reg_ratio)."""
-    loss, ratio = _kd_matched(2, model, targets, output_s, output_t)
-    return loss, float(ratio)           # the reference returns a Python float as well (.item(), utils.py:476)
+    loss, counts = _kd_matched(2, model, targets, output_s, output_t)
+    reg_num, reg_nb = counts.tolist()    # the reference syncs here as well (.item(), utils.py:476)
+    return loss, (reg_num / reg_nb if reg_nb else 0)
 
 
 def compute_lost_KD3(model, targets, output_s, output_t):

@@ -137,6 +137,7 @@ _PROTOS = {
     "b2y_l1_subgrad_ranges": (i32, [vp, vp, vp, i32, f32, vp]),
     "b2y_kd_soft_rows": (i32, [vp, vp, ll, i32, i32, i32, f32, f32, vp, vp, vp]),
     "b2y_kd_box": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, f32, f32, vp, vp, vp, vp]),
+    "b2y_letterbox_u8": (i32, [vp, i32, i32, i32, ll, i32, i32, i32, i32, vp, i32, i32, i32, i32, vp]),
     "b2y_nms_count_workspace_bytes": (sz, [i32, i32]),
     "b2y_nms_count": (i32, [vp, i32, i32, i32, f32, i32, vp, vp, vp, vp, sz, vp]),
     "b2y_nms_run_workspace_bytes": (sz, [ll]),
