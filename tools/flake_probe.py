@@ -1,0 +1,71 @@
+"""Diagnostic: repeat the yolov4 8x640x640 training step and compare every BatchNorm layer's dbeta / dgamma with sums
+recomputed from the engine's own dy and z (the layer-wise gate of tests/test_gpu_baseline_sizes.py, reduced to the BN
+parameter gradients).  Environment knobs are read once per process, so run one process per configuration:
+
+    B2Y_PDL=0 python tools/flake_probe.py 4
+"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import torch  # noqa: E402
+
+from helpers import attach_hyp, build_model, orc  # noqa: E402
+
+
+def nchw(t):
+    return t.float().permute(0, 3, 1, 2).contiguous()
+
+
+def one(it, graph):
+    from utils import utils as my_utils
+    model = attach_hyp(build_model("yolov4", device="cuda")).train()
+    model.use_cuda_graph = graph
+    x = orc.synth_images(8, 640, 640, seed=0).cuda()
+    t = orc.synth_targets(8, 8, 80, seed=1).cuda()
+    steps = 3 if graph else 1
+    for _ in range(steps):
+        for p in model.parameters():
+            p.grad = None
+        pred, _ = model(x)
+        loss, _ = my_utils.compute_loss(pred, t, model)
+        loss.backward()
+    torch.cuda.synchronize()
+    plan = model.engine().last_plan
+    worst = (0.0, None)
+    bad = []
+    for r in plan.convs:
+        bn = r.bn
+        if r.stem or bn is None:
+            continue
+        z = nchw(r.z.view())
+        mean_e, invstd_e = r.save[0].view(1, -1, 1, 1), r.save[1].view(1, -1, 1, 1)
+        gam, bet = bn.weight.detach().float().view(1, -1, 1, 1), bn.bias.detach().float().view(1, -1, 1, 1)
+        xhat = (z - mean_e) * invstd_e
+        u = (xhat * gam + bet).requires_grad_(True)
+        yr = orc.activation(u, r.act, r.slope)
+        dy = nchw(plan.grad_of[id(r.y)].view())
+        du, = torch.autograd.grad(yr, u, dy)
+        dbeta = du.sum(dim=(0, 2, 3))
+        dgamma = (du * xhat).sum(dim=(0, 2, 3))
+        eb = float((bn.bias.grad - dbeta).abs().max() / dbeta.abs().max())
+        eg = float((bn.weight.grad - dgamma).abs().max() / dgamma.abs().max())
+        if eb > 1e-4 or eg > 1e-4:
+            bad.append((r.i, r.act, tuple(z.shape[1:]), "%.2g" % eb, "%.2g" % eg))
+        if eb > worst[0]:
+            worst = (eb, r.i)
+        del z, xhat, u, yr, dy, du
+    print("iter %d graph=%s: worst dbeta err %.3g (layer %s); layers above 1e-4: %s" % (it, graph, worst[0], worst[1], bad),
+          flush=True)
+    del model
+    torch.cuda.empty_cache()
+
+
+if __name__ == "__main__":
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+    graph = len(sys.argv) > 2 and sys.argv[2] == "graph"
+    knobs = {k: v for k, v in os.environ.items() if k.startswith("B2Y_")}
+    print("knobs", knobs, flush=True)
+    for i in range(n):
+        one(i, graph)
