@@ -37,7 +37,7 @@ def one(it, graph):
     bad = []
     for r in plan.convs:
         bn = r.bn
-        if r.stem or bn is None:
+        if r.stem or bn is None or r.y.H > 80:        # the small maps (short kernels) are where the timing is tight
             continue
         z = nchw(r.z.view())
         mean_e, invstd_e = r.save[0].view(1, -1, 1, 1), r.save[1].view(1, -1, 1, 1)
