@@ -241,13 +241,24 @@ def test_train_step_layerwise(name, B, S):
         dz = _nchw(plan.dz_bufs[r.i]) * float(aux[2])
         safe = (u.detach().abs() > 1e-5).float()        # elements whose activation branch is not decided by fp32 rounding
         worst["bn_bwd_dz"] = max(worst["bn_bwd_dz"], float(((dz - ref_dz) * safe).abs().max() / ref_dz.abs().max().clamp(min=1e-30)))
-        e_g = float((bn.weight.grad - dgamma_ref).abs().max() / dgamma_ref.abs().max())
-        e_b = float((bn.bias.grad - dbeta_ref).abs().max() / dbeta_ref.abs().max())
+        # Elements sitting on the kink of a piecewise-linear activation (|u| below fp32 rounding: the engine forms
+        # u = fma(z, gamma*invstd, beta - mean*gamma*invstd), this reference ((z - mean)*invstd)*gamma + beta) take the
+        # other branch in one of the two computations; ONE such element moves a channel's dbeta by up to |dy| -- 1e-2 of
+        # the layer maximum on the 20x20 / 40x40 maps -- and which elements they are changes from run to run with the
+        # summation order of the batch statistics (atomics).  Their worst-case contribution is therefore subtracted per
+        # channel before the comparison (measured with tools/flake_probe.py: leaky layers only, 1e-3..3e-2 in ~1/3 of
+        # the runs, never on the smooth Mish layers); everything else must agree to fp32 summation order.
+        amb = (u.detach().abs() <= 1e-5).float()
+        slack_b = (amb * dy.abs()).sum(dim=(0, 2, 3))
+        slack_g = (amb * (dy * xhat).abs()).sum(dim=(0, 2, 3))
+        e_g = float(((bn.weight.grad - dgamma_ref).abs() - slack_g).clamp(min=0).max() / dgamma_ref.abs().max())
+        e_b = float(((bn.bias.grad - dbeta_ref).abs() - slack_b).clamp(min=0).max() / dbeta_ref.abs().max())
         if e_b > 1e-4 or e_g > 1e-4:        # diagnostics: which layer, how large its gradients are
             ch = int((bn.bias.grad - dbeta_ref).abs().argmax())
-            print("  [layer %d %s out %dx%dx%d act=%s res=%s] dgamma err %.3g (max |dgamma| %.3g) dbeta err %.3g (max |dbeta| "
+            print("  [layer %d %s out %dx%dx%d act=%s res=%s, %d elements on the kink] dgamma err %.3g (max |dgamma| %.3g) dbeta err %.3g (max |dbeta| "
                   "%.3g; channel %d: engine %.6g ref %.6g) max |dy| %.3g"
-                  % (r.i, tuple(conv.weight.shape), z.shape[1], z.shape[2], z.shape[3], r.act, r.res is not None, e_g,
+                  % (r.i, tuple(conv.weight.shape), z.shape[1], z.shape[2], z.shape[3], r.act, r.res is not None,
+                     int(amb.sum()), e_g,
                      float(dgamma_ref.abs().max()), e_b, float(dbeta_ref.abs().max()), ch, float(bn.bias.grad[ch]),
                      float(dbeta_ref[ch]), float(dy.abs().max())))
         worst["bn_dgamma"] = max(worst["bn_dgamma"], e_g)
