@@ -3,7 +3,7 @@
 // torchvision NMS with its stable score sort and double-precision threshold compare, 'merge' box refinement) and the
 // per-image true-positive matching loop of test.py:150-170.  HBM / latency bound integer + fp32 work: no tensor cores.
 //
-//   rows pass (count)  : one warp per prediction row -> number of candidates of the row
+//   rows pass (count)  : one warp per 32 prediction rows (a lane per row header) -> number of candidates of every row
 //   cub exclusive scan : candidate offsets = the order nonzero() enumerates them (row-major, class ascending)
 //   rows pass (emit)   : candidates (xyxy, conf, class) + 64-bit sort keys (image | descending score)
 //   cub radix sort     : stable, so equal scores keep ascending candidate order = torch's stable descending sort
@@ -49,13 +49,33 @@ __device__ __forceinline__ float box_iou(float4 a, float aarea, float4 b, float 
     const float inter = __fmul_rn(w, h);
     return __fdiv_rn(inter, __fsub_rn(__fadd_rn(aarea, barea), inter));
 }
+// `IoU > threshold` without the division when the boxes do not intersect: w == 0 or h == 0 gives inter = +0, so the
+// quotient is +-0 or NaN and the comparison is false for every threshold >= 0 -- the result is bit-identical to evaluating
+// the quotient (callers pass nonneg = threshold >= 0; otherwise the quotient is always formed).
+__device__ __forceinline__ bool iou_gt_d(float4 a, float aarea, float4 b, float barea, double thr, bool nonneg) {
+    const float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y), xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
+    const float w = fmaxf(0.f, __fsub_rn(xx2, xx1)), h = fmaxf(0.f, __fsub_rn(yy2, yy1));
+    if (nonneg && (w == 0.f || h == 0.f)) return false;
+    const float inter = __fmul_rn(w, h);
+    return (double)__fdiv_rn(inter, __fsub_rn(__fadd_rn(aarea, barea), inter)) > thr;     // torchvision: double threshold
+}
+__device__ __forceinline__ bool iou_gt_f(float4 a, float aarea, float4 b, float barea, float thr, bool nonneg) {
+    const float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y), xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
+    const float w = fmaxf(0.f, __fsub_rn(xx2, xx1)), h = fmaxf(0.f, __fsub_rn(yy2, yy1));
+    if (nonneg && (w == 0.f || h == 0.f)) return false;
+    const float inter = __fmul_rn(w, h);
+    return __fdiv_rn(inter, __fsub_rn(__fadd_rn(aarea, barea), inter)) > thr;             // torch: scalar cast to fp32
+}
 __device__ __forceinline__ float4 shift_box(float4 b, float cls, int agnostic) {
     const float o = agnostic ? 0.f : __fmul_rn(cls, kMaxWH);        // boxes + c * max_wh (utils.py:840-841)
     return make_float4(__fadd_rn(b.x, o), __fadd_rn(b.y, o), __fadd_rn(b.z, o), __fadd_rn(b.w, o));
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// One warp per prediction row.  EMIT = false: counts[row] = number of candidates.  EMIT = true: write them.
+// One warp per 32 consecutive prediction rows: every lane loads the 5-float header of its own row (32 rows in flight per
+// warp instead of one), the rows that pass the confidence / size filters -- a few per cent for a trained detector -- are
+// then expanded one after the other by the whole warp.  EMIT = false: counts[row] = number of candidates of the row.
+// EMIT = true: the candidates are written at row_off[row] in class order.
 template <bool EMIT>
 __global__ void nms_rows_kernel(const float* __restrict__ pred, long long rows, int R, int nc, float conf_thres,
                                 int multi_label, const unsigned char* __restrict__ allow, int* __restrict__ counts,
@@ -63,74 +83,84 @@ __global__ void nms_rows_kernel(const float* __restrict__ pred, long long rows, 
                                 float* __restrict__ cand_conf, float* __restrict__ cand_cls,
                                 unsigned long long* __restrict__ keys, unsigned* __restrict__ vals) {
     const int lane = threadIdx.x & 31;
-    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= rows) return;
-    const float* x = pred + row * (long long)(5 + nc);
-    const float v = lane < 5 ? x[lane] : 0.f;
-    const float cx = __shfl_sync(~0u, v, 0), cy = __shfl_sync(~0u, v, 1), w = __shfl_sync(~0u, v, 2),
-                h = __shfl_sync(~0u, v, 3), obj = __shfl_sync(~0u, v, 4);
-    // x[:, 4] > conf_thres, then ((x[:, 2:4] > min_wh) & (x[:, 2:4] < max_wh)).all(1)     (utils.py:799-802)
-    const bool ok = obj > conf_thres && w > kMinWH && w < kMaxWH && h > kMinWH && h < kMaxWH;
-    if (!ok) {
-        if (!EMIT && lane == 0) counts[row] = 0;
-        return;
+    const long long row0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32;
+    if (row0 >= rows) return;
+    const long long my_row = row0 + lane;
+    const int no = 5 + nc;
+    float h0 = 0.f, h1 = 0.f, h2 = 0.f, h3 = 0.f, h4 = 0.f;
+    bool my_ok = false;
+    if (my_row < rows) {
+        const float* hx = pred + my_row * (long long)no;
+        h0 = hx[0]; h1 = hx[1]; h2 = hx[2]; h3 = hx[3]; h4 = hx[4];
+        // x[:, 4] > conf_thres, then ((x[:, 2:4] > min_wh) & (x[:, 2:4] < max_wh)).all(1)     (utils.py:799-802)
+        my_ok = h4 > conf_thres && h2 > kMinWH && h2 < kMaxWH && h3 > kMinWH && h3 < kMaxWH;
+        if (!EMIT && !my_ok) counts[my_row] = 0;
     }
-    // xywh2xyxy (utils.py:138-146)
-    const float hw = __fmul_rn(w, 0.5f), hh = __fmul_rn(h, 0.5f);
-    const float4 box = make_float4(__fsub_rn(cx, hw), __fsub_rn(cy, hh), __fadd_rn(cx, hw), __fadd_rn(cy, hh));
-    const bool box_ok = is_finite(box.x) && is_finite(box.y) && is_finite(box.z) && is_finite(box.w);
-    const unsigned long long img = (unsigned long long)(row / R);
-    const int base = EMIT ? row_off[row] : 0;
-    int n = 0;
-    if (multi_label) {
-        // (x[:, 5:] * obj > conf_thres).nonzero(): classes in ascending order within the row (utils.py:816-818)
-        for (int c0 = 0; c0 < nc; c0 += 32) {
-            const int c = c0 + lane;
-            float conf = 0.f;
-            bool take = false;
-            if (c < nc) {
-                conf = __fmul_rn(x[5 + c], obj);
-                take = conf > conf_thres && is_finite(conf) && box_ok && (allow == nullptr || allow[c] != 0);
+    unsigned todo = __ballot_sync(~0u, my_ok);
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const long long row = row0 + src;
+        const float* x = pred + row * (long long)no;
+        const float cx = __shfl_sync(~0u, h0, src), cy = __shfl_sync(~0u, h1, src), w = __shfl_sync(~0u, h2, src),
+                    h = __shfl_sync(~0u, h3, src), obj = __shfl_sync(~0u, h4, src);
+        // xywh2xyxy (utils.py:138-146)
+        const float hw = __fmul_rn(w, 0.5f), hh = __fmul_rn(h, 0.5f);
+        const float4 box = make_float4(__fsub_rn(cx, hw), __fsub_rn(cy, hh), __fadd_rn(cx, hw), __fadd_rn(cy, hh));
+        const bool box_ok = is_finite(box.x) && is_finite(box.y) && is_finite(box.z) && is_finite(box.w);
+        const unsigned long long img = (unsigned long long)(row / R);
+        const int base = EMIT ? row_off[row] : 0;
+        int n = 0;
+        if (multi_label) {
+            // (x[:, 5:] * obj > conf_thres).nonzero(): classes in ascending order within the row (utils.py:816-818)
+            for (int c0 = 0; c0 < nc; c0 += 32) {
+                const int c = c0 + lane;
+                float conf = 0.f;
+                bool take = false;
+                if (c < nc) {
+                    conf = __fmul_rn(x[5 + c], obj);
+                    take = conf > conf_thres && is_finite(conf) && box_ok && (allow == nullptr || allow[c] != 0);
+                }
+                const unsigned bal = __ballot_sync(~0u, take);
+                if (EMIT && take) {
+                    const int pos = base + n + __popc(bal & lanemask_lt());
+                    cand_box[pos] = box;
+                    cand_conf[pos] = conf;
+                    cand_cls[pos] = (float)c;
+                    keys[pos] = (img << 32) | desc_key(conf);
+                    vals[pos] = (unsigned)pos;
+                }
+                n += __popc(bal);
             }
-            const unsigned bal = __ballot_sync(~0u, take);
-            if (EMIT && take) {
-                const int pos = base + n + __popc(bal & lanemask_lt());
-                cand_box[pos] = box;
-                cand_conf[pos] = conf;
-                cand_cls[pos] = (float)c;
-                keys[pos] = (img << 32) | desc_key(conf);
-                vals[pos] = (unsigned)pos;
+        } else {
+            // conf, j = x[:, 5:].max(1): first index of the maximum, NaN propagates (and is dropped as non-finite)
+            float best = -INFINITY;
+            int arg = 0x7fffffff;
+            bool nan = false;
+            for (int c = lane; c < nc; c += 32) {
+                const float conf = __fmul_rn(x[5 + c], obj);
+                nan |= (conf != conf);
+                if (conf > best) { best = conf; arg = c; }
             }
-            n += __popc(bal);
-        }
-    } else {
-        // conf, j = x[:, 5:].max(1): first index of the maximum, NaN propagates (and is dropped as non-finite)
-        float best = -INFINITY;
-        int arg = 0x7fffffff;
-        bool nan = false;
-        for (int c = lane; c < nc; c += 32) {
-            const float conf = __fmul_rn(x[5 + c], obj);
-            nan |= (conf != conf);
-            if (conf > best) { best = conf; arg = c; }
-        }
-        nan = __any_sync(~0u, nan);
+            nan = __any_sync(~0u, nan);
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float ob = __shfl_xor_sync(~0u, best, o);
-            const int oa = __shfl_xor_sync(~0u, arg, o);
-            if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ob = __shfl_xor_sync(~0u, best, o);
+                const int oa = __shfl_xor_sync(~0u, arg, o);
+                if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+            }
+            const bool take = !nan && arg < nc && is_finite(best) && box_ok && (allow == nullptr || allow[arg] != 0);
+            if (EMIT && take && lane == 0) {
+                cand_box[base] = box;
+                cand_conf[base] = best;
+                cand_cls[base] = (float)arg;
+                keys[base] = (img << 32) | desc_key(best);
+                vals[base] = (unsigned)base;
+            }
+            n = take ? 1 : 0;
         }
-        const bool take = !nan && arg < nc && is_finite(best) && box_ok && (allow == nullptr || allow[arg] != 0);
-        if (EMIT && take && lane == 0) {
-            cand_box[base] = box;
-            cand_conf[base] = best;
-            cand_cls[base] = (float)arg;
-            keys[base] = (img << 32) | desc_key(best);
-            vals[base] = (unsigned)base;
-        }
-        n = take ? 1 : 0;
+        if (!EMIT && lane == 0) counts[row] = n;
     }
-    if (!EMIT && lane == 0) counts[row] = n;
 }
 
 __global__ void nms_image_offsets_kernel(const int* __restrict__ row_off, int B, int R, int* __restrict__ img_off) {
@@ -156,6 +186,7 @@ __global__ void __launch_bounds__(NT) nms_greedy_kernel(const int* __restrict__ 
 
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int off = img_off[b], n = img_off[b + 1] - off;
+    const bool nonneg = iou_thres >= 0.0;
     if (tid == 0) s_kept = 0;
     __syncthreads();
 
@@ -185,7 +216,7 @@ __global__ void __launch_bounds__(NT) nms_greedy_kernel(const int* __restrict__ 
             if (alive) {
                 for (int q = 0; q < kn; ++q) {
                     // torchvision: iarea (the kept box) + areas[j] - inter; `ovr > iou_threshold` with a double threshold
-                    if ((double)box_iou(s_box[q], s_area[q], box, area) > iou_thres) { alive = false; break; }
+                    if (iou_gt_d(s_box[q], s_area[q], box, area, iou_thres, nonneg)) { alive = false; break; }
                 }
             }
         }
@@ -202,8 +233,7 @@ __global__ void __launch_bounds__(NT) nms_greedy_kernel(const int* __restrict__ 
 #pragma unroll 4
                 for (int bit = 0; bit < 32; ++bit) {
                     const int j = j0 + bit;
-                    if (j > tid && j < cnt && s_alive[j] &&
-                        (double)box_iou(box, area, s_box[j], s_area[j]) > iou_thres)
+                    if (j > tid && j < cnt && s_alive[j] && iou_gt_d(box, area, s_box[j], s_area[j], iou_thres, nonneg))
                         word |= 1u << bit;
                 }
             }
@@ -264,7 +294,7 @@ __global__ void nms_finish_kernel(const int* __restrict__ img_off, const int* __
             for (int j = lane; j < n; j += 32) {
                 const float4 raw = cand_box[off + j];
                 const float4 sb = shift_box(raw, cand_cls[off + j], agnostic);
-                if (box_iou(kb, karea, sb, box_area(sb)) > iou_thres) {
+                if (iou_gt_f(kb, karea, sb, box_area(sb), iou_thres, iou_thres >= 0.f)) {
                     const double wgt = (double)cand_conf[off + j];
                     sx1 += wgt * raw.x; sy1 += wgt * raw.y; sx2 += wgt * raw.z; sy2 += wgt * raw.w;
                     sw += wgt;
@@ -381,8 +411,8 @@ extern "C" int b2y_nms_count(const float* pred, int batch, int rows, int nc, flo
     if (workspace_bytes < b2y_nms_count_workspace_bytes(batch, rows)) return B2Y_ERR_INVALID;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int multi = (multi_label && nc > 1) ? 1 : 0;              // multi_label &= nc > 1 (utils.py:794)
-    const int wpb = 8;
-    const unsigned grid = (unsigned)((total_rows + wpb - 1) / wpb);
+    const int wpb = 4;                                              // 4 warps x 32 rows per CTA
+    const unsigned grid = (unsigned)((total_rows + wpb * 32 - 1) / (wpb * 32));
     nms_rows_kernel<false><<<grid, wpb * 32, 0, st>>>(pred, total_rows, rows, nc, conf_thres, multi, class_allow,
                                                        row_off, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
     B2Y_CUDA_CHECK(cudaGetLastError());
@@ -427,8 +457,8 @@ extern "C" int b2y_nms_run(const float* pred, int batch, int rows, int nc, float
 
     const long long total_rows = (long long)batch * rows;
     const int multi = (multi_label && nc > 1) ? 1 : 0;
-    const int wpb = 8;
-    const unsigned grid = (unsigned)((total_rows + wpb - 1) / wpb);
+    const int wpb = 4;
+    const unsigned grid = (unsigned)((total_rows + wpb * 32 - 1) / (wpb * 32));
     nms_rows_kernel<true><<<grid, wpb * 32, 0, st>>>(pred, total_rows, rows, nc, conf_thres, multi, class_allow, nullptr,
                                                       row_off, cand_box, cand_conf, cand_cls, keys_in, vals_in);
     B2Y_CUDA_CHECK(cudaGetLastError());
