@@ -1,5 +1,6 @@
 #!/bin/bash
-# Final validation of the session: full GPU suite, bench line, ncu launch list of the NMS path.
+# End-of-round-2 evidence (third session): full GPU suite with its printed parity values, the bench line, an ncu launch list
+# of the NMS path.  Run on the GPU box:  bash profiles/capture_r02c.sh   (results land in gpurun_out/, copies in profiles/r02c/)
 mkdir -p gpurun_out
 S=gpurun_out/summary_final_r02c.txt
 : > $S
