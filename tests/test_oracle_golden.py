@@ -241,3 +241,35 @@ def test_preprocess_oracle_matches_reference():
         assert np.array_equal(out, g["out%d" % i]), (i, kw)
         assert np.array_equal(np.array(ratio, np.float64), g["ratio%d" % i])
         assert np.array_equal(np.array(pad, np.float64), g["pad%d" % i])
+
+
+def test_metrics_oracle_nms_modes_match_reference():
+    """oracle/metrics_oracle.nms in the modes map_case.npz does not exercise (best-class, class-agnostic, `classes=` filter,
+    single-class model, non-finite / out-of-range rows, an image without candidates) against the reference's own
+    non_max_suppression outputs (oracle/gen_golden_nms.py -> nms_modes_case.npz).  The kept set, its order, scores and
+    classes must be identical; merged boxes agree to the summation order of torch.mm (same library here: exact)."""
+    from oracle import metrics_oracle as mo
+    g = golden("nms_modes_case")
+    modes = {
+        "multi": dict(conf_thres=0.1, iou_thres=0.6),
+        "best": dict(conf_thres=0.1, iou_thres=0.6, multi_label=False),
+        "agnostic": dict(conf_thres=0.1, iou_thres=0.45, agnostic=True),
+        "classes": dict(conf_thres=0.1, iou_thres=0.6, classes=[1, 4, 7]),
+    }
+    checked = 0
+    for tag in ("nc10", "nc1"):
+        pred = torch.from_numpy(g["pred_" + tag])
+        for mode, kw in modes.items():
+            if ("%s_%s_0" % (tag, mode)) not in g.files:
+                continue
+            dets = mo.nms(pred.clone(), **kw)
+            for b, d in enumerate(dets):
+                ref = g["%s_%s_%d" % (tag, mode, b)]
+                if ref.shape[0] == 0:
+                    assert d is None, (tag, mode, b)
+                    continue
+                assert d is not None and tuple(d.shape) == ref.shape, (tag, mode, b)
+                assert np.array_equal(d[:, 4:].numpy(), ref[:, 4:]), (tag, mode, b)
+                np.testing.assert_allclose(d[:, :4].numpy(), ref[:, :4], rtol=1e-6, atol=1e-5)
+                checked += 1
+    assert checked >= 12
