@@ -634,6 +634,30 @@ def run_nms(args, dev, dd):
                         "of the candidate / detection counts" % (B, R, nc)}
 
 
+def run_tool_block(script, extra, what, timeout=170, env=None):
+    """Secondary block measured by one of the repo's stand-alone benchmark tools in its OWN process (tools/*.py print one
+    JSON line): a failure or a hang there cannot touch the headline that was measured above."""
+    cmd = [sys.executable, os.path.join(ROOT, "tools", script)] + list(extra)
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout,
+                           env=dict(os.environ, **env) if env else None)
+    except subprocess.TimeoutExpired:
+        return {"error": "%s: no result within %d s" % (script, timeout)}
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    if r.returncode != 0 or not lines:
+        tail = (r.stderr or r.stdout).strip().splitlines()[-1:] or [""]
+        return {"error": "%s exited with %d: %s" % (script, r.returncode, tail[0][:300])}
+    d = json.loads(lines[-1])
+    out = {k: d[k] for k in ("value", "unit", "ms_per_step") if k in d}
+    out["workload"] = what
+    out["measured_by"] = "tools/%s %s (own process%s)" % (script, " ".join(extra),
+                                                          ", " + " ".join("%s=%s" % kv for kv in env.items()) if env else "")
+    for k in ("loss_items", "calibration", "dtype"):
+        if k in d:
+            out[k] = d[k]
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -686,6 +710,21 @@ def main():
             secondary["nms_bs%d" % INFER_BATCH] = run_nms(args, dev, dd)
         except Exception as e:
             secondary["nms_bs%d" % INFER_BATCH] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+        # the two remaining BASELINE configurations, per-GPU slices, each in its own process
+        torch.cuda.empty_cache()
+        mb_args = ["--model", "yolov3-mobilenet", "--batch", "32", "--size", str(SIZE), "--steps", "10"]
+        mb_what = ("yolov3-mobilenet.cfg (depthwise-separable backbone) training step, 32 images / GPU, 640x640: forward + "
+                   "YOLO loss + backward + gradient exchange + fused SGD-Nesterov (BASELINE configs[3]: bs 128 on 4 GPUs)")
+        blk = run_tool_block("bench_train.py", mb_args, mb_what)
+        if "error" in blk:          # second attempt with eager launches instead of CUDA-graph replay
+            first = blk["error"]
+            blk = run_tool_block("bench_train.py", mb_args, mb_what, env={"B2Y_NO_GRAPH": "1"})
+            blk["first_attempt"] = first
+        secondary["yolov3_mobilenet_train_bs32"] = blk
+        secondary["yolov3_int8_ptq_infer_bs%d" % INFER_BATCH] = run_tool_block(
+            "bench_ptq_native.py", ["--batch", str(INFER_BATCH), "--size", str(SIZE), "--steps", "10"],
+            "yolov3.cfg INT8 PTQ inference bs=%d 640x640 (BASELINE configs[4] at the batch of configs[1]): native "
+            "calibration, then the tcgen05 kind::i8 graph" % INFER_BATCH)
 
     cpu, tgpu = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
