@@ -634,7 +634,7 @@ def run_nms(args, dev, dd):
                         "of the candidate / detection counts" % (B, R, nc)}
 
 
-def run_tool_block(script, extra, what, timeout=170, env=None):
+def run_tool_block(script, extra, what, timeout=120, env=None):
     """Secondary block measured by one of the repo's stand-alone benchmark tools in its OWN process (tools/*.py print one
     JSON line): a failure or a hang there cannot touch the headline that was measured above."""
     cmd = [sys.executable, os.path.join(ROOT, "tools", script)] + list(extra)
