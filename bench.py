@@ -641,13 +641,15 @@ def run_tool_block(script, extra, what, timeout=120, env=None):
     try:
         r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout,
                            env=dict(os.environ, **env) if env else None)
+        lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+        if r.returncode != 0 or not lines:
+            tail = (r.stderr or r.stdout).strip().splitlines()[-1:] or [""]
+            return {"error": "%s exited with %d: %s" % (script, r.returncode, tail[0][:300])}
+        d = json.loads(lines[-1])
     except subprocess.TimeoutExpired:
         return {"error": "%s: no result within %d s" % (script, timeout)}
-    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
-    if r.returncode != 0 or not lines:
-        tail = (r.stderr or r.stdout).strip().splitlines()[-1:] or [""]
-        return {"error": "%s exited with %d: %s" % (script, r.returncode, tail[0][:300])}
-    d = json.loads(lines[-1])
+    except Exception as e:          # a secondary block must never take the headline down
+        return {"error": "%s: %s: %s" % (script, type(e).__name__, str(e)[:300])}
     out = {k: d[k] for k in ("value", "unit", "ms_per_step") if k in d}
     out["workload"] = what
     out["measured_by"] = "tools/%s %s (own process%s)" % (script, " ".join(extra),
