@@ -60,3 +60,30 @@ def test_device_pixel_code_on_host_matches_reference(host_lib):
         assert rc == 0
         assert np.array_equal(out, g["out%d" % i]), "case %d %s differs from cv2 in %d bytes" % (
             i, kw, int((out != g["out%d" % i]).sum()))
+
+
+def test_resize_arithmetic_matches_cv2_on_random_sizes(host_lib):
+    """Property check beyond the fixture: for 40 seeded (source, target) size pairs -- strong up- and down-scaling,
+    1-pixel-wide sources, exact integer ratios, 1 and 3 channels -- the device per-pixel code (host harness) and the numpy
+    oracle both reproduce cv2.resize(..., INTER_LINEAR) byte for byte.  OpenCV is what the reference's letterbox calls;
+    it ships in this image (skipped where it does not)."""
+    cv2 = pytest.importorskip("cv2")
+    import preprocess_oracle as po
+    rng = np.random.default_rng(123)
+    pairs = [(1, 37, 64, 64), (37, 1, 64, 64), (2, 2, 96, 160), (480, 640, 480, 640), (300, 300, 100, 100),
+             (300, 300, 900, 900), (511, 13, 64, 257), (1080, 1920, 135, 240)]
+    while len(pairs) < 40:
+        pairs.append(tuple(int(v) for v in (rng.integers(1, 400), rng.integers(1, 400), rng.integers(1, 400),
+                                            rng.integers(1, 400))))
+    for k, (h, w, dh, dw) in enumerate(pairs):
+        c = 1 if k % 5 == 4 else 3
+        img = rng.integers(0, 256, (h, w, c), dtype=np.uint8)
+        ref = cv2.resize(img if c == 3 else img[:, :, 0], (dw, dh), interpolation=cv2.INTER_LINEAR).reshape(dh, dw, c)
+        if (h, w) == (dh, dw):
+            assert np.array_equal(ref, img)
+            continue
+        assert np.array_equal(po.resize_linear_u8(img, dw, dh), ref), ("oracle", h, w, dh, dw, c)
+        out = np.zeros((c, dh, dw), np.uint8)
+        host_lib.b2y_letterbox_u8_host(img.ctypes.data_as(C.c_void_p), h, w, c, C.c_longlong(w * c), dh, dw, 0, 0,
+                                       out.ctypes.data_as(C.c_void_p), dh, dw, 0, 114)
+        assert np.array_equal(out.transpose(1, 2, 0), ref), ("device code", h, w, dh, dw, c)
