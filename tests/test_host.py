@@ -175,3 +175,29 @@ def test_generated_cfg_equals_reference_cfg(name, rel):
             assert a.get(k) == b.get(k), (name, k, a, b)
         if 'anchors' in b:
             assert np.array_equal(a['anchors'], b['anchors'])
+
+
+def test_prepare_labels_matches_the_reference_expressions():
+    """b200yolo.detect.prepare_labels (host-side torch ops feeding the TP-matching kernel) against test.py:124, 145-148
+    evaluated image by image: labels = targets[targets[:, 0] == si, 1:]; tbox = xywh2xyxy(labels[:, 1:5]) * whwh."""
+    import torch
+    from b200yolo import detect
+    from utils import utils as U
+    g = torch.Generator().manual_seed(4)
+    B, W, H = 5, 640, 416
+    t = torch.rand(23, 6, generator=g)
+    t[:, 0] = torch.tensor([3, 0, 0, 4, 3, 1, 0, 4, 4, 1, 3, 0, 1, 1, 0, 3, 4, 0, 1, 3, 0, 4, 1]).float()   # image 2 is empty
+    t[:, 1] = torch.randint(0, 80, (23,), generator=g).float()
+    tcls, tbox, lab_off = detect.prepare_labels(t, B, W, H, torch.device("cpu"))
+    whwh = torch.tensor([W, H, W, H], dtype=torch.float32)
+    off = 0
+    for si in range(B):
+        labels = t[t[:, 0] == si, 1:]
+        n = labels.shape[0]
+        assert int(lab_off[si]) == off and int(lab_off[si + 1]) == off + n
+        if n:
+            assert torch.equal(tcls[off:off + n], labels[:, 0])
+            assert torch.equal(tbox[off:off + n], U.xywh2xyxy(labels[:, 1:5]) * whwh)
+        off += n
+    e = detect.prepare_labels(torch.zeros(0, 6), B, W, H, torch.device("cpu"))
+    assert e[0].numel() == 0 and e[1].shape == (0, 4) and e[2].tolist() == [0] * (B + 1)

@@ -117,6 +117,32 @@ def match_labels(packed, tcls, tbox, lab_off, iouv, clip_w=0.0, clip_h=0.0):
     return out
 
 
+def prepare_labels(targets, batch, width, height, device):
+    """targets [nT, 6] (image, cls, xywh normalised) -> (tcls [nT], tbox [nT, 4] xyxy px, lab_off int32 [batch + 1]) with the
+    labels grouped by image in their given order, exactly what test.py:124, 145-148 builds per image:
+    labels = targets[targets[:, 0] == si, 1:];  tbox = xywh2xyxy(labels[:, 1:5]) * whwh.  Device-agnostic torch ops."""
+    if targets is None or targets.numel() == 0:
+        return (torch.zeros((0,), dtype=torch.float32, device=device),
+                torch.zeros((0, 4), dtype=torch.float32, device=device),
+                torch.zeros((batch + 1,), dtype=torch.int32, device=device))
+    t = targets.to(device).float()
+    img = t[:, 0].long()
+    order = torch.sort(img, stable=True)[1]       # labels = targets[targets[:, 0] == si] keeps the given order
+    t = t[order]
+    whwh = torch.tensor([width, height, width, height], dtype=torch.float32, device=device)
+    xywh = t[:, 2:6]
+    tbox = torch.empty_like(xywh)                 # xywh2xyxy(labels[:, 1:5]) * whwh   (test.py:148)
+    tbox[:, 0] = xywh[:, 0] - xywh[:, 2] / 2
+    tbox[:, 1] = xywh[:, 1] - xywh[:, 3] / 2
+    tbox[:, 2] = xywh[:, 0] + xywh[:, 2] / 2
+    tbox[:, 3] = xywh[:, 1] + xywh[:, 3] / 2
+    tbox = tbox * whwh
+    cnt = torch.bincount(img.clamp(0, batch - 1), minlength=batch)[:batch]
+    lab_off = torch.zeros((batch + 1,), dtype=torch.int32, device=device)
+    lab_off[1:] = torch.cumsum(cnt, 0).to(torch.int32)
+    return t[:, 1], tbox, lab_off
+
+
 def match_batch(packed, targets, width, height, iouv, clip=True):
     """test.py:123-175 for the whole batch.  packed: PackedDetections; targets [nT, 6] (image, cls, xywh normalised) on
     the device; iouv: the IoU thresholds (torch.linspace(0.5, 0.95, 10)).  Boxes are clipped in place to the image like
@@ -124,28 +150,7 @@ def match_batch(packed, targets, width, height, iouv, clip=True):
     the image has no detections): a prediction is a true positive at threshold q when it is the first prediction, in
     score order, whose best same-class target is that target and its IoU exceeds iouv[q]."""
     dev = packed.det.device
-    B = len(packed)
     with torch.cuda.device(dev):
-        if targets is None or targets.numel() == 0:
-            tcls = torch.zeros((0,), dtype=torch.float32, device=dev)
-            tbox = torch.zeros((0, 4), dtype=torch.float32, device=dev)
-            lab_off = torch.zeros((B + 1,), dtype=torch.int32, device=dev)
-        else:
-            t = targets.to(dev).float()
-            img = t[:, 0].long()
-            order = torch.sort(img, stable=True)[1]       # labels = targets[targets[:, 0] == si] keeps the given order
-            t = t[order]
-            whwh = torch.tensor([width, height, width, height], dtype=torch.float32, device=dev)
-            xywh = t[:, 2:6]
-            tbox = torch.empty_like(xywh)                 # xywh2xyxy(labels[:, 1:5]) * whwh   (test.py:148)
-            tbox[:, 0] = xywh[:, 0] - xywh[:, 2] / 2
-            tbox[:, 1] = xywh[:, 1] - xywh[:, 3] / 2
-            tbox[:, 2] = xywh[:, 0] + xywh[:, 2] / 2
-            tbox[:, 3] = xywh[:, 1] + xywh[:, 3] / 2
-            tbox = tbox * whwh
-            tcls = t[:, 1]
-            cnt = torch.bincount(img.clamp(0, B - 1), minlength=B)[:B]
-            lab_off = torch.zeros((B + 1,), dtype=torch.int32, device=dev)
-            lab_off[1:] = torch.cumsum(cnt, 0).to(torch.int32)
+        tcls, tbox, lab_off = prepare_labels(targets, len(packed), width, height, dev)
     cw, ch = (float(width), float(height)) if clip else (0.0, 0.0)
     return match_labels(packed, tcls, tbox, lab_off, iouv, cw, ch)
