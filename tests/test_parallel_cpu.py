@@ -88,3 +88,23 @@ def test_flat_data_parallel_gloo():
     assert r0["n_decay"] == n_decay and names[0] == "module_list.0.Conv2d.weight"
     assert sorted(names) == sorted(n for n, _ in ref.named_parameters())
     assert r0["params"].numel() == sum(p.numel() for p in ref.parameters()) == 8852366
+
+
+def test_bn_sparsity_range_table_points_at_the_bn_scales():
+    """FlatDataParallel.set_bn_sparsity (BNOptimizer.updateBN, prune_utils.py:133-138): the (offset, length) rows handed to
+    b2y_l1_subgrad_ranges address exactly the BatchNorm scale vectors of the listed layers inside the flat buffers (the
+    kernel itself is checked on the GPU, tests/test_gpu_train_kernels.py)."""
+    from b200yolo.parallel import FlatDataParallel
+    m = _real_model()
+    dp = FlatDataParallel(m)
+    prune_idx = [0, 4, 8, 12]
+    dp.set_bn_sparsity(prune_idx, 0.001)
+    table, s = dp._l1
+    assert s == 0.001 and table.dtype == torch.int64 and tuple(table.shape) == (len(prune_idx), 2)
+    for (off, ln), idx in zip(table.tolist(), prune_idx):
+        bn = m.module_list[idx][1]
+        assert isinstance(bn, nn.BatchNorm2d) and ln == bn.weight.numel()
+        assert dp.flat_param[off:off + ln].data_ptr() == bn.weight.data_ptr()
+        assert dp.flat_grad[off:off + ln].data_ptr() == bn.weight.grad.data_ptr()
+    dp.set_bn_sparsity(prune_idx, 0.0)          # s = 0 switches it off
+    assert dp._l1 is None
